@@ -1,0 +1,136 @@
+/* mdb_b200.h -- C ABI of the B200-native per-frame analysis path of MDDatasetBuilder.
+ *
+ * This is the drop-in boundary.  The reference has no FFI registry
+ * for this path; its per-frame work sits behind Python call sites that run inside
+ * multiprocessing.Pool children.  Each entry point below names the reference
+ * interface (file:line under /root/reference/mddatasetbuilder) whose arithmetic it
+ * replaces.  Signatures use plain pointers and sizes only (no torch types); the
+ * reference-side ctypes stubs are in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All functions return 0 on success, non-zero on error; mdb_last_error() gives
+ *    the message (thread-local).  Python maps non-zero to RuntimeError, like the
+ *    reference's own error behaviour for malformed frames (detect.py:49,83,174,189).
+ *  - Pointers named d_* are DEVICE pointers owned by the caller; h_* are HOST
+ *    pointers.  Work is enqueued on `stream` (a cudaStream_t passed as void*); the
+ *    call returns without synchronising unless stated.
+ *  - A batch holds `nframes` frames of `natoms` atoms (the reference requires a
+ *    constant atom count, detect.py:182-191).  Positions are double [F][N][3] in
+ *    atom-id order (id-1), cells are double [F][9] = three lattice-vector rows, as
+ *    DetectDump.readcrd builds them (detect.py:326-345).
+ *  - types[i] is the 0-based index into `atomname` (LAMMPS type - 1;
+ *    detect.py:87,193,314).
+ *  - Neighbour lists are exchanged as ELL rows: int32 [F][N][maxb], ascending
+ *    partner index, padded with -1 (one 32-byte sector per atom at maxb = 8), and on
+ *    request as CSR (rowptr int32 [F][N+1] frame-local, col int32 [F][colcap]).
+ *  - Scratch memory comes from an arena owned by the context; it grows on first use
+ *    of a batch shape and is reused afterwards (no allocation in steady state).
+ */
+#ifndef MDB_B200_H
+#define MDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mdb_ctx mdb_ctx;
+
+#define MDB_ORDER_INDEX 0 /* rows ascending by partner index (canonical) */
+#define MDB_ORDER_OB 1    /* rows in Open Babel bond-iteration order = ascending partner (z, index) */
+
+/* ---- library / context ------------------------------------------------------ */
+int mdb_version(void);
+const char *mdb_last_error(void);
+
+/* One context per (process, GPU).  Replaces the per-process state the reference
+ * keeps in a Pool child (utils.py:198-231): one context drives one GPU. */
+int mdb_create(int device, mdb_ctx **out);
+void mdb_destroy(mdb_ctx *ctx);
+
+/* Element table: atomic number per type index (atomname -> Z, as
+ * ase.data.atomic_numbers at datasetbuilder.py:145-147).  Fixes the covalent radii,
+ * max-valence and Coulomb diagonal (Z^2.4/2) tables used by the kernels. */
+int mdb_set_elements(mdb_ctx *ctx, int ntypes, const int *atomic_numbers);
+
+/* Tunables: "cell_edge" (A; 0 = heuristic), "max_bonds" (8 or 16),
+ * "frames_per_launch" (0 = heuristic).  Returns non-zero for an unknown key. */
+int mdb_set_option(mdb_ctx *ctx, const char *key, double value);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t mdb_launch_count(const mdb_ctx *ctx);
+size_t mdb_arena_bytes(const mdb_ctx *ctx);
+
+/* ---- K1+K2: bond detection from coordinates ---------------------------------
+ * Replaces DetectDump._crd2bond(step_atoms, readlevel=False) (detect.py:249-292):
+ * Open Babel ConnectTheDots = pairs with 0.16 <= d2_MIC <= (Rcov_i+Rcov_j+0.45)^2
+ * followed by the index-ordered valence / 45-degree-angle cleanup.
+ * h_cell: host [F][9]; periodic: 0/1 (DatasetBuilder(pbc=...)).
+ * d_ell: out int32 [F][N][max_bonds]. */
+int mdb_bonds_from_coords(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                          const double *h_cell, const uint8_t *d_types, int periodic,
+                          int32_t *d_ell, void *stream);
+
+/* ELL -> CSR (adjacency lists of detect.py:278-291).  order = MDB_ORDER_INDEX or
+ * MDB_ORDER_OB (needs d_pos for the z sort).  d_rowptr [F][N+1], d_col [F][colcap].
+ * Fails (after synchronising) if a frame holds more than colcap entries. */
+int mdb_ell_to_csr(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, int order,
+                   const double *d_pos, int32_t *d_rowptr, int32_t *d_col, int colcap,
+                   void *stream);
+
+/* ---- K3: bond-type keys ------------------------------------------------------
+ * Replaces the per-atom key of DetectDump.readatombondtype (detect.py:219-225) in
+ * dump-only mode: (element, sorted bond orders) with every order 1 (tier-1
+ * deviation: PerceiveBondOrders is not restated).  Key packing: bits 56..63
+ * element index + 1, bits 48..55 number of levels, nibble k = k-th smallest level.
+ * Also writes the union-find seed (parent = min(self, smallest neighbour)) when
+ * d_parent != NULL, so that mdb_components can skip its own init pass. */
+int mdb_bond_keys(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell,
+                  const uint8_t *d_types, uint64_t *d_keys, int32_t *d_parent, void *stream);
+
+/* Bond-file mode keys, replaces DetectBond.readatombondtype (detect.py:105-119):
+ * level = max(1, round_half_even(bo)), sorted ascending.  d_bo: double per ELL slot. */
+int mdb_bond_keys_bo(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell,
+                     const double *d_bo, const uint8_t *d_types, uint64_t *d_keys, void *stream);
+
+/* ---- K4: connectivity --------------------------------------------------------
+ * Replaces the partition computed by dps(bonds) (dps.pyx:17-46): d_labels[f][i] =
+ * smallest atom index of the molecule containing i (the DFS root the reference
+ * starts each molecule from).  seeded != 0 means d_labels already holds the seed
+ * written by mdb_bond_keys. */
+int mdb_components(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell,
+                   int32_t *d_labels, int seeded, void *stream);
+
+/* Exact dps output (molecule order by smallest index, members in the reference's
+ * LIFO-DFS visiting order, dps.pyx:27-43) for one frame, from a CSR whose row
+ * order is the adjacency order.  d_mol_atoms [N], d_mol_ptr [N+1], *h_nmol out
+ * (synchronises). */
+int mdb_dps(mdb_ctx *ctx, int natoms, const int32_t *d_rowptr, const int32_t *d_col,
+            int32_t *d_mol_atoms, int32_t *d_mol_ptr, int *h_nmol, void *stream);
+
+/* ---- fused per-frame bond path (the benchmark "step") -------------------------
+ * cell list -> bonds -> cleanup -> keys -> connectivity for a batch, i.e. what
+ * readatombondtype + readmolecule produce per frame in dump-only mode.
+ * Any output pointer may be NULL. */
+int mdb_analyze_frames(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                       const double *h_cell, const uint8_t *d_types, int periodic,
+                       int32_t *d_ell, uint64_t *d_keys, int32_t *d_labels, void *stream);
+
+/* Host-buffer variant (the e2e path): copies positions H2D, runs
+ * mdb_analyze_frames, copies ELL / keys / labels D2H, pipelined over internal
+ * streams in chunks of frames; synchronises before returning.  Buffers should be
+ * page-locked for full PCIe bandwidth. */
+int mdb_analyze_frames_host(mdb_ctx *ctx, int nframes, int natoms, const double *h_pos,
+                            const double *h_cell, const uint8_t *h_types, int periodic,
+                            int32_t *h_ell, uint64_t *h_keys, int32_t *h_labels);
+
+/* Diagnostics of the last bond batch: counts summed over frames (synchronises). */
+int mdb_bond_stats(mdb_ctx *ctx, long long *n_violators, long long *n_exact_tests,
+                   long long *n_overflow);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDB_B200_H */

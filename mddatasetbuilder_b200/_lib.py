@@ -1,0 +1,65 @@
+"""ctypes binding of libmdb_b200.so (the C ABI declared in include/mdb_b200.h).
+
+There is no CPU fallback: if the CUDA library has not been built, or no sm_100a device is
+present, every entry point raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``mddatasetbuilder_b200/csrc/build.sh``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmdb_b200.so")
+_lib = None
+
+c_ctx = C.c_void_p
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/mdb_b200.h one to one
+SIGNATURES = {
+    "mdb_version": (C.c_int, []),
+    "mdb_last_error": (C.c_char_p, []),
+    "mdb_create": (C.c_int, [C.c_int, C.POINTER(c_ctx)]),
+    "mdb_destroy": (None, [c_ctx]),
+    "mdb_set_elements": (C.c_int, [c_ctx, C.c_int, C.POINTER(C.c_int)]),
+    "mdb_set_option": (C.c_int, [c_ctx, C.c_char_p, C.c_double]),
+    "mdb_launch_count": (C.c_uint64, [c_ctx]),
+    "mdb_arena_bytes": (C.c_size_t, [c_ctx]),
+    "mdb_bonds_from_coords": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "mdb_ell_to_csr": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
+    "mdb_bond_keys": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mdb_bond_keys_bo": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mdb_components": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "mdb_dps": (C.c_int, [c_ctx, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp]),
+    "mdb_analyze_frames": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "mdb_analyze_frames_host": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "mdb_bond_stats": (C.c_int, [c_ctx, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+}
+
+
+def lib():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA library of mddatasetbuilder_b200 has not been built "
+                "(run mddatasetbuilder_b200/csrc/build.sh). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = header and library out of sync
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().mdb_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {last_error()}")

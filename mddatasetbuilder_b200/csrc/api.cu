@@ -1,0 +1,278 @@
+// api.cu -- extern "C" entry points declared in include/mdb_b200.h.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+static int check_ctx(mdb_ctx *c, const char *fn, bool need_elements = true) {
+    if (!c) {
+        mdb_set_error(std::string(fn) + ": context is NULL");
+        return -1;
+    }
+    if (need_elements && !c->have_elements) {
+        mdb_set_error(std::string(fn) + ": call mdb_set_elements first");
+        return -1;
+    }
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return mdb_cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    return 0;
+}
+
+static const char *err_text(int e) {
+    switch (e) {
+        case MDB_ERR_CELL_OVERFLOW:
+            return "more than 255 atoms fell into one cell (overlapping atoms?)";
+        case MDB_ERR_BOND_OVERFLOW:
+            return "an atom has more raw neighbours than max_bonds; set option max_bonds=16";
+        case MDB_ERR_CSR_OVERFLOW:
+            return "CSR column capacity exceeded";
+        case MDB_ERR_TYPE_RANGE:
+            return "atom type index outside the element table";
+        default:
+            return "unknown device-side error";
+    }
+}
+
+static int frames_per_chunk(const mdb_ctx *c, int nframes, int natoms) {
+    if (c->opt_frames_per_launch > 0) return std::min(nframes, c->opt_frames_per_launch);
+    long long per = std::max(1LL, (4LL << 20) / std::max(natoms, 1));
+    per = std::min<long long>(per, ((1LL << 30) / std::max(natoms, 1)));
+    return (int)std::max(1LL, std::min<long long>(per, nframes));
+}
+
+// one chunk of frames through cell list -> bonds -> cleanup [-> keys -> components]
+static int analyze_chunk(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
+                         int periodic, int32_t *d_ell, uint64_t *d_keys, int32_t *d_labels, cudaStream_t stream) {
+    std::vector<double> bbox;
+    if (!periodic) {
+        bbox.resize((size_t)F * 6);
+        if (bbox_frames(c, F, N, d_pos, bbox.data(), stream)) return -1;
+    } else if (!h_cell) {
+        mdb_set_error("periodic frames need a cell");
+        return -1;
+    }
+    std::vector<FrameGeom> geom;
+    long long total_cells = 0;
+    const double edge_min = (double)c->el.rc_max * 1.0005;
+    if (build_geometry(c, F, N, h_cell, periodic, bbox.data(), edge_min, c->opt_cell_edge, geom, &total_cells)) return -1;
+    double lmax = 0;
+    bool all_ortho = true;
+    for (const FrameGeom &g : geom) {
+        all_ortho = all_ortho && g.is_ortho;
+        for (int v = 0; v < 3; ++v) {
+            double l = sqrt(g.ortho[v] * g.ortho[v] + g.ortho[3 + v] * g.ortho[3 + v] + g.ortho[6 + v] * g.ortho[6 + v]);
+            lmax = std::max(lmax, l);
+        }
+    }
+    // float screening error: |delta d2| <~ 8 * rc * 2^-24 * L * sqrt(3); x1.5 safety
+    c->el.margin = (float)(1.25e-6 * c->el.rc_max * lmax + 1e-5);
+
+    const int maxb = c->opt_max_bonds;
+    size_t fn = (size_t)F * N;
+    size_t need = align256(geom.size() * sizeof(FrameGeom)) + cells_workspace_bytes(F, N, total_cells) +
+                  bonds_workspace_bytes(F, N) + (d_ell ? 0 : align256(fn * maxb * sizeof(int32_t))) +
+                  (d_labels ? 0 : align256(fn * sizeof(int32_t))) + 4096;
+    if (arena_reserve(c, need, stream)) return -1;
+    arena_reset(c);
+    FrameGeom *d_geom = (FrameGeom *)arena_alloc(c, geom.size() * sizeof(FrameGeom));
+    if (!d_ell) d_ell = (int32_t *)arena_alloc(c, fn * maxb * sizeof(int32_t));
+    if (!d_geom || !d_ell) {
+        mdb_set_error("analyze_chunk: arena too small (internal sizing error)");
+        return -1;
+    }
+    if (upload_geometry(c, geom, d_geom, stream)) return -1;
+    CellList cl;
+    if (cells_build(c, F, N, d_pos, d_types, d_geom, total_cells, periodic, &cl, &c->d_stats->err, stream)) return -1;
+    cl.all_ortho = all_ortho;
+    if (bonds_run(c, F, N, d_pos, d_types, cl, periodic, d_ell, stream)) return -1;
+    if (d_keys || d_labels) {
+        if (keys_run(c, F, N, d_ell, d_types, d_keys, d_labels, stream)) return -1;
+        if (d_labels && components_run(c, F, N, d_ell, d_labels, 1, stream)) return -1;
+    }
+    return 0;
+}
+
+static int analyze_frames(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                          const uint8_t *d_types, int periodic, int32_t *d_ell, uint64_t *d_keys, int32_t *d_labels,
+                          cudaStream_t stream) {
+    if (nframes < 0 || natoms < 0 || (long long)natoms >= (1LL << MDB_IDX_BITS)) {
+        mdb_set_error("bad batch shape (natoms must be < 2^27)");
+        return -1;
+    }
+    MDB_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(BondStats), stream));
+    if (nframes == 0 || natoms == 0) return 0;
+    const int per = frames_per_chunk(c, nframes, natoms);
+    const int maxb = c->opt_max_bonds;
+    for (int f0 = 0; f0 < nframes; f0 += per) {
+        int F = std::min(per, nframes - f0);
+        size_t o = (size_t)f0 * natoms;
+        if (analyze_chunk(c, F, natoms, d_pos + o * 3, h_cell ? h_cell + (size_t)f0 * 9 : nullptr, d_types, periodic,
+                          d_ell ? d_ell + o * maxb : nullptr, d_keys ? d_keys + o : nullptr,
+                          d_labels ? d_labels + o : nullptr, stream))
+            return -1;
+    }
+    return 0;
+}
+
+extern "C" int mdb_bonds_from_coords(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                     const uint8_t *d_types, int periodic, int32_t *d_ell, void *stream) {
+    if (check_ctx(c, "mdb_bonds_from_coords")) return -1;
+    if (!d_ell) {
+        mdb_set_error("mdb_bonds_from_coords: d_ell is NULL");
+        return -1;
+    }
+    return analyze_frames(c, nframes, natoms, d_pos, h_cell, d_types, periodic, d_ell, nullptr, nullptr,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int mdb_analyze_frames(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                  const uint8_t *d_types, int periodic, int32_t *d_ell, uint64_t *d_keys,
+                                  int32_t *d_labels, void *stream) {
+    if (check_ctx(c, "mdb_analyze_frames")) return -1;
+    return analyze_frames(c, nframes, natoms, d_pos, h_cell, d_types, periodic, d_ell, d_keys, d_labels,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int mdb_ell_to_csr(mdb_ctx *c, int nframes, int natoms, const int32_t *d_ell, int order, const double *d_pos,
+                              int32_t *d_rowptr, int32_t *d_col, int colcap, void *stream) {
+    if (check_ctx(c, "mdb_ell_to_csr", false)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((long long)nframes * natoms >= (1LL << 31) - 64) {
+        mdb_set_error("mdb_ell_to_csr: batch too large, split the frames");
+        return -1;
+    }
+    if (ell_to_csr_run(c, nframes, natoms, d_ell, order, d_pos, d_rowptr, d_col, colcap, s)) return -1;
+    int err = 0;
+    MDB_CUDA(cudaMemcpyAsync(&err, &c->d_stats->err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MDB_CUDA(cudaStreamSynchronize(s));
+    if (err) {
+        mdb_set_error(std::string("mdb_ell_to_csr: ") + err_text(err));
+        return err;
+    }
+    return 0;
+}
+
+extern "C" int mdb_bond_keys(mdb_ctx *c, int nframes, int natoms, const int32_t *d_ell, const uint8_t *d_types,
+                             uint64_t *d_keys, int32_t *d_parent, void *stream) {
+    if (check_ctx(c, "mdb_bond_keys", false)) return -1;
+    return keys_run(c, nframes, natoms, d_ell, d_types, d_keys, d_parent, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_bond_keys_bo(mdb_ctx *c, int nframes, int natoms, const int32_t *d_ell, const double *d_bo,
+                                const uint8_t *d_types, uint64_t *d_keys, void *stream) {
+    if (check_ctx(c, "mdb_bond_keys_bo", false)) return -1;
+    return keys_bo_run(c, nframes, natoms, d_ell, d_bo, d_types, d_keys, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_components(mdb_ctx *c, int nframes, int natoms, const int32_t *d_ell, int32_t *d_labels, int seeded,
+                              void *stream) {
+    if (check_ctx(c, "mdb_components", false)) return -1;
+    return components_run(c, nframes, natoms, d_ell, d_labels, seeded, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_dps(mdb_ctx *c, int natoms, const int32_t *d_rowptr, const int32_t *d_col, int32_t *d_mol_atoms,
+                       int32_t *d_mol_ptr, int *h_nmol, void *stream) {
+    if (check_ctx(c, "mdb_dps", false)) return -1;
+    return dps_run(c, natoms, d_rowptr, d_col, d_mol_atoms, d_mol_ptr, h_nmol, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_bond_stats(mdb_ctx *c, long long *n_violators, long long *n_exact, long long *n_overflow) {
+    if (check_ctx(c, "mdb_bond_stats", false)) return -1;
+    MDB_CUDA(cudaDeviceSynchronize());
+    BondStats h;
+    MDB_CUDA(cudaMemcpy(&h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    if (n_violators) *n_violators = (long long)h.violators;
+    if (n_exact) *n_exact = (long long)h.exact_tests;
+    if (n_overflow) *n_overflow = (long long)h.overflow;
+    if (h.err) {
+        mdb_set_error(std::string("device-side error: ") + err_text(h.err));
+        return h.err;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer pipeline: H2D(k+1) | compute(k) | D2H(k-1) on three streams, double buffered.
+// ---------------------------------------------------------------------------------------------
+struct PipeBuf {
+    double *pos = nullptr;
+    int32_t *ell = nullptr;
+    uint64_t *keys = nullptr;
+    int32_t *labels = nullptr;
+};
+
+extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
+                                       const uint8_t *h_types, int periodic, int32_t *h_ell, uint64_t *h_keys,
+                                       int32_t *h_labels) {
+    if (check_ctx(c, "mdb_analyze_frames_host")) return -1;
+    if (nframes <= 0 || natoms <= 0) return 0;
+    const int maxb = c->opt_max_bonds;
+    const int per = frames_per_chunk(c, nframes, natoms);
+    const size_t cn = (size_t)per * natoms;
+    const size_t sz_pos = align256(cn * 3 * sizeof(double)), sz_ell = align256(cn * maxb * sizeof(int32_t)),
+                 sz_keys = align256(cn * sizeof(uint64_t)), sz_lab = align256(cn * sizeof(int32_t));
+    const size_t need = sz_pos + sz_ell + sz_keys + sz_lab;
+    PipeBuf b[2];
+    for (int k = 0; k < 2; ++k) {
+        if (c->pipe_cap[k] < need) {
+            MDB_CUDA(cudaDeviceSynchronize());
+            if (c->pipe_mem[k]) MDB_CUDA(cudaFree(c->pipe_mem[k]));
+            c->pipe_mem[k] = nullptr;
+            c->pipe_cap[k] = 0;
+            MDB_CUDA(cudaMalloc(&c->pipe_mem[k], need));
+            c->pipe_cap[k] = need;
+        }
+        char *m = c->pipe_mem[k];
+        b[k].pos = (double *)m;
+        b[k].ell = (int32_t *)(m + sz_pos);
+        b[k].keys = (uint64_t *)(m + sz_pos + sz_ell);
+        b[k].labels = (int32_t *)(m + sz_pos + sz_ell + sz_keys);
+    }
+    if (c->pipe_types_cap < (size_t)natoms) {
+        MDB_CUDA(cudaDeviceSynchronize());
+        if (c->pipe_types) MDB_CUDA(cudaFree(c->pipe_types));
+        c->pipe_types = nullptr;
+        MDB_CUDA(cudaMalloc(&c->pipe_types, (size_t)natoms + 256));
+        c->pipe_types_cap = (size_t)natoms + 256;
+    }
+    cudaStream_t s_in = c->pipe[0], s_c = c->pipe[1], s_out = c->pipe[2];
+    MDB_CUDA(cudaMemcpyAsync(c->pipe_types, h_types, natoms, cudaMemcpyHostToDevice, s_c));
+    MDB_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(BondStats), s_c));
+    int chunk = 0;
+    for (int f0 = 0; f0 < nframes; f0 += per, ++chunk) {
+        const int F = std::min(per, nframes - f0);
+        const size_t o = (size_t)f0 * natoms, n = (size_t)F * natoms;
+        const int k = chunk & 1;
+        PipeBuf &B = b[k];
+        if (chunk >= 2) MDB_CUDA(cudaStreamWaitEvent(s_in, c->pipe_comp[k], 0));
+        MDB_CUDA(cudaMemcpyAsync(B.pos, h_pos + o * 3, n * 3 * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        MDB_CUDA(cudaEventRecord(c->pipe_in[k], s_in));
+        MDB_CUDA(cudaStreamWaitEvent(s_c, c->pipe_in[k], 0));
+        if (chunk >= 2) MDB_CUDA(cudaStreamWaitEvent(s_c, c->pipe_out[k], 0));
+        if (analyze_chunk(c, F, natoms, B.pos, h_cell ? h_cell + (size_t)f0 * 9 : nullptr, c->pipe_types, periodic, B.ell,
+                          h_keys ? B.keys : nullptr, h_labels ? B.labels : nullptr, s_c)) {
+            cudaDeviceSynchronize();
+            return -1;
+        }
+        MDB_CUDA(cudaEventRecord(c->pipe_comp[k], s_c));
+        MDB_CUDA(cudaStreamWaitEvent(s_out, c->pipe_comp[k], 0));
+        if (h_ell)
+            MDB_CUDA(cudaMemcpyAsync(h_ell + o * maxb, B.ell, n * maxb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        if (h_keys) MDB_CUDA(cudaMemcpyAsync(h_keys + o, B.keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_out));
+        if (h_labels)
+            MDB_CUDA(cudaMemcpyAsync(h_labels + o, B.labels, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        MDB_CUDA(cudaEventRecord(c->pipe_out[k], s_out));
+    }
+    MDB_CUDA(cudaStreamSynchronize(s_in));
+    MDB_CUDA(cudaStreamSynchronize(s_c));
+    MDB_CUDA(cudaStreamSynchronize(s_out));
+    BondStats hs;
+    MDB_CUDA(cudaMemcpy(&hs, c->d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    if (hs.err) {
+        mdb_set_error(std::string("mdb_analyze_frames_host: ") + err_text(hs.err));
+        return hs.err;
+    }
+    return 0;
+}

@@ -1,0 +1,137 @@
+// common.cuh -- shared definitions of the sm_100a kernels behind include/mdb_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mdb_b200.h"
+
+#define MDB_IDX_BITS 27
+#define MDB_IDX_MASK ((1u << MDB_IDX_BITS) - 1u)
+// flag bits carried in ELL slots while the cleanup pass runs (never visible to callers)
+#define MDB_TOMB 0x80000000u   // this neighbour entry was deleted
+#define MDB_PEND 0x40000000u   // (slot 0) row owner is a pending valence/angle violator
+#define MDB_DIRTY 0x20000000u  // (slot 0) row needs compaction
+#define MDB_MAXT 8             // max element types per trajectory
+#define MDB_MAXZ 18
+
+#define MDB_ERR_CELL_OVERFLOW 1  // > 255 atoms in one cell
+#define MDB_ERR_BOND_OVERFLOW 2  // more raw neighbours than max_bonds
+#define MDB_ERR_CSR_OVERFLOW 3
+#define MDB_ERR_TYPE_RANGE 4
+
+struct FrameGeom {
+    double ortho[9];    // fractional -> cartesian (lattice vectors as columns), OB's _mOrtho
+    double frac[9];     // cartesian -> fractional, adjugate/det like matrix3x3::inverse
+    double origin[3];   // non-periodic frames: bounding-box origin (0 when periodic)
+    float h[9];         // grid-unit delta -> cartesian: h[r*3+c] = ortho[r][c] / n[c]
+    int n[3];           // cells per axis
+    int reduce[3];      // 1: axis holds a single cell and deltas are min-image reduced
+    long long cell_base;  // first cell of this frame in the batch-wide cell arrays
+    int ncell;
+    int is_ortho;       // cell matrix is diagonal
+};
+
+struct ElemTables {
+    double cut2[MDB_MAXT * MDB_MAXT];  // (Rcov_i + Rcov_j + 0.45)^2, exact double
+    float cut2f[MDB_MAXT * MDB_MAXT];
+    int maxbonds[MDB_MAXT];
+    int Z[MDB_MAXT];
+    double diag[MDB_MAXT];  // Z^2.4 / 2
+    int nt;
+    float margin;  // half-width (A^2) of the band re-tested in double
+    float rc_max;
+};
+
+struct BondStats {
+    unsigned long long violators, exact_tests, overflow;
+    int err;
+};
+
+struct mdb_ctx {
+    int device = 0;
+    ElemTables el{};
+    bool have_elements = false;
+    double opt_cell_edge = 0.0;
+    int opt_max_bonds = 8;
+    int opt_frames_per_launch = 0;
+    uint64_t launches = 0;
+    // arena
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t arena_off = 0;
+    // pinned staging ring for per-call geometry
+    static const int kRing = 8;
+    FrameGeom *h_geom[kRing] = {};
+    size_t h_geom_cap[kRing] = {};
+    cudaEvent_t h_geom_ev[kRing] = {};
+    int ring_pos = 0;
+    // persistent small device state
+    BondStats *d_stats = nullptr;
+    // streams for the host-buffer pipeline
+    cudaStream_t pipe[3] = {};
+    cudaEvent_t pipe_ev[3] = {};
+    // double-buffered device staging of the host-buffer pipeline (grow-only)
+    char *pipe_mem[2] = {};
+    size_t pipe_cap[2] = {};
+    cudaEvent_t pipe_in[2] = {}, pipe_comp[2] = {}, pipe_out[2] = {};
+    uint8_t *pipe_types = nullptr;
+    size_t pipe_types_cap = 0;
+};
+
+void mdb_set_error(const std::string &msg);
+int mdb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define MDB_CUDA(x)                                                           \
+    do {                                                                      \
+        cudaError_t e__ = (x);                                                \
+        if (e__ != cudaSuccess) return mdb_cuda_fail(e__, #x, __FILE__, __LINE__); \
+    } while (0)
+
+// bump allocation from the context arena (256-byte aligned); returns nullptr when
+// the arena is too small -- callers size it first with arena_reserve().
+int arena_reserve(mdb_ctx *ctx, size_t bytes, cudaStream_t stream);
+void arena_reset(mdb_ctx *ctx);
+void *arena_alloc(mdb_ctx *ctx, size_t bytes);
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// host geometry
+int build_geometry(mdb_ctx *ctx, int nframes, int natoms, const double *h_cell, int periodic,
+                   const double *h_bbox, double edge_min, double edge_hint, std::vector<FrameGeom> &out,
+                   long long *total_cells);
+int upload_geometry(mdb_ctx *ctx, const std::vector<FrameGeom> &g, FrameGeom *d_geom, cudaStream_t stream);
+
+// cells.cu
+struct CellList {
+    const FrameGeom *d_geom;
+    int *cell_start;   // [total_cells + 1] exclusive scan over the batch (global slot offsets)
+    float4 *rec;       // [F*N] sorted records: grid-unit coords + (type << 27 | index)
+    long long total_cells;
+    bool all_ortho;    // every frame of the batch has a diagonal cell matrix
+};
+size_t cells_workspace_bytes(int nframes, int natoms, long long total_cells);
+int cells_build(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const uint8_t *d_types,
+                const FrameGeom *d_geom, long long total_cells, int periodic, CellList *out, int *d_err,
+                cudaStream_t stream);
+int device_exclusive_scan(mdb_ctx *ctx, int *d_data, long long n, void *d_scratch, cudaStream_t stream);
+size_t scan_scratch_bytes(long long n);
+int bbox_frames(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, double *h_bbox, cudaStream_t stream);
+
+// bonds.cu
+int bonds_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const uint8_t *d_types,
+              const CellList &cl, int periodic, int32_t *d_ell, cudaStream_t stream);
+size_t bonds_workspace_bytes(int nframes, int natoms);
+int ell_to_csr_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, int order, const double *d_pos,
+                   int32_t *d_rowptr, int32_t *d_col, int colcap, cudaStream_t stream);
+
+// graph.cu
+int keys_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const uint8_t *d_types, uint64_t *d_keys,
+             int32_t *d_parent, cudaStream_t stream);
+int keys_bo_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const double *d_bo,
+                const uint8_t *d_types, uint64_t *d_keys, cudaStream_t stream);
+int components_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, int32_t *d_labels, int seeded,
+                   cudaStream_t stream);
+int dps_run(mdb_ctx *ctx, int natoms, const int32_t *d_rowptr, const int32_t *d_col, int32_t *d_mol_atoms,
+            int32_t *d_mol_ptr, int *h_nmol, cudaStream_t stream);
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }

@@ -1,0 +1,235 @@
+"""One GPU's analysis engine: thin Python wrappers over the C ABI (include/mdb_b200.h).
+
+PyTorch supplies device memory and streams only; every computation on the path is a
+hand-written sm_100a kernel inside libmdb_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+ATOMIC_NUMBERS = {"H": 1, "He": 2, "Li": 3, "Be": 4, "B": 5, "C": 6, "N": 7, "O": 8, "F": 9, "Ne": 10,
+                  "Na": 11, "Mg": 12, "Al": 13, "Si": 14, "P": 15, "S": 16, "Cl": 17, "Ar": 18}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class Engine:
+    """Owns one ``mdb_ctx`` (one per process and GPU, like one Pool worker of the
+    reference, utils.py:198-231, but driving a whole device)."""
+
+    def __init__(self, device: int = 0, atomname=("C", "H", "O"), max_bonds: int = 8):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mddatasetbuilder_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.L = _lib.lib()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        ctx = C.c_void_p()
+        _lib.check(self.L.mdb_create(int(device), C.byref(ctx)), "mdb_create")
+        self.ctx = ctx
+        self.max_bonds = 8
+        self.set_elements(atomname)
+        if max_bonds != 8:
+            self.set_option("max_bonds", max_bonds)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.mdb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ config
+    def set_elements(self, atomname):
+        self.atomname = [str(s) for s in atomname]
+        try:
+            z = [ATOMIC_NUMBERS[s] for s in self.atomname]
+        except KeyError as e:
+            raise RuntimeError(f"element {e} is outside the built-in table (Z = 1..18)") from None
+        arr = (C.c_int * len(z))(*z)
+        _lib.check(self.L.mdb_set_elements(self.ctx, len(z), arr), "mdb_set_elements")
+        self.Z = np.array(z, dtype=np.int32)
+
+    def set_option(self, key: str, value: float):
+        _lib.check(self.L.mdb_set_option(self.ctx, key.encode(), float(value)), f"mdb_set_option({key})")
+        if key == "max_bonds":
+            self.max_bonds = int(value)
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.mdb_launch_count(self.ctx))
+
+    def stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ helpers
+    def _cells(self, cell, nframes):
+        if cell is None:
+            return None
+        c = np.ascontiguousarray(np.asarray(cell, dtype=np.float64))
+        if c.size == 3:
+            c = np.diag(c.reshape(3))
+        if c.size == 9:
+            c = np.broadcast_to(c.reshape(1, 9), (nframes, 9))
+        c = np.ascontiguousarray(c.reshape(nframes, 9))
+        return c
+
+    def to_device_pos(self, pos):
+        torch = _torch()
+        if isinstance(pos, np.ndarray):
+            pos = torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float64))
+        pos = pos.to(self.device, dtype=torch.float64).contiguous()
+        if pos.dim() == 2:
+            pos = pos[None]
+        return pos
+
+    def to_device_types(self, types):
+        torch = _torch()
+        if isinstance(types, np.ndarray):
+            types = torch.from_numpy(np.ascontiguousarray(types).astype(np.uint8))
+        return types.to(self.device, dtype=torch.uint8).contiguous()
+
+    # ------------------------------------------------------------------ path
+    def analyze(self, pos, cell, types, periodic=True, want_ell=True, want_keys=True, want_labels=True,
+                out=None):
+        """cell list -> bonds -> cleanup -> keys -> molecule labels for a batch of frames.
+
+        pos [F,N,3] float64 (device tensor or numpy), cell [F,9]/[9]/[3] host, types [N]
+        0-based element index.  Returns dict of device tensors: ell [F,N,max_bonds] int32,
+        keys [F,N] int64 (bit pattern of the uint64 key), labels [F,N] int32."""
+        torch = _torch()
+        pos = self.to_device_pos(pos)
+        types = self.to_device_types(types)
+        F, N = int(pos.shape[0]), int(pos.shape[1])
+        cells = self._cells(cell, F) if periodic else None
+        out = out or {}
+        ell = out.get("ell") if want_ell else None
+        keys = out.get("keys") if want_keys else None
+        labels = out.get("labels") if want_labels else None
+        if want_ell and ell is None:
+            ell = torch.empty((F, N, self.max_bonds), dtype=torch.int32, device=self.device)
+        if want_keys and keys is None:
+            keys = torch.empty((F, N), dtype=torch.int64, device=self.device)
+        if want_labels and labels is None:
+            labels = torch.empty((F, N), dtype=torch.int32, device=self.device)
+        rc = self.L.mdb_analyze_frames(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                       _ptr(ell), _ptr(keys), _ptr(labels), self.stream())
+        _lib.check(rc, "mdb_analyze_frames")
+        return {"ell": ell, "keys": keys, "labels": labels, "pos": pos, "types": types}
+
+    def check(self):
+        """Synchronise and raise if a kernel flagged an error (cell/bond overflow ...)."""
+        v = C.c_longlong()
+        e = C.c_longlong()
+        o = C.c_longlong()
+        _lib.check(self.L.mdb_bond_stats(self.ctx, C.byref(v), C.byref(e), C.byref(o)), "device check")
+        return {"violators": v.value, "exact_tests": e.value, "overflow": o.value}
+
+    def ell_to_csr(self, ell, order=0, pos=None, colcap=None):
+        torch = _torch()
+        F, N, _ = ell.shape
+        colcap = int(colcap or max(1, N * self.max_bonds))
+        rowptr = torch.empty((F, N + 1), dtype=torch.int32, device=self.device)
+        col = torch.full((F, colcap), -1, dtype=torch.int32, device=self.device)
+        rc = self.L.mdb_ell_to_csr(self.ctx, int(F), int(N), _ptr(ell), int(order), _ptr(pos), _ptr(rowptr), _ptr(col),
+                                   colcap, self.stream())
+        _lib.check(rc, "mdb_ell_to_csr")
+        return rowptr, col
+
+    def bond_keys_bo(self, ell, bo, types):
+        torch = _torch()
+        F, N, _ = ell.shape
+        keys = torch.empty((F, N), dtype=torch.int64, device=self.device)
+        rc = self.L.mdb_bond_keys_bo(self.ctx, int(F), int(N), _ptr(ell), _ptr(bo), _ptr(types), _ptr(keys),
+                                     self.stream())
+        _lib.check(rc, "mdb_bond_keys_bo")
+        return keys
+
+    def components(self, ell):
+        torch = _torch()
+        F, N, _ = ell.shape
+        labels = torch.empty((F, N), dtype=torch.int32, device=self.device)
+        _lib.check(self.L.mdb_components(self.ctx, int(F), int(N), _ptr(ell), _ptr(labels), 0, self.stream()),
+                   "mdb_components")
+        return labels
+
+    def dps(self, rowptr, col):
+        """Exact ``dps`` output (dps.pyx:17-46) for one frame: (mol_atoms, mol_ptr) device tensors."""
+        torch = _torch()
+        N = int(rowptr.numel()) - 1
+        mol_atoms = torch.empty(max(N, 1), dtype=torch.int32, device=self.device)
+        mol_ptr = torch.empty(N + 1, dtype=torch.int32, device=self.device)
+        nm = C.c_int(0)
+        rc = self.L.mdb_dps(self.ctx, N, _ptr(rowptr), _ptr(col), _ptr(mol_atoms), _ptr(mol_ptr), C.byref(nm),
+                            self.stream())
+        _lib.check(rc, "mdb_dps")
+        return mol_atoms[:N], mol_ptr[: nm.value + 1]
+
+    def analyze_host(self, pos, cell, types, periodic=True, want_keys=True, want_labels=True, out=None):
+        """Host-buffer path (e2e): numpy / pinned tensors in, numpy out; H2D and D2H copies
+        are pipelined inside the library."""
+        torch = _torch()
+        if isinstance(pos, torch.Tensor):
+            pos_np = pos.numpy()
+        else:
+            pos_np = np.ascontiguousarray(pos, dtype=np.float64)
+        if pos_np.ndim == 2:
+            pos_np = pos_np[None]
+        F, N = pos_np.shape[0], pos_np.shape[1]
+        types_np = np.ascontiguousarray(np.asarray(types).astype(np.uint8))
+        cells = self._cells(cell, F) if periodic else None
+        out = out or {}
+        ell = out.get("ell")
+        if ell is None:
+            ell = np.empty((F, N, self.max_bonds), dtype=np.int32)
+        keys = out.get("keys") if want_keys else None
+        if want_keys and keys is None:
+            keys = np.empty((F, N), dtype=np.uint64)
+        labels = out.get("labels") if want_labels else None
+        if want_labels and labels is None:
+            labels = np.empty((F, N), dtype=np.int32)
+
+        def p(a):
+            if a is None:
+                return C.c_void_p(0)
+            return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else C.c_void_p(a.ctypes.data)
+
+        rc = self.L.mdb_analyze_frames_host(self.ctx, int(F), int(N), p(pos_np), _np_ptr(cells), p(types_np),
+                                            int(bool(periodic)), p(ell), p(keys), p(labels))
+        _lib.check(rc, "mdb_analyze_frames_host")
+        return {"ell": ell, "keys": keys, "labels": labels}
+
+
+_ENGINES = {}
+
+
+def get_engine(device: int = 0, atomname=("C", "H", "O")) -> Engine:
+    """Process-wide engine per device (re-targeted when the element list changes)."""
+    e = _ENGINES.get(device)
+    if e is None:
+        e = Engine(device, atomname)
+        _ENGINES[device] = e
+    elif list(atomname) != e.atomname:
+        e.set_elements(atomname)
+    return e
