@@ -130,6 +130,12 @@ int mdb_analyze_frames_host(mdb_ctx *ctx, int nframes, int natoms, const double 
 int mdb_bond_stats(mdb_ctx *ctx, long long *n_violators, long long *n_exact_tests,
                    long long *n_overflow);
 
+/* Per-launch CUDA-event timing on the launching stream (bench.py's live roofline
+ * measurement).  mdb_profile_read synchronises and writes "name count total_ms" lines
+ * accumulated since the previous read into buf. */
+int mdb_profile_enable(mdb_ctx *ctx, int on);
+int mdb_profile_read(mdb_ctx *ctx, char *buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,7 +60,7 @@ static int analyze_chunk(mdb_ctx *c, int F, int N, const double *d_pos, const do
     double lmax = 0;
     bool all_ortho = true;
     for (const FrameGeom &g : geom) {
-        all_ortho = all_ortho && g.is_ortho;
+        all_ortho = all_ortho && g.is_ortho && !g.reduce[0] && !g.reduce[1] && !g.reduce[2];
         for (int v = 0; v < 3; ++v) {
             double l = sqrt(g.ortho[v] * g.ortho[v] + g.ortho[3 + v] * g.ortho[3 + v] + g.ortho[6 + v] * g.ortho[6 + v]);
             lmax = std::max(lmax, l);
@@ -84,12 +84,14 @@ static int analyze_chunk(mdb_ctx *c, int F, int N, const double *d_pos, const do
     }
     if (upload_geometry(c, geom, d_geom, stream)) return -1;
     CellList cl;
-    if (cells_build(c, F, N, d_pos, d_types, d_geom, total_cells, periodic, &cl, &c->d_stats->err, stream)) return -1;
-    cl.all_ortho = all_ortho;
-    if (bonds_run(c, F, N, d_pos, d_types, cl, periodic, d_ell, stream)) return -1;
-    if (d_keys || d_labels) {
-        if (keys_run(c, F, N, d_ell, d_types, d_keys, d_labels, stream)) return -1;
-        if (d_labels && components_run(c, F, N, d_ell, d_labels, 1, stream)) return -1;
+    if (cells_build(c, F, N, d_pos, d_types, d_geom, total_cells, periodic, all_ortho ? 1 : 0, &cl, &c->d_stats->err,
+                    stream))
+        return -1;
+    if (bonds_run(c, F, N, d_pos, d_types, cl, periodic, d_ell, d_labels, stream)) return -1;
+    if (d_labels) {
+        if (keys_components_run(c, F, N, d_ell, d_types, d_keys, d_labels, stream)) return -1;
+    } else if (d_keys) {
+        if (keys_run(c, F, N, d_ell, d_types, d_keys, nullptr, stream)) return -1;
     }
     return 0;
 }
@@ -189,6 +191,47 @@ extern "C" int mdb_bond_stats(mdb_ctx *c, long long *n_violators, long long *n_e
     if (h.err) {
         mdb_set_error(std::string("device-side error: ") + err_text(h.err));
         return h.err;
+    }
+    return 0;
+}
+
+// per-kernel timing: "name count total_ms" lines, accumulated since the last read
+extern "C" int mdb_profile_enable(mdb_ctx *c, int on) {
+    if (check_ctx(c, "mdb_profile_enable", false)) return -1;
+    c->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int mdb_profile_read(mdb_ctx *c, char *buf, size_t cap) {
+    if (check_ctx(c, "mdb_profile_read", false)) return -1;
+    MDB_CUDA(cudaDeviceSynchronize());
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<long long> cnt;
+    for (auto &r : c->prof_recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        size_t k = 0;
+        for (; k < names.size(); ++k)
+            if (names[k] == r.name) break;
+        if (k == names.size()) {
+            names.push_back(r.name);
+            ms.push_back(0);
+            cnt.push_back(0);
+        }
+        ms[k] += t;
+        cnt[k] += 1;
+        c->prof_free.push_back(r.a);
+        c->prof_free.push_back(r.b);
+    }
+    c->prof_recs.clear();
+    std::string out;
+    for (size_t k = 0; k < names.size(); ++k)
+        out += names[k] + " " + std::to_string(cnt[k]) + " " + std::to_string(ms[k]) + "\n";
+    if (buf && cap) {
+        size_t n = std::min(cap - 1, out.size());
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
     }
     return 0;
 }

@@ -6,9 +6,9 @@
 // d = FracToCart(frac - round(frac)), then -- atoms in index order -- while an atom exceeds its
 // max valence or has a bond angle < 45 deg: drop its first H-H bond if it is H, else its longest.
 //
-// Exactness: candidate pairs are screened in float on grid-unit deltas; any pair whose float d2
-// lies within `margin` of either bound is re-evaluated in double with the oracle's operation
-// order (__dmul_rn/__dadd_rn, no FMA contraction), so the bond set is bit-identical to the CPU
+// Exactness: candidate pairs are screened in float; any pair whose float d2 lies within `margin`
+// of either bound is re-evaluated in double with the oracle's operation order
+// (__dmul_rn/__dadd_rn, no FMA contraction), so the bond set is bit-identical to the CPU
 // restatement.  The cleanup runs entirely in double.
 #include "common.cuh"
 
@@ -18,15 +18,17 @@
 
 struct BondParams {
     const float4 *rec;
+    const uint32_t *ccell;
     const int *cell_start;
     const FrameGeom *geom;
     const double *pos;
     const uint8_t *types;
     int32_t *ell;
-    int *viol;    // [F][N] violator lists
-    int *nviol;   // [F]
-    int *dirty;   // [F][N]
-    int *ndirty;  // [F]
+    int32_t *parent;  // optional union-find seed (min(self, smallest neighbour))
+    int *viol;        // [F][N] violator lists
+    int *nviol;       // [F]
+    int *dirty;       // [F][N]
+    int *ndirty;      // [F]
     BondStats *stats;
     int N;
     int periodic;
@@ -67,36 +69,40 @@ __device__ __forceinline__ void delta_exact(const double *pos, const FrameGeom &
     ob_mic(G, periodic, d, out);
 }
 
-__device__ __forceinline__ int axis_list(int c, int n, int reduce, int periodic, int q[3], float s[3]) {
+// one neighbour cell coordinate along an axis: wrapped index and the shift to add to the
+// neighbour's coordinate; returns false when the cell does not exist (open boundary / reduced axis)
+__device__ __forceinline__ bool nbr_cell(int c, int d, int n, int reduce, int periodic, float period, int &q, float &sh) {
     if (reduce) {
-        q[0] = 0;
-        s[0] = 0.f;
-        return 1;
+        q = 0;
+        sh = 0.f;
+        return d == 0;
     }
-    int cnt = 0;
-#pragma unroll
-    for (int d = -1; d <= 1; ++d) {
-        int v = c + d;
-        float sh = 0.f;
-        if (v < 0) {
-            if (!periodic) continue;
-            v += n;
-            sh = -(float)n;
-        } else if (v >= n) {
-            if (!periodic) continue;
-            v -= n;
-            sh = (float)n;
-        }
-        q[cnt] = v;
-        s[cnt] = sh;
-        ++cnt;
+    q = c + d;
+    sh = 0.f;
+    if (q < 0) {
+        if (!periodic) return false;
+        q += n;
+        sh = -period;
+    } else if (q >= n) {
+        if (!periodic) return false;
+        q -= n;
+        sh = period;
     }
-    return cnt;
+    return true;
 }
 
-template <int MAXB, bool ORTHO>
+// MODE 0: every frame orthorhombic with >= 3 cells per axis -- records hold wrapped Angstrom
+//         coordinates, the float distance is 3 adds + 3 fused multiply-adds, and neighbour rows /
+//         cells farther from the atom than its largest cutoff are skipped.
+// MODE 1: general cell (triclinic and/or single-cell "reduce" axes) -- records hold grid units.
+// Phase 1 streams the candidates of the (pruned) 3x3 rows and keeps the few that pass the coarse
+// float test in a per-thread pending list; phase 2 decides them (type-specific cutoff, borderline
+// cases in double) and phase 3 sorts, flags and writes the row.
+#define BOND_PEND 12
+template <int MAXB, int MODE>
 __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ BondParams P) {
     __shared__ float4 s_nb[MAXB][BOND_THREADS];
+    __shared__ int s_pend[BOND_PEND][BOND_THREADS];
     __shared__ float s_cut2f[MDB_MAXT * MDB_MAXT];
     const int tid = threadIdx.x;
     if (tid < MDB_MAXT * MDB_MAXT) s_cut2f[tid] = P.el.cut2f[tid];
@@ -110,106 +116,187 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
     const float4 *__restrict__ rec = P.rec;
     const int *__restrict__ cs = P.cell_start;
     const float4 me = rec[fbase + p];
+    const uint32_t cc = P.ccell[fbase + p];
+    const int cx = (int)(cc & 1023u), cy = (int)((cc >> 10) & 1023u), cz = (int)(cc >> 20);
     const unsigned mw = (unsigned)__float_as_int(me.w);
     const int i = (int)(mw & MDB_IDX_MASK);
     const int ti = (int)(mw >> MDB_IDX_BITS);
-    const int nx = G.n[0], ny = G.n[1];
-    const int rx = G.reduce[0], ry = G.reduce[1], rz = G.reduce[2];
-    float h[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) h[k] = G.h[k];
+    const int nx = G.n[0], ny = G.n[1], nz = G.n[2];
+    const int periodic = P.periodic;
     const float m = P.el.margin;
-    const long long cbase = G.cell_base;
+    const int cbase = (int)G.cell_base;
+    const float *cutrow = s_cut2f + ti * MDB_MAXT;
+    float cmax = 0.f;
+#pragma unroll
+    for (int k = 0; k < MDB_MAXT; ++k) cmax = fmaxf(cmax, cutrow[k]);
+    cmax += m;
+    const float dmin = 0.16f - m;
 
-    int yq[3], zq[3];
-    float ys[3], zs[3];
-    const int nyq = axis_list((int)me.y, ny, ry, P.periodic, yq, ys);
-    const int nzq = axis_list((int)me.z, G.n[2], rz, P.periodic, zq, zs);
-    // x: contiguous run of cells plus at most one wrapped cell on either side
-    int xa[3], xb[3];
-    float xs[3];
-    int nxs = 0;
-    {
-        const int cx = (int)me.x;
-        if (rx) {
-            xa[0] = 0;
-            xb[0] = 0;
-            xs[0] = 0.f;
-            nxs = 1;
-        } else {
-            int lo = cx - 1, hi = cx + 1;
-            xa[0] = lo < 0 ? 0 : lo;
-            xb[0] = hi >= nx ? nx - 1 : hi;
-            xs[0] = 0.f;
-            nxs = 1;
-            if (P.periodic && lo < 0) {
-                xa[nxs] = nx - 1;
-                xb[nxs] = nx - 1;
-                xs[nxs] = -(float)nx;
-                ++nxs;
-            }
-            if (P.periodic && hi >= nx) {
-                xa[nxs] = 0;
-                xb[nxs] = 0;
-                xs[nxs] = (float)nx;
-                ++nxs;
-            }
+    // MODE 0: periods / cell widths in Angstrom; MODE 1: periods in grid units + grid->cartesian matrix
+    float px, py, pz;
+    float h[9];
+    int rx = 0, ry = 0, rz = 0;
+    // squared distance from the atom to the lower / upper face of its cell per axis (MODE 0 pruning)
+    float flo[3] = {0.f, 0.f, 0.f}, fhi[3] = {0.f, 0.f, 0.f};
+    if (MODE == 0) {
+        px = (float)G.ortho[0];
+        py = (float)G.ortho[4];
+        pz = (float)G.ortho[8];
+        const float w[3] = {G.h[0], G.h[4], G.h[8]};
+        const float mc[3] = {me.x, me.y, me.z};
+        const int c3[3] = {cx, cy, cz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            // conservative: shrink the face distances by the float error of the coordinates
+            float lo = fmaxf(mc[a] - (float)c3[a] * w[a] - 2e-4f * w[a], 0.f);
+            float hi = fmaxf((float)(c3[a] + 1) * w[a] - mc[a] - 2e-4f * w[a], 0.f);
+            flo[a] = lo * lo;
+            fhi[a] = hi * hi;
         }
+    } else {
+        px = (float)nx;
+        py = (float)ny;
+        pz = (float)nz;
+        rx = G.reduce[0];
+        ry = G.reduce[1];
+        rz = G.reduce[2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) h[k] = G.h[k];
     }
 
+    int np = 0;
+    auto scan = [&](int lo, int hi, float ax, float ay, float az) {
+#pragma unroll 2
+        for (int q = lo; q < hi; ++q) {
+            const float4 o = rec[q];
+            float dx, dy, dz;
+            if (MODE == 0) {
+                dx = o.x + ax;
+                dy = o.y + ay;
+                dz = o.z + az;
+            } else {
+                float du = o.x + ax, dv = o.y + ay, dw = o.z + az;
+                if (rx) du -= rintf(du);
+                if (ry) dv -= rintf(dv);
+                if (rz) dw -= rintf(dw);
+                dx = h[0] * du + h[1] * dv + h[2] * dw;
+                dy = h[3] * du + h[4] * dv + h[5] * dw;
+                dz = h[6] * du + h[7] * dv + h[8] * dw;
+            }
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d2 <= cmax && d2 >= dmin) {
+                if (np < BOND_PEND) s_pend[np][tid] = q;
+                ++np;
+            }
+        }
+    };
+
+    // 9 (dy, dz) rows; the cell_start bounds of row r+1 are fetched before row r is scanned
+    int lo_n = 0, hi_n = 0, lo2_n = 0, hi2_n = 0;
+    float ay_n = 0.f, az_n = 0.f, ax2_n = 0.f;
+    auto fetch = [&](int r) {
+        const int dzc = r / 3 - 1, dyc = r - (r / 3) * 3 - 1;
+        int y, z;
+        float sy, sz;
+        lo_n = hi_n = lo2_n = hi2_n = 0;
+        if (!nbr_cell(cy, dyc, ny, ry, periodic, py, y, sy)) return;
+        if (!nbr_cell(cz, dzc, nz, rz, periodic, pz, z, sz)) return;
+        int xa = cx, xb = cx, xw = -1;
+        float xws = 0.f;
+        if (MODE == 0) {
+            const float base = (dyc < 0 ? flo[1] : dyc > 0 ? fhi[1] : 0.f) + (dzc < 0 ? flo[2] : dzc > 0 ? fhi[2] : 0.f);
+            if (base > cmax) return;  // the whole row is out of reach
+            if (base + flo[0] <= cmax) xa = cx - 1;
+            if (base + fhi[0] <= cmax) xb = cx + 1;
+        } else if (rx) {
+            xa = xb = 0;
+        } else {
+            xa = cx - 1;
+            xb = cx + 1;
+        }
+        if (xa < 0) {
+            xa = 0;
+            if (periodic) {
+                xw = nx - 1;
+                xws = -px;
+            }
+        }
+        if (xb >= nx) {
+            xb = nx - 1;
+            if (periodic) {
+                xw = 0;
+                xws = px;
+            }
+        }
+        const int rowbase = cbase + (z * ny + y) * nx;
+        lo_n = cs[rowbase + xa];
+        hi_n = cs[rowbase + xb + 1];
+        if (xw >= 0) {
+            lo2_n = cs[rowbase + xw];
+            hi2_n = cs[rowbase + xw + 1];
+        }
+        ay_n = sy - me.y;
+        az_n = sz - me.z;
+        ax2_n = xws - me.x;
+    };
+    fetch(0);
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int lo = lo_n, hi = hi_n, lo2 = lo2_n, hi2 = hi2_n;
+        const float ay = ay_n, az = az_n, ax2 = ax2_n;
+        if (r < 8) fetch(r + 1);
+        scan(lo, hi, -me.x, ay, az);
+        if (lo2 < hi2) scan(lo2, hi2, ax2, ay, az);
+    }
+    if (np > BOND_PEND) {
+        atomicAdd(&P.stats->overflow, 1ull);
+        atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        np = BOND_PEND;
+    }
+
+    // phase 2: decide the pending candidates
     int cnt = 0;
-    const float *cutrow = s_cut2f + ti * MDB_MAXT;
-#pragma unroll
-    for (int iz = 0; iz < 3; ++iz) {
-        if (iz >= nzq) break;
-#pragma unroll
-        for (int iy = 0; iy < 3; ++iy) {
-            if (iy >= nyq) break;
-            const long long rowbase = cbase + ((long long)zq[iz] * ny + yq[iy]) * nx;
-            const float sy = ys[iy] - me.y, sz = zs[iz] - me.z;
-#pragma unroll
-            for (int is = 0; is < 3; ++is) {
-                if (is >= nxs) break;
-                const int lo = cs[rowbase + xa[is]];
-                const int hi = cs[rowbase + xb[is] + 1];
-                const float sx = xs[is] - me.x;
-                for (int q = lo; q < hi; ++q) {
-                    const float4 o = rec[q];
-                    float du = o.x + sx, dv = o.y + sy, dw = o.z + sz;
-                    if (rx) du -= rintf(du);
-                    if (ry) dv -= rintf(dv);
-                    if (rz) dw -= rintf(dw);
-                    float dx, dy, dz;
-                    if (ORTHO) {
-                        dx = h[0] * du;
-                        dy = h[4] * dv;
-                        dz = h[8] * dw;
-                    } else {
-                        dx = h[0] * du + h[1] * dv + h[2] * dw;
-                        dy = h[3] * du + h[4] * dv + h[5] * dw;
-                        dz = h[6] * du + h[7] * dv + h[8] * dw;
-                    }
-                    const float d2 = dx * dx + dy * dy + dz * dz;
-                    const unsigned ow = (unsigned)__float_as_int(o.w);
-                    const float c2 = cutrow[ow >> MDB_IDX_BITS];
-                    if (d2 <= c2 + m && d2 >= 0.16f - m) {
-                        const int j = (int)(ow & MDB_IDX_MASK);
-                        bool ok = true;
-                        if (!(d2 < c2 - m && d2 > 0.16f + m)) {
-                            // borderline: decide in double exactly like the oracle
-                            double v[3];
-                            delta_exact(P.pos + fbase * 3, G, P.periodic, i, j, v);
-                            const double e2 = len2_rn(v);
-                            const double cut2 = P.el.cut2[ti * MDB_MAXT + (int)(ow >> MDB_IDX_BITS)];
-                            ok = !(e2 > cut2) && !(e2 < 0.16) && (i != j);
-                            atomicAdd(&P.stats->exact_tests, 1ull);
-                        }
-                        if (ok) {
-                            if (cnt < MAXB) s_nb[cnt][tid] = make_float4(dx, dy, dz, __int_as_float(j));
-                            ++cnt;
-                        }
-                    }
-                }
+    for (int k = 0; k < np; ++k) {
+        const float4 o = rec[s_pend[k][tid]];
+        float dx, dy, dz;
+        if (MODE == 0) {
+            dx = o.x - me.x;
+            dy = o.y - me.y;
+            dz = o.z - me.z;
+            if (periodic) {  // >= 3 cells per axis: the stencil image is the minimum image
+                dx -= px * rintf(dx / px);
+                dy -= py * rintf(dy / py);
+                dz -= pz * rintf(dz / pz);
+            }
+        } else {
+            float du = o.x - me.x, dv = o.y - me.y, dw = o.z - me.z;
+            if (periodic) {
+                du -= px * rintf(du / px);
+                dv -= py * rintf(dv / py);
+                dw -= pz * rintf(dw / pz);
+            }
+            dx = h[0] * du + h[1] * dv + h[2] * dw;
+            dy = h[3] * du + h[4] * dv + h[5] * dw;
+            dz = h[6] * du + h[7] * dv + h[8] * dw;
+        }
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const unsigned ow = (unsigned)__float_as_int(o.w);
+        const int tj = (int)(ow >> MDB_IDX_BITS);
+        const float c2 = cutrow[tj];
+        if (d2 <= c2 + m) {
+            const int j = (int)(ow & MDB_IDX_MASK);
+            bool ok = true;
+            if (!(d2 < c2 - m && d2 > 0.16f + m)) {
+                // borderline: decide in double exactly like the oracle
+                double v[3];
+                delta_exact(P.pos + fbase * 3, G, periodic, i, j, v);
+                const double e2 = len2_rn(v);
+                ok = !(e2 > P.el.cut2[ti * MDB_MAXT + tj]) && !(e2 < 0.16) && (i != j);
+                atomicAdd(&P.stats->exact_tests, 1ull);
+            }
+            if (ok) {
+                if (cnt < MAXB) s_nb[cnt][tid] = make_float4(dx, dy, dz, __int_as_float(j));
+                ++cnt;
             }
         }
     }
@@ -249,6 +336,7 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
     unsigned row[MAXB];
 #pragma unroll
     for (int k = 0; k < MAXB; ++k) row[k] = k < cnt ? (unsigned)__float_as_int(s_nb[k][tid].w) : EMPTY_SLOT;
+    if (P.parent) P.parent[fbase + i] = (cnt > 0 && (int)row[0] < i) ? (int)row[0] : i;
     if (flag) {
         row[0] |= MDB_PEND;
         const int k = atomicAdd(&P.nviol[f], 1);
@@ -266,19 +354,28 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
 // sequential index-ordered semantics of Open Babel (a deletion only ever affects the two end
 // atoms, and only deletions made by lower-index atoms can precede an atom's own turn).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ld_vol(const unsigned *p) { return *((const volatile unsigned *)p); }
+template <int MAXB>
+__device__ __forceinline__ void load_row(const unsigned *ell, int v, unsigned e[MAXB]) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(ell + (size_t)v * MAXB);
+#pragma unroll
+    for (int k = 0; k < MAXB / 4; ++k) {
+        uint4 q = __ldcg(src + k);  // L2 view: sees the atomics of other threads of this kernel
+        e[4 * k] = q.x;
+        e[4 * k + 1] = q.y;
+        e[4 * k + 2] = q.z;
+        e[4 * k + 3] = q.w;
+    }
+}
 
 template <int MAXB>
 __device__ void kill_bond(unsigned *ell, int v, int slot_v, int w, int *dirty, int *ndirty) {
     atomicOr(&ell[(size_t)v * MAXB + slot_v], MDB_TOMB);
-    for (int s = 0; s < MAXB; ++s) {
-        unsigned e = ld_vol(&ell[(size_t)w * MAXB + s]);
-        if (e == EMPTY_SLOT) break;
-        if (!(e & MDB_TOMB) && (int)(e & MDB_IDX_MASK) == v) {
+    unsigned e[MAXB];
+    load_row<MAXB>(ell, w, e);
+#pragma unroll
+    for (int s = 0; s < MAXB; ++s)
+        if (e[s] != EMPTY_SLOT && !(e[s] & MDB_TOMB) && (int)(e[s] & MDB_IDX_MASK) == v)
             atomicOr(&ell[(size_t)w * MAXB + s], MDB_TOMB);
-            break;
-        }
-    }
     unsigned o = atomicOr(&ell[(size_t)v * MAXB], MDB_DIRTY);
     if (!(o & MDB_DIRTY)) dirty[atomicAdd(ndirty, 1)] = v;
     o = atomicOr(&ell[(size_t)w * MAXB], MDB_DIRTY);
@@ -287,42 +384,41 @@ __device__ void kill_bond(unsigned *ell, int v, int slot_v, int w, int *dirty, i
 
 template <int MAXB>
 __device__ void resolve_atom(const BondParams &P, const FrameGeom &G, unsigned *ell, const double *pos, int v,
-                             int *dirty, int *ndirty) {
+                             const unsigned e[MAXB], int *dirty, int *ndirty) {
     int nb[MAXB], slot[MAXB];
     double z[MAXB], vec[MAXB][3], len[MAXB];
     int cnt = 0;
+#pragma unroll
     for (int s = 0; s < MAXB; ++s) {
-        unsigned e = ld_vol(&ell[(size_t)v * MAXB + s]);
-        if (e == EMPTY_SLOT) break;
-        if (e & MDB_TOMB) continue;
-        nb[cnt] = (int)(e & MDB_IDX_MASK);
+        if (e[s] == EMPTY_SLOT || (e[s] & MDB_TOMB)) continue;
+        nb[cnt] = (int)(e[s] & MDB_IDX_MASK);
         slot[cnt] = s;
-        z[cnt] = pos[(size_t)nb[cnt] * 3 + 2];
         ++cnt;
     }
+    double pv[3] = {pos[(size_t)v * 3], pos[(size_t)v * 3 + 1], pos[(size_t)v * 3 + 2]};
+    for (int k = 0; k < cnt; ++k) {
+        const double *q = pos + (size_t)nb[k] * 3;
+        double d[3] = {__dsub_rn(q[0], pv[0]), __dsub_rn(q[1], pv[1]), __dsub_rn(q[2], pv[2])};
+        z[k] = q[2];
+        ob_mic(G, P.periodic, d, vec[k]);
+        len[k] = sqrt(len2_rn(vec[k]));
+    }
     // creation order of the atom's bonds = ascending partner (z, index)  
+    int ord[MAXB];
+    for (int a = 0; a < cnt; ++a) ord[a] = a;
     for (int a = 1; a < cnt; ++a) {
-        int n0 = nb[a], s0 = slot[a];
-        double z0 = z[a];
+        int o0 = ord[a];
         int b = a - 1;
-        while (b >= 0 && (z[b] > z0 || (z[b] == z0 && nb[b] > n0))) {
-            nb[b + 1] = nb[b];
-            slot[b + 1] = slot[b];
-            z[b + 1] = z[b];
+        while (b >= 0 && (z[ord[b]] > z[o0] || (z[ord[b]] == z[o0] && nb[ord[b]] > nb[o0]))) {
+            ord[b + 1] = ord[b];
             --b;
         }
-        nb[b + 1] = n0;
-        slot[b + 1] = s0;
-        z[b + 1] = z0;
-    }
-    for (int k = 0; k < cnt; ++k) {
-        delta_exact(pos, G, P.periodic, nb[k], v, vec[k]);
-        len[k] = sqrt(len2_rn(vec[k]));
+        ord[b + 1] = o0;
     }
     const int tv = P.types[v];
     const int maxb = P.el.maxbonds[tv];
     const bool isH = P.el.Z[tv] == 1;
-    unsigned alive = cnt >= 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+    unsigned alive = (1u << cnt) - 1u;  // bit a <-> ord position a
     for (;;) {
         const int deg = __popc(alive);
         if (deg == 0) break;
@@ -331,15 +427,17 @@ __device__ void resolve_atom(const BondParams &P, const FrameGeom &G, unsigned *
             double mindeg = 360.0;
             for (int a = 0; a < cnt; ++a) {
                 if (!(alive >> a & 1u)) continue;
+                const int ka = ord[a];
                 for (int b = a + 1; b < cnt; ++b) {
                     if (!(alive >> b & 1u)) continue;
+                    const int kb = ord[b];
                     double ang;
-                    if (fabs(len[a]) < 1.0e-3 || fabs(len[b]) < 1.0e-3)
+                    if (fabs(len[ka]) < 1.0e-3 || fabs(len[kb]) < 1.0e-3)
                         ang = 0.0;
                     else {
-                        double dot = __dadd_rn(__dadd_rn(__dmul_rn(vec[a][0], vec[b][0]), __dmul_rn(vec[a][1], vec[b][1])),
-                                               __dmul_rn(vec[a][2], vec[b][2]));
-                        double dp = __ddiv_rn(dot, __dmul_rn(len[a], len[b]));
+                        double dot = __dadd_rn(__dadd_rn(__dmul_rn(vec[ka][0], vec[kb][0]), __dmul_rn(vec[ka][1], vec[kb][1])),
+                                               __dmul_rn(vec[ka][2], vec[kb][2]));
+                        double dp = __ddiv_rn(dot, __dmul_rn(len[ka], len[kb]));
                         if (dp < -0.999999) dp = -0.9999999;
                         if (dp > 0.9999999) dp = 0.9999999;
                         ang = __dmul_rn(180.0 / 3.14159265358979323846, acos(dp));
@@ -353,7 +451,7 @@ __device__ void resolve_atom(const BondParams &P, const FrameGeom &G, unsigned *
         int victim = -1;
         if (isH) {
             for (int a = 0; a < cnt; ++a)
-                if ((alive >> a & 1u) && P.el.Z[P.types[nb[a]]] == 1) {
+                if ((alive >> a & 1u) && P.el.Z[P.types[nb[ord[a]]]] == 1) {
                     victim = a;
                     break;
                 }
@@ -361,13 +459,13 @@ __device__ void resolve_atom(const BondParams &P, const FrameGeom &G, unsigned *
         if (victim < 0) {
             double mx = -1.0;
             for (int a = 0; a < cnt; ++a)
-                if ((alive >> a & 1u) && (victim < 0 || len[a] > mx)) {
+                if ((alive >> a & 1u) && (victim < 0 || len[ord[a]] > mx)) {
                     victim = a;
-                    mx = len[a];
+                    mx = len[ord[a]];
                 }
         }
         alive &= ~(1u << victim);
-        kill_bond<MAXB>(ell, v, slot[victim], nb[victim], dirty, ndirty);
+        kill_bond<MAXB>(ell, v, slot[ord[victim]], nb[ord[victim]], dirty, ndirty);
     }
 }
 
@@ -388,25 +486,24 @@ __global__ void __launch_bounds__(256) k_cleanup(const __grid_constant__ BondPar
         for (int t = threadIdx.x; t < nv; t += blockDim.x) {
             const int v = viol[t];
             if (v < 0) continue;
-            bool blocked = false;
+            unsigned e[MAXB];
+            load_row<MAXB>(ell, v, e);
+            // blocked while a still-pending violator with a smaller index is bonded to v
+            unsigned s0[MAXB];
+#pragma unroll
             for (int s = 0; s < MAXB; ++s) {
-                unsigned e = ld_vol(&ell[(size_t)v * MAXB + s]);
-                if (e == EMPTY_SLOT) break;
-                if (e & MDB_TOMB) continue;
-                int w = (int)(e & MDB_IDX_MASK);
-                if (w < v) {
-                    unsigned s0 = ld_vol(&ell[(size_t)w * MAXB]);
-                    if (s0 != EMPTY_SLOT && (s0 & MDB_PEND)) {
-                        blocked = true;
-                        break;
-                    }
-                }
+                const int w = (int)(e[s] & MDB_IDX_MASK);
+                const bool look = e[s] != EMPTY_SLOT && !(e[s] & MDB_TOMB) && w < v;
+                s0[s] = look ? __ldcg(&ell[(size_t)w * MAXB]) : EMPTY_SLOT;
             }
+            bool blocked = false;
+#pragma unroll
+            for (int s = 0; s < MAXB; ++s) blocked |= (s0[s] != EMPTY_SLOT && (s0[s] & MDB_PEND));
             if (blocked) {
                 ++pending;
                 continue;
             }
-            resolve_atom<MAXB>(P, G, ell, pos, v, dirty, ndirty);
+            resolve_atom<MAXB>(P, G, ell, pos, v, e, dirty, ndirty);
             __threadfence();
             atomicAnd(&ell[(size_t)v * MAXB], ~MDB_PEND);
             viol[t] = ~v;
@@ -418,15 +515,25 @@ __global__ void __launch_bounds__(256) k_cleanup(const __grid_constant__ BondPar
     const int nd = *((volatile int *)ndirty);
     for (int t = threadIdx.x; t < nd; t += blockDim.x) {
         const int r = dirty[t];
-        unsigned keep[MAXB];
+        unsigned e[MAXB], keep[MAXB];
+        load_row<MAXB>(ell, r, e);
         int c = 0;
+#pragma unroll
         for (int s = 0; s < MAXB; ++s) {
-            unsigned e = ld_vol(&ell[(size_t)r * MAXB + s]);
-            if (e == EMPTY_SLOT) break;
-            if (e & MDB_TOMB) continue;
-            keep[c++] = e & MDB_IDX_MASK;
+            keep[s] = EMPTY_SLOT;
         }
-        for (int s = 0; s < MAXB; ++s) ell[(size_t)r * MAXB + s] = s < c ? keep[s] : EMPTY_SLOT;
+#pragma unroll
+        for (int s = 0; s < MAXB; ++s)
+            if (e[s] != EMPTY_SLOT && !(e[s] & MDB_TOMB)) {
+#pragma unroll
+                for (int k = 0; k < MAXB; ++k)
+                    if (k == c) keep[k] = e[s] & MDB_IDX_MASK;
+                ++c;
+            }
+        uint4 *dst = reinterpret_cast<uint4 *>(ell + (size_t)r * MAXB);
+#pragma unroll
+        for (int k = 0; k < MAXB / 4; ++k) dst[k] = make_uint4(keep[4 * k], keep[4 * k + 1], keep[4 * k + 2], keep[4 * k + 3]);
+        if (P.parent) P.parent[(size_t)f * N + r] = (c > 0 && (int)keep[0] < r) ? (int)keep[0] : r;
     }
 }
 
@@ -436,15 +543,17 @@ size_t bonds_workspace_bytes(int nframes, int natoms) {
 }
 
 int bonds_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const uint8_t *d_types, const CellList &cl,
-              int periodic, int32_t *d_ell, cudaStream_t stream) {
+              int periodic, int32_t *d_ell, int32_t *d_parent, cudaStream_t stream) {
     size_t fn = (size_t)nframes * natoms;
     BondParams P;
     P.rec = cl.rec;
+    P.ccell = cl.ccell;
     P.cell_start = cl.cell_start;
     P.geom = cl.d_geom;
     P.pos = d_pos;
     P.types = d_types;
     P.ell = d_ell;
+    P.parent = d_parent;
     P.viol = (int *)arena_alloc(ctx, fn * sizeof(int));
     P.dirty = (int *)arena_alloc(ctx, fn * sizeof(int));
     // nviol and ndirty share one zero-initialised block
@@ -458,23 +567,33 @@ int bonds_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const 
     P.N = natoms;
     P.periodic = periodic;
     P.el = ctx->el;
-    MDB_CUDA(cudaMemsetAsync(P.nviol, 0, 2 * align256((size_t)nframes * sizeof(int)), stream));
+    {
+        ProfScope ps(ctx, "memset", stream);
+        MDB_CUDA(cudaMemsetAsync(P.nviol, 0, 2 * align256((size_t)nframes * sizeof(int)), stream));
+    }
     if (natoms == 0 || nframes == 0) return 0;
     dim3 grid(cdiv(natoms, BOND_THREADS), nframes);
     const int maxb = ctx->opt_max_bonds;
-    // the float screen takes the diagonal shortcut only when every frame of the batch is orthorhombic
-    if (maxb == 8) {
-        if (cl.all_ortho)
-            k_bonds<8, true><<<grid, BOND_THREADS, 0, stream>>>(P);
+    {
+        ProfScope ps(ctx, "k_bonds", stream);
+        if (maxb == 8) {
+            if (cl.rec_mode == 1)
+                k_bonds<8, 0><<<grid, BOND_THREADS, 0, stream>>>(P);
+            else
+                k_bonds<8, 1><<<grid, BOND_THREADS, 0, stream>>>(P);
+        } else {
+            if (cl.rec_mode == 1)
+                k_bonds<16, 0><<<grid, BOND_THREADS, 0, stream>>>(P);
+            else
+                k_bonds<16, 1><<<grid, BOND_THREADS, 0, stream>>>(P);
+        }
+    }
+    {
+        ProfScope ps(ctx, "k_cleanup", stream);
+        if (maxb == 8)
+            k_cleanup<8><<<nframes, 256, 0, stream>>>(P);
         else
-            k_bonds<8, false><<<grid, BOND_THREADS, 0, stream>>>(P);
-        k_cleanup<8><<<nframes, 256, 0, stream>>>(P);
-    } else {
-        if (cl.all_ortho)
-            k_bonds<16, true><<<grid, BOND_THREADS, 0, stream>>>(P);
-        else
-            k_bonds<16, false><<<grid, BOND_THREADS, 0, stream>>>(P);
-        k_cleanup<16><<<nframes, 256, 0, stream>>>(P);
+            k_cleanup<16><<<nframes, 256, 0, stream>>>(P);
     }
     ctx->launches += 2;
     MDB_CUDA(cudaGetLastError());

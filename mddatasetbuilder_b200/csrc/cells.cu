@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256) k_bin(const double *__restrict__ pos, con
 __global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ pos, const uint8_t *__restrict__ types,
                                                  const FrameGeom *__restrict__ geom, int N, int periodic,
                                                  const int *__restrict__ cell_start, const uint32_t *__restrict__ cr,
-                                                 float4 *__restrict__ rec, int nt, int *__restrict__ err) {
+                                                 float4 *__restrict__ rec, uint32_t *__restrict__ ccell, int rec_mode,
+                                                 int nt, int *__restrict__ err) {
     int f = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -74,11 +75,19 @@ __global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ pos,
     }
     int slot = cell_start[G.cell_base + (v >> 8)] + (int)(v & 255u);
     float4 r;
-    r.x = u[0];
-    r.y = u[1];
-    r.z = u[2];
+    if (rec_mode == 1) {
+        // wrapped Angstrom coordinates (diagonal cell): u / n * L per axis
+        r.x = u[0] * G.h[0];
+        r.y = u[1] * G.h[4];
+        r.z = u[2] * G.h[8];
+    } else {
+        r.x = u[0];
+        r.y = u[1];
+        r.z = u[2];
+    }
     r.w = __int_as_float((int)(((uint32_t)t << MDB_IDX_BITS) | (uint32_t)i));
     rec[slot] = r;
+    ccell[slot] = (uint32_t)c[0] | ((uint32_t)c[1] << 10) | ((uint32_t)c[2] << 20);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,8 +202,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int *__restrict__ data, l
 int device_exclusive_scan(mdb_ctx *ctx, int *d_data, long long n, void *d_scratch, cudaStream_t stream) {
     if (n <= 0) return 0;
     long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    MDB_CUDA(cudaMemsetAsync(d_scratch, 0, scan_scratch_bytes(n), stream));
-    k_scan<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(d_data, n, (ScanScratch *)d_scratch);
+    {
+        ProfScope ps(ctx, "memset", stream);
+        MDB_CUDA(cudaMemsetAsync(d_scratch, 0, scan_scratch_bytes(n), stream));
+    }
+    {
+        ProfScope ps(ctx, "k_scan", stream);
+        k_scan<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(d_data, n, (ScanScratch *)d_scratch);
+    }
     ctx->launches++;
     MDB_CUDA(cudaGetLastError());
     return 0;
@@ -204,35 +219,48 @@ int device_exclusive_scan(mdb_ctx *ctx, int *d_data, long long n, void *d_scratc
 size_t cells_workspace_bytes(int nframes, int natoms, long long total_cells) {
     size_t fn = (size_t)nframes * natoms;
     // cell arrays are padded so the scan's int4 path stays aligned
-    return align256((size_t)(total_cells + 16) * sizeof(int)) + align256(fn * sizeof(uint32_t)) +
+    return align256((size_t)(total_cells + 16) * sizeof(int)) + 2 * align256(fn * sizeof(uint32_t)) +
            align256(fn * sizeof(float4)) + align256(scan_scratch_bytes(total_cells + 1)) + 1024;
 }
 
 int cells_build(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const uint8_t *d_types,
-                const FrameGeom *d_geom, long long total_cells, int periodic, CellList *out, int *d_err,
-                cudaStream_t stream) {
+                const FrameGeom *d_geom, long long total_cells, int periodic, int rec_mode, CellList *out,
+                int *d_err, cudaStream_t stream) {
     size_t fn = (size_t)nframes * natoms;
     int *cell_start = (int *)arena_alloc(ctx, (size_t)(total_cells + 16) * sizeof(int));
     uint32_t *cr = (uint32_t *)arena_alloc(ctx, fn * sizeof(uint32_t));
     float4 *rec = (float4 *)arena_alloc(ctx, fn * sizeof(float4));
+    uint32_t *ccell = (uint32_t *)arena_alloc(ctx, fn * sizeof(uint32_t));
     void *scan_tmp = arena_alloc(ctx, scan_scratch_bytes(total_cells + 1));
-    if (!cell_start || !cr || !rec || !scan_tmp) {
+    if (!cell_start || !cr || !rec || !ccell || !scan_tmp) {
         mdb_set_error("cells_build: arena too small (internal sizing error)");
         return -1;
     }
-    MDB_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(total_cells + 16) * sizeof(int), stream));
+    {
+        ProfScope ps(ctx, "memset", stream);
+        MDB_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(total_cells + 16) * sizeof(int), stream));
+    }
     dim3 grid(cdiv(natoms, 256), nframes);
-    k_bin<<<grid, 256, 0, stream>>>(d_pos, d_geom, natoms, periodic, cell_start, cr, d_err);
+    {
+        ProfScope ps(ctx, "k_bin", stream);
+        k_bin<<<grid, 256, 0, stream>>>(d_pos, d_geom, natoms, periodic, cell_start, cr, d_err);
+    }
     ctx->launches++;
     MDB_CUDA(cudaGetLastError());
     // exclusive scan over every cell of the batch (+1 sentinel): frame f's cells start at f*N
     if (device_exclusive_scan(ctx, cell_start, total_cells + 1, scan_tmp, stream)) return -1;
-    k_scatter<<<grid, 256, 0, stream>>>(d_pos, d_types, d_geom, natoms, periodic, cell_start, cr, rec, ctx->el.nt, d_err);
+    {
+        ProfScope ps(ctx, "k_scatter", stream);
+        k_scatter<<<grid, 256, 0, stream>>>(d_pos, d_types, d_geom, natoms, periodic, cell_start, cr, rec, ccell,
+                                            rec_mode, ctx->el.nt, d_err);
+    }
     ctx->launches++;
     MDB_CUDA(cudaGetLastError());
     out->d_geom = d_geom;
     out->cell_start = cell_start;
     out->rec = rec;
+    out->ccell = ccell;
+    out->rec_mode = rec_mode;
     out->total_cells = total_cells;
     return 0;
 }

@@ -78,6 +78,39 @@ struct mdb_ctx {
     cudaEvent_t pipe_in[2] = {}, pipe_comp[2] = {}, pipe_out[2] = {};
     uint8_t *pipe_types = nullptr;
     size_t pipe_types_cap = 0;
+    // optional per-launch CUDA-event timing (bench.py's live roofline measurement)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_free;
+    struct ProfRec {
+        const char *name;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfRec> prof_recs;
+};
+
+// RAII timing scope around one launch: records events on the launching stream when profiling is on
+struct ProfScope {
+    mdb_ctx *c;
+    cudaStream_t s;
+    cudaEvent_t b = nullptr;
+    ProfScope(mdb_ctx *ctx, const char *name, cudaStream_t stream) : c(ctx), s(stream) {
+        if (!c->prof_on) return;
+        cudaEvent_t a;
+        auto get = [&](cudaEvent_t &e) {
+            if (!c->prof_free.empty()) {
+                e = c->prof_free.back();
+                c->prof_free.pop_back();
+            } else
+                cudaEventCreate(&e);
+        };
+        get(a);
+        get(b);
+        cudaEventRecord(a, s);
+        c->prof_recs.push_back({name, a, b});
+    }
+    ~ProfScope() {
+        if (b) cudaEventRecord(b, s);
+    }
 };
 
 void mdb_set_error(const std::string &msg);
@@ -105,21 +138,23 @@ int upload_geometry(mdb_ctx *ctx, const std::vector<FrameGeom> &g, FrameGeom *d_
 struct CellList {
     const FrameGeom *d_geom;
     int *cell_start;   // [total_cells + 1] exclusive scan over the batch (global slot offsets)
-    float4 *rec;       // [F*N] sorted records: grid-unit coords + (type << 27 | index)
+    float4 *rec;       // [F*N] sorted records: coords + (type << 27 | index)
+    uint32_t *ccell;   // [F*N] sorted: packed cell coordinates cx | cy << 10 | cz << 20
     long long total_cells;
-    bool all_ortho;    // every frame of the batch has a diagonal cell matrix
+    int rec_mode;      // 1: rec holds wrapped Angstrom coords (all frames orthorhombic, >= 3 cells per
+                       //    periodic axis); 0: rec holds grid units (general cells / reduced axes)
 };
 size_t cells_workspace_bytes(int nframes, int natoms, long long total_cells);
 int cells_build(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const uint8_t *d_types,
-                const FrameGeom *d_geom, long long total_cells, int periodic, CellList *out, int *d_err,
-                cudaStream_t stream);
+                const FrameGeom *d_geom, long long total_cells, int periodic, int rec_mode, CellList *out,
+                int *d_err, cudaStream_t stream);
 int device_exclusive_scan(mdb_ctx *ctx, int *d_data, long long n, void *d_scratch, cudaStream_t stream);
 size_t scan_scratch_bytes(long long n);
 int bbox_frames(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, double *h_bbox, cudaStream_t stream);
 
 // bonds.cu
 int bonds_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const uint8_t *d_types,
-              const CellList &cl, int periodic, int32_t *d_ell, cudaStream_t stream);
+              const CellList &cl, int periodic, int32_t *d_ell, int32_t *d_parent, cudaStream_t stream);
 size_t bonds_workspace_bytes(int nframes, int natoms);
 int ell_to_csr_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, int order, const double *d_pos,
                    int32_t *d_rowptr, int32_t *d_col, int colcap, cudaStream_t stream);
@@ -131,6 +166,9 @@ int keys_bo_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, con
                 const uint8_t *d_types, uint64_t *d_keys, cudaStream_t stream);
 int components_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, int32_t *d_labels, int seeded,
                    cudaStream_t stream);
+// keys + union-find hooks in one pass over the ELL rows (d_labels must hold the seed), then flatten
+int keys_components_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const uint8_t *d_types,
+                        uint64_t *d_keys, int32_t *d_labels, cudaStream_t stream);
 int dps_run(mdb_ctx *ctx, int natoms, const int32_t *d_rowptr, const int32_t *d_col, int32_t *d_mol_atoms,
             int32_t *d_mol_ptr, int *h_nmol, cudaStream_t stream);
 

@@ -64,10 +64,13 @@ int keys_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const 
              int32_t *d_parent, cudaStream_t stream) {
     long long fn = (long long)nframes * natoms;
     if (fn == 0) return 0;
-    if (ctx->opt_max_bonds == 8)
-        k_keys<8><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, d_types, natoms, fn, d_keys, d_parent);
-    else
-        k_keys<16><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, d_types, natoms, fn, d_keys, d_parent);
+    {
+        ProfScope ps(ctx, "k_keys", stream);
+        if (ctx->opt_max_bonds == 8)
+            k_keys<8><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, d_types, natoms, fn, d_keys, d_parent);
+        else
+            k_keys<16><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, d_types, natoms, fn, d_keys, d_parent);
+    }
     ctx->launches++;
     MDB_CUDA(cudaGetLastError());
     return 0;
@@ -134,6 +137,38 @@ __global__ void __launch_bounds__(256) k_uf_hook(const int32_t *__restrict__ ell
     }
 }
 
+// keys + hooks in one pass over the rows (parent already seeded by k_bonds / k_cleanup)
+template <int MAXB>
+__global__ void __launch_bounds__(256) k_keys_hook(const int32_t *__restrict__ ell, const uint8_t *__restrict__ types,
+                                                   int N, long long fn, uint64_t *__restrict__ keys, int *parent) {
+    long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= fn) return;
+    const int i = (int)(a % N);
+    int *par = parent + (a - i);
+    const int4 *row = reinterpret_cast<const int4 *>(ell + a * MAXB);
+    int nb[MAXB];
+#pragma unroll
+    for (int k = 0; k < MAXB / 4; ++k) {
+        int4 q = row[k];
+        nb[4 * k] = q.x;
+        nb[4 * k + 1] = q.y;
+        nb[4 * k + 2] = q.z;
+        nb[4 * k + 3] = q.w;
+    }
+    int deg = 0;
+#pragma unroll
+    for (int k = 0; k < MAXB; ++k) deg += nb[k] >= 0;
+    if (keys) {
+        const int nl = deg > 12 ? 12 : deg;
+        const uint64_t ones = nl == 0 ? 0ull : (0x111111111111ull >> (4 * (12 - nl)));
+        keys[a] = ((uint64_t)(types[i] + 1) << 56) | ((uint64_t)deg << 48) | ones;
+    }
+    // slot 0 (the smallest neighbour) is already the seed; hook the remaining smaller neighbours
+#pragma unroll
+    for (int k = 1; k < MAXB; ++k)
+        if (nb[k] >= 0 && nb[k] < i) uf_union(par, i, nb[k]);
+}
+
 __global__ void __launch_bounds__(256) k_uf_flatten(int N, long long fn, int *parent) {
     long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= fn) return;
@@ -155,11 +190,37 @@ int components_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, 
     if (!seeded) {
         if (keys_run(ctx, nframes, natoms, d_ell, nullptr, nullptr, d_labels, stream)) return -1;
     }
-    if (ctx->opt_max_bonds == 8)
-        k_uf_hook<8><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, natoms, fn, d_labels);
-    else
-        k_uf_hook<16><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, natoms, fn, d_labels);
-    k_uf_flatten<<<cdiv(fn, 256), 256, 0, stream>>>(natoms, fn, d_labels);
+    {
+        ProfScope ps(ctx, "k_uf_hook", stream);
+        if (ctx->opt_max_bonds == 8)
+            k_uf_hook<8><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, natoms, fn, d_labels);
+        else
+            k_uf_hook<16><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, natoms, fn, d_labels);
+    }
+    {
+        ProfScope ps(ctx, "k_uf_flatten", stream);
+        k_uf_flatten<<<cdiv(fn, 256), 256, 0, stream>>>(natoms, fn, d_labels);
+    }
+    ctx->launches += 2;
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int keys_components_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const uint8_t *d_types,
+                        uint64_t *d_keys, int32_t *d_labels, cudaStream_t stream) {
+    long long fn = (long long)nframes * natoms;
+    if (fn == 0) return 0;
+    {
+        ProfScope ps(ctx, "k_keys_hook", stream);
+        if (ctx->opt_max_bonds == 8)
+            k_keys_hook<8><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, d_types, natoms, fn, d_keys, d_labels);
+        else
+            k_keys_hook<16><<<cdiv(fn, 256), 256, 0, stream>>>(d_ell, d_types, natoms, fn, d_keys, d_labels);
+    }
+    {
+        ProfScope ps(ctx, "k_uf_flatten", stream);
+        k_uf_flatten<<<cdiv(fn, 256), 256, 0, stream>>>(natoms, fn, d_labels);
+    }
     ctx->launches += 2;
     MDB_CUDA(cudaGetLastError());
     return 0;

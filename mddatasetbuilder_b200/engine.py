@@ -80,6 +80,19 @@ class Engine:
     def launches(self) -> int:
         return int(self.L.mdb_launch_count(self.ctx))
 
+    def profile(self, on: bool):
+        _lib.check(self.L.mdb_profile_enable(self.ctx, int(on)), "mdb_profile_enable")
+
+    def profile_read(self):
+        """{kernel name: (launch count, total ms)} since the last read (synchronises)."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(self.L.mdb_profile_read(self.ctx, buf, len(buf)), "mdb_profile_read")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
+
     def stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 

@@ -427,6 +427,49 @@ int orc_connect_the_dots(int n, const int *Z, const double *pos, const double *c
     return nb_alive;
 }
 
+/* Bounded sample of the O(N^2) pair loop for the CPU baseline: runs the periodic pair loop of
+ * mode 0 for z-ranks j = offset, offset+stride, ... only (no cleanup) and returns the number of
+ * bonds found.  One full frame costs `stride` times the sampled time; the rows are strided so
+ * the triangular loop (k > j) is sampled evenly. */
+long orc_ctd_sample(int n, const int *Z, const double *pos, const double *cell, int periodic, int stride,
+                    int offset) {
+    ctd_sys s;
+    s.n = n;
+    s.Z = Z;
+    s.pos = pos;
+    s.periodic = periodic;
+    if (periodic) ob_cell_init(&s.uc, cell);
+    zrec *zs = (zrec *)malloc((size_t)(n > 0 ? n : 1) * sizeof(zrec));
+    double *rad = (double *)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+    for (int i = 0; i < n; ++i) {
+        zs[i].z = pos[i * 3 + 2];
+        zs[i].idx = i;
+    }
+    qsort(zs, (size_t)n, sizeof(zrec), zrec_cmp);
+    double maxrad = 0.0;
+    for (int j = 0; j < n; ++j) {
+        rad[j] = orc_rcov(Z[zs[j].idx]);
+        if (rad[j] > maxrad) maxrad = rad[j];
+    }
+    bondvec bv = {0, 0, 0};
+    for (int j = offset; j < n; j += stride) {
+        double maxcut = rad[j] + maxrad + 0.45;
+        maxcut = maxcut * maxcut;
+        for (int k = j + 1; k < n; ++k) {
+            if (!periodic) {
+                double dz = pos[zs[j].idx * 3 + 2] - pos[zs[k].idx * 3 + 2];
+                if (dz * dz > maxcut) break;
+            }
+            ctd_try_pair(&s, zs, rad, j, k, &bv);
+        }
+    }
+    long nb = bv.n;
+    free(bv.v);
+    free(zs);
+    free(rad);
+    return nb;
+}
+
 /* adjacency in the order detect.py:282-291 appends it: for each bond in
  * iteration order, bond[s1].append(s2); bond[s2].append(s1).  rowptr[n+1], col[2*nb]. */
 void orc_bonds_to_csr(int n, int nb, const int *bonds, int *rowptr, int *col) {

@@ -63,6 +63,8 @@ def lib():
         L.orc_connect_the_dots.restype = C.c_int
         L.orc_connect_the_dots.argtypes = [C.c_int, ip, dp, dp, C.c_int, C.c_int,
                                            C.POINTER(C.POINTER(C.c_int)), ip]
+        L.orc_ctd_sample.restype = C.c_long
+        L.orc_ctd_sample.argtypes = [C.c_int, ip, dp, dp, C.c_int, C.c_int, C.c_int]
         L.orc_bonds_to_csr.argtypes = [C.c_int, C.c_int, ip, ip, ip]
         L.orc_dps.restype = C.c_int
         L.orc_dps.argtypes = [C.c_int, ip, ip, ip, ip, ip]
@@ -114,6 +116,15 @@ def connect_the_dots(Z, pos, cell=None, periodic=True, mode=1):
     bonds = np.ctypeslib.as_array(out, shape=(max(nb, 1), 2))[:nb].copy()
     lib().orc_free(out)
     return bonds, ndel.value
+
+
+def ctd_sample(Z, pos, cell, periodic, stride, offset):
+    """Bounded sample of the O(N^2) ConnectTheDots pair loop (CPU-baseline timing only):
+    z-ranks offset, offset+stride, ...; a full frame costs ~stride x this call."""
+    Z = _i32(Z)
+    pos = _f64(pos).reshape(-1, 3)
+    cell = _f64(cell).reshape(9)
+    return lib().orc_ctd_sample(len(Z), _i(Z), _d(pos), _d(cell), int(bool(periodic)), int(stride), int(offset))
 
 
 def bonds_to_csr(n, bonds):
