@@ -37,7 +37,9 @@ static const char *err_text(int e) {
 
 static int frames_per_chunk(const mdb_ctx *c, int nframes, int natoms) {
     if (c->opt_frames_per_launch > 0) return std::min(nframes, c->opt_frames_per_launch);
-    long long per = std::max(1LL, (4LL << 20) / std::max(natoms, 1));
+    // ~16M atom-frames per launch: large enough that launch gaps and the per-frame cleanup blocks
+    // amortise (measured on B200: 5 -> 160 frames of 100k atoms = 43.9 -> 13.3 ms per 1e8 atom-frames)
+    long long per = std::max(1LL, (16LL << 20) / std::max(natoms, 1));
     per = std::min<long long>(per, ((1LL << 30) / std::max(natoms, 1)));
     return (int)std::max(1LL, std::min<long long>(per, nframes));
 }

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
     }
 
     // phase 2: decide the pending candidates
+    const float hpx = 0.5f * px, hpy = 0.5f * py, hpz = 0.5f * pz;
     int cnt = 0;
     for (int k = 0; k < np; ++k) {
         const float4 o = rec[s_pend[k][tid]];
@@ -264,16 +265,16 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
             dy = o.y - me.y;
             dz = o.z - me.z;
             if (periodic) {  // >= 3 cells per axis: the stencil image is the minimum image
-                dx -= px * rintf(dx / px);
-                dy -= py * rintf(dy / py);
-                dz -= pz * rintf(dz / pz);
+                dx += dx > hpx ? -px : (dx < -hpx ? px : 0.f);
+                dy += dy > hpy ? -py : (dy < -hpy ? py : 0.f);
+                dz += dz > hpz ? -pz : (dz < -hpz ? pz : 0.f);
             }
         } else {
             float du = o.x - me.x, dv = o.y - me.y, dw = o.z - me.z;
             if (periodic) {
-                du -= px * rintf(du / px);
-                dv -= py * rintf(dv / py);
-                dw -= pz * rintf(dw / pz);
+                du += du > hpx ? -px : (du < -hpx ? px : 0.f);
+                dv += dv > hpy ? -py : (dv < -hpy ? py : 0.f);
+                dw += dw > hpz ? -pz : (dw < -hpz ? pz : 0.f);
             }
             dx = h[0] * du + h[1] * dv + h[2] * dw;
             dy = h[3] * du + h[4] * dv + h[5] * dw;
@@ -319,14 +320,20 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
     // candidate violators of the valence / 45-degree rule (resolved exactly by k_cleanup)
     bool flag = cnt > P.el.maxbonds[ti];
     if (!flag && cnt >= 2) {
+        // unit vectors once, then one dot product per pair
+        for (int a = 0; a < cnt; ++a) {
+            float4 v = s_nb[a][tid];
+            const float inv = rsqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+            v.x *= inv;
+            v.y *= inv;
+            v.z *= inv;
+            s_nb[a][tid] = v;
+        }
         for (int a = 0; a < cnt && !flag; ++a) {
             const float4 va = s_nb[a][tid];
-            const float la = va.x * va.x + va.y * va.y + va.z * va.z;
             for (int b = a + 1; b < cnt; ++b) {
                 const float4 vb = s_nb[b][tid];
-                const float lb = vb.x * vb.x + vb.y * vb.y + vb.z * vb.z;
-                const float dp = (va.x * vb.x + va.y * vb.y + va.z * vb.z) * rsqrtf(la * lb);
-                if (dp > COS_FLAG) {
+                if (va.x * vb.x + va.y * vb.y + va.z * vb.z > COS_FLAG) {
                     flag = true;
                     break;
                 }
