@@ -126,6 +126,33 @@ int mdb_analyze_frames_host(mdb_ctx *ctx, int nframes, int natoms, const double 
                             const double *h_cell, const uint8_t *h_types, int periodic,
                             int32_t *h_ell, uint64_t *h_keys, int32_t *h_labels);
 
+/* ---- K5: element composition of the cutoff sphere -----------------------------
+ * Replaces, per target atom, `distances = get_distances(a, all, mic=True);
+ * Counter(symbols[distances < cutoff])` (datasetbuilder.py:312-322): d_counts
+ * [ntargets][ntypes] (the sphere includes the target itself), and updates the
+ * running per-element maximum h_maxcount[ntypes] (in/out; the reference's
+ * max_counter, datasetbuilder.py:271) -- synchronises.  d_targets: batch-local
+ * atom-frame indices f*natoms + i (int32), or NULL for every atom of every frame.
+ * Orthorhombic cells only. */
+int mdb_compositions(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                     const double *h_cell, const uint8_t *d_types, int periodic, double cutoff,
+                     const int32_t *d_targets, long long ntargets, int32_t *d_counts,
+                     int32_t *h_maxcount, void *stream);
+
+/* ---- K6: Coulomb-matrix eigen-spectrum descriptor -------------------------------
+ * Replaces _writestepmatrix + _calcoulumbmatrix (datasetbuilder.py:283-349) and the
+ * feature assembly (datasetbuilder.py:236-276).  For every target:
+ *   d_eig [ntargets][eigcap]  ascending eigenvalues (NaN padded), optional;
+ *   d_n   [ntargets]          cluster size, optional;
+ *   d_X   [ntargets][D]       sort(eigenvalues U pads), D = sum(h_maxcount), optional,
+ * where d_counts are the compositions from mdb_compositions for the same targets and
+ * h_maxcount the per-element maxima over ALL rows of the bond type. */
+int mdb_descriptors(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                    const double *h_cell, const uint8_t *d_types, int periodic, double cutoff,
+                    const int32_t *d_targets, long long ntargets, const int32_t *d_counts,
+                    const int32_t *h_maxcount, double *d_X, double *d_eig, int eigcap,
+                    int32_t *d_n, void *stream);
+
 /* Diagnostics of the last bond batch: counts summed over frames (synchronises). */
 int mdb_bond_stats(mdb_ctx *ctx, long long *n_violators, long long *n_exact_tests,
                    long long *n_overflow);

@@ -35,6 +35,10 @@ SIGNATURES = {
     "mdb_dps": (C.c_int, [c_ctx, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp]),
     "mdb_analyze_frames": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "mdb_analyze_frames_host": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "mdb_compositions": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, _vp, C.c_longlong,
+                                   _vp, _vp, _vp]),
+    "mdb_descriptors": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, _vp, C.c_longlong,
+                                  _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "mdb_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "mdb_profile_read": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),
     "mdb_bond_stats": (C.c_int, [c_ctx, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

@@ -30,6 +30,8 @@ static const char *err_text(int e) {
             return "CSR column capacity exceeded";
         case MDB_ERR_TYPE_RANGE:
             return "atom type index outside the element table";
+        case MDB_ERR_EIG_NOCONV:
+            return "QL eigenvalue iteration did not converge";
         default:
             return "unknown device-side error";
     }
@@ -195,6 +197,31 @@ extern "C" int mdb_bond_stats(mdb_ctx *c, long long *n_violators, long long *n_e
         return h.err;
     }
     return 0;
+}
+
+extern "C" int mdb_compositions(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                const uint8_t *d_types, int periodic, double cutoff, const int32_t *d_targets,
+                                long long ntargets, int32_t *d_counts, int32_t *h_maxcount, void *stream) {
+    if (check_ctx(c, "mdb_compositions")) return -1;
+    if ((long long)nframes * natoms >= (1LL << 31) - 64) {
+        mdb_set_error("mdb_compositions: batch too large, split the frames");
+        return -1;
+    }
+    return compositions_run(c, nframes, natoms, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, d_counts,
+                            h_maxcount, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_descriptors(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                               const uint8_t *d_types, int periodic, double cutoff, const int32_t *d_targets,
+                               long long ntargets, const int32_t *d_counts, const int32_t *h_maxcount, double *d_X,
+                               double *d_eig, int eigcap, int32_t *d_n, void *stream) {
+    if (check_ctx(c, "mdb_descriptors")) return -1;
+    if ((long long)nframes * natoms >= (1LL << 31) - 64) {
+        mdb_set_error("mdb_descriptors: batch too large, split the frames");
+        return -1;
+    }
+    return descriptors_run(c, nframes, natoms, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, d_counts,
+                           h_maxcount, d_X, d_eig, eigcap, d_n, (cudaStream_t)stream);
 }
 
 // per-kernel timing: "name count total_ms" lines, accumulated since the last read

@@ -260,6 +260,7 @@ int cells_build(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, cons
     out->cell_start = cell_start;
     out->rec = rec;
     out->ccell = ccell;
+    out->cr = cr;
     out->rec_mode = rec_mode;
     out->total_cells = total_cells;
     return 0;

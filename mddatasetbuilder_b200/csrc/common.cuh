@@ -20,6 +20,7 @@
 #define MDB_ERR_BOND_OVERFLOW 2  // more raw neighbours than max_bonds
 #define MDB_ERR_CSR_OVERFLOW 3
 #define MDB_ERR_TYPE_RANGE 4
+#define MDB_ERR_EIG_NOCONV 5  // QL iteration did not converge
 
 struct FrameGeom {
     double ortho[9];    // fractional -> cartesian (lattice vectors as columns), OB's _mOrtho
@@ -140,6 +141,7 @@ struct CellList {
     int *cell_start;   // [total_cells + 1] exclusive scan over the batch (global slot offsets)
     float4 *rec;       // [F*N] sorted records: coords + (type << 27 | index)
     uint32_t *ccell;   // [F*N] sorted: packed cell coordinates cx | cy << 10 | cz << 20
+    uint32_t *cr;      // [F*N] per atom (original order): cell id << 8 | rank within the cell
     long long total_cells;
     int rec_mode;      // 1: rec holds wrapped Angstrom coords (all frames orthorhombic, >= 3 cells per
                        //    periodic axis); 0: rec holds grid units (general cells / reduced axes)
@@ -158,6 +160,14 @@ int bonds_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const 
 size_t bonds_workspace_bytes(int nframes, int natoms);
 int ell_to_csr_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, int order, const double *d_pos,
                    int32_t *d_rowptr, int32_t *d_col, int colcap, cudaStream_t stream);
+
+// descriptor.cu
+int compositions_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
+                     int periodic, double cutoff, const int *d_targets, long long ntargets, int *d_counts,
+                     int *h_maxcount, cudaStream_t stream);
+int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
+                    int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
+                    const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream);
 
 // graph.cu
 int keys_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const uint8_t *d_types, uint64_t *d_keys,

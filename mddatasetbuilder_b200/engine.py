@@ -199,6 +199,51 @@ class Engine:
         _lib.check(rc, "mdb_dps")
         return mol_atoms[:N], mol_ptr[: nm.value + 1]
 
+    def compositions(self, pos, cell, types, cutoff, targets=None, periodic=True, maxcount=None):
+        """Element composition of every target's cutoff sphere (datasetbuilder.py:312-322).
+        Returns (counts [T, ntypes] int32 device tensor, maxcount numpy [ntypes] running max)."""
+        torch = _torch()
+        pos = self.to_device_pos(pos)
+        types = self.to_device_types(types)
+        F, N = int(pos.shape[0]), int(pos.shape[1])
+        cells = self._cells(cell, F) if periodic else None
+        nt = len(self.atomname)
+        if targets is not None:
+            targets = torch.as_tensor(targets, dtype=torch.int32, device=self.device).contiguous()
+            T = int(targets.numel())
+        else:
+            T = F * N
+        counts = torch.zeros((T, nt), dtype=torch.int32, device=self.device)
+        mc = np.zeros(nt, dtype=np.int32) if maxcount is None else np.ascontiguousarray(maxcount, dtype=np.int32).copy()
+        rc = self.L.mdb_compositions(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                     float(cutoff), _ptr(targets), T, _ptr(counts), _np_ptr(mc), self.stream())
+        _lib.check(rc, "mdb_compositions")
+        return counts, mc
+
+    def descriptors(self, pos, cell, types, cutoff, counts, maxcount, targets=None, periodic=True, want_X=True,
+                    want_eig=False, eigcap=128):
+        """Coulomb-matrix spectrum + padded sorted feature rows (datasetbuilder.py:236-349)."""
+        torch = _torch()
+        pos = self.to_device_pos(pos)
+        types = self.to_device_types(types)
+        F, N = int(pos.shape[0]), int(pos.shape[1])
+        cells = self._cells(cell, F) if periodic else None
+        if targets is not None:
+            targets = torch.as_tensor(targets, dtype=torch.int32, device=self.device).contiguous()
+            T = int(targets.numel())
+        else:
+            T = F * N
+        mc = np.ascontiguousarray(maxcount, dtype=np.int32)
+        D = int(mc.sum())
+        X = torch.empty((T, D), dtype=torch.float64, device=self.device) if want_X else None
+        eig = torch.empty((T, eigcap), dtype=torch.float64, device=self.device) if want_eig else None
+        n = torch.empty((T,), dtype=torch.int32, device=self.device)
+        rc = self.L.mdb_descriptors(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                    float(cutoff), _ptr(targets), T, _ptr(counts), _np_ptr(mc), _ptr(X), _ptr(eig),
+                                    int(eigcap), _ptr(n), self.stream())
+        _lib.check(rc, "mdb_descriptors")
+        return {"X": X, "eig": eig, "n": n}
+
     def analyze_host(self, pos, cell, types, periodic=True, want_keys=True, want_labels=True, out=None):
         """Host-buffer path (e2e): numpy / pinned tensors in, numpy out; H2D and D2H copies
         are pipelined inside the library."""
