@@ -153,6 +153,40 @@ int mdb_descriptors(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
                     const int32_t *h_maxcount, double *d_X, double *d_eig, int eigcap,
                     int32_t *d_n, void *stream);
 
+/* ---- MinMaxScaler (datasetbuilder.py:369-370; sklearn preprocessing/_data.py) ------
+ * fit: column minima / maxima of d_X [rows][D] (row stride ldx doubles) into d_min /
+ * d_max [D] (device).  transform: X = X * scale + min_ in place with scale = 1/range
+ * (range < 10 eps -> 1) and min_ = 0 - data_min * scale, as two rounded operations. */
+int mdb_minmax_fit(mdb_ctx *ctx, long long rows, int D, const double *d_X, long long ldx,
+                   double *d_min, double *d_max, void *stream);
+int mdb_minmax_transform(mdb_ctx *ctx, long long rows, int D, double *d_X, long long ldx,
+                         const double *h_min, const double *h_max, void *stream);
+
+/* ---- K7: k-means assignment ---------------------------------------------------------
+ * Replaces sklearn _labels_inertia / lloyd_iter_chunked_dense(update_centers=False)
+ * (cluster/_k_means_lloyd.pyx:168-213) as driven by MiniBatchKMeans.fit_predict at
+ * datasetbuilder.py:371-376: label = argmin_j ||c_j||^2 - 2 x.c_j in float64, strict
+ * '<' so the lowest centroid index wins ties.  d_rowidx (optional) selects rows of X
+ * (a mini-batch) without gathering them.  d_mindist (optional) = ||x - c_label||^2;
+ * h_inertia (optional, synchronises) = sum(weight * mindist). */
+int mdb_kmeans_assign(mdb_ctx *ctx, long long rows, int D, int K, const double *d_X,
+                      long long ldx, const int32_t *d_rowidx, const double *d_centers,
+                      int32_t *d_labels, double *d_mindist, const double *d_weights,
+                      double *h_inertia, void *stream);
+
+/* ---- K8: mini-batch centroid update -------------------------------------------------
+ * Replaces _minibatch_update_dense (cluster/_k_means_minibatch.pyx:59-108) in two
+ * halves so that ranks can all-reduce between them: partial_sums writes, per centre,
+ * sum(weight * x) over the batch members (ascending sample order when the batch holds
+ * <= 4096 rows) and the summed weight; apply_update performs
+ * centre = (centre * weight_sums + sums) / (weight_sums + wsum); weight_sums += wsum
+ * for every centre with wsum > 0. */
+int mdb_kmeans_partial_sums(mdb_ctx *ctx, long long nbatch, int D, int K, const double *d_X,
+                            long long ldx, const int32_t *d_rowidx, const double *d_weights,
+                            const int32_t *d_labels, double *d_sums, double *d_wsum, void *stream);
+int mdb_kmeans_apply_update(mdb_ctx *ctx, int K, int D, double *d_centers, double *d_weight_sums,
+                            const double *d_sums, const double *d_wsum, void *stream);
+
 /* Diagnostics of the last bond batch: counts summed over frames (synchronises). */
 int mdb_bond_stats(mdb_ctx *ctx, long long *n_violators, long long *n_exact_tests,
                    long long *n_overflow);

@@ -39,6 +39,13 @@ SIGNATURES = {
                                    _vp, _vp, _vp]),
     "mdb_descriptors": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, _vp, C.c_longlong,
                                   _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "mdb_minmax_fit": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp]),
+    "mdb_minmax_transform": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp]),
+    "mdb_kmeans_assign": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp, _vp,
+                                    C.POINTER(C.c_double), _vp]),
+    "mdb_kmeans_partial_sums": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp,
+                                          _vp, _vp]),
+    "mdb_kmeans_apply_update": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdb_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "mdb_profile_read": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),
     "mdb_bond_stats": (C.c_int, [c_ctx, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

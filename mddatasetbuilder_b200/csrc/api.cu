@@ -224,6 +224,39 @@ extern "C" int mdb_descriptors(mdb_ctx *c, int nframes, int natoms, const double
                            h_maxcount, d_X, d_eig, eigcap, d_n, (cudaStream_t)stream);
 }
 
+extern "C" int mdb_kmeans_assign(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx,
+                                 const int32_t *d_rowidx, const double *d_centers, int32_t *d_labels, double *d_mindist,
+                                 const double *d_weights, double *h_inertia, void *stream) {
+    if (check_ctx(c, "mdb_kmeans_assign", false)) return -1;
+    return kmeans_assign_run(c, rows, D, K, d_X, ldx, d_rowidx, d_centers, d_labels, d_mindist, h_inertia, d_weights,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int mdb_kmeans_partial_sums(mdb_ctx *c, long long nbatch, int D, int K, const double *d_X, long long ldx,
+                                       const int32_t *d_rowidx, const double *d_weights, const int32_t *d_labels,
+                                       double *d_sums, double *d_wsum, void *stream) {
+    if (check_ctx(c, "mdb_kmeans_partial_sums", false)) return -1;
+    return kmeans_sums_run(c, nbatch, D, K, d_X, ldx, d_rowidx, d_weights, d_labels, d_sums, d_wsum, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_kmeans_apply_update(mdb_ctx *c, int K, int D, double *d_centers, double *d_weight_sums,
+                                       const double *d_sums, const double *d_wsum, void *stream) {
+    if (check_ctx(c, "mdb_kmeans_apply_update", false)) return -1;
+    return kmeans_apply_run(c, K, D, d_centers, d_weight_sums, d_sums, d_wsum, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_minmax_fit(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx, double *d_min,
+                              double *d_max, void *stream) {
+    if (check_ctx(c, "mdb_minmax_fit", false)) return -1;
+    return minmax_fit_run(c, rows, D, d_X, ldx, d_min, d_max, 0, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_minmax_transform(mdb_ctx *c, long long rows, int D, double *d_X, long long ldx, const double *h_min,
+                                    const double *h_max, void *stream) {
+    if (check_ctx(c, "mdb_minmax_transform", false)) return -1;
+    return minmax_transform_run(c, rows, D, d_X, ldx, h_min, h_max, (cudaStream_t)stream);
+}
+
 // per-kernel timing: "name count total_ms" lines, accumulated since the last read
 extern "C" int mdb_profile_enable(mdb_ctx *c, int on) {
     if (check_ctx(c, "mdb_profile_enable", false)) return -1;

@@ -169,6 +169,19 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
                     int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
                     const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream);
 
+// kmeans.cu
+int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
+                      const double *d_C, int *d_labels, double *d_mind, double *h_inertia, const double *d_w,
+                      cudaStream_t stream);
+int kmeans_sums_run(mdb_ctx *c, long long B, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
+                    const double *d_w, const int *d_labels, double *d_sums, double *d_wsum, cudaStream_t stream);
+int kmeans_apply_run(mdb_ctx *c, int K, int D, double *d_C, double *d_weight_sums, const double *d_sums,
+                     const double *d_wsum, cudaStream_t stream);
+int minmax_fit_run(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx, double *d_min, double *d_max,
+                   int accumulate, cudaStream_t stream);
+int minmax_transform_run(mdb_ctx *c, long long rows, int D, double *d_X, long long ldx, const double *h_min,
+                         const double *h_max, cudaStream_t stream);
+
 // graph.cu
 int keys_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const uint8_t *d_types, uint64_t *d_keys,
              int32_t *d_parent, cudaStream_t stream);

@@ -1,0 +1,484 @@
+// kmeans.cu -- K7 assignment, K8 mini-batch centroid update, and the MinMaxScaler arithmetic.
+//
+// Replaces, inside DatasetBuilder._clusterdatas (reference datasetbuilder.py:351-384), the
+// scikit-learn kernels it drives:
+//   MinMaxScaler.fit_transform           sklearn preprocessing/_data.py:127-132,537-575
+//   assignment  argmin_j ||c_j||^2 - 2 x.c_j (strict <, lowest index wins ties)
+//                                        sklearn cluster/_k_means_lloyd.pyx:168-213
+//   mini-batch update                    sklearn cluster/_k_means_minibatch.pyx:59-108
+// The assignment is a double-precision tiled contraction (128 rows x 128 centroids per block,
+// 8x8 register tiles) with the argmin fused into the epilogue, so labels are decided on the same
+// quantity scikit-learn compares (float64 ||c||^2 - 2 x.c).
+#include <float.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+#define AS_BM 128
+#define AS_BN 128
+#define AS_KC 16
+#define AS_THREADS 256
+#define AS_PITCH (AS_BM + 2)
+
+__global__ void __launch_bounds__(256) k_cnorm(const double *__restrict__ C, int K, int D, double *__restrict__ cn) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) {
+        double v = C[(size_t)j * D + k];
+        s += v * v;
+    }
+    cn[j] = s;
+}
+
+// grid: (row tiles, centroid splits).  part_val/part_idx: [splits][rows]
+__global__ void __launch_bounds__(AS_THREADS) k_assign(const double *__restrict__ X, long long ldx, long long rows,
+                                                       const int *__restrict__ rowidx, const double *__restrict__ C, int K,
+                                                       int D, const double *__restrict__ cn, int tiles_per_split,
+                                                       double *__restrict__ part_val, int *__restrict__ part_idx) {
+    __shared__ double xs[AS_KC][AS_PITCH];
+    __shared__ double cs[AS_KC][AS_PITCH];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long row0 = (long long)blockIdx.x * AS_BM;
+    const int ctile0 = blockIdx.y * tiles_per_split;
+    const int ntiles = (K + AS_BN - 1) / AS_BN;
+    const int ctile1 = min(ntiles, ctile0 + tiles_per_split);
+    // loader mapping: 2 threads per row, 8 consecutive features each
+    const int lr = tid >> 1, lk = (tid & 1) * 8;
+    long long xrow = row0 + lr;
+    const bool xok = xrow < rows;
+    if (xok && rowidx) xrow = rowidx[xrow];
+    const double *xptr = X + (xok ? xrow : 0) * ldx;
+
+    double bestv[8];
+    int besti[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        bestv[i] = DBL_MAX;
+        besti[i] = 0x7fffffff;
+    }
+    for (int ct = ctile0; ct < ctile1; ++ct) {
+        const int col0 = ct * AS_BN;
+        double acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        const int crow = col0 + lr;
+        const bool cok = crow < K;
+        const double *cptr = C + (size_t)(cok ? crow : 0) * D;
+        for (int k0 = 0; k0 < D; k0 += AS_KC) {
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = k0 + lk + q;
+                xs[lk + q][lr] = (xok && k < D) ? xptr[k] : 0.0;
+                cs[lk + q][lr] = (cok && k < D) ? cptr[k] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < AS_KC; ++kk) {
+                double a[8], b[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double2 va = *reinterpret_cast<const double2 *>(&xs[kk][ty * 2 + 32 * i]);
+                    const double2 vb = *reinterpret_cast<const double2 *>(&cs[kk][tx * 2 + 32 * i]);
+                    a[2 * i] = va.x;
+                    a[2 * i + 1] = va.y;
+                    b[2 * i] = vb.x;
+                    b[2 * i + 1] = vb.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+        }
+        // epilogue: dist = ||c||^2 - 2 x.c ; per-row argmin over this tile, lowest index on ties
+        double cnv[8];
+        int cidx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            cidx[j] = col0 + tx * 2 + (j & 1) + 32 * (j >> 1);
+            cnv[j] = cidx[j] < K ? cn[cidx[j]] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = DBL_MAX;
+            int ix = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double dj = fma(-2.0, acc[i][j], cnv[j]);
+                if (cidx[j] < K && (dj < v || (dj == v && cidx[j] < ix))) {
+                    v = dj;
+                    ix = cidx[j];
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+                if (ov < v || (ov == v && oi < ix)) {
+                    v = ov;
+                    ix = oi;
+                }
+            }
+            if (v < bestv[i] || (v == bestv[i] && ix < besti[i])) {
+                bestv[i] = v;
+                besti[i] = ix;
+            }
+        }
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long r = row0 + ty * 2 + (i & 1) + 32 * (i >> 1);
+            if (r < rows) {
+                part_val[(size_t)blockIdx.y * rows + r] = bestv[i];
+                part_idx[(size_t)blockIdx.y * rows + r] = besti[i];
+            }
+        }
+    }
+}
+
+// combine the centroid splits (ascending split = ascending centroid index), emit labels and
+// the squared distance to the chosen centre computed directly (sklearn _inertia_dense)
+__global__ void __launch_bounds__(256) k_assign_finish(const double *__restrict__ X, long long ldx, long long rows,
+                                                       const int *__restrict__ rowidx, const double *__restrict__ C, int D,
+                                                       int splits, const double *__restrict__ part_val,
+                                                       const int *__restrict__ part_idx, int *__restrict__ labels,
+                                                       double *__restrict__ mind) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double v = part_val[r];
+    int ix = part_idx[r];
+    for (int s = 1; s < splits; ++s) {
+        const double ov = part_val[(size_t)s * rows + r];
+        const int oi = part_idx[(size_t)s * rows + r];
+        if (ov < v || (ov == v && oi < ix)) {
+            v = ov;
+            ix = oi;
+        }
+    }
+    labels[r] = ix;
+    if (mind) {
+        const double *x = X + (rowidx ? (long long)rowidx[r] : r) * ldx;
+        const double *c = C + (size_t)ix * D;
+        double s = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double t = x[k] - c[k];
+            s += t * t;
+        }
+        mind[r] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sum(const double *__restrict__ v, const double *__restrict__ w, long long n,
+                                             double *__restrict__ out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        acc += w ? v[i] * w[i] : v[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, s[0]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mini-batch update: partial sums per centre (members added in ascending sample order when the
+// batch fits one block, so the result does not depend on scheduling), then the running-mean step
+// ---------------------------------------------------------------------------------------------
+#define MB_MAX 4096
+__global__ void __launch_bounds__(1024) k_mb_sums_sorted(const double *__restrict__ X, long long ldx,
+                                                         const int *__restrict__ rowidx, const double *__restrict__ w,
+                                                         const int *__restrict__ labels, int B, int D,
+                                                         double *__restrict__ sums, double *__restrict__ wsum) {
+    __shared__ unsigned long long key[MB_MAX];
+    int P = 1;
+    while (P < B) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        key[i] = i < B ? (((unsigned long long)(unsigned)labels[i] << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = key[i], b = key[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        key[i] = b;
+                        key[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // one warp per run of equal labels; lanes span the features, members are added in order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = warp; i < B; i += nw) {
+        const unsigned lab = (unsigned)(key[i] >> 32);
+        if (i > 0 && (unsigned)(key[i - 1] >> 32) == lab) continue;  // not a run head
+        int e = i;
+        while (e < B && (unsigned)(key[e] >> 32) == lab) ++e;
+        double ws = 0.0;
+        for (int m = i; m < e; ++m) {
+            const int smp = (int)(unsigned)key[m];
+            ws += w ? w[smp] : 1.0;
+        }
+        for (int f0 = 0; f0 < D; f0 += 32) {
+            const int f = f0 + lane;
+            if (f < D) {
+                double acc = 0.0;
+                for (int m = i; m < e; ++m) {
+                    const int smp = (int)(unsigned)key[m];
+                    const double *x = X + (rowidx ? (long long)rowidx[smp] : (long long)smp) * ldx;
+                    acc = __dadd_rn(acc, __dmul_rn(x[f], w ? w[smp] : 1.0));
+                }
+                sums[(size_t)lab * D + f] = acc;
+            }
+        }
+        if (lane == 0) wsum[lab] = ws;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mb_sums_atomic(const double *__restrict__ X, long long ldx,
+                                                        const int *__restrict__ rowidx, const double *__restrict__ w,
+                                                        const int *__restrict__ labels, long long B, int D,
+                                                        double *__restrict__ sums, double *__restrict__ wsum) {
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= B) return;
+    const int lane = threadIdx.x & 31;
+    const int lab = labels[i];
+    const double wi = w ? w[i] : 1.0;
+    const double *x = X + (rowidx ? (long long)rowidx[i] : i) * ldx;
+    for (int f = lane; f < D; f += 32) atomicAdd(&sums[(size_t)lab * D + f], x[f] * wi);
+    if (lane == 0) atomicAdd(&wsum[lab], wi);
+}
+
+// centers = (centers * weight_sums + sums) / (weight_sums + wsum) for touched centres
+// (sklearn _k_means_minibatch.pyx:84-104); weight_sums += wsum
+__global__ void __launch_bounds__(256) k_mb_apply(double *__restrict__ C, double *__restrict__ weight_sums,
+                                                  const double *__restrict__ sums, const double *__restrict__ wsum, int K,
+                                                  int D) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= K) return;
+    const int lane = threadIdx.x & 31;
+    const double ws = wsum[j];
+    if (!(ws > 0.0)) return;
+    const double w0 = weight_sums[j];
+    const double alpha = 1.0 / (w0 + ws);
+    for (int f = lane; f < D; f += 32) {
+        const double v = __dadd_rn(__dmul_rn(C[(size_t)j * D + f], w0), sums[(size_t)j * D + f]);
+        C[(size_t)j * D + f] = __dmul_rn(v, alpha);
+    }
+    __syncwarp();
+    if (lane == 0) weight_sums[j] = w0 + ws;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MinMaxScaler
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dbl_order(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dbl_unorder(unsigned long long u) {
+    u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)u);
+}
+
+__global__ void __launch_bounds__(256) k_colminmax(const double *__restrict__ X, long long ldx, long long rows, int D,
+                                                   unsigned long long *__restrict__ omin,
+                                                   unsigned long long *__restrict__ omax) {
+    // thread -> column (threadIdx.x % D-tile), rows strided by blocks
+    const int cols_per_block = 32;
+    const int c = blockIdx.y * cols_per_block + (threadIdx.x & 31);
+    const int rlane = threadIdx.x >> 5, nr = blockDim.x >> 5;
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    if (c < D)
+        for (long long r = (long long)blockIdx.x * nr + rlane; r < rows; r += (long long)gridDim.x * nr) {
+            const double v = X[r * ldx + c];
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
+    __shared__ double smn[8][32], smx[8][32];
+    smn[rlane][threadIdx.x & 31] = mn;
+    smx[rlane][threadIdx.x & 31] = mx;
+    __syncthreads();
+    if (rlane == 0 && c < D) {
+        for (int k = 1; k < nr; ++k) {
+            mn = fmin(mn, smn[k][threadIdx.x]);
+            mx = fmax(mx, smx[k][threadIdx.x]);
+        }
+        if (mn <= mx) {
+            atomicMin(&omin[c], dbl_order(mn));
+            atomicMax(&omax[c], dbl_order(mx));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_minmax_init(unsigned long long *omin, unsigned long long *omax, int D) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < D) {
+        omin[c] = dbl_order(DBL_MAX);
+        omax[c] = dbl_order(-DBL_MAX);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_minmax_decode(const unsigned long long *omin, const unsigned long long *omax,
+                                                       double *mn, double *mx, int D) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < D) {
+        mn[c] = dbl_unorder(omin[c]);
+        mx[c] = dbl_unorder(omax[c]);
+    }
+}
+
+// X = X * scale + min_ as two rounded operations (sklearn _data.py:574-575)
+__global__ void __launch_bounds__(256) k_scale(double *__restrict__ X, long long ldx, long long rows, int D,
+                                               const double *__restrict__ scale, const double *__restrict__ shift) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * D) return;
+    const long long r = i / D;
+    const int c = (int)(i - r * D);
+    double *p = X + r * ldx + c;
+    *p = __dadd_rn(__dmul_rn(*p, scale[c]), shift[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host wrappers
+// ---------------------------------------------------------------------------------------------
+int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
+                      const double *d_C, int *d_labels, double *d_mind, double *h_inertia, const double *d_w,
+                      cudaStream_t stream) {
+    if (rows <= 0) {
+        if (h_inertia) *h_inertia = 0.0;
+        return 0;
+    }
+    if (K <= 0 || D <= 0) {
+        mdb_set_error("kmeans_assign: K and D must be positive");
+        return -1;
+    }
+    const int ntiles = (K + AS_BN - 1) / AS_BN;
+    const long long rtiles = (rows + AS_BM - 1) / AS_BM;
+    // enough blocks for ~2 waves over 148 SMs even for a 1024-row mini-batch
+    int splits = (int)std::min<long long>(ntiles, std::max<long long>(1, (296 + rtiles - 1) / rtiles));
+    const int tps = (ntiles + splits - 1) / splits;
+    splits = (ntiles + tps - 1) / tps;
+    const bool need_mind = d_mind != nullptr || h_inertia != nullptr;
+    size_t need = align256((size_t)K * sizeof(double)) + align256((size_t)splits * rows * sizeof(double)) +
+                  align256((size_t)splits * rows * sizeof(int)) + (need_mind && !d_mind ? align256(rows * sizeof(double)) : 0) +
+                  1024;
+    if (arena_reserve(c, need, stream)) return -1;
+    arena_reset(c);
+    double *cn = (double *)arena_alloc(c, (size_t)K * sizeof(double));
+    double *pv = (double *)arena_alloc(c, (size_t)splits * rows * sizeof(double));
+    int *pi = (int *)arena_alloc(c, (size_t)splits * rows * sizeof(int));
+    double *mind = d_mind;
+    if (need_mind && !mind) mind = (double *)arena_alloc(c, rows * sizeof(double));
+    double *acc = (double *)arena_alloc(c, 256);
+    if (!cn || !pv || !pi || !acc || (need_mind && !mind)) {
+        mdb_set_error("kmeans_assign: arena too small (internal sizing error)");
+        return -1;
+    }
+    {
+        ProfScope ps(c, "k_cnorm", stream);
+        k_cnorm<<<cdiv(K, 256), 256, 0, stream>>>(d_C, K, D, cn);
+    }
+    {
+        ProfScope ps(c, "k_assign", stream);
+        dim3 grid((unsigned)rtiles, (unsigned)splits);
+        k_assign<<<grid, AS_THREADS, 0, stream>>>(d_X, ldx, rows, d_rowidx, d_C, K, D, cn, tps, pv, pi);
+    }
+    {
+        ProfScope ps(c, "k_assign_finish", stream);
+        k_assign_finish<<<cdiv(rows, 256), 256, 0, stream>>>(d_X, ldx, rows, d_rowidx, d_C, D, splits, pv, pi, d_labels, mind);
+    }
+    c->launches += 3;
+    if (h_inertia) {
+        MDB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), stream));
+        k_sum<<<std::min<unsigned>(cdiv(rows, 256), 1024u), 256, 0, stream>>>(mind, d_w, rows, acc);
+        c->launches++;
+        MDB_CUDA(cudaMemcpyAsync(h_inertia, acc, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kmeans_sums_run(mdb_ctx *c, long long B, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
+                    const double *d_w, const int *d_labels, double *d_sums, double *d_wsum, cudaStream_t stream) {
+    MDB_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)K * D * sizeof(double), stream));
+    MDB_CUDA(cudaMemsetAsync(d_wsum, 0, (size_t)K * sizeof(double), stream));
+    if (B <= 0) return 0;
+    ProfScope ps(c, "k_mb_sums", stream);
+    if (B <= MB_MAX)
+        k_mb_sums_sorted<<<1, 1024, 0, stream>>>(d_X, ldx, d_rowidx, d_w, d_labels, (int)B, D, d_sums, d_wsum);
+    else
+        k_mb_sums_atomic<<<cdiv(B, 8), 256, 0, stream>>>(d_X, ldx, d_rowidx, d_w, d_labels, B, D, d_sums, d_wsum);
+    c->launches++;
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kmeans_apply_run(mdb_ctx *c, int K, int D, double *d_C, double *d_weight_sums, const double *d_sums,
+                     const double *d_wsum, cudaStream_t stream) {
+    ProfScope ps(c, "k_mb_apply", stream);
+    k_mb_apply<<<cdiv(K, 8), 256, 0, stream>>>(d_C, d_weight_sums, d_sums, d_wsum, K, D);
+    c->launches++;
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int minmax_fit_run(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx, double *d_min, double *d_max,
+                   int accumulate, cudaStream_t stream) {
+    size_t need = 2 * align256((size_t)D * sizeof(unsigned long long)) + 1024;
+    if (arena_reserve(c, need, stream)) return -1;
+    arena_reset(c);
+    unsigned long long *omin = (unsigned long long *)arena_alloc(c, (size_t)D * sizeof(unsigned long long));
+    unsigned long long *omax = (unsigned long long *)arena_alloc(c, (size_t)D * sizeof(unsigned long long));
+    if (!omin || !omax) return -1;
+    k_minmax_init<<<cdiv(D, 256), 256, 0, stream>>>(omin, omax, D);
+    if (rows > 0) {
+        dim3 grid((unsigned)std::min<long long>(2048, (rows + 7) / 8), cdiv(D, 32));
+        k_colminmax<<<grid, 256, 0, stream>>>(d_X, ldx, rows, D, omin, omax);
+    }
+    c->launches += 2;
+    (void)accumulate;
+    k_minmax_decode<<<cdiv(D, 256), 256, 0, stream>>>(omin, omax, d_min, d_max, D);
+    c->launches++;
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int minmax_transform_run(mdb_ctx *c, long long rows, int D, double *d_X, long long ldx, const double *h_min,
+                         const double *h_max, cudaStream_t stream) {
+    // scale_ = 1 / range with range < 10 eps -> 1 ; min_ = 0 - data_min * scale_   (_data.py:127-132,537-541)
+    std::vector<double> sc(2 * (size_t)D);
+    for (int k = 0; k < D; ++k) {
+        double range = h_max[k] - h_min[k];
+        if (range < 10 * DBL_EPSILON) range = 1.0;
+        sc[k] = 1.0 / range;
+        sc[D + k] = 0.0 - h_min[k] * sc[k];
+    }
+    size_t need = align256(2 * (size_t)D * sizeof(double)) + 1024;
+    if (arena_reserve(c, need, stream)) return -1;
+    arena_reset(c);
+    double *d_sc = (double *)arena_alloc(c, 2 * (size_t)D * sizeof(double));
+    if (!d_sc) return -1;
+    MDB_CUDA(cudaMemcpyAsync(d_sc, sc.data(), 2 * (size_t)D * sizeof(double), cudaMemcpyHostToDevice, stream));
+    MDB_CUDA(cudaStreamSynchronize(stream));  // sc is a stack-lifetime host buffer
+    if (rows > 0) {
+        k_scale<<<cdiv(rows * D, 256), 256, 0, stream>>>(d_X, ldx, rows, D, d_sc, d_sc + D);
+        c->launches++;
+    }
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}

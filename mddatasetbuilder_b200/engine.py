@@ -244,6 +244,59 @@ class Engine:
         _lib.check(rc, "mdb_descriptors")
         return {"X": X, "eig": eig, "n": n}
 
+    # ------------------------------------------------------------------ clustering
+    def minmax_fit(self, X):
+        torch = _torch()
+        rows, D = X.shape
+        mn = torch.empty(D, dtype=torch.float64, device=self.device)
+        mx = torch.empty(D, dtype=torch.float64, device=self.device)
+        _lib.check(self.L.mdb_minmax_fit(self.ctx, int(rows), int(D), _ptr(X), int(X.stride(0)), _ptr(mn), _ptr(mx),
+                                         self.stream()), "mdb_minmax_fit")
+        return mn, mx
+
+    def minmax_transform(self, X, data_min, data_max):
+        """In-place MinMaxScaler.transform; data_min / data_max are host arrays [D]."""
+        rows, D = X.shape
+        mn = np.ascontiguousarray(data_min, dtype=np.float64)
+        mx = np.ascontiguousarray(data_max, dtype=np.float64)
+        _lib.check(self.L.mdb_minmax_transform(self.ctx, int(rows), int(D), _ptr(X), int(X.stride(0)), _np_ptr(mn),
+                                               _np_ptr(mx), self.stream()), "mdb_minmax_transform")
+        return X
+
+    def kmeans_assign(self, X, centers, rowidx=None, weights=None, want_inertia=False, want_mindist=False):
+        torch = _torch()
+        D = int(X.shape[1])
+        K = int(centers.shape[0])
+        rows = int(rowidx.numel()) if rowidx is not None else int(X.shape[0])
+        labels = torch.empty(rows, dtype=torch.int32, device=self.device)
+        mind = torch.empty(rows, dtype=torch.float64, device=self.device) if want_mindist else None
+        inertia = C.c_double(0.0)
+        rc = self.L.mdb_kmeans_assign(self.ctx, rows, D, K, _ptr(X), int(X.stride(0)), _ptr(rowidx), _ptr(centers),
+                                      _ptr(labels), _ptr(mind), _ptr(weights),
+                                      C.byref(inertia) if want_inertia else None, self.stream())
+        _lib.check(rc, "mdb_kmeans_assign")
+        return labels, (inertia.value if want_inertia else None), mind
+
+    def kmeans_partial_sums(self, X, labels, K, rowidx=None, weights=None, out=None):
+        torch = _torch()
+        D = int(X.shape[1])
+        B = int(labels.numel())
+        if out is None:
+            sums = torch.empty((K, D), dtype=torch.float64, device=self.device)
+            wsum = torch.empty(K, dtype=torch.float64, device=self.device)
+        else:
+            sums, wsum = out
+        rc = self.L.mdb_kmeans_partial_sums(self.ctx, B, D, int(K), _ptr(X), int(X.stride(0)), _ptr(rowidx),
+                                            _ptr(weights), _ptr(labels), _ptr(sums), _ptr(wsum), self.stream())
+        _lib.check(rc, "mdb_kmeans_partial_sums")
+        return sums, wsum
+
+    def kmeans_apply_update(self, centers, weight_sums, sums, wsum):
+        K, D = centers.shape
+        rc = self.L.mdb_kmeans_apply_update(self.ctx, int(K), int(D), _ptr(centers), _ptr(weight_sums), _ptr(sums),
+                                            _ptr(wsum), self.stream())
+        _lib.check(rc, "mdb_kmeans_apply_update")
+
     def analyze_host(self, pos, cell, types, periodic=True, want_keys=True, want_labels=True, out=None):
         """Host-buffer path (e2e): numpy / pinned tensors in, numpy out; H2D and D2H copies
         are pipelined inside the library."""

@@ -1,0 +1,78 @@
+"""GPU parity: MinMaxScaler, k-means assignment and mini-batch update vs the real scikit-learn
+(the library the reference calls at datasetbuilder.py:369-376)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(engine, a, dtype=None):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(a), device=engine.device, dtype=dtype)
+
+
+def test_minmax_scaler_bit_exact(engine):
+    rng = np.random.default_rng(1)
+    X = rng.normal(3.0, 40.0, size=(7013, 45))
+    X[:, 3] = 7.25            # constant column -> scale 1
+    X[:, 9] = 1.0 + rng.random(7013) * 1e-16   # range below 10 eps
+    X[:, 11] *= 1e-9
+    Xs, dmin, dmax, scale, min_ = O.minmax_scale(X)
+    d = _t(engine, X)
+    mn, mx = engine.minmax_fit(d)
+    assert np.array_equal(mn.cpu().numpy(), dmin) and np.array_equal(mx.cpu().numpy(), dmax)
+    engine.minmax_transform(d, mn.cpu().numpy(), mx.cpu().numpy())
+    assert np.array_equal(d.cpu().numpy(), Xs), "scaled matrix differs from sklearn MinMaxScaler"
+
+
+@pytest.mark.parametrize("rows,D,K", [(5000, 37, 1000), (1024, 20, 10000), (777, 121, 130), (300, 5, 3)])
+def test_assign_labels_match_sklearn(engine, rows, D, K):
+    rng = np.random.default_rng(rows + D)
+    X = rng.random((rows, D))
+    centers = X[rng.choice(rows, K, replace=K > rows)] + rng.normal(0, 0.01, (K, D))
+    if K >= 20:
+        centers[17] = centers[5]      # exact duplicate: the lowest index must win
+        X[3] = centers[5]
+    labels, inertia = O.kmeans_labels(X, centers)
+    got, gin, mind = engine.kmeans_assign(_t(engine, X), _t(engine, centers), want_inertia=True, want_mindist=True)
+    got = got.cpu().numpy()
+    assert np.array_equal(got, labels), f"{(got != labels).sum()} labels differ from sklearn"
+    assert abs(gin - inertia) <= 1e-12 * max(inertia, 1e-300)
+    d2 = ((X - centers[labels]) ** 2).sum(axis=1)
+    assert np.allclose(mind.cpu().numpy(), d2, rtol=1e-12, atol=0)
+
+
+def test_assign_rowidx_and_weights(engine):
+    rng = np.random.default_rng(5)
+    X = rng.random((4000, 33))
+    centers = rng.random((500, 33))
+    idx = rng.integers(0, 4000, 1024).astype(np.int32)
+    w = rng.random(1024)
+    labels, inertia = O.kmeans_labels(X[idx], centers)
+    from sklearn.cluster._kmeans import _labels_inertia
+
+    _, inertia_w = _labels_inertia(np.ascontiguousarray(X[idx]), w, centers, n_threads=1)
+    got, gin, _ = engine.kmeans_assign(_t(engine, X), _t(engine, centers), rowidx=_t(engine, idx), weights=_t(engine, w),
+                                       want_inertia=True)
+    assert np.array_equal(got.cpu().numpy(), labels)
+    assert abs(gin - inertia_w) <= 1e-12 * inertia_w
+
+
+@pytest.mark.parametrize("B,D,K", [(1024, 40, 10000), (1024, 17, 50), (6000, 23, 300)])
+def test_minibatch_update_matches_sklearn(engine, B, D, K):
+    rng = np.random.default_rng(B + K)
+    X = rng.random((B, D))
+    centers = rng.random((K, D))
+    wsums = rng.integers(0, 50, K).astype(np.float64)
+    sw = np.ones(B) if B != 6000 else rng.random(B) + 0.5
+    labels, _ = O.kmeans_labels(X, centers)
+    ref_c, ref_w = O.minibatch_update(X, sw, centers, wsums, labels)
+    dX, dC, dW = _t(engine, X), _t(engine, centers), _t(engine, wsums)
+    sums, wsum = engine.kmeans_partial_sums(dX, _t(engine, labels.astype(np.int32)), K, weights=_t(engine, sw))
+    engine.kmeans_apply_update(dC, dW, sums, wsum)
+    # tolerance on centroid coordinates stated for this path: 1e-12 relative
+    assert np.allclose(dC.cpu().numpy(), ref_c, rtol=1e-12, atol=1e-15)
+    assert np.allclose(dW.cpu().numpy(), ref_w, rtol=1e-14, atol=0)
