@@ -139,6 +139,15 @@ int mdb_compositions(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
                      const int32_t *d_targets, long long ntargets, int32_t *d_counts,
                      int32_t *h_maxcount, void *stream);
 
+/* Sphere membership lists: for every target the atoms with MIC distance < cutoff in ascending
+ * index (the target included) -- `np.where(distances < self.cutoff)` of the output cut,
+ * datasetbuilder.py:554-557.  d_members [ntargets][cap] (-1 padded), d_nmem [ntargets] (a
+ * value above cap means the list was truncated). */
+int mdb_sphere_members(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                       const double *h_cell, const uint8_t *d_types, int periodic, double cutoff,
+                       const int32_t *d_targets, long long ntargets, int cap, int32_t *d_members,
+                       int32_t *d_nmem, void *stream);
+
 /* ---- K6: Coulomb-matrix eigen-spectrum descriptor -------------------------------
  * Replaces _writestepmatrix + _calcoulumbmatrix (datasetbuilder.py:283-349) and the
  * feature assembly (datasetbuilder.py:236-276).  For every target:
@@ -187,9 +196,40 @@ int mdb_kmeans_partial_sums(mdb_ctx *ctx, long long nbatch, int D, int K, const 
 int mdb_kmeans_apply_update(mdb_ctx *ctx, int K, int D, double *d_centers, double *d_weight_sums,
                             const double *d_sums, const double *d_wsum, void *stream);
 
+/* k-means++ seeding step (sklearn cluster/_kmeans.py:180-279, run by MiniBatchKMeans on
+ * its init subset): for ncand (<= 32) candidate rows, d_dist[t][i] = min(d_closest[i],
+ * ||x_i - x_cand[t]||^2) and d_pot[t] = sum_i weight_i * d_dist[t][i].  d_closest may be
+ * NULL for the first centre.  Rows are addressed through d_rowidx when given (the init
+ * subset), and d_cand indexes the same row numbering. */
+int mdb_kpp_step(mdb_ctx *ctx, long long n, int D, const double *d_X, long long ldx,
+                 const int32_t *d_rowidx, const int32_t *d_cand, int ncand,
+                 const double *d_closest, const double *d_weights, double *d_dist, double *d_pot,
+                 void *stream);
+
 /* Diagnostics of the last bond batch: counts summed over frames (synchronises). */
 int mdb_bond_stats(mdb_ctx *ctx, long long *n_violators, long long *n_exact_tests,
                    long long *n_overflow);
+
+/* ---- LAMMPS text readers (host side) -------------------------------------------------
+ * Replace the per-line Python parsing of DetectDump._readN / readcrd (detect.py:151-194,
+ * 294-345), DetectBond._readN / readatombondtype / readmolecule (detect.py:56-88, 105-119,
+ * 137-142) and the frame slicing of DatasetBuilder.lineiter (datasetbuilder.py:616-638).
+ * kind 0 = dump, 1 = fix reaxff/bonds table.  Opening scans the first two frames like
+ * _readN (atom count, lines per frame, id/type/x/y/z columns, per-id LAMMPS types). */
+typedef struct mdb_reader mdb_reader;
+int mdb_reader_open(int kind, const char *const *paths, int npaths, int nthreads, mdb_reader **out);
+void mdb_reader_close(mdb_reader *r);
+int mdb_reader_info(const mdb_reader *r, int *natoms, long *steplinenum, int *cols5);
+int mdb_reader_types(const mdb_reader *r, int32_t *types /* [N] LAMMPS type by id-1 */);
+int mdb_reader_rewind(mdb_reader *r);
+/* Next up to max_frames kept frames (every stride-th frame of each file).  dump: h_pos
+ * [max_frames][N][3] in id order, h_cell [max_frames][9].  bonds: h_nbr [max_frames][N][width]
+ * neighbours in file order (0-based, -1 padded), h_bo same shape (optional). */
+int mdb_reader_next(mdb_reader *r, int stride, int max_frames, double *h_pos, double *h_cell,
+                    int32_t *h_nbr, double *h_bo, int width, int *nread);
+/* One frame already in memory (the lines a per-frame drop-in method receives). */
+int mdb_reader_parse_buffer(const mdb_reader *r, const char *buf, size_t len, double *h_pos,
+                            double *h_cell, int32_t *h_nbr, double *h_bo, int width);
 
 /* Per-launch CUDA-event timing on the launching stream (bench.py's live roofline
  * measurement).  mdb_profile_read synchronises and writes "name count total_ms" lines

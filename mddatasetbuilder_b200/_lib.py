@@ -37,6 +37,8 @@ SIGNATURES = {
     "mdb_analyze_frames_host": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "mdb_compositions": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, _vp, C.c_longlong,
                                    _vp, _vp, _vp]),
+    "mdb_sphere_members": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, _vp, C.c_longlong,
+                                     C.c_int, _vp, _vp, _vp]),
     "mdb_descriptors": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, _vp, C.c_longlong,
                                   _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "mdb_minmax_fit": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp]),
@@ -46,6 +48,15 @@ SIGNATURES = {
     "mdb_kmeans_partial_sums": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp,
                                           _vp, _vp]),
     "mdb_kmeans_apply_update": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mdb_kpp_step": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
+                               _vp]),
+    "mdb_reader_open": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(_vp)]),
+    "mdb_reader_close": (None, [_vp]),
+    "mdb_reader_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_int)]),
+    "mdb_reader_types": (C.c_int, [_vp, _vp]),
+    "mdb_reader_rewind": (C.c_int, [_vp]),
+    "mdb_reader_next": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    "mdb_reader_parse_buffer": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _vp, _vp, _vp, _vp, C.c_int]),
     "mdb_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "mdb_profile_read": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),
     "mdb_bond_stats": (C.c_int, [c_ctx, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

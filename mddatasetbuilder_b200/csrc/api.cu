@@ -211,6 +211,18 @@ extern "C" int mdb_compositions(mdb_ctx *c, int nframes, int natoms, const doubl
                             h_maxcount, (cudaStream_t)stream);
 }
 
+int members_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
+                int periodic, double cutoff, const int *d_targets, long long ntargets, int cap, int *d_members,
+                int *d_nmem, cudaStream_t stream);
+
+extern "C" int mdb_sphere_members(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                  const uint8_t *d_types, int periodic, double cutoff, const int32_t *d_targets,
+                                  long long ntargets, int cap, int32_t *d_members, int32_t *d_nmem, void *stream) {
+    if (check_ctx(c, "mdb_sphere_members")) return -1;
+    return members_run(c, nframes, natoms, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, cap, d_members,
+                       d_nmem, (cudaStream_t)stream);
+}
+
 extern "C" int mdb_descriptors(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
                                const uint8_t *d_types, int periodic, double cutoff, const int32_t *d_targets,
                                long long ntargets, const int32_t *d_counts, const int32_t *h_maxcount, double *d_X,
@@ -243,6 +255,17 @@ extern "C" int mdb_kmeans_apply_update(mdb_ctx *c, int K, int D, double *d_cente
                                        const double *d_sums, const double *d_wsum, void *stream) {
     if (check_ctx(c, "mdb_kmeans_apply_update", false)) return -1;
     return kmeans_apply_run(c, K, D, d_centers, d_weight_sums, d_sums, d_wsum, (cudaStream_t)stream);
+}
+
+int kpp_step_run(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, const int *d_cand,
+                 int T, const double *d_closest, const double *d_w, double *d_dist, double *d_pot, cudaStream_t stream);
+
+extern "C" int mdb_kpp_step(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int32_t *d_rowidx,
+                            const int32_t *d_cand, int ncand, const double *d_closest, const double *d_weights,
+                            double *d_dist, double *d_pot, void *stream) {
+    if (check_ctx(c, "mdb_kpp_step", false)) return -1;
+    return kpp_step_run(c, n, D, d_X, ldx, d_rowidx, d_cand, ncand, d_closest, d_weights, d_dist, d_pot,
+                        (cudaStream_t)stream);
 }
 
 extern "C" int mdb_minmax_fit(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx, double *d_min,

@@ -181,6 +181,38 @@ __global__ void __launch_bounds__(256) k_composition(const __grid_constant__ Des
     if (threadIdx.x < P.nt && s_max[threadIdx.x] > 0) atomicMax(&maxcount[threadIdx.x], s_max[threadIdx.x]);
 }
 
+// sphere membership lists (ascending atom index, includes the target): the `np.where(distances <
+// cutoff)` of the output cut, datasetbuilder.py:554-557.  One warp per target, cap <= 1024.
+__global__ void __launch_bounds__(256) k_members(const __grid_constant__ DescParams P, int cap, int *__restrict__ members,
+                                                 int *__restrict__ nmem) {
+    extern __shared__ int s_mem[];  // [8][cap]
+    __shared__ int s_n[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * 8 + w;
+    if (t >= P.ntargets) return;
+    const int g = P.targets ? P.targets[t] : (int)t;
+    const int f = g / P.N, a = g - f * P.N;
+    int *mine = s_mem + w * cap;
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
+    sphere_scan(P, f, a, [&](int j, int) {
+        const int k = atomicAdd(&s_n[w], 1);
+        if (k < cap) mine[k] = j;
+    });
+    __syncwarp();
+    int n = s_n[w];
+    if (lane == 0) nmem[t] = n;
+    if (n > cap) n = cap;
+    // rank sort: each element's position = number of smaller elements (indices are distinct)
+    for (int k = lane; k < n; k += 32) {
+        const int v = mine[k];
+        int r = 0;
+        for (int q = 0; q < n; ++q) r += mine[q] < v;
+        members[t * cap + r] = v;
+    }
+    for (int k = n + lane; k < cap; k += 32) members[t * cap + k] = -1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K6a: gather the cluster, build the Coulomb matrix in shared memory, Householder-tridiagonalise.
 // One warp per target.  Output: diagonal d[0..n) and off-diagonal e[0..n-1) into a scratch laid out
@@ -530,6 +562,24 @@ int compositions_run(mdb_ctx *c, int F, int N, const double *d_pos, const double
     MDB_CUDA(cudaGetLastError());
     MDB_CUDA(cudaMemcpyAsync(h_maxcount, d_max, c->el.nt * sizeof(int), cudaMemcpyDeviceToHost, stream));
     MDB_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int members_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
+                int periodic, double cutoff, const int *d_targets, long long ntargets, int cap, int *d_members,
+                int *d_nmem, cudaStream_t stream) {
+    if (cap < 1 || cap > 1024) {
+        mdb_set_error("mdb_sphere_members: cap must be in 1..1024");
+        return -1;
+    }
+    DescParams P;
+    if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, 1024)) return -1;
+    if (P.ntargets > 0) {
+        ProfScope ps(c, "k_members", stream);
+        k_members<<<cdiv(P.ntargets, 8), 256, (size_t)8 * cap * sizeof(int), stream>>>(P, cap, d_members, d_nmem);
+        c->launches++;
+    }
+    MDB_CUDA(cudaGetLastError());
     return 0;
 }
 

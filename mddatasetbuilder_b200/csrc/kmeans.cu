@@ -353,6 +353,66 @@ __global__ void __launch_bounds__(256) k_scale(double *__restrict__ X, long long
 }
 
 // ---------------------------------------------------------------------------------------------
+// k-means++ seeding step (sklearn cluster/_kmeans.py:180-279): squared distances from T candidate
+// rows to every row, clipped against the current closest distance, and the weighted potential of
+// each candidate.  One warp per row; lanes span the features.
+// ---------------------------------------------------------------------------------------------
+#define KPP_MAXT 32
+__global__ void __launch_bounds__(256) k_kpp_step(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
+                                                  long long n, int D, const int *__restrict__ cand, int T,
+                                                  const double *__restrict__ closest, const double *__restrict__ w,
+                                                  double *__restrict__ dist, double *__restrict__ pot) {
+    __shared__ double s_pot[8][KPP_MAXT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < KPP_MAXT) s_pot[warp][lane] = 0.0;
+    __syncwarp();
+    for (long long i = (long long)blockIdx.x * 8 + warp; i < n; i += (long long)gridDim.x * 8) {
+        const double *x = X + (rowidx ? (long long)rowidx[i] : i) * ldx;
+        const double cl = closest ? closest[i] : DBL_MAX;
+        const double wi = w ? w[i] : 1.0;
+        for (int t = 0; t < T; ++t) {
+            const int ci = cand[t];
+            const double *y = X + (rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx;
+            double s = 0.0;
+            for (int k = lane; k < D; k += 32) {
+                const double df = x[k] - y[k];
+                s += df * df;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            s = fmin(s, cl);
+            if (lane == 0) {
+                dist[(size_t)t * n + i] = s;
+                s_pot[warp][t] += s * wi;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < T) {
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += s_pot[k][threadIdx.x];
+        atomicAdd(&pot[threadIdx.x], s);
+    }
+}
+
+int kpp_step_run(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, const int *d_cand,
+                 int T, const double *d_closest, const double *d_w, double *d_dist, double *d_pot, cudaStream_t stream) {
+    if (T < 1 || T > KPP_MAXT) {
+        mdb_set_error("kpp_step: between 1 and 32 candidates");
+        return -1;
+    }
+    MDB_CUDA(cudaMemsetAsync(d_pot, 0, (size_t)T * sizeof(double), stream));
+    if (n > 0) {
+        ProfScope ps(c, "k_kpp_step", stream);
+        k_kpp_step<<<(unsigned)std::min<long long>((n + 7) / 8, 148 * 8), 256, 0, stream>>>(d_X, ldx, d_rowidx, n, D, d_cand, T,
+                                                                                         d_closest, d_w, d_dist, d_pot);
+        c->launches++;
+    }
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host wrappers
 // ---------------------------------------------------------------------------------------------
 int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,

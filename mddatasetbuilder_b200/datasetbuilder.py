@@ -1,0 +1,612 @@
+"""MDDatasetBuilder (B200-native analysis path).
+
+Run 'datasetbuilder -h' for more details.
+
+Please cite
+-----------
+Complex reaction processes in combustion unraveled by neural network-based
+molecular dynamics simulation, Nature Communications, 11, 5713 (2020).
+"""
+
+# Drop-in for reference mddatasetbuilder/datasetbuilder.py: same DatasetBuilder constructor,
+# attributes, builddataset() steps, CLI flags and on-disk outputs.  The per-frame work the reference
+# fans out over a multiprocessing.Pool (run_mp, utils.py:198-231) is batched onto the GPU instead:
+#   step 0  _readtimestepsbond   (datasetbuilder.py:185-214)  C++ text parser -> cell list -> bonds ->
+#                                                              cleanup -> bond-type keys
+#   step 1  _writecoulumbmatrix  (:216-281)                    sphere composition -> Coulomb spectrum ->
+#                                                              feature rows -> MinMaxScaler -> MiniBatchKMeans
+#   step 2  _writexyzfiles       (:386-444, 523-606)           molecules (union-find + dps order) -> sphere
+#                                                              cut completed to molecules -> wrap -> xyz / gjf
+# Intermediate state stays in memory (the reference's lz4+pickle temp files are private).  With
+# torch.distributed initialised, frames are sharded over the ranks in batches.
+
+__author__ = "Jinzhe Zeng"
+__email__ = "jzzeng@stu.ecnu.edu.cn"
+__update__ = "2019-10-17"
+__date__ = "2018-07-18"
+
+import argparse
+import gc
+import os
+import time
+from collections import Counter, defaultdict
+from typing import List, Optional
+
+import numpy as np
+
+from ._logger import logger
+from ._version import version as __version__
+from .atoms import atomic_numbers
+from .detect import Detect, DetectDump, unpack_key
+from .utils import must_be_list
+from .writer import detect_multiplicity as _detect_multiplicity
+from .writer import wrap_positions, write_gjf, write_xyz
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return None
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+class DatasetBuilder:
+    r"""Dataset Builder.
+
+    Parameters
+    ----------
+    atomname: list, optional, default=['C', 'H', 'O']
+        Atom names.
+    clusteratom: list, optional, default=None
+        Cluster elements. If None (default), all elements will be clustered.
+    bondfilename: str, optional, default=None
+        The filename of LAMMPS bond file. If None (default), bond files will
+        not be used.
+    dumpfilename: str, optional, default="dump.reaxc"
+        The filename of LAMMPS dump file.
+    dataset_name: str, optional, default="md"
+        The name of dataset, which will be part of filenames of dataset.
+    cutoff: float, optional, default=5.
+        The cutoff for taking clusters.
+    stepinterval: int, optional, default=1
+        The interval for taking frames.
+    n_clusters: int, optional, default=10000
+        The maximum number of clusters for each atom type.
+    n_each: int, optional, default=1
+        The numbers of structures taken from each cluster.
+    qmkeywords: str, optional, default="%nproc=4\n#force mn15/6-31g(d,p)"
+        Gaussian keywords.
+    nproc: int, optional, default=None
+        Accepted for compatibility (host threads of the text parser).
+    pbc: bool, optional, default=True
+        If True (default), apply the periodic boundary conditions (PBC).
+    fragment: bool, optional, default=False
+        Use `Guess=Fragment` for Gaussian calculation.
+    errorfilename: str, optional, default=None
+        The atomic model deviation file of DeePMD-kit. If None, no file will be used.
+    errorlimit: float, optional, default=0.
+        The lower bound of the model deviation.
+    atom_pref: bool, optional, default=False
+        (Deprecated) Generator atom_pref information for each cluster.
+    seed: int, optional, default=0
+        Seed of the clustering and of the per-cluster selection (the reference seeds neither).
+    """
+
+    def __init__(
+        self,
+        atomname=None,
+        clusteratom=None,
+        bondfilename=None,
+        dumpfilename="dump.reaxc",
+        dataset_name="md",
+        cutoff=5.0,
+        stepinterval=1,
+        n_clusters=10000,
+        n_each=1,
+        qmkeywords="%nproc=4\n#force mn15/6-31g(d,p) Geom=PrintInputOrient",
+        nproc=None,
+        pbc=True,
+        fragment=False,
+        errorfilename: Optional[List[str]] = None,
+        errorlimit=0.0,
+        atom_pref=False,
+        seed=0,
+    ):
+        """Init the builder."""
+        print(__doc__)
+        print(f"Author:{__author__}  Email:{__email__}")
+        atomname = np.array(atomname) if atomname is not None and len(atomname) else np.array(["C", "H", "O"])
+        self.atomname = atomname
+        self.crddetector = Detect.gettype("dump")(
+            filename=dumpfilename, atomname=atomname, pbc=pbc, errorfilename=errorfilename, errorlimit=errorlimit)
+        if bondfilename is None:
+            self.bonddetector = self.crddetector
+        else:
+            self.bonddetector = Detect.gettype("bond")(filename=bondfilename, atomname=atomname, pbc=pbc)
+        self.dataset_dir = f"dataset_{dataset_name}"
+        self.xyzfilename = dataset_name
+        self.clusteratom = clusteratom if clusteratom else atomname
+        self.atombondtype = []
+        self.stepinterval = stepinterval
+        if nproc:
+            self.nproc = nproc
+        else:
+            try:
+                self.nproc = len(os.sched_getaffinity(0))
+            except AttributeError:  # pragma: no cover
+                self.nproc = os.cpu_count()
+        self.cutoff = cutoff
+        self.n_clusters = n_clusters
+        self.n_each = n_each
+        self.writegjf = True
+        self.gjfdir = f"{self.dataset_dir}_gjf"
+        self.qmkeywords = must_be_list(qmkeywords)
+        self.fragment = fragment
+        self._coulumbdiag = {symbol: atomic_numbers[symbol] ** 2.4 / 2 for symbol in atomname}
+        self._nstructure = 0
+        self.bondtyperestore = {}
+        self.errorfilename = errorfilename
+        self.errorlimit = errorlimit
+        self.atom_pref = atom_pref
+        self.pbc = pbc
+        self.seed = seed
+        self.frames_per_batch = int(os.environ.get("MDB_FRAMES_PER_BATCH", "0"))
+        self._cache_bytes = int(float(os.environ.get("MDB_CACHE_GB", "8")) * (1 << 30))
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def engine(self):
+        from .engine import get_engine
+
+        return get_engine(int(os.environ.get("LOCAL_RANK", "0")), [str(a) for a in self.atomname])
+
+    def _rank_world(self):
+        d = _dist()
+        return (d.get_rank(), d.get_world_size()) if d is not None else (0, 1)
+
+    def _batch_frames(self):
+        if self.frames_per_batch > 0:
+            return self.frames_per_batch
+        n = max(self.crddetector._N, 1)
+        return int(max(1, min(256, (4 << 20) // n)))
+
+    def _dump_batches(self):
+        """Yield (first step, positions [F,N,3] on the GPU, cells [F,9]) for the batches this rank
+        owns.  Parsed frames are kept on the GPU for the later passes while they fit the cache
+        budget; otherwise the text is parsed again (like the reference does for every bond type,
+        datasetbuilder.py:243)."""
+        import torch
+
+        if getattr(self, "_dump_cache", None) is not None:
+            yield from self._dump_cache
+            return
+        rank, world = self._rank_world()
+        rd = self.crddetector.reader
+        rd.rewind()
+        B = self._batch_frames()
+        step0, b, cache, used = 0, 0, [], 0
+        while True:
+            if b % world == rank:
+                pos, cell = rd.read(B, self.stepinterval)
+                if len(pos) == 0:
+                    break
+                item = (step0, torch.from_numpy(pos).to(self.engine.device), cell.copy())
+                if cache is not None:
+                    used += pos.nbytes
+                    if used <= self._cache_bytes:
+                        cache.append(item)
+                    else:
+                        cache = None
+                nf = len(pos)
+                yield item
+            else:
+                nf = rd.skip(B, self.stepinterval)
+                if nf == 0:
+                    break
+            step0 += nf
+            b += 1
+        self._dump_cache = cache
+
+    def _bond_batches(self):
+        rank, world = self._rank_world()
+        rd = self.bonddetector.reader
+        rd.rewind()
+        B = self._batch_frames()
+        step0, b = 0, 0
+        width = self.engine.max_bonds
+        while True:
+            if b % world == rank:
+                nbr, bo = rd.read(B, self.stepinterval, width=width)
+                nf = len(nbr)
+                if nf == 0:
+                    break
+                yield step0, nbr, bo
+            else:
+                nf = rd.skip(B, self.stepinterval)
+                if nf == 0:
+                    break
+            step0 += nf
+            b += 1
+
+    # ------------------------------------------------------------------ pipeline
+    def builddataset(self, writegjf=True):
+        """Build a dataset.
+
+        Parameters
+        ----------
+        writegjf : bool, optional, default=True
+            Write gjf files.
+        """
+        self.writegjf = writegjf
+        timearray = [time.time()]
+        for runstep in range(3):
+            if runstep == 0:
+                self._readtimestepsbond()
+            elif runstep == 1:
+                self._chosen = {}
+                for bondtype in self.atombondtype:
+                    self._writecoulumbmatrix(bondtype, None)
+                    gc.collect()
+            elif runstep == 2:
+                os.makedirs(self.dataset_dir, exist_ok=True)
+                if self.writegjf:
+                    os.makedirs(self.gjfdir, exist_ok=True)
+                self._writexyzfiles()
+            gc.collect()
+            timearray.append(time.time())
+            logger.info(f"Step {len(timearray) - 1} Done! Time consumed (s): {timearray[-1] - timearray[-2]:.3f}")
+
+    def _bondtype(self, key):
+        """'C1111', 'H1', 'O2' ... (datasetbuilder.py:608-614) from a packed 64-bit key."""
+        key = int(key)
+        if key in self.bondtyperestore:
+            return self.bondtyperestore[key]
+        elem, levels = unpack_key(key)
+        typestr = f"{self.atomname[elem]}{''.join(map(str, levels))}"
+        self.bondtyperestore[key] = typestr
+        return typestr
+
+    def _readtimestepsbond(self):
+        """Read and store the bond of each atom in each frame (datasetbuilder.py:185-214)."""
+        import torch
+
+        eng = self.engine
+        N = self.crddetector._N
+        types0 = (self.bonddetector.atomtype - 1).astype(np.uint8)
+        d_types = eng.to_device_types(types0)
+        typerows = defaultdict(list)   # type string -> [(step, atom ids 1-based ascending)]
+        first_seen = {}
+        nstep = 0
+        errors = self._error_rows() if self.errorfilename is not None else None
+
+        def collect(step0, keys):
+            nonlocal nstep
+            for f in range(keys.shape[0]):
+                kf = keys[f]
+                order = np.argsort(kf, kind="stable")
+                ks = kf[order]
+                cut = np.nonzero(np.diff(ks))[0] + 1
+                starts = np.concatenate([[0], cut])
+                ends = np.concatenate([cut, [len(ks)]])
+                step = step0 + f
+                keep = None
+                if errors is not None:
+                    keep = errors[step] > self.errorlimit
+                for a, b in zip(starts, ends):
+                    ids = order[a:b]
+                    if keep is not None:
+                        ids = ids[keep[ids]]
+                        if ids.size == 0:
+                            continue
+                    t = self._bondtype(ks[a])
+                    typerows[t].append((step, (ids + 1).astype(np.int64)))
+                    fs = (step, int(ids[0]))
+                    if t not in first_seen or fs < first_seen[t]:
+                        first_seen[t] = fs
+                nstep += 1
+
+        if self.bonddetector is self.crddetector:
+            for step0, pos, cell in self._dump_batches():
+                out = eng.analyze(pos, cell, d_types, self.pbc, want_ell=False, want_keys=True, want_labels=False)
+                eng.check()
+                collect(step0, out["keys"].cpu().numpy().view(np.uint64))
+        else:
+            for step0, nbr, bo in self._bond_batches():
+                keys = eng.bond_keys_bo(torch.from_numpy(nbr).to(eng.device), torch.from_numpy(bo).to(eng.device), d_types)
+                collect(step0, keys.cpu().numpy().view(np.uint64))
+        counts = {t: sum(len(ids) for _, ids in rows) for t, rows in typerows.items()}
+        d = _dist()
+        if d is not None:
+            gathered = [None] * d.get_world_size()
+            d.all_gather_object(gathered, (first_seen, counts, nstep))
+            first_seen, counts, nstep = {}, Counter(), 0
+            for fs, cn, ns in gathered:
+                for t, v in fs.items():
+                    if t not in first_seen or v < first_seen[t]:
+                        first_seen[t] = v
+                counts.update(cn)
+                nstep += ns
+        # first-seen order (the reference's order depends on imap_unordered arrival; this is the
+        # order it produces with one worker)
+        self.atombondtype = sorted(first_seen, key=lambda t: first_seen[t])
+        self._typerows = typerows
+        self._typecounts = dict(counts)
+        self._nstep = nstep
+
+    def _error_rows(self):
+        """Model-deviation rows by step (datasetbuilder.py:640-653: one header line per file,
+        one line per frame, per-atom values from column 7 on, assumed in atom-id order)."""
+        rows = []
+        for fn in must_be_list(self.errorfilename):
+            with open(fn) as f:
+                for k, line in enumerate(f):
+                    if k == 0:
+                        continue
+                    rows.append(np.array(line.split(), dtype=float)[7:])
+        return rows[:: self.stepinterval] if self.stepinterval > 1 else rows
+
+    def _writecoulumbmatrix(self, trajatomfilename, fc):
+        """Descriptors + clustering of one bond type (datasetbuilder.py:216-281); stores the
+        chosen [(step, atom)] rows in ``self._chosen[type]``."""
+        import torch
+
+        from .kmeans import clusterdatas
+
+        eng = self.engine
+        rows = self._typerows.get(trajatomfilename, [])
+        self.dstep = {step: ids for step, ids in rows}
+        n_atoms = self._typecounts.get(trajatomfilename, 0)
+        d = _dist()
+        if n_atoms > self.n_clusters:
+            N = self.crddetector._N
+            d_types = eng.to_device_types((self.crddetector.atomtype - 1).astype(np.uint8))
+            nt = len(self.atomname)
+            # pass A: sphere compositions -> max_counter over every row of this type
+            maxc = np.zeros(nt, dtype=np.int32)
+            per_batch = []
+            for step0, pos, cell in self._dump_batches():
+                tg, sa = [], []
+                for f in range(pos.shape[0]):
+                    ids = self.dstep.get(step0 + f)
+                    if ids is not None and len(ids):
+                        tg.append(f * N + (ids - 1))
+                        sa.append(np.stack([np.full(len(ids), step0 + f), ids], axis=1))
+                if not tg:
+                    continue
+                targets = np.concatenate(tg).astype(np.int32)
+                counts, maxc = eng.compositions(pos, cell, d_types, self.cutoff, targets=targets, periodic=self.pbc,
+                                                maxcount=maxc)
+                per_batch.append((step0, targets, counts, np.concatenate(sa)))
+            if d is not None:
+                t = torch.as_tensor(maxc, device=eng.device)
+                d.all_reduce(t, op=d.ReduceOp.MAX)
+                maxc = t.cpu().numpy().astype(np.int32)
+            logger.info(f"Max counter of {trajatomfilename} is "
+                        f"{Counter({str(a): int(c) for a, c in zip(self.atomname, maxc) if c})}")
+            # pass B: Coulomb-matrix spectra -> padded sorted feature rows
+            todo = {step0: (targets, counts, sa) for step0, targets, counts, sa in per_batch}
+            Xs, stepatoms = [], []
+            for step0, pos, cell in self._dump_batches():
+                if step0 not in todo:
+                    continue
+                targets, counts, sa = todo[step0]
+                out = eng.descriptors(pos, cell, d_types, self.cutoff, counts, maxc, targets=targets, periodic=self.pbc)
+                Xs.append(out["X"])
+                stepatoms.append(sa)
+            eng.check()
+            D = int(maxc.sum())
+            X = torch.cat(Xs) if Xs else torch.zeros((0, D), dtype=torch.float64, device=eng.device)
+            stepatom = np.concatenate(stepatoms) if stepatoms else np.zeros((0, 2), dtype=np.int64)
+            del Xs, todo, per_batch
+            picks, tags = clusterdatas(eng, X, self.n_clusters, self.n_each, seed=self.seed, with_tags=True)
+            chosen = [(int(stepatom[i, 0]), int(stepatom[i, 1]), (int(t[0]), int(t[1]))) for i, t in zip(picks, tags)]
+            del X
+        else:
+            chosen = [(int(step), int(a), (step, int(a))) for step, ids in rows for a in ids]
+        if d is not None:
+            gathered = [None] * d.get_world_size()
+            d.all_gather_object(gathered, chosen)
+            chosen = [c for part in gathered for c in part]
+        chosen.sort(key=lambda c: c[2])
+        self._chosen[trajatomfilename] = [(c[0], c[1]) for c in chosen]
+        self._nstructure += len(chosen)
+
+    @classmethod
+    def _clusterdatas(cls, X, n_clusters, n_each=1, seed=0):
+        """Select data using Mini Batch Kmeans (datasetbuilder.py:351-384), on the GPU."""
+        import torch
+
+        from .engine import get_engine
+        from .kmeans import clusterdatas
+
+        eng = get_engine(int(os.environ.get("LOCAL_RANK", "0")), None)
+        Xd = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64), device=eng.device).clone()
+        return clusterdatas(eng, Xd, n_clusters, n_each, seed=seed)
+
+    def _calcoulumbmatrix(self, atoms):
+        """Eigenvalues of the Coulomb matrix of `atoms` (datasetbuilder.py:327-349): the cluster
+        is treated as given (every atom a member), orthorhombic cell."""
+        import torch
+
+        from .detect import _engine
+        from .atoms import SYMBOLS
+
+        numbers = np.asarray(atoms.get_atomic_numbers(), dtype=int)
+        zs = sorted(set(int(z) for z in numbers))
+        eng = _engine([SYMBOLS[z] for z in zs])
+        lut = {z: k for k, z in enumerate(zs)}
+        types = np.array([lut[int(z)] for z in numbers], dtype=np.uint8)
+        n = len(numbers)
+        periodic = bool(np.asarray(atoms.pbc).any())
+        cell = np.asarray(atoms.cell, dtype=float).reshape(3, 3)
+        # one target whose "sphere" is the whole cluster: a cutoff larger than any MIC distance
+        big = float(np.linalg.norm(np.abs(cell).sum(axis=0)) + np.ptp(atoms.positions, axis=0).sum() + 1.0)
+        counts = torch.as_tensor(np.bincount(types, minlength=len(zs))[None].astype(np.int32), device=eng.device)
+        out = eng.descriptors(np.asarray(atoms.positions, dtype=float)[None], cell.reshape(9), types, big, counts,
+                              np.bincount(types, minlength=len(zs)), targets=np.zeros(1, dtype=np.int32),
+                              periodic=periodic, want_X=False, want_eig=True, eigcap=max(n, 1))
+        eng.check()
+        return out["eig"].cpu().numpy()[0, :n]
+
+    def _writexyzfiles(self):
+        """Write xyz (and gjf) files of the chosen clusters (datasetbuilder.py:386-444)."""
+        self.dstep = defaultdict(list)
+        typecounter = Counter()
+        for trajatomfilename in self.atombondtype:
+            for step, atoma in self._chosen.get(trajatomfilename, []):
+                self.dstep[step].append((atoma, trajatomfilename, typecounter[trajatomfilename], typecounter["total"]))
+                typecounter[trajatomfilename] += 1
+                typecounter["total"] += 1
+        self.maxlength = len(str(self.n_clusters))
+        foldernum = self._nstructure // 1000 + 1
+        self.foldermaxlength = len(str(foldernum))
+        foldernames = [str(i).zfill(self.foldermaxlength) for i in range(foldernum)]
+        for folder in foldernames:
+            os.makedirs(os.path.join(self.dataset_dir, folder), exist_ok=True)
+        if self.writegjf:
+            for folder in foldernames:
+                os.makedirs(os.path.join(self.gjfdir, folder), exist_ok=True)
+        written = 0
+        if self.crddetector is self.bonddetector:
+            for step0, pos, cell in self._dump_batches():
+                for f in range(pos.shape[0]):
+                    if (step0 + f) in self.dstep:
+                        written += self._writestepxyzfile((step0 + f, (pos[f], cell[f], None)))
+        else:
+            bonds = self._bond_batches()
+            for (step0, pos, cell), (bstep0, nbr, _) in zip(self._dump_batches(), bonds):
+                # bond file and dump are matched by frame index (datasetbuilder.py:428-433)
+                for f in range(min(pos.shape[0], nbr.shape[0])):
+                    if (step0 + f) in self.dstep:
+                        written += self._writestepxyzfile((step0 + f, (pos[f], cell[f], nbr[f])))
+        return written
+
+    @staticmethod
+    def detect_multiplicity(symbols):
+        """Caculate multiplicity (datasetbuilder.py:446-466)."""
+        return _detect_multiplicity(symbols)
+
+    def _writestepxyzfile(self, item):
+        """Write xyz files and GJF files in a timestep (datasetbuilder.py:523-606).
+
+        item = (step, (positions [N,3] device tensor, cell [9], bond table [N,width] or None))."""
+        import torch
+
+        from .dps import dps_from_ell_arrays
+
+        step, (pos, cell, nbr) = item
+        if step not in self.dstep:
+            return 0
+        eng = self.engine
+        N = self.crddetector._N
+        d_types = eng.to_device_types((self.crddetector.atomtype - 1).astype(np.uint8))
+        pos_h = pos.cpu().numpy()
+        cell3 = np.asarray(cell, dtype=float).reshape(3, 3)
+        if nbr is None:
+            out = eng.analyze(pos[None], cell, d_types, self.pbc, want_keys=False, want_labels=False)
+            eng.check()
+            rowptr, col = eng.ell_to_csr(out["ell"], order=1, pos=out["pos"])
+            ma, mp = eng.dps(rowptr[0].contiguous(), col[0].contiguous())
+            mol_atoms, mol_ptr = ma.cpu().numpy(), mp.cpu().numpy()
+        else:
+            mol_atoms, mol_ptr = dps_from_ell_arrays(eng, nbr)
+        molrank = np.empty(N, dtype=np.int64)
+        molrank[mol_atoms] = np.repeat(np.arange(len(mol_ptr) - 1), np.diff(mol_ptr))
+        sel = self.dstep[step]
+        members = eng.sphere_members(pos[None], cell, d_types, self.cutoff,
+                                     np.array([a - 1 for a, *_ in sel], dtype=np.int32), periodic=self.pbc)
+        symbols_all = np.asarray(self.crddetector.atomnames)
+        lengths = np.linalg.norm(cell3, axis=1)
+        results = 0
+        for (atoma, trajatomfilename, itype, itotal), cutoffatomid in zip(sel, members):
+            folder = str(itotal // 1000).zfill(self.foldermaxlength)
+            atomtypenum = str(itype).zfill(self.maxlength)
+            # make cutoff atoms in molecules: every molecule with ANY atom inside the sphere (:562-567)
+            mols = np.unique(molrank[cutoffatomid])
+            takenatomids = [mol_atoms[mol_ptr[m]:mol_ptr[m + 1]] for m in mols]
+            takenatomidindex, idsum = [], 0
+            for t in takenatomids:
+                takenatomidindex.append(range(idsum, idsum + len(t)))
+                idsum += len(t)
+            idx = np.concatenate(takenatomids)
+            symbols = symbols_all[idx]
+            tags = np.zeros(len(idx), dtype=int)
+            tags[np.nonzero(idx == atoma - 1)[0][0]] = 1
+            positions = wrap_positions(pos_h[idx], cell3, pos_h[atoma - 1] / lengths, self.pbc)
+            name = f"{self.xyzfilename}_{trajatomfilename}_{atomtypenum}"
+            write_xyz(os.path.join(self.dataset_dir, folder, name + ".xyz"), symbols, positions)
+            if self.writegjf:
+                write_gjf(os.path.join(self.gjfdir, folder, name + ".gjf"), takenatomidindex, symbols, positions,
+                          self.qmkeywords, self.fragment)
+            if self.atom_pref:
+                np.save(os.path.join(self.gjfdir, folder, name + ".atom_pref.npy"), np.array([tags]))
+            results += 1
+        return results
+
+    def lineiter(self, detector):
+        """Iterate over file(s) in groups of ``steplinenum`` lines with the frame stride
+        (datasetbuilder.py:616-638); kept for callers of the per-frame methods."""
+        import itertools
+
+        fns = must_be_list(detector.filename)
+        for fn in fns:
+            with open(fn) as f:
+                it = itertools.islice(itertools.zip_longest(*[f] * detector.steplinenum), 0, None, self.stepinterval)
+                yield from it
+
+    def erroriter(self):
+        """Iterate over the model deviation file (datasetbuilder.py:640-653)."""
+        import itertools
+
+        assert self.errorfilename is not None
+        for fn in must_be_list(self.errorfilename):
+            with open(fn) as f:
+                yield from itertools.islice(f, 1, None)
+
+
+def _commandline():
+    parser = argparse.ArgumentParser(description="MDDatasetBuilder", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("-d", "--dumpfile", nargs="*", help="Input dump file, e.g. dump.reaxc", required=True)
+    parser.add_argument(
+        "-b", "--bondfile", nargs="*",
+        help="Input bond file, e.g. bonds.reaxc. If not given, Open Babel will be used to determine bond connectivity.")
+    parser.add_argument("-a", "--atomname", help="Atomic names in the trajectory, e.g. C H O", nargs="*", required=True)
+    parser.add_argument("-np", "--nproc", help="Number of processes used by MDDatasetBuilder", type=int)
+    parser.add_argument(
+        "-c", "--cutoff",
+        help="Cutoff radius to take clusters from the trajectory. Note that only a complete molecule or free radical will be taken.",
+        type=float, default=5.0)
+    parser.add_argument(
+        "-i", "--interval",
+        help="Step interval to collect from the trajectory. 1 means collect from every step in the trajectory.",
+        type=int, default=1)
+    parser.add_argument("-s", "--size", help="Collected dataset size for each bond type.", type=int, default=10000)
+    parser.add_argument(
+        "-k", "--qmkeywords",
+        help='Gaussian QM keywords. Note that it should include "force" keyword to compute forces. Add "Geom=PrintInputOrient" if the number of atoms will be more than 50.',
+        default="force mn15/6-31g** Geom=PrintInputOrient")
+    parser.add_argument("--nprocjob", help="CPU number that each Gaussian job uses.", default=4, type=int)
+    parser.add_argument("-n", "--name", help="Dataset name", default="md")
+    parser.add_argument(
+        "--errorfile",
+        help="Model deviation file generated by DeePMD-kit plugin for LAMMPS. atomic should be enabled.", nargs="*")
+    parser.add_argument(
+        "-e", "--errorlimit",
+        help="Model deviation lower threshold. Atoms whose model deviation is less than the threshold will not be collected.",
+        type=float, default=0.0)
+    parser.add_argument("--version", action="version", version=f"MDDatasetBuilder {__version__}")
+    args = parser.parse_args()
+    DatasetBuilder(
+        atomname=args.atomname,
+        bondfilename=args.bondfile,
+        dumpfilename=args.dumpfile,
+        dataset_name=args.name,
+        cutoff=args.cutoff,
+        stepinterval=args.interval,
+        n_clusters=args.size,
+        qmkeywords=f"%nproc={args.nprocjob}\n#{args.qmkeywords}",
+        nproc=args.nproc,
+        errorfilename=args.errorfile,
+        errorlimit=args.errorlimit,
+    ).builddataset()

@@ -220,6 +220,29 @@ class Engine:
         _lib.check(rc, "mdb_compositions")
         return counts, mc
 
+    def sphere_members(self, pos, cell, types, cutoff, targets, periodic=True, cap=256):
+        """Ascending member lists of the cutoff spheres of `targets` (datasetbuilder.py:554-557)."""
+        torch = _torch()
+        pos = self.to_device_pos(pos)
+        types = self.to_device_types(types)
+        F, N = int(pos.shape[0]), int(pos.shape[1])
+        cells = self._cells(cell, F) if periodic else None
+        targets = torch.as_tensor(targets, dtype=torch.int32, device=self.device).contiguous()
+        T = int(targets.numel())
+        while True:
+            members = torch.empty((T, cap), dtype=torch.int32, device=self.device)
+            nmem = torch.empty(T, dtype=torch.int32, device=self.device)
+            rc = self.L.mdb_sphere_members(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                           float(cutoff), _ptr(targets), T, int(cap), _ptr(members), _ptr(nmem),
+                                           self.stream())
+            _lib.check(rc, "mdb_sphere_members")
+            n = nmem.cpu().numpy()
+            if T == 0 or n.max() <= cap or cap >= 1024:
+                break
+            cap = min(1024, 2 * cap)
+        m = members.cpu().numpy()
+        return [m[k, : min(n[k], cap)] for k in range(T)]
+
     def descriptors(self, pos, cell, types, cutoff, counts, maxcount, targets=None, periodic=True, want_X=True,
                     want_eig=False, eigcap=128):
         """Coulomb-matrix spectrum + padded sorted feature rows (datasetbuilder.py:236-349)."""
@@ -291,6 +314,15 @@ class Engine:
         _lib.check(rc, "mdb_kmeans_partial_sums")
         return sums, wsum
 
+    def kpp_step(self, X, cand, closest, dist_out, pot_out, rowidx=None, weights=None):
+        """One k-means++ seeding step: distances of the candidate rows to every row (clipped
+        against `closest`) and the weighted potential of each candidate."""
+        n = int(rowidx.numel()) if rowidx is not None else int(X.shape[0])
+        rc = self.L.mdb_kpp_step(self.ctx, n, int(X.shape[1]), _ptr(X), int(X.stride(0)), _ptr(rowidx), _ptr(cand),
+                                 int(cand.numel()), _ptr(closest), _ptr(weights), _ptr(dist_out), _ptr(pot_out),
+                                 self.stream())
+        _lib.check(rc, "mdb_kpp_step")
+
     def kmeans_apply_update(self, centers, weight_sums, sums, wsum):
         K, D = centers.shape
         rc = self.L.mdb_kmeans_apply_update(self.ctx, int(K), int(D), _ptr(centers), _ptr(weight_sums), _ptr(sums),
@@ -336,11 +368,12 @@ _ENGINES = {}
 
 
 def get_engine(device: int = 0, atomname=("C", "H", "O")) -> Engine:
-    """Process-wide engine per device (re-targeted when the element list changes)."""
+    """Process-wide engine per device (re-targeted when the element list changes;
+    atomname=None keeps whatever table is loaded)."""
     e = _ENGINES.get(device)
     if e is None:
-        e = Engine(device, atomname)
+        e = Engine(device, atomname if atomname is not None else ("C", "H", "O"))
         _ENGINES[device] = e
-    elif list(atomname) != e.atomname:
+    elif atomname is not None and [str(a) for a in atomname] != e.atomname:
         e.set_elements(atomname)
     return e

@@ -1,0 +1,295 @@
+"""MinMaxScaler + MiniBatchKMeans + per-cluster selection on the GPU.
+
+Drop-in for the arithmetic of ``DatasetBuilder._clusterdatas`` (reference
+datasetbuilder.py:351-384), which calls scikit-learn's ``MinMaxScaler`` and
+``MiniBatchKMeans(n_clusters, init_size=min(3K, rows), n_init=3).fit_predict``.  The control
+flow below follows scikit-learn 1.9 step by step (``cluster/_kmeans.py``: ``_kmeans_plusplus``
+:180-279, ``_mini_batch_step`` :1601-1697, ``MiniBatchKMeans.fit`` :2060-2226 and its helpers
+``_random_reassign`` / ``_mini_batch_convergence``); the heavy steps run in the kernels of
+``csrc/kmeans.cu``.  All random draws come from one ``numpy.random.RandomState(seed)`` in the
+same order scikit-learn draws them.  The reference seeds nothing (its results differ from run
+to run); this implementation is reproducible for a given ``seed``.
+
+Multi-GPU: when ``torch.distributed`` is initialised every rank holds a shard of the rows;
+the mini-batch is drawn ``batch_size / world`` rows per rank, the centroid partial sums and
+weights are all-reduced (NCCL) before the update, scaler bounds are all-reduced MIN/MAX, and the
+seeding subset is all-gathered so every rank computes identical initial centres.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+class MinMaxScalerB200:
+    """``sklearn.preprocessing.MinMaxScaler`` (feature_range (0, 1)) on device rows."""
+
+    def __init__(self, engine):
+        self.eng = engine
+
+    def fit_transform(self, X):
+        import torch
+
+        mn, mx = self.eng.minmax_fit(X)
+        d = _dist()
+        if d is not None:
+            if X.shape[0] == 0:
+                mn.fill_(float("inf"))
+                mx.fill_(float("-inf"))
+            d.all_reduce(mn, op=d.ReduceOp.MIN)
+            d.all_reduce(mx, op=d.ReduceOp.MAX)
+        self.data_min_ = mn.cpu().numpy()
+        self.data_max_ = mx.cpu().numpy()
+        self.eng.minmax_transform(X, self.data_min_, self.data_max_)
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        return X
+
+
+class MiniBatchKMeansB200:
+    def __init__(self, engine, n_clusters=8, init_size=None, n_init=3, batch_size=1024, max_iter=100,
+                 max_no_improvement=10, reassignment_ratio=0.01, seed=0, verbose=False):
+        self.eng = engine
+        self.n_clusters = int(n_clusters)
+        self.init_size = init_size
+        self.n_init = n_init
+        self.batch_size = batch_size
+        self.max_iter = max_iter
+        self.max_no_improvement = max_no_improvement
+        self.reassignment_ratio = reassignment_ratio
+        self.seed = seed
+        self.verbose = verbose
+
+    # ------------------------------------------------------------------ seeding
+    def _kmeans_plusplus(self, X, rowidx, rs):
+        """sklearn _kmeans_plusplus on the rows X[rowidx] (unit sample weights)."""
+        import torch
+
+        eng = self.eng
+        n = int(rowidx.numel())
+        K = self.n_clusters
+        n_local_trials = 2 + int(np.log(K))
+        center_id = int(rs.choice(n, p=np.full(n, 1.0 / n)))
+        indices = np.full(K, -1, dtype=np.int64)
+        indices[0] = center_id
+        dist = torch.empty((n_local_trials, n), dtype=torch.float64, device=eng.device)
+        pot = torch.empty(n_local_trials, dtype=torch.float64, device=eng.device)
+        cand = torch.tensor([center_id], dtype=torch.int32, device=eng.device)
+        eng.kpp_step(X, cand, None, dist, pot, rowidx=rowidx)
+        closest = dist[0].clone()
+        current_pot = float(pot[0].item())
+        for c in range(1, K):
+            rand_vals = rs.uniform(size=n_local_trials) * current_pot
+            csum = torch.cumsum(closest, dim=0)
+            cand = torch.searchsorted(csum, torch.as_tensor(rand_vals, device=eng.device)).clamp_(max=n - 1).to(torch.int32)
+            eng.kpp_step(X, cand, closest, dist, pot, rowidx=rowidx)
+            best = int(torch.argmin(pot).item())
+            current_pot = float(pot[best].item())
+            closest = dist[best].clone()
+            indices[c] = int(cand[best].item())
+        idx_t = torch.as_tensor(indices, device=eng.device)
+        return X[rowidx.long()[idx_t]].clone()
+
+    def _init_centroids(self, X, rs, init_size):
+        import torch
+
+        n = X.shape[0]
+        if init_size is not None and init_size < n:
+            init_indices = rs.randint(0, n, init_size)
+        else:
+            init_indices = np.arange(n)
+        rowidx = torch.as_tensor(init_indices, dtype=torch.int32, device=self.eng.device)
+        return self._kmeans_plusplus(X, rowidx, rs)
+
+    # ------------------------------------------------------------------ one mini-batch step
+    def _mini_batch_step(self, X, batch_idx, centers, weight_sums, rs, random_reassign):
+        """sklearn _mini_batch_step; updates centers / weight_sums in place, returns inertia."""
+        import torch
+
+        eng = self.eng
+        K = self.n_clusters
+        labels, inertia, _ = eng.kmeans_assign(X, centers, rowidx=batch_idx, want_inertia=True)
+        sums, wsum = eng.kmeans_partial_sums(X, labels, K, rowidx=batch_idx, out=self._sums_buf)
+        d = _dist()
+        if d is not None:
+            d.all_reduce(sums)
+            d.all_reduce(wsum)
+            t = torch.tensor([inertia], dtype=torch.float64, device=eng.device)
+            d.all_reduce(t)
+            inertia = float(t.item())
+        eng.kmeans_apply_update(centers, weight_sums, sums, wsum)
+        if random_reassign and self.reassignment_ratio > 0:
+            ws = weight_sums.cpu().numpy()
+            B = int(batch_idx.numel())
+            to_reassign = ws < self.reassignment_ratio * ws.max()
+            if to_reassign.sum() > 0.5 * B:
+                indices_dont_reassign = np.argsort(ws)[int(0.5 * B):]
+                to_reassign[indices_dont_reassign] = False
+            n_reassigns = int(to_reassign.sum())
+            if n_reassigns:
+                new_centers = rs.choice(B, replace=False, size=n_reassigns)
+                rows = batch_idx.long()[torch.as_tensor(new_centers, device=eng.device)]
+                centers[torch.as_tensor(np.nonzero(to_reassign)[0], device=eng.device)] = X[rows]
+            if (~to_reassign).any():
+                ws[to_reassign] = np.min(ws[~to_reassign])
+                weight_sums.copy_(torch.as_tensor(ws, device=eng.device))
+        return inertia
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, X):
+        import torch
+
+        eng = self.eng
+        d = _dist()
+        world = d.get_world_size() if d is not None else 1
+        rank = d.get_rank() if d is not None else 0
+        n_local = int(X.shape[0])
+        n_samples = n_local
+        if d is not None:
+            t = torch.tensor([n_local], dtype=torch.int64, device=eng.device)
+            d.all_reduce(t)
+            n_samples = int(t.item())
+        K = self.n_clusters
+        D = int(X.shape[1])
+        batch_size = min(self.batch_size, n_samples)
+        init_size = self.init_size
+        if init_size is None:
+            init_size = 3 * batch_size
+        if init_size < K:
+            init_size = 3 * K
+        init_size = min(init_size, n_samples)
+        rs = np.random.RandomState(self.seed)
+        self._sums_buf = (torch.empty((K, D), dtype=torch.float64, device=eng.device),
+                          torch.empty(K, dtype=torch.float64, device=eng.device))
+
+        # seeding pool: in the distributed case every rank contributes init_size / world rows
+        if d is not None:
+            share = -(-init_size // world)
+            take = np.random.RandomState(self.seed + 7919 * (rank + 1)).randint(0, max(n_local, 1), share)
+            part = X[torch.as_tensor(take, device=eng.device)] if n_local else torch.zeros((share, D), dtype=X.dtype,
+                                                                                            device=eng.device)
+            gathered = [torch.empty_like(part) for _ in range(world)]
+            d.all_gather(gathered, part.contiguous())
+            pool = torch.cat(gathered)[:init_size].contiguous()
+            pool_is_all = False
+        else:
+            pool = X
+            pool_is_all = True
+        n_pool = int(pool.shape[0])
+        validation_indices = rs.randint(0, n_pool, init_size)
+        valid_idx = torch.as_tensor(validation_indices, dtype=torch.int32, device=eng.device)
+        best_inertia, centers = None, None
+        for _ in range(self.n_init):
+            c = self._init_centroids(pool, rs, init_size if pool_is_all else None)
+            _, inertia, _ = eng.kmeans_assign(pool, c, rowidx=valid_idx, want_inertia=True)
+            if best_inertia is None or inertia < best_inertia:
+                centers, best_inertia = c, inertia
+        centers = centers.contiguous()
+        weight_sums = torch.zeros(K, dtype=torch.float64, device=eng.device)
+        ewa, ewa_min, no_improvement = None, None, 0
+        n_since_last_reassign = 0
+        n_steps = (self.max_iter * n_samples) // batch_size
+        local_batch = batch_size if d is None else max(1, batch_size // world)
+        rs_local = rs if d is None else np.random.RandomState(self.seed + 104729 * (rank + 1))
+        i = -1
+        for i in range(n_steps):
+            idx = rs_local.randint(0, max(n_local, 1), local_batch)
+            batch_idx = torch.as_tensor(idx, dtype=torch.int32, device=eng.device)
+            n_since_last_reassign += batch_size
+            counts_zero = bool((weight_sums == 0).any().item())
+            random_reassign = counts_zero or n_since_last_reassign >= 10 * K
+            if random_reassign:
+                n_since_last_reassign = 0
+            batch_inertia = self._mini_batch_step(X, batch_idx, centers, weight_sums, rs, random_reassign)
+            # _mini_batch_convergence (tol = 0)
+            batch_inertia /= batch_size
+            step = i + 1
+            if step == 1:
+                continue
+            if ewa is None:
+                ewa = batch_inertia
+            else:
+                alpha = min(batch_size * 2.0 / (n_samples + 1), 1)
+                ewa = ewa * (1 - alpha) + batch_inertia * alpha
+            if ewa_min is None or ewa < ewa_min:
+                no_improvement = 0
+                ewa_min = ewa
+            else:
+                no_improvement += 1
+            if self.max_no_improvement is not None and no_improvement >= self.max_no_improvement:
+                break
+        self.cluster_centers_ = centers
+        self.counts_ = weight_sums
+        self.n_steps_ = i + 1
+        self.labels_, self.inertia_, _ = eng.kmeans_assign(X, centers, want_inertia=True)
+        if d is not None:
+            t = torch.tensor([self.inertia_], dtype=torch.float64, device=eng.device)
+            d.all_reduce(t)
+            self.inertia_ = float(t.item())
+        return self
+
+    def fit_predict(self, X):
+        return self.fit(X).labels_
+
+
+def choose_per_cluster(labels_local, n_clusters, n_each, seed, rank=0, world=1, all_counts=None, with_tags=False):
+    """Per non-empty cluster pick ``n_each`` rows uniformly WITH replacement
+    (``default_rng().choice(idx, n_each)``, datasetbuilder.py:378-383), seeded.
+
+    Distributed: ``all_counts`` [world, K] holds every rank's member count per cluster; each
+    rank runs the same draws and keeps the picks that fall into its own shard.  Returns the local
+    row indices picked on this rank, in ascending cluster order."""
+    labels_local = np.asarray(labels_local)
+    order = np.argsort(labels_local, kind="stable")
+    counts = np.bincount(labels_local, minlength=n_clusters)[:n_clusters]
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    if all_counts is None:
+        all_counts = counts[None, :]
+    all_counts = np.asarray(all_counts)
+    totals = all_counts.sum(axis=0)
+    offsets = np.cumsum(all_counts, axis=0) - all_counts  # first global member index of each rank
+    rng = np.random.default_rng(seed)
+    picks, tags = [], []
+    for k in range(n_clusters):
+        if totals[k] == 0:
+            continue
+        draws = rng.integers(0, totals[k], size=n_each)
+        for j, g in enumerate(draws):
+            loc = g - offsets[rank, k]
+            if 0 <= loc < all_counts[rank, k]:
+                picks.append(order[starts[k] + loc])
+                tags.append((k, j))
+    picks = np.asarray(picks, dtype=np.int64)
+    if with_tags:
+        return picks, np.asarray(tags, dtype=np.int64).reshape(-1, 2)
+    return picks
+
+
+def clusterdatas(engine, X, n_clusters, n_each=1, seed=0, with_tags=False):
+    """``DatasetBuilder._clusterdatas`` (datasetbuilder.py:351-384) on device rows X [rows, D];
+    X is scaled in place.  Returns the selected LOCAL row indices (numpy) -- with_tags adds the
+    (cluster, draw) pair of every pick, which orders the picks globally across ranks."""
+    import torch
+
+    MinMaxScalerB200(engine).fit_transform(X)
+    d = _dist()
+    n_total = int(X.shape[0])
+    if d is not None:
+        t = torch.tensor([n_total], dtype=torch.int64, device=engine.device)
+        d.all_reduce(t)
+        n_total = int(t.item())
+    clus = MiniBatchKMeansB200(engine, n_clusters=n_clusters, init_size=min(3 * n_clusters, n_total), n_init=3,
+                               seed=seed)
+    labels = clus.fit_predict(X).cpu().numpy()
+    if d is None:
+        return choose_per_cluster(labels, n_clusters, n_each, seed, with_tags=with_tags)
+    counts = torch.as_tensor(np.bincount(labels, minlength=n_clusters)[:n_clusters], device=engine.device)
+    allc = [torch.empty_like(counts) for _ in range(d.get_world_size())]
+    d.all_gather(allc, counts)
+    return choose_per_cluster(labels, n_clusters, n_each, seed, d.get_rank(), d.get_world_size(),
+                              torch.stack(allc).cpu().numpy(), with_tags=with_tags)

@@ -1,0 +1,279 @@
+"""CPU suite (-m "not gpu"): pins the oracle against the reference's own known answers and the
+committed golden fixtures, and checks the host-side logic and the C-ABI surface.  No GPU compute."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from mddatasetbuilder_b200 import synth
+from oracle import oracle as O
+from oracle import refrun
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(GOLD, "golden.json")) as f:
+        return json.load(f)
+
+
+# ---------------------------------------------------------------- reference known answers
+def test_reference_test_bond_vectors():
+    # /root/reference/tests/test_bond.py:9-34
+    cell = np.diag([20.0, 20.0, 20.0])
+    pos = [[0.0, 0.0, 0.0], [19.0, 19.0, 19.0]]
+    assert O.crd2bond([8, 8], pos, cell, True, readlevel=False) == [[1], [0]]
+    assert O.crd2bond([8, 8], pos, cell, True, readlevel=True) == [[1], [1]]
+    assert O.crd2bond([8, 8], pos, cell, False, readlevel=False) == [[], []]
+    assert O.crd2bond([8, 8], pos, cell, False, readlevel=True) == [[], []]
+    for mode in (0, 1):
+        assert O.crd2bond([8, 8], pos, cell, True, mode=mode) == [[1], [0]]
+
+
+def test_dps_known_answers_and_reference_extension():
+    # SURVEY.md ground facts (probed with the reference's compiled dps)
+    assert O.dps_lists([[1], [0, 2], [1], [], [5], [4]]) == [[0, 1, 2], [3], [4, 5]]
+    assert O.dps_lists([[2, 1], [0], [0, 3], [2]]) == [[0, 1, 2, 3]]
+    ref = O.ref_dps()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 60, 500):
+        adj = [[] for _ in range(n)]
+        for _ in range(int(n * 0.8)):
+            a, b = rng.integers(0, n, 2)
+            if a != b and b not in adj[a]:
+                adj[a].append(int(b))
+                adj[b].append(int(a))
+        for row in adj:
+            rng.shuffle(row)
+        assert O.dps_lists(adj) == ref(adj)
+
+
+def test_oracle_modes_agree_and_cleanup_is_exercised():
+    s = synth.make_system(2500, 0.06, seed=synth.BASE_SEED + 77, reactive_fraction=0.05)
+    Z = np.array([O.ATOMIC_NUMBERS[s.atomname[t]] for t in s.types])
+    fr = synth.frame_positions(s, 2)[1]
+    b0, nd0 = O.connect_the_dots(Z, fr, s.cell(), True, mode=0)
+    b1, nd1 = O.connect_the_dots(Z, fr, s.cell(), True, mode=1)
+    assert np.array_equal(b0, b1) and nd0 == nd1 and nd0 > 0
+    b0, _ = O.connect_the_dots(Z, fr, s.cell(), False, mode=0)
+    b1, _ = O.connect_the_dots(Z, fr, s.cell(), False, mode=1)
+    assert np.array_equal(b0, b1)
+
+
+# ---------------------------------------------------------------- golden fixtures
+def _reader(kind, name):
+    from mddatasetbuilder_b200.reader import TextReader
+
+    return TextReader(kind, os.path.join(GOLD, "traj", name), nthreads=2)
+
+
+def test_text_reader_matches_reference_readN_and_readcrd(golden):
+    rd = _reader(0, "dump.small")
+    assert rd.natoms == golden["natoms"] and rd.steplinenum == golden["dump_steplinenum"]
+    assert rd.atomtype.tolist() == golden["atomtype"]
+    pos, cell = rd.read(100, 1)
+    assert len(pos) == golden["nframes"]
+    for k, fr in enumerate(golden["frames"]):
+        assert hashlib.sha256(np.ascontiguousarray(pos[k]).tobytes()).hexdigest() == fr["pos_sha"]
+        assert np.array_equal(cell[k].reshape(3, 3), np.array(fr["cell"]))
+    # stride and skip follow islice(zip_longest(...), 0, None, stride)
+    rd.rewind()
+    p2, _ = rd.read(100, 2)
+    assert len(p2) == 3 and np.array_equal(p2[1], pos[2])
+    rd.rewind()
+    assert rd.skip(1, 2) == 1
+    p3, _ = rd.read(1, 2)
+    assert np.array_equal(p3[0], pos[2])
+    # per-frame parse of a tuple of lines (with the None padding zip_longest produces)
+    with open(os.path.join(GOLD, "traj", "dump.small")) as f:
+        lines = f.readlines()
+    n = rd.steplinenum
+    pp, cc = rd.parse_lines(tuple(lines[n:2 * n]) + (None,))
+    assert np.array_equal(pp, pos[1])
+
+
+def test_bond_reader_keys_and_molecules_match_reference(golden):
+    rb = _reader(1, "bonds.small")
+    assert rb.natoms == golden["natoms"] and rb.steplinenum == golden["bond_steplinenum"]
+    nbr, bo = rb.read(100, 1, width=8)
+    names = golden["atomname"]
+    types = np.array(golden["atomtype"]) - 1
+    for k, fr in enumerate(golden["frames"]):
+        adj = [[int(x) for x in row[row >= 0]] for row in nbr[k]]
+        assert O.dps_lists(adj) == fr["bond_molecules"]
+        rowptr, _ = O.lists_to_csr(adj)
+        flat = np.concatenate([bo[k][i, : len(adj[i])] for i in range(len(adj))])
+        keys = O.bond_keys_bondfile(types, rowptr, flat)
+        got = {}
+        for i, key in enumerate(keys):
+            e, lv = O.unpack_key(key)
+            got.setdefault((names[e], tuple(lv)), []).append(i + 1)
+        want = {(n, tuple(lv)): ids for n, lv, ids in fr["bond_keys"]}
+        assert got == want
+
+
+def test_oracle_bonds_and_molecules_match_reference_through_shims(golden):
+    rd = _reader(0, "dump.small")
+    pos, cell = rd.read(100, 1)
+    Z = np.array([O.ATOMIC_NUMBERS[golden["atomname"][t - 1]] for t in golden["atomtype"]])
+    for k, fr in enumerate(golden["frames"]):
+        for mode in (0, 1):
+            adj = O.crd2bond(Z, pos[k], cell[k].reshape(3, 3), True, mode=mode)
+            assert adj == fr["dump_adjacency"]
+        assert O.dps_lists(adj) == fr["dump_molecules"]
+        want = {(n, tuple(lv)): ids for n, lv, ids in fr["dump_keys"]}
+        got = {}
+        for i, a in enumerate(adj):
+            got.setdefault((golden["atomname"][golden["atomtype"][i] - 1], tuple([1] * len(a))), []).append(i + 1)
+        assert got == want
+
+
+def test_oracle_descriptors_match_reference_writestepmatrix(golden):
+    rd = _reader(0, "dump.small")
+    pos, cell = rd.read(100, 1)
+    names = golden["atomname"]
+    types = np.array(golden["atomtype"]) - 1
+    Z = np.array([O.ATOMIC_NUMBERS[names[t]] for t in types])
+    diag = O.coulomb_diag(names)
+    dba = np.array([diag[names[t]] for t in types])
+    L = np.diag(cell[1].reshape(3, 3))
+    rows = golden["stepmatrix_frame1"]
+    targets = np.array([r["atom"] - 1 for r in rows], dtype=np.int32)
+    counts, members, mats = O.descriptor_gather(Z, dba, pos[1], L, True, 5.0, targets)
+    eigs = O.coulomb_eigs(mats)
+    for r, m, e in zip(rows, members, eigs):
+        assert {names[t]: int(c) for t, c in enumerate(np.bincount(types[m], minlength=len(names))) if c} == r["counter"]
+        assert np.allclose(e, r["eig"], rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.skipif(not refrun.available(), reason="reference tree not mounted")
+def test_golden_fixtures_are_reproducible_from_the_reference(golden, tmp_path):
+    """Re-run a slice of make_golden.py against /root/reference and compare with the committed file."""
+    refrun.load()
+    from mddatasetbuilder.detect import DetectDump
+
+    dd = DetectDump(filename=os.path.join(GOLD, "traj", "dump.small"), atomname=np.array(golden["atomname"]), pbc=True)
+    with open(os.path.join(GOLD, "traj", "dump.small")) as f:
+        lines = f.readlines()
+    n = dd.steplinenum
+    mols, _ = dd.readmolecule(tuple(lines[2 * n:3 * n]))
+    assert [[int(a) for a in m] for m in mols] == golden["frames"][2]["dump_molecules"]
+
+
+# ---------------------------------------------------------------- C ABI surface
+def test_c_abi_exports_every_declared_symbol():
+    from mddatasetbuilder_b200 import _lib
+
+    with open(os.path.join(ROOT, "include", "mdb_b200.h")) as f:
+        hdr = f.read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} is declared in include/mdb_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes prototypes out of sync with the header"
+    assert _lib.lib().mdb_version() >= 100
+
+
+def test_cli_help_runs_without_gpu():
+    # reference tests/test_cli.py:7-9
+    subprocess.check_output([sys.executable, "-m", "mddatasetbuilder_b200", "-h"], cwd=ROOT)
+
+
+# ---------------------------------------------------------------- host logic
+def test_writer_formats_and_wrap():
+    from mddatasetbuilder_b200.writer import detect_multiplicity, wrap_positions
+
+    assert detect_multiplicity(["O", "O"]) == 3
+    assert detect_multiplicity(["H"]) == 2 and detect_multiplicity(["C", "H", "H", "H", "H"]) == 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    try:
+        from ase import Atoms
+    finally:
+        sys.path.pop(0)
+    rng = np.random.default_rng(2)
+    cell = np.diag([11.0, 12.5, 9.0])
+    pos = rng.uniform(-5, 20, (30, 3))
+    a = Atoms("H30", positions=pos.copy(), cell=cell, pbc=True)
+    center = pos[3] / np.array([11.0, 12.5, 9.0])
+    a.wrap(center=center, pbc=a.get_pbc())
+    assert np.array_equal(wrap_positions(pos, cell, center, True), a.positions)
+
+
+def test_choose_per_cluster_single_and_sharded_agree():
+    from mddatasetbuilder_b200.kmeans import choose_per_cluster
+
+    rng = np.random.default_rng(4)
+    labels = rng.integers(0, 40, 1000)
+    labels[labels == 7] = 8  # an empty cluster
+    picks, tags = choose_per_cluster(labels, 40, 2, seed=3, with_tags=True)
+    assert len(picks) == 2 * len(np.unique(labels))
+    assert all(labels[p] == t[0] for p, t in zip(picks, tags))
+    # the same rows split over two ranks: the union of the ranks' picks is the single-process pick
+    cut = 600
+    parts = [labels[:cut], labels[cut:]]
+    allc = np.stack([np.bincount(p, minlength=40) for p in parts])
+    merged = {}
+    for r, (p, off) in enumerate(zip(parts, (0, cut))):
+        pk, tg = choose_per_cluster(p, 40, 2, seed=3, rank=r, world=2, all_counts=allc, with_tags=True)
+        for i, t in zip(pk, tg):
+            merged[tuple(t)] = labels[off + i]
+    assert len(merged) == len(picks)
+    assert all(merged[tuple(t)] == t[0] for t in tags)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mddatasetbuilder_b200.kmeans import choose_per_cluster
+
+    rng = np.random.default_rng(11)
+    labels = rng.integers(0, 25, 800)
+    mine = labels[rank::world]
+    counts = torch.as_tensor(np.bincount(mine, minlength=25))
+    allc = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    picks, tags = choose_per_cluster(mine, 25, 1, seed=5, rank=rank, world=world,
+                                     all_counts=torch.stack(allc).numpy(), with_tags=True)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [(int(t[0]), int(t[1]), int(mine[p])) for p, t in zip(picks, tags)])
+    # scaler-bound reduction used by MinMaxScalerB200
+    mn = torch.tensor([float(rank), 5.0 - rank])
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(([x for part in gathered for x in part], mn.tolist()))
+    dist.destroy_process_group()
+
+
+def test_distributed_selection_bookkeeping_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged, mn = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(merged) == 25 and sorted(k for k, _, _ in merged) == list(range(25))
+    assert all(k == lab for k, _, lab in merged), "every pick must belong to the cluster it was drawn for"
+    assert mn == [0.0, 4.0]
