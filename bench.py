@@ -161,6 +161,47 @@ def run_reference(args):
     return 0
 
 
+def measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_ranks, world, peaks):
+    """Descriptor and k-means stages of the metric, device-resident, CUDA-event timed, on a slice
+    of the same frames (every atom a target, like a bond type that covers the whole frame;
+    K = 10,000 centroids as the reference's default n_clusters)."""
+    nf = max(1, min(frames, (1 << 20) // natoms))       # ~1M targets per pass
+    sub = pos[:nf]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    res = {}
+    maxc = None
+    for it in range(2):                                   # pass 0 warms up
+        ev[0].record()
+        counts, maxc = eng.compositions(sub, cell, types, 5.0, periodic=True)
+        ev[1].record()
+        out = eng.descriptors(sub, cell, types, 5.0, counts, maxc, periodic=True)
+        ev[2].record()
+        torch.cuda.synchronize()
+    X = out["X"]
+    rows, D = int(X.shape[0]), int(X.shape[1])
+    n_mean = float(out["n"].double().mean().item())
+    t_comp = max_over_ranks(ev[0].elapsed_time(ev[1]))
+    t_desc = max_over_ranks(ev[1].elapsed_time(ev[2]))
+    res["composition"] = {"atom_frames_per_s": world * rows / (t_comp / 1e3), "ms": t_comp, "targets": rows}
+    res["descriptor"] = {"atom_frames_per_s": world * rows / (t_desc / 1e3), "ms": t_desc, "targets": rows,
+                         "mean_cluster_size": n_mean, "D": D,
+                         "hbm_frac_algorithmic": (16 + 8 * D) * rows / (t_desc / 1e3) / 1e9 / peaks["hbm_gbs"],
+                         "note": "FP64-pipe bound (Householder + QL), not HBM bound; see DESIGN.md"}
+    mn, mx = eng.minmax_fit(X)
+    eng.minmax_transform(X, mn.cpu().numpy(), mx.cpu().numpy())
+    K = 10000
+    centers = X[torch.randperm(rows, device=X.device)[:K]].contiguous()
+    for it in range(2):
+        ev[3].record()
+        labels, _, _ = eng.kmeans_assign(X, centers)
+        ev[4].record()
+        torch.cuda.synchronize()
+    t_as = max_over_ranks(ev[3].elapsed_time(ev[4]))
+    res["kmeans_assign"] = {"atom_frames_per_s": world * rows / (t_as / 1e3), "ms": t_as, "rows": rows, "K": K, "D": D,
+                            "fp64_tflops": 2.0 * rows * K * D / (t_as / 1e3) / 1e12}
+    return res
+
+
 # --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -172,6 +213,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override frames per rank (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stages", action="store_true")
     ap.add_argument("--cell-edge", type=float, default=0.0)
     ap.add_argument("--frames-per-launch", type=int, default=0)
     args = ap.parse_args()
@@ -193,6 +235,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -322,6 +366,11 @@ def main():
                "api": "Engine.analyze_host -> mdb_analyze_frames_host (pinned host buffers, pipelined H2D/compute/D2H)"}
         del h_pos, h_out
 
+    # ---- the other two stages of the metric, on the same frames (reported beside the headline) ----
+    stages = None
+    if not args.no_stages:
+        stages = measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_ranks, world, peaks)
+
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline(natoms, density, dense, synth.BASE_SEED + 2)
@@ -337,7 +386,8 @@ def main():
                            "l2": f"inputs are {frames * natoms * 24 / 1e6:.0f} MB per step per rank (> 126 MB L2)"
                                  if frames * natoms * 24 > 126e6 else "inputs fit L2 (not a headline configuration)",
                            "seed": synth.BASE_SEED + 2},
-                "roofline": roofline, "kernels": kern, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "kernels": kern, "stages": stages, "cpu_baseline": base, "e2e": e2e,
+                "gpu_launches": int(launches),
                 "clocks": clocks,
                 "bond_stats_per_step": stats}
         print(json.dumps(line))
