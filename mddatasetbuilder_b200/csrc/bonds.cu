@@ -191,62 +191,66 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
         }
     };
 
-    // 9 (dy, dz) rows; the cell_start bounds of row r+1 are fetched before row r is scanned
-    int lo_n = 0, hi_n = 0, lo2_n = 0, hi2_n = 0;
-    float ay_n = 0.f, az_n = 0.f, ax2_n = 0.f;
-    auto fetch = [&](int r) {
-        const int dzc = r / 3 - 1, dyc = r - (r / 3) * 3 - 1;
-        int y, z;
-        float sy, sz;
-        lo_n = hi_n = lo2_n = hi2_n = 0;
-        if (!nbr_cell(cy, dyc, ny, ry, periodic, py, y, sy)) return;
-        if (!nbr_cell(cz, dzc, nz, rz, periodic, pz, z, sz)) return;
-        int xa = cx, xb = cx, xw = -1;
-        float xws = 0.f;
+    // per-axis neighbour cells for d = -1, 0, +1 (wrapped index pre-multiplied to a cell offset, the
+    // shift to add to a neighbour's coordinate, and -- MODE 0 -- the squared distance to that slab)
+    int yoff[3], zoff[3];
+    float ysh[3], zsh[3], yb2[3], zb2[3];
+    bool yok[3], zok[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int q;
+        yok[d] = nbr_cell(cy, d - 1, ny, ry, periodic, py, q, ysh[d]);
+        yoff[d] = q * nx;
+        zok[d] = nbr_cell(cz, d - 1, nz, rz, periodic, pz, q, zsh[d]);
+        zoff[d] = q * ny * nx;
+        yb2[d] = d == 0 ? flo[1] : (d == 2 ? fhi[1] : 0.f);
+        zb2[d] = d == 0 ? flo[2] : (d == 2 ? fhi[2] : 0.f);
+    }
+    // all 9 (dy, dz) rows: bounds of the x-contiguous run are loaded up front (independent loads),
+    // then the rows are scanned; fully unrolled so every index above is a register
+    int lo[9], hi[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int iz = r / 3, iy = r % 3;
+        bool ok = yok[iy] && zok[iz];
+        int xa = cx - 1, xb = cx + 1;
         if (MODE == 0) {
-            const float base = (dyc < 0 ? flo[1] : dyc > 0 ? fhi[1] : 0.f) + (dzc < 0 ? flo[2] : dzc > 0 ? fhi[2] : 0.f);
-            if (base > cmax) return;  // the whole row is out of reach
-            if (base + flo[0] <= cmax) xa = cx - 1;
-            if (base + fhi[0] <= cmax) xb = cx + 1;
+            const float base = yb2[iy] + zb2[iz];
+            ok = ok && base <= cmax;
+            if (base + flo[0] > cmax) xa = cx;
+            if (base + fhi[0] > cmax) xb = cx;
         } else if (rx) {
             xa = xb = 0;
-        } else {
-            xa = cx - 1;
-            xb = cx + 1;
         }
-        if (xa < 0) {
-            xa = 0;
-            if (periodic) {
-                xw = nx - 1;
-                xws = -px;
-            }
-        }
-        if (xb >= nx) {
-            xb = nx - 1;
-            if (periodic) {
-                xw = 0;
-                xws = px;
-            }
-        }
-        const int rowbase = cbase + (z * ny + y) * nx;
-        lo_n = cs[rowbase + xa];
-        hi_n = cs[rowbase + xb + 1];
-        if (xw >= 0) {
-            lo2_n = cs[rowbase + xw];
-            hi2_n = cs[rowbase + xw + 1];
-        }
-        ay_n = sy - me.y;
-        az_n = sz - me.z;
-        ax2_n = xws - me.x;
-    };
-    fetch(0);
+        xa = max(xa, 0);
+        xb = min(xb, nx - 1);
+        const int rowbase = cbase + zoff[iz] + yoff[iy];
+        lo[r] = ok ? cs[rowbase + xa] : 0;
+        hi[r] = ok ? cs[rowbase + xb + 1] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) scan(lo[r], hi[r], -me.x, ysh[r % 3] - me.y, zsh[r / 3] - me.z);
+    // atoms in the first / last x cell also see one wrapped cell per row (rare: 2 of nx columns)
+    if (periodic && !rx && (cx == 0 || cx == nx - 1)) {
+        const int xw = cx == 0 ? nx - 1 : 0;
+        const float xws = cx == 0 ? -px : px;
+        const float fx = cx == 0 ? flo[0] : fhi[0];
+        const bool both = nx == 1;  // cannot happen (rx would be set); kept for clarity
+        (void)both;
 #pragma unroll 1
-    for (int r = 0; r < 9; ++r) {
-        const int lo = lo_n, hi = hi_n, lo2 = lo2_n, hi2 = hi2_n;
-        const float ay = ay_n, az = az_n, ax2 = ax2_n;
-        if (r < 8) fetch(r + 1);
-        scan(lo, hi, -me.x, ay, az);
-        if (lo2 < hi2) scan(lo2, hi2, ax2, ay, az);
+        for (int r = 0; r < 9; ++r) {
+            const int dzc = r / 3 - 1, dyc = r - (r / 3) * 3 - 1;
+            int y, z;
+            float sy, sz;
+            if (!nbr_cell(cy, dyc, ny, ry, periodic, py, y, sy)) continue;
+            if (!nbr_cell(cz, dzc, nz, rz, periodic, pz, z, sz)) continue;
+            if (MODE == 0) {
+                const float base = (dyc < 0 ? flo[1] : dyc > 0 ? fhi[1] : 0.f) + (dzc < 0 ? flo[2] : dzc > 0 ? fhi[2] : 0.f);
+                if (base + fx > cmax) continue;
+            }
+            const int rowbase = cbase + (z * ny + y) * nx;
+            scan(cs[rowbase + xw], cs[rowbase + xw + 1], xws - me.x, sy - me.y, sz - me.z);
+        }
     }
     if (np > BOND_PEND) {
         atomicAdd(&P.stats->overflow, 1ull);
