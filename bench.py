@@ -199,6 +199,17 @@ def measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_
     t_as = max_over_ranks(ev[3].elapsed_time(ev[4]))
     res["kmeans_assign"] = {"atom_frames_per_s": world * rows / (t_as / 1e3), "ms": t_as, "rows": rows, "K": K, "D": D,
                             "fp64_tflops": 2.0 * rows * K * D / (t_as / 1e3) / 1e12}
+    # tensor-core screening pass + float64 re-check of near-ties (same labels)
+    for it in range(2):
+        ev[3].record()
+        labels_tc, nre = eng.kmeans_assign_tc(X, centers)
+        ev[4].record()
+        torch.cuda.synchronize()
+    t_tc = max_over_ranks(ev[3].elapsed_time(ev[4]))
+    res["kmeans_assign_tc"] = {"atom_frames_per_s": world * rows / (t_tc / 1e3), "ms": t_tc, "rows": rows, "K": K, "D": D,
+                               "rechecked_in_float64": nre, "labels_equal_float64_path": bool(torch.equal(labels, labels_tc)),
+                               "effective_tflops": 2.0 * rows * K * D / (t_tc / 1e3) / 1e12,
+                               "tensor_tflops_issued": 2.0 * rows * K * (3 * ((D + 15) // 16 * 16)) / (t_tc / 1e3) / 1e12}
     return res
 
 

@@ -183,6 +183,13 @@ int mdb_kmeans_assign(mdb_ctx *ctx, long long rows, int D, int K, const double *
                       int32_t *d_labels, double *d_mindist, const double *d_weights,
                       double *h_inertia, void *stream);
 
+/* Same labels as mdb_kmeans_assign, computed with a tcgen05 (tensor-core) screening pass on
+ * split-fp16 operands; rows whose best / second-best gap is inside the error bound are
+ * re-decided by the float64 kernel (*h_nrecheck = how many).  D <= 128.  Synchronises. */
+int mdb_kmeans_assign_tc(mdb_ctx *ctx, long long rows, int D, int K, const double *d_X,
+                         long long ldx, const int32_t *d_rowidx, const double *d_centers,
+                         int32_t *d_labels, long long *h_nrecheck, void *stream);
+
 /* ---- K8: mini-batch centroid update -------------------------------------------------
  * Replaces _minibatch_update_dense (cluster/_k_means_minibatch.pyx:59-108) in two
  * halves so that ranks can all-reduce between them: partial_sums writes, per centre,

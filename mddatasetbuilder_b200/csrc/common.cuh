@@ -79,6 +79,9 @@ struct mdb_ctx {
     cudaEvent_t pipe_in[2] = {}, pipe_comp[2] = {}, pipe_out[2] = {};
     uint8_t *pipe_types = nullptr;
     size_t pipe_types_cap = 0;
+    // operands / results of the tensor-core assignment (grow-only)
+    char *tc_mem = nullptr;
+    size_t tc_bytes = 0;
     // optional per-launch CUDA-event timing (bench.py's live roofline measurement)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_free;

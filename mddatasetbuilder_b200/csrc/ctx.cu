@@ -79,6 +79,7 @@ extern "C" void mdb_destroy(mdb_ctx *c) {
         if (c->pipe_out[i]) cudaEventDestroy(c->pipe_out[i]);
     }
     if (c->pipe_types) cudaFree(c->pipe_types);
+    if (c->tc_mem) cudaFree(c->tc_mem);
     for (int i = 0; i < mdb_ctx::kRing; ++i) {
         if (c->h_geom[i]) cudaFreeHost(c->h_geom[i]);
         if (c->h_geom_ev[i]) cudaEventDestroy(c->h_geom_ev[i]);

@@ -1,0 +1,461 @@
+// tc_assign.cu -- K7 on the 5th-generation tensor cores: a screening pass for the k-means assignment.
+//
+// The reference's assignment (scikit-learn lloyd_iter_chunked_dense, cluster/_k_means_lloyd.pyx:168-213,
+// driven from datasetbuilder.py:371-376) compares float64 scores ||c_j||^2 - 2 x.c_j.  Here the
+// contraction runs as tcgen05.mma (kind::f16, fp32 accumulation in TMEM) on split-fp16 operands
+//     x ~ x_hi + x_lo,  c ~ c_hi + c_lo,   x.c ~ x_hi.c_hi + x_hi.c_lo + x_lo.c_hi
+// (one GEMM with the inner dimension tripled: A' = [x_hi | x_hi | x_lo], B' = [c_hi | c_lo | c_hi]),
+// after centring both operands on the centroid mean so that the products stay small.  The epilogue
+// keeps, per row, the best and second-best approximate score.  A row whose gap exceeds its error
+// bound takes the tensor-core label; the others (near-ties) are re-decided by the exact float64
+// kernel (kmeans.cu: k_assign), so the final labels are those of the float64 comparison.
+//
+// One CTA = one 128-row tile against all centroids: A' stays in shared memory (TMA, 128B swizzle),
+// B' tiles of 128 centroids stream through a TMA/mbarrier ring, accumulators are double-buffered
+// in TMEM (2 x 128 columns), 4 epilogue warps read them back with tcgen05.ld.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <float.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+#define TC_BM 128
+#define TC_BN 128
+#define TC_KCH 64                      // fp16 elements per 128-byte swizzle row
+#define TC_CHUNK_BYTES (TC_BM * 128)   // one [128 rows][64 elem] slab
+#define TC_THREADS 192
+#define TC_MAXCH 6                     // 3*Kd <= 384
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    // bounded spin: a protocol bug traps instead of hanging the GPU
+    for (uint32_t it = 0; it < (1u << 27); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major, 128B-swizzled operand slab: rows are 128 B, 8-row groups are 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcParams {
+    int rows, K, Kin, nch, stages;
+    const float *cn;   // [K] squared norm of the centred centroids
+    float *best1, *best2;
+    int *idx1;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_assign_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // carve: A slabs | B ring | barriers | cn staging | tmem base
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
+    unsigned char *gen = smem + (sbase - smem_u32(smem));
+    const int nch = P.nch, S = P.stages;
+    const uint32_t sA = sbase;
+    const uint32_t sB = sA + (uint32_t)nch * TC_CHUNK_BYTES;
+    const uint32_t tail = sB + (uint32_t)S * nch * TC_CHUNK_BYTES;
+    unsigned char *gtail = gen + (tail - sbase);
+    const uint32_t bar_afull = tail;                 // 8 B each
+    const uint32_t bar_bfull = tail + 8;             // [S]
+    const uint32_t bar_bempty = bar_bfull + 8 * 4;   // [S] (S <= 4)
+    const uint32_t bar_tfull = bar_bempty + 8 * 4;   // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;      // [2]
+    float *cn_s = reinterpret_cast<float *>(gtail + 128);          // [2][128]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 128 + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * TC_BM;
+    const int ntiles = (P.K + TC_BN - 1) / TC_BN;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_afull, 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_afull, (uint32_t)nch * TC_CHUNK_BYTES);
+            for (int c = 0; c < nch; ++c) tma_load_2d(sA + c * TC_CHUNK_BYTES, &tmA, c * TC_KCH, row0, bar_afull);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % S;
+                const uint32_t ph = (uint32_t)(t / S) & 1u;
+                mbar_wait(bar_bempty + 8 * s, ph ^ 1u);
+                mbar_expect_tx(bar_bfull + 8 * s, (uint32_t)nch * TC_CHUNK_BYTES);
+                for (int c = 0; c < nch; ++c)
+                    tma_load_2d(sB + (s * nch + c) * TC_CHUNK_BYTES, &tmB, c * TC_KCH, t * TC_BN, bar_bfull + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        mbar_wait(bar_afull, 0);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % S;
+            const uint32_t ph = (uint32_t)(t / S) & 1u;
+            const int a = t & 1;
+            const uint32_t aph = (uint32_t)(t >> 1) & 1u;
+            mbar_wait(bar_tempty + 8 * a, aph ^ 1u);
+            mbar_wait(bar_bfull + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                uint32_t first = 0;
+                for (int c = 0; c < nch; ++c) {
+                    const int kvalid = min(TC_KCH, P.Kin - c * TC_KCH);
+                    const int ksteps = (kvalid + 15) / 16;
+                    const uint64_t da = umma_desc(sA + c * TC_CHUNK_BYTES);
+                    const uint64_t db = umma_desc(sB + (s * nch + c) * TC_CHUNK_BYTES);
+                    for (int k = 0; k < ksteps; ++k) {
+                        // advance 16 elements = 32 bytes inside the swizzle row
+                        umma_f16(tmem_base + (uint32_t)a * TC_BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first);
+                        first = 1;
+                    }
+                }
+                umma_commit(bar_bempty + 8 * s);
+                umma_commit(bar_tfull + 8 * a);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        const int e = (warp - 2) * 32 + lane;     // 0..127: staging index for cn
+        const int myrow = row0 + q * 32 + lane;
+        float b1 = FLT_MAX, b2 = FLT_MAX;
+        int i1 = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int a = t & 1;
+            const uint32_t aph = (uint32_t)(t >> 1) & 1u;
+            const int col0 = t * TC_BN;
+            // the staging buffer `a` was last read two tiles ago; the barrier below orders the reuse
+            cn_s[a * TC_BN + e] = (col0 + e < P.K) ? P.cn[col0 + e] : FLT_MAX;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bar_tfull + 8 * a, aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int j = 0; j < TC_BN / 32; ++j) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + j * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const float *cnp = cn_s + a * TC_BN + j * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float sc = fmaf(-2.0f, __uint_as_float(r[i]), cnp[i]);
+                    if (sc < b1) {
+                        b2 = b1;
+                        b1 = sc;
+                        i1 = col0 + j * 32 + i;
+                    } else if (sc < b2)
+                        b2 = sc;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
+        }
+        if (myrow < P.rows) {
+            P.best1[myrow] = b1;
+            P.best2[myrow] = b2;
+            P.idx1[myrow] = i1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_col_mean(const double *__restrict__ C, int K, int D, double *__restrict__ mu) {
+    const int k = blockIdx.x;
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < K; j += 256) acc += C[(size_t)j * D + k];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mu[k] = s[0] / K;
+}
+
+// rows of X (or of C when is_c) -> split fp16, tripled inner dimension
+//   X:  [hi | hi | lo]      C:  [hi | lo | hi]
+__global__ void __launch_bounds__(256) k_split_fp16(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
+                                                    long long rows, int D, int Kd, const double *__restrict__ mu, int is_c,
+                                                    __half *__restrict__ out, float *__restrict__ norm2) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double *x = X + (rowidx ? (long long)rowidx[r] : r) * ldx;
+    __half *o = out + (size_t)r * 3 * Kd;
+    double n2 = 0.0;
+    for (int k = lane; k < Kd; k += 32) {
+        __half hi = __float2half(0.f), lo = hi;
+        if (k < D) {
+            const double v = x[k] - mu[k];
+            hi = __double2half(v);
+            lo = __double2half(v - (double)__half2float(hi));
+            n2 += v * v;
+        }
+        o[k] = hi;
+        o[Kd + k] = is_c ? lo : hi;
+        o[2 * Kd + k] = is_c ? hi : lo;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, s);
+    if (lane == 0) norm2[r] = (float)n2;
+}
+
+__global__ void __launch_bounds__(256) k_fmax(const float *__restrict__ v, int n, float *__restrict__ out) {
+    __shared__ float s[256];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, v[i]);
+    s[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] = fmaxf(s[threadIdx.x], s[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s[0];
+}
+
+// accept the tensor-core label when the gap beats the error bound; list the rest for float64
+__global__ void __launch_bounds__(256) k_tc_decide(const float *__restrict__ b1, const float *__restrict__ b2,
+                                                   const int *__restrict__ i1, const float *__restrict__ xn2,
+                                                   const float *__restrict__ cmax2, long long rows, float relerr,
+                                                   const int *__restrict__ rowidx, int *__restrict__ labels,
+                                                   int *__restrict__ amb_pos, int *__restrict__ amb_row, int *__restrict__ namb) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    // |score error| <= 2 * relerr * ||x|| * max||c||  (Cauchy-Schwarz on the centred operands) + cn rounding
+    const float bound = 2.f * relerr * sqrtf(xn2[r] * (*cmax2)) + 1e-6f * (*cmax2) + 1e-30f;
+    if (b2[r] - b1[r] > 2.f * bound) {
+        labels[r] = i1[r];
+    } else {
+        const int k = atomicAdd(namb, 1);
+        amb_pos[k] = (int)r;
+        amb_row[k] = rowidx ? rowidx[r] : (int)r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_labels(const int *__restrict__ pos, const int *__restrict__ lab, int n,
+                                                        int *__restrict__ labels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) labels[pos[i]] = lab[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *m, void *base, long long rows, int kin) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        mdb_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return -1;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)kin, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)kin * sizeof(__half)};
+    cuuint32_t box[2] = {TC_KCH, TC_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        mdb_set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+        return -1;
+    }
+    return 0;
+}
+
+int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
+                      const double *d_C, int *d_labels, double *d_mind, double *h_inertia, const double *d_w,
+                      cudaStream_t stream);
+
+// Tensor-core assignment with float64 resolution of near-ties.  *h_namb (optional) receives the
+// number of rows that went through the float64 kernel.
+int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
+                         const double *d_C, int *d_labels, long long *h_namb, cudaStream_t stream) {
+    if (rows <= 0) {
+        if (h_namb) *h_namb = 0;
+        return 0;
+    }
+    const int Kd = (D + 15) / 16 * 16;
+    const int Kin = 3 * Kd;
+    const int nch = (Kin + TC_KCH - 1) / TC_KCH;
+    if (nch > TC_MAXCH || rows >= (1LL << 31) || K < 1) {
+        mdb_set_error("kmeans_assign_tc: D must be <= 128 and rows < 2^31");
+        return -1;
+    }
+    int stages = nch <= 2 ? 4 : (nch <= 3 ? 3 : (nch <= 4 ? 2 : 1));
+    size_t smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1024 + 64;
+    while (smem > 227 * 1024 && stages > 1) {
+        --stages;
+        smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1024 + 64;
+    }
+    if (smem > 227 * 1024) {
+        mdb_set_error("kmeans_assign_tc: tile does not fit shared memory");
+        return -1;
+    }
+    // the exact kernel below re-uses the arena, so everything that must survive it lives in its own
+    // allocation (kept for the lifetime of the context, grown on demand)
+    const size_t needA = align256((size_t)rows * Kin * sizeof(__half)), needB = align256((size_t)K * Kin * sizeof(__half));
+    const size_t needf = align256((size_t)rows * sizeof(float));
+    const size_t total = needA + needB + 4 * needf + 3 * align256((size_t)rows * sizeof(int)) + align256((size_t)K * sizeof(float)) +
+                         align256((size_t)D * sizeof(double)) + 4096;
+    if (c->tc_bytes < total) {
+        MDB_CUDA(cudaDeviceSynchronize());
+        if (c->tc_mem) MDB_CUDA(cudaFree(c->tc_mem));
+        c->tc_mem = nullptr;
+        c->tc_bytes = 0;
+        MDB_CUDA(cudaMalloc(&c->tc_mem, total + total / 8));
+        c->tc_bytes = total + total / 8;
+    }
+    char *p = c->tc_mem;
+    auto take = [&](size_t b) {
+        char *q = p;
+        p += align256(b);
+        return q;
+    };
+    __half *A = (__half *)take(needA);
+    __half *B = (__half *)take(needB);
+    float *b1 = (float *)take(needf), *b2 = (float *)take(needf), *xn2 = (float *)take(needf);
+    int *i1 = (int *)take(rows * sizeof(int)), *amb_pos = (int *)take(rows * sizeof(int)), *amb_row = (int *)take(rows * sizeof(int));
+    float *cn = (float *)take((size_t)K * sizeof(float));
+    double *mu = (double *)take((size_t)D * sizeof(double));
+    float *cmax2 = (float *)take(256);
+    int *namb = (int *)(cmax2 + 8);
+    int *amb_lab = (int *)take(needf);
+
+    MDB_CUDA(cudaMemsetAsync(namb, 0, sizeof(int), stream));
+    k_col_mean<<<D, 256, 0, stream>>>(d_C, K, D, mu);
+    k_split_fp16<<<cdiv(K, 8), 256, 0, stream>>>(d_C, D, nullptr, K, D, Kd, mu, 1, B, cn);
+    k_fmax<<<1, 256, 0, stream>>>(cn, K, cmax2);
+    k_split_fp16<<<cdiv(rows, 8), 256, 0, stream>>>(d_X, ldx, d_rowidx, rows, D, Kd, mu, 0, A, xn2);
+    c->launches += 4;
+    CUtensorMap tmA, tmB;
+    if (make_map(&tmA, A, rows, Kin) || make_map(&tmB, B, K, Kin)) return -1;
+    TcParams P;
+    P.rows = (int)rows;
+    P.K = K;
+    P.Kin = Kin;
+    P.nch = nch;
+    P.stages = stages;
+    P.cn = cn;
+    P.best1 = b1;
+    P.best2 = b2;
+    P.idx1 = i1;
+    MDB_CUDA(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope ps(c, "k_assign_tc", stream);
+        k_assign_tc<<<cdiv(rows, TC_BM), TC_THREADS, smem, stream>>>(tmA, tmB, P);
+    }
+    c->launches++;
+    // per-product relative error of the split-fp16 contraction with fp32 accumulation over Kin terms
+    const float relerr = 4.0f * 2.3841858e-7f + (float)Kin * 1.1920929e-7f;
+    k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, relerr, d_rowidx, d_labels, amb_pos, amb_row,
+                                                    namb);
+    c->launches++;
+    int h = 0;
+    MDB_CUDA(cudaMemcpyAsync(&h, namb, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MDB_CUDA(cudaStreamSynchronize(stream));
+    MDB_CUDA(cudaGetLastError());
+    if (h_namb) *h_namb = h;
+    if (h > 0) {
+        if (kmeans_assign_run(c, h, D, K, d_X, ldx, amb_row, d_C, amb_lab, nullptr, nullptr, nullptr, stream)) return -1;
+        k_scatter_labels<<<cdiv(h, 256), 256, 0, stream>>>(amb_pos, amb_lab, h, d_labels);
+        c->launches++;
+        MDB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}

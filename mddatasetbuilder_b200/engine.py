@@ -300,6 +300,20 @@ class Engine:
         _lib.check(rc, "mdb_kmeans_assign")
         return labels, (inertia.value if want_inertia else None), mind
 
+    def kmeans_assign_tc(self, X, centers, rowidx=None):
+        """Labels via the tensor-core screening pass + float64 re-check of near-ties.
+        Returns (labels, number of rows re-checked in float64)."""
+        torch = _torch()
+        D = int(X.shape[1])
+        K = int(centers.shape[0])
+        rows = int(rowidx.numel()) if rowidx is not None else int(X.shape[0])
+        labels = torch.empty(rows, dtype=torch.int32, device=self.device)
+        nre = C.c_longlong(0)
+        rc = self.L.mdb_kmeans_assign_tc(self.ctx, rows, D, K, _ptr(X), int(X.stride(0)), _ptr(rowidx), _ptr(centers),
+                                         _ptr(labels), C.byref(nre), self.stream())
+        _lib.check(rc, "mdb_kmeans_assign_tc")
+        return labels, int(nre.value)
+
     def kmeans_partial_sums(self, X, labels, K, rowidx=None, weights=None, out=None):
         torch = _torch()
         D = int(X.shape[1])

@@ -76,3 +76,33 @@ def test_minibatch_update_matches_sklearn(engine, B, D, K):
     # tolerance on centroid coordinates stated for this path: 1e-12 relative
     assert np.allclose(dC.cpu().numpy(), ref_c, rtol=1e-12, atol=1e-15)
     assert np.allclose(dW.cpu().numpy(), ref_w, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("rows,D,K", [(5000, 37, 1000), (4096, 35, 10000), (777, 121, 130), (300, 5, 3), (20000, 64, 2500)])
+def test_tensor_core_assign_matches_sklearn(engine, rows, D, K):
+    """tcgen05 screening pass + float64 re-check of near-ties: identical labels to sklearn."""
+    rng = np.random.default_rng(rows * 7 + D)
+    X = rng.random((rows, D))
+    centers = X[rng.choice(rows, K, replace=K > rows)] + rng.normal(0, 0.01, (K, D))
+    if K >= 20:
+        centers[17] = centers[5]
+        X[3] = centers[5]
+    labels, _ = O.kmeans_labels(X, centers)
+    got, nre = engine.kmeans_assign_tc(_t(engine, X), _t(engine, centers))
+    got = got.cpu().numpy()
+    assert np.array_equal(got, labels), f"{(got != labels).sum()} labels differ from sklearn ({nre} re-checked)"
+    assert nre < 0.25 * rows + 64, f"too many rows fell back to float64: {nre} of {rows}"
+    idx = rng.integers(0, rows, 1500).astype(np.int32)
+    got2, _ = engine.kmeans_assign_tc(_t(engine, X), _t(engine, centers), rowidx=_t(engine, idx))
+    assert np.array_equal(got2.cpu().numpy(), labels[idx])
+
+
+def test_tensor_core_assign_clustered_data(engine):
+    """Descriptor-like data: tight clusters, many near-duplicate rows, unscaled magnitudes."""
+    rng = np.random.default_rng(11)
+    proto = rng.normal(0, 30.0, (400, 40))
+    X = np.concatenate([p + rng.normal(0, 1e-3, (60, 40)) for p in proto])
+    centers = np.concatenate([proto + rng.normal(0, 1e-4, proto.shape), proto[:100] + rng.normal(0, 1e-4, (100, 40))])
+    labels, _ = O.kmeans_labels(X, centers)
+    got, nre = engine.kmeans_assign_tc(_t(engine, X), _t(engine, centers))
+    assert np.array_equal(got.cpu().numpy(), labels), f"{(got.cpu().numpy() != labels).sum()} differ; {nre} re-checked"
