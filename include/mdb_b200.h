@@ -188,7 +188,16 @@ int mdb_kmeans_assign(mdb_ctx *ctx, long long rows, int D, int K, const double *
  * re-decided by the float64 kernel (*h_nrecheck = how many).  D <= 128.  Synchronises. */
 int mdb_kmeans_assign_tc(mdb_ctx *ctx, long long rows, int D, int K, const double *d_X,
                          long long ldx, const int32_t *d_rowidx, const double *d_centers,
-                         int32_t *d_labels, long long *h_nrecheck, void *stream);
+                         int32_t *d_labels, long long *h_nrecheck, float *d_diag, void *stream);
+/* d_diag (optional, float [4*rows+1]): per row the best and second-best approximate scores,
+ * the best index (int bits) and ||x - mean||^2, then max_j ||c_j - mean||^2 -- what the
+ * error bound of the screening pass is validated against in the tests. */
+
+/* Inertia of given labels: sum_i weight_i ||x_i - c_label(i)||^2 (sklearn _inertia_dense).
+ * Synchronises. */
+int mdb_kmeans_inertia(mdb_ctx *ctx, long long rows, int D, const double *d_X, long long ldx,
+                       const int32_t *d_rowidx, const double *d_centers, const int32_t *d_labels,
+                       const double *d_weights, double *h_inertia, void *stream);
 
 /* ---- K8: mini-batch centroid update -------------------------------------------------
  * Replaces _minibatch_update_dense (cluster/_k_means_minibatch.pyx:59-108) in two

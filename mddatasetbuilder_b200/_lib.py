@@ -46,7 +46,9 @@ SIGNATURES = {
     "mdb_kmeans_assign": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp, _vp,
                                     C.POINTER(C.c_double), _vp]),
     "mdb_kmeans_assign_tc": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp,
-                                       C.POINTER(C.c_longlong), _vp]),
+                                       C.POINTER(C.c_longlong), _vp, _vp]),
+    "mdb_kmeans_inertia": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp,
+                                     C.POINTER(C.c_double), _vp]),
     "mdb_kmeans_partial_sums": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp,
                                           _vp, _vp]),
     "mdb_kmeans_apply_update": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),

@@ -245,13 +245,25 @@ extern "C" int mdb_kmeans_assign(mdb_ctx *c, long long rows, int D, int K, const
 }
 
 int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
-                         const double *d_C, int *d_labels, long long *h_namb, cudaStream_t stream);
+                         const double *d_C, int *d_labels, long long *h_namb, float *d_diag, cudaStream_t stream);
 
 extern "C" int mdb_kmeans_assign_tc(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx,
                                     const int32_t *d_rowidx, const double *d_centers, int32_t *d_labels,
-                                    long long *h_nrecheck, void *stream) {
+                                    long long *h_nrecheck, float *d_diag, void *stream) {
     if (check_ctx(c, "mdb_kmeans_assign_tc", false)) return -1;
-    return kmeans_assign_tc_run(c, rows, D, K, d_X, ldx, d_rowidx, d_centers, d_labels, h_nrecheck, (cudaStream_t)stream);
+    return kmeans_assign_tc_run(c, rows, D, K, d_X, ldx, d_rowidx, d_centers, d_labels, h_nrecheck, d_diag,
+                                (cudaStream_t)stream);
+}
+
+int kmeans_inertia_run(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx, const int *d_rowidx,
+                       const double *d_C, const int *d_labels, const double *d_w, double *h_inertia, cudaStream_t stream);
+
+extern "C" int mdb_kmeans_inertia(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx,
+                                  const int32_t *d_rowidx, const double *d_centers, const int32_t *d_labels,
+                                  const double *d_weights, double *h_inertia, void *stream) {
+    if (check_ctx(c, "mdb_kmeans_inertia", false)) return -1;
+    return kmeans_inertia_run(c, rows, D, d_X, ldx, d_rowidx, d_centers, d_labels, d_weights, h_inertia,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int mdb_kmeans_partial_sums(mdb_ctx *c, long long nbatch, int D, int K, const double *d_X, long long ldx,

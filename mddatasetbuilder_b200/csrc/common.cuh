@@ -82,6 +82,7 @@ struct mdb_ctx {
     // operands / results of the tensor-core assignment (grow-only)
     char *tc_mem = nullptr;
     size_t tc_bytes = 0;
+    long long tc_fallbacks = 0;  // calls whose float64 self-check disagreed (whole call redone in float64)
     // optional per-launch CUDA-event timing (bench.py's live roofline measurement)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_free;

@@ -473,6 +473,40 @@ int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_
     return 0;
 }
 
+// inertia of given labels: sum_i w_i ||x_i - c_label(i)||^2 (sklearn _inertia_dense)
+__global__ void __launch_bounds__(256) k_label_dist(const double *__restrict__ X, long long ldx, long long rows,
+                                                    const int *__restrict__ rowidx, const double *__restrict__ C, int D,
+                                                    const int *__restrict__ labels, double *__restrict__ mind) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double *x = X + (rowidx ? (long long)rowidx[r] : r) * ldx;
+    const double *cc = C + (size_t)labels[r] * D;
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) {
+        const double t = x[k] - cc[k];
+        s += t * t;
+    }
+    mind[r] = s;
+}
+
+int kmeans_inertia_run(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx, const int *d_rowidx,
+                       const double *d_C, const int *d_labels, const double *d_w, double *h_inertia, cudaStream_t stream) {
+    *h_inertia = 0.0;
+    if (rows <= 0) return 0;
+    if (arena_reserve(c, align256(rows * sizeof(double)) + 1024, stream)) return -1;
+    arena_reset(c);
+    double *mind = (double *)arena_alloc(c, rows * sizeof(double));
+    double *acc = (double *)arena_alloc(c, 256);
+    if (!mind || !acc) return -1;
+    k_label_dist<<<cdiv(rows, 256), 256, 0, stream>>>(d_X, ldx, rows, d_rowidx, d_C, D, d_labels, mind);
+    MDB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), stream));
+    k_sum<<<std::min<unsigned>(cdiv(rows, 256), 1024u), 256, 0, stream>>>(mind, d_w, rows, acc);
+    c->launches += 2;
+    MDB_CUDA(cudaMemcpyAsync(h_inertia, acc, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    MDB_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+}
+
 int kmeans_sums_run(mdb_ctx *c, long long B, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
                     const double *d_w, const int *d_labels, double *d_sums, double *d_wsum, cudaStream_t stream) {
     MDB_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)K * D * sizeof(double), stream));

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) k_tc_decide(const float *__restrict__ b1,
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     // |score error| <= 2 * relerr * ||x|| * max||c||  (Cauchy-Schwarz on the centred operands) + cn rounding
-    const float bound = 2.f * relerr * sqrtf(xn2[r] * (*cmax2)) + 1e-6f * (*cmax2) + 1e-30f;
+    const float bound = 2.f * relerr * sqrtf(xn2[r] * (*cmax2)) + 2.4e-7f * (*cmax2) + 1e-30f;
     if (b2[r] - b1[r] > 2.f * bound) {
         labels[r] = i1[r];
     } else {
@@ -318,6 +318,21 @@ __global__ void __launch_bounds__(256) k_scatter_labels(const int *__restrict__ 
                                                         int *__restrict__ labels) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) labels[pos[i]] = lab[i];
+}
+
+__global__ void __launch_bounds__(256) k_sample_rows(long long rows, int ns, const int *__restrict__ rowidx,
+                                                     int *__restrict__ pos, int *__restrict__ row) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ns) return;
+    const long long p = (long long)k * rows / ns;
+    pos[k] = (int)p;
+    row[k] = rowidx ? rowidx[p] : (int)p;
+}
+
+__global__ void __launch_bounds__(256) k_count_mismatch(const int *__restrict__ pos, const int *__restrict__ lab, int n,
+                                                        const int *__restrict__ labels, int *__restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && labels[pos[i]] != lab[i]) atomicAdd(bad, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -365,7 +380,7 @@ int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_
 // Tensor-core assignment with float64 resolution of near-ties.  *h_namb (optional) receives the
 // number of rows that went through the float64 kernel.
 int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
-                         const double *d_C, int *d_labels, long long *h_namb, cudaStream_t stream) {
+                         const double *d_C, int *d_labels, long long *h_namb, float *d_diag, cudaStream_t stream) {
     if (rows <= 0) {
         if (h_namb) *h_namb = 0;
         return 0;
@@ -442,10 +457,23 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     }
     c->launches++;
     // per-product relative error of the split-fp16 contraction with fp32 accumulation over Kin terms
-    const float relerr = 4.0f * 2.3841858e-7f + (float)Kin * 1.1920929e-7f;
+    // error model of the split-fp16 contraction, relative to sum_k |x_k c_k| <= ||x|| ||c||:
+    //   operand split residuals + dropped lo*lo term            4 * 2^-22
+    //   one fp32 rounding of the running sum per MMA k-step    (Kin / 16) * 2^-23
+    //   alignment truncation inside a 16-product MMA           16 * 2^-24
+    // times a safety factor of 2.  Measured on B200 (scratch/tc_err.py): the largest observed error is
+    // 1.5e-6 (Kin = 144) to 3.5e-6 (Kin = 384) in these units, i.e. 2.7x to 4x below this bound.
+    const float relerr = 2.0f * (4.0f * 2.3841858e-7f + (float)(Kin / 16) * 1.1920929e-7f + 16.0f * 5.9604645e-8f);
     k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, relerr, d_rowidx, d_labels, amb_pos, amb_row,
                                                     namb);
     c->launches++;
+    if (d_diag) {  // diagnostics: best / second-best approximate score, index, ||x'||^2 per row, then max ||c'||^2
+        MDB_CUDA(cudaMemcpyAsync(d_diag, b1, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(d_diag + rows, b2, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(d_diag + 2 * rows, i1, rows * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(d_diag + 3 * rows, xn2, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(d_diag + 4 * rows, cmax2, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
     int h = 0;
     MDB_CUDA(cudaMemcpyAsync(&h, namb, sizeof(int), cudaMemcpyDeviceToHost, stream));
     MDB_CUDA(cudaStreamSynchronize(stream));
@@ -456,6 +484,22 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
         k_scatter_labels<<<cdiv(h, 256), 256, 0, stream>>>(amb_pos, amb_lab, h, d_labels);
         c->launches++;
         MDB_CUDA(cudaGetLastError());
+    }
+    // self-check: a strided sample of the rows is re-decided in float64; any disagreement (a violated
+    // error model) sends the whole call through the float64 kernel -- "used only if it matches"
+    const int ns = (int)std::min<long long>(rows, 4096);
+    k_sample_rows<<<cdiv(ns, 256), 256, 0, stream>>>(rows, ns, d_rowidx, amb_pos, amb_row);
+    if (kmeans_assign_run(c, ns, D, K, d_X, ldx, amb_row, d_C, amb_lab, nullptr, nullptr, nullptr, stream)) return -1;
+    MDB_CUDA(cudaMemsetAsync(namb, 0, sizeof(int), stream));
+    k_count_mismatch<<<cdiv(ns, 256), 256, 0, stream>>>(amb_pos, amb_lab, ns, d_labels, namb);
+    c->launches += 2;
+    int bad = 0;
+    MDB_CUDA(cudaMemcpyAsync(&bad, namb, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MDB_CUDA(cudaStreamSynchronize(stream));
+    if (bad) {
+        c->tc_fallbacks++;
+        if (h_namb) *h_namb = rows;
+        return kmeans_assign_run(c, rows, D, K, d_X, ldx, d_rowidx, d_C, d_labels, nullptr, nullptr, nullptr, stream);
     }
     return 0;
 }

@@ -300,7 +300,7 @@ class Engine:
         _lib.check(rc, "mdb_kmeans_assign")
         return labels, (inertia.value if want_inertia else None), mind
 
-    def kmeans_assign_tc(self, X, centers, rowidx=None):
+    def kmeans_assign_tc(self, X, centers, rowidx=None, diag=False):
         """Labels via the tensor-core screening pass + float64 re-check of near-ties.
         Returns (labels, number of rows re-checked in float64)."""
         torch = _torch()
@@ -309,10 +309,21 @@ class Engine:
         rows = int(rowidx.numel()) if rowidx is not None else int(X.shape[0])
         labels = torch.empty(rows, dtype=torch.int32, device=self.device)
         nre = C.c_longlong(0)
+        dg = torch.empty(4 * rows + 1, dtype=torch.float32, device=self.device) if diag else None
         rc = self.L.mdb_kmeans_assign_tc(self.ctx, rows, D, K, _ptr(X), int(X.stride(0)), _ptr(rowidx), _ptr(centers),
-                                         _ptr(labels), C.byref(nre), self.stream())
+                                         _ptr(labels), C.byref(nre), _ptr(dg), self.stream())
         _lib.check(rc, "mdb_kmeans_assign_tc")
+        if diag:
+            return labels, int(nre.value), dg
         return labels, int(nre.value)
+
+    def kmeans_inertia(self, X, centers, labels, rowidx=None, weights=None):
+        rows = int(labels.numel())
+        v = C.c_double(0.0)
+        rc = self.L.mdb_kmeans_inertia(self.ctx, rows, int(X.shape[1]), _ptr(X), int(X.stride(0)), _ptr(rowidx),
+                                       _ptr(centers), _ptr(labels), _ptr(weights), C.byref(v), self.stream())
+        _lib.check(rc, "mdb_kmeans_inertia")
+        return v.value
 
     def kmeans_partial_sums(self, X, labels, K, rowidx=None, weights=None, out=None):
         torch = _torch()

@@ -226,7 +226,12 @@ class MiniBatchKMeansB200:
         self.cluster_centers_ = centers
         self.counts_ = weight_sums
         self.n_steps_ = i + 1
-        self.labels_, self.inertia_, _ = eng.kmeans_assign(X, centers, want_inertia=True)
+        # final full-data assignment: tensor-core screening + float64 re-check (same labels as float64)
+        if D <= 128 and n_local >= 4096:
+            self.labels_, self.n_rechecked_ = eng.kmeans_assign_tc(X, centers)
+            self.inertia_ = eng.kmeans_inertia(X, centers, self.labels_)
+        else:
+            self.labels_, self.inertia_, _ = eng.kmeans_assign(X, centers, want_inertia=True)
         if d is not None:
             t = torch.tensor([self.inertia_], dtype=torch.float64, device=eng.device)
             d.all_reduce(t)
