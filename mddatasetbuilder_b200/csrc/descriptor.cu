@@ -232,137 +232,179 @@ struct TriSmem {
     double p[NMAX];
     int z[NMAX];
     int t[NMAX];
+    double L[3];
     int n;
 };
 
-template <int NMAX, int WARPS>
+template <int LPM>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = LPM / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// LPM lanes cooperate on one matrix, so a warp works on 32 / LPM matrices at once (small clusters
+// would otherwise leave most lanes idle).  The gather is warp-cooperative per target; matrix build
+// and tridiagonalisation run concurrently in the lane groups, in lock step to the largest n.
+template <int NMAX, int WARPS, int LPM>
 __global__ void __launch_bounds__(WARPS * 32) k_tridiag(const __grid_constant__ DescParams P,
                                                         const int *__restrict__ list,  // target ordinals of this bucket
                                                         int nlist, int slot0, int nslots, double *__restrict__ dsc,
                                                         double *__restrict__ esc, int *__restrict__ nsc) {
+    constexpr int G = 32 / LPM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TriSmem<NMAX> *S = reinterpret_cast<TriSmem<NMAX> *>(smem_raw) + (threadIdx.x >> 5);
+    TriSmem<NMAX> *Sw = reinterpret_cast<TriSmem<NMAX> *>(smem_raw) + (threadIdx.x >> 5) * G;
     const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * WARPS + (threadIdx.x >> 5);  // slot within this chunk
-    if (s >= nslots) return;
-    const int ord = list[slot0 + s];
-    const int g = P.targets ? P.targets[ord] : ord;
-    const int f = g / P.N, a = g - f * P.N;
-    const FrameGeom &G = P.geom[f];
-    const double *pos = P.pos + (size_t)f * P.N * 3;
-    if (lane == 0) S->n = 0;
-    __syncwarp();
-    const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
-    const double L[3] = {G.ortho[0], G.ortho[4], G.ortho[8]};
-    sphere_scan(P, f, a, [&](int j, int tj) {
-        const int k = atomicAdd(&S->n, 1);
-        if (k < NMAX) {
+    const int grp = lane / LPM, gl = lane % LPM;
+    const int sw0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * G;  // first slot of this warp
+    if (sw0 >= nslots) return;
+    for (int g = 0; g < G; ++g) {
+        const int sg = sw0 + g;
+        if (sg >= nslots) break;
+        TriSmem<NMAX> *Sg = Sw + g;
+        const int ord = list[slot0 + sg];
+        const int gt = P.targets ? P.targets[ord] : ord;
+        const int f = gt / P.N, a = gt - f * P.N;
+        const FrameGeom &G0 = P.geom[f];
+        const double *pos = P.pos + (size_t)f * P.N * 3;
+        if (lane == 0) Sg->n = 0;
+        __syncwarp();
+        const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
+        const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
+        sphere_scan(P, f, a, [&](int j, int tj) {
+            const int k = atomicAdd(&Sg->n, 1);
+            if (k < NMAX) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double D = pos[(size_t)j * 3 + c] - pa[c];
-                if (P.periodic) D -= L[c] * rint(D / L[c]);
-                S->vec[k][c] = D;
+                for (int c = 0; c < 3; ++c) {
+                    double D = pos[(size_t)j * 3 + c] - pa[c];
+                    if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
+                    Sg->vec[k][c] = D;
+                }
+                Sg->z[k] = P.Z[tj];
+                Sg->t[k] = tj;
             }
-            S->z[k] = P.Z[tj];
-            S->t[k] = tj;
+        });
+        if (lane == 0) {
+            Sg->L[0] = Lg[0];
+            Sg->L[1] = Lg[1];
+            Sg->L[2] = Lg[2];
         }
-    });
-    __syncwarp();
-    int n = S->n;
+        __syncwarp();
+    }
+    TriSmem<NMAX> *S = Sw + grp;
+    const int s = sw0 + grp;
+    const bool valid = s < nslots;
+    int n = valid ? S->n : 0;
     if (n > NMAX) {
-        if (lane == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
         n = NMAX;
     }
-    // Coulomb matrix (datasetbuilder.py:341-348); pair vectors are differences of the target-centred
-    // minimum-image vectors, reduced once more for boxes shorter than twice the cluster diameter
-    for (int i = lane; i < n; i += 32) {
-        S->A[i][i] = P.diag[S->t[i]];
-        const double xi = S->vec[i][0], yi = S->vec[i][1], zi = S->vec[i][2];
-        const double zz = (double)S->z[i];
-        for (int j = 0; j < i; ++j) {
-            double dx = S->vec[j][0] - xi, dy = S->vec[j][1] - yi, dz = S->vec[j][2] - zi;
+    // Coulomb matrix (datasetbuilder.py:341-348).  The n(n-1)/2 pairs are dealt evenly to the lanes of
+    // the group: pair p -> (i, j), j < i.  Both vectors lie within +-L/2 of the target, so one
+    // conditional shift per axis gives the minimum image.
+    for (int i = gl; i < n; i += LPM) S->A[i][i] = P.diag[S->t[i]];
+    if (n > 1) {
+        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
+        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
+        const int npair = n * (n - 1) / 2;
+        for (int p = gl; p < npair; p += LPM) {
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (i * (i - 1) / 2 > p) --i;
+            while ((i + 1) * i / 2 <= p) ++i;
+            const int j = p - i * (i - 1) / 2;
+            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
             if (P.periodic) {
-                dx -= L[0] * rint(dx / L[0]);
-                dy -= L[1] * rint(dy / L[1]);
-                dz -= L[2] * rint(dz / L[2]);
+                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
             }
             const double r2 = dx * dx + dy * dy + dz * dz;
-            double m = r2 > 0.0 ? zz * (double)S->z[j] * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-            S->A[i][j] = m;
-            S->A[j][i] = m;
+            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+            S->A[i][j] = mv;
+            S->A[j][i] = mv;
         }
     }
     __syncwarp();
+    int nmax = n;
+#pragma unroll
+    for (int o = 16; o >= LPM; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
     // Householder tridiagonalisation, column k eliminates A[k+2.., k]
     double *dout = dsc + s;
     double *eout = esc + s;
-    for (int k = 0; k < n - 1; ++k) {
+    for (int k = 0; k < nmax - 1; ++k) {
+        const bool act = k < n - 1;
         const int m = n - k - 1;  // length of the sub-column x = A[k+1.., k]
-        if (m == 1) {
-            if (lane == 0) {
-                dout[(size_t)k * nslots] = S->A[k][k];
-                eout[(size_t)k * nslots] = S->A[k + 1][k];
-            }
-            continue;
-        }
         double sc = 0.0;
-        for (int r = lane; r < m; r += 32) sc += fabs(S->A[k + 1 + r][k]);
-        sc = warp_sum(sc);
-        if (sc == 0.0) {
-            if (lane == 0) {
-                dout[(size_t)k * nslots] = S->A[k][k];
-                eout[(size_t)k * nslots] = 0.0;
-            }
-            continue;
+        if (act && m > 1)
+            for (int r = gl; r < m; r += LPM) sc += fabs(S->A[k + 1 + r][k]);
+        sc = group_sum<LPM>(sc);
+        const bool doit = act && m > 1 && sc != 0.0;
+        if (act && !doit && gl == 0) {
+            dout[(size_t)k * nslots] = S->A[k][k];
+            eout[(size_t)k * nslots] = (m == 1) ? S->A[k + 1][k] : 0.0;
         }
         double hh = 0.0;
-        const double isc = 1.0 / sc;
-        for (int r = lane; r < m; r += 32) {
-            const double x = S->A[k + 1 + r][k] * isc;
-            S->v[r] = x;
-            hh += x * x;
+        if (doit) {
+            const double isc = 1.0 / sc;
+            for (int r = gl; r < m; r += LPM) {
+                const double x = S->A[k + 1 + r][k] * isc;
+                S->v[r] = x;
+                hh += x * x;
+            }
         }
-        hh = warp_sum(hh);
+        hh = group_sum<LPM>(hh);
         __syncwarp();
-        const double f0 = S->v[0];
-        const double gg = f0 >= 0.0 ? -sqrt(hh) : sqrt(hh);
-        hh -= f0 * gg;
+        double f0 = 0.0, gg = 0.0;
+        if (doit) {
+            f0 = S->v[0];
+            gg = f0 >= 0.0 ? -sqrt(hh) : sqrt(hh);
+            hh -= f0 * gg;
+        }
         __syncwarp();
-        if (lane == 0) {
+        if (doit && gl == 0) {
             S->v[0] = f0 - gg;
             dout[(size_t)k * nslots] = S->A[k][k];
             eout[(size_t)k * nslots] = sc * gg;
         }
         __syncwarp();
         // p = A22 v / h ; K = v.p / (2h) ; w = p - K v ; A22 -= v w^T + w v^T
-        const double ih = 1.0 / hh;
+        const double ih = doit ? 1.0 / hh : 0.0;
         double vp = 0.0;
-        for (int r = lane; r < m; r += 32) {
-            const double *row = &S->A[k + 1 + r][k + 1];
-            double acc = 0.0;
-            for (int c = 0; c < m; ++c) acc += row[c] * S->v[c];
-            acc *= ih;
-            S->p[r] = acc;
-            vp += acc * S->v[r];
-        }
-        vp = warp_sum(vp);
+        if (doit)
+            for (int r = gl; r < m; r += LPM) {
+                const double *row = &S->A[k + 1 + r][k + 1];
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // independent chains hide the DFMA latency
+                int c = 0;
+                for (; c + 4 <= m; c += 4) {
+                    acc0 += row[c] * S->v[c];
+                    acc1 += row[c + 1] * S->v[c + 1];
+                    acc2 += row[c + 2] * S->v[c + 2];
+                    acc3 += row[c + 3] * S->v[c + 3];
+                }
+                for (; c < m; ++c) acc0 += row[c] * S->v[c];
+                const double acc = ((acc0 + acc1) + (acc2 + acc3)) * ih;
+                S->p[r] = acc;
+                vp += acc * S->v[r];
+            }
+        vp = group_sum<LPM>(vp);
         const double K = vp * 0.5 * ih;
         __syncwarp();
-        for (int r = lane; r < m; r += 32) S->p[r] -= K * S->v[r];
+        if (doit)
+            for (int r = gl; r < m; r += LPM) S->p[r] -= K * S->v[r];
         __syncwarp();
-        for (int r = lane; r < m; r += 32) {
-            double *row = &S->A[k + 1 + r][k + 1];
-            const double vr = S->v[r], wr = S->p[r];
-            for (int c = 0; c < m; ++c) row[c] -= vr * S->p[c] + wr * S->v[c];
-        }
+        if (doit)
+            for (int r = gl; r < m; r += LPM) {
+                double *row = &S->A[k + 1 + r][k + 1];
+                const double vr = S->v[r], wr = S->p[r];
+#pragma unroll 4
+                for (int c = 0; c < m; ++c) row[c] -= vr * S->p[c] + wr * S->v[c];
+            }
         __syncwarp();
     }
-    if (lane == 0) {
+    if (valid && gl == 0) {
         if (n > 0) dout[(size_t)(n - 1) * nslots] = S->A[n - 1][n - 1];
         nsc[s] = n;
     }
-    // element composition for the padding (recomputed here so the QL kernel is self-contained)
-    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -402,14 +444,14 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
                     break;
                 }
                 double g = (d[l + 1][tid] - d[l][tid]) / (2.0 * e[l][tid]);
-                double r = hypot(g, 1.0);
+                double r = sqrt(g * g + 1.0);
                 g = d[m][tid] - d[l][tid] + e[l][tid] / (g + (g >= 0.0 ? fabs(r) : -fabs(r)));
                 double sn = 1.0, c = 1.0, p = 0.0;
                 int i;
                 for (i = m - 1; i >= l; --i) {
                     double f = sn * e[i][tid];
                     const double b = c * e[i][tid];
-                    r = hypot(f, g);
+                    r = sqrt(f * f + g * g);
                     e[i + 1][tid] = r;
                     if (r == 0.0) {
                         d[i + 1][tid] -= p;
@@ -583,19 +625,20 @@ int members_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_c
     return 0;
 }
 
-template <int NMAX, int WARPS, int QTHREADS>
+template <int NMAX, int WARPS, int LPM, int QTHREADS>
 static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int ofs, int cnt, double *dsc, double *esc,
                       int *nsc, int chunk, const int *d_counts, const int *d_padorder, const double *d_padval,
                       const int *d_maxcount, int D, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream) {
-    const size_t smem_tri = sizeof(TriSmem<NMAX>) * WARPS;
+    constexpr int G = 32 / LPM;
+    const size_t smem_tri = sizeof(TriSmem<NMAX>) * WARPS * G;
     const size_t smem_ql = (size_t)2 * NMAX * QTHREADS * sizeof(double);
-    MDB_CUDA(cudaFuncSetAttribute(k_tridiag<NMAX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+    MDB_CUDA(cudaFuncSetAttribute(k_tridiag<NMAX, WARPS, LPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
     MDB_CUDA(cudaFuncSetAttribute(k_tql<NMAX, QTHREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ql));
     for (int s0 = 0; s0 < cnt; s0 += chunk) {
         const int ns = std::min(chunk, cnt - s0);
         {
             ProfScope ps(c, "k_tridiag", stream);
-            k_tridiag<NMAX, WARPS><<<cdiv(ns, WARPS), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc, esc, nsc);
+            k_tridiag<NMAX, WARPS, LPM><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc, esc, nsc);
         }
         {
             ProfScope ps(c, "k_tql", stream);
@@ -669,16 +712,16 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     MDB_CUDA(cudaMemcpyAsync(d_book + 10, ofs, sizeof(ofs), cudaMemcpyHostToDevice, stream));
     k_bucket_fill<<<cdiv(T, 256), 256, 0, stream>>>(d_nsum, T, d_book + 10, d_book + 5, d_list);
     c->launches++;
-    if (hb[0] && run_bucket<16, 8, 128>(c, P, d_list, ofs[0], hb[0], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
+    if (hb[0] && run_bucket<16, 8, 8, 128>(c, P, d_list, ofs[0], hb[0], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
                                        d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
         return -1;
-    if (hb[1] && run_bucket<32, 8, 128>(c, P, d_list, ofs[1], hb[1], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
+    if (hb[1] && run_bucket<32, 5, 16, 128>(c, P, d_list, ofs[1], hb[1], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
                                        d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
         return -1;
-    if (hb[2] && run_bucket<64, 4, 64>(c, P, d_list, ofs[2], hb[2], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
+    if (hb[2] && run_bucket<64, 4, 32, 64>(c, P, d_list, ofs[2], hb[2], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
                                       d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
         return -1;
-    if (hb[3] && run_bucket<128, 1, 64>(c, P, d_list, ofs[3], hb[3], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
+    if (hb[3] && run_bucket<128, 1, 32, 64>(c, P, d_list, ofs[3], hb[3], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
                                        d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
         return -1;
     return 0;

@@ -461,7 +461,7 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     //   operand split residuals + dropped lo*lo term            4 * 2^-22
     //   one fp32 rounding of the running sum per MMA k-step    (Kin / 16) * 2^-23
     //   alignment truncation inside a 16-product MMA           16 * 2^-24
-    // times a safety factor of 2.  Measured on B200 (scratch/tc_err.py): the largest observed error is
+    // times a safety factor of 2.  Measured on B200 (tools/tc_error_probe.py): the largest observed error is
     // 1.5e-6 (Kin = 144) to 3.5e-6 (Kin = 384) in these units, i.e. 2.7x to 4x below this bound.
     const float relerr = 2.0f * (4.0f * 2.3841858e-7f + (float)(Kin / 16) * 1.1920929e-7f + 16.0f * 5.9604645e-8f);
     k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, relerr, d_rowidx, d_labels, amb_pos, amb_row,
