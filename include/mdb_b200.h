@@ -124,7 +124,10 @@ int mdb_analyze_frames(mdb_ctx *ctx, int nframes, int natoms, const double *d_po
  * page-locked for full PCIe bandwidth. */
 int mdb_analyze_frames_host(mdb_ctx *ctx, int nframes, int natoms, const double *h_pos,
                             const double *h_cell, const uint8_t *h_types, int periodic,
-                            int32_t *h_ell, uint64_t *h_keys, int32_t *h_labels);
+                            int32_t *h_ell, int ell_width, uint64_t *h_keys, int32_t *h_labels);
+/* ell_width: slots per row of h_ell -- 0 or max_bonds for the full rows, 4 to return
+ * [F][N][4] (lossless whenever every element's max valence is <= 4, e.g. C/H/O/N: the cleanup
+ * guarantees degree <= MaxBonds; a longer row is an error). */
 
 /* ---- K5: element composition of the cutoff sphere -----------------------------
  * Replaces, per target atom, `distances = get_distances(a, all, mic=True);

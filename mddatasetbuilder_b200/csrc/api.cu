@@ -346,16 +346,28 @@ extern "C" int mdb_profile_read(mdb_ctx *c, char *buf, size_t cap) {
 // ---------------------------------------------------------------------------------------------
 // host-buffer pipeline: H2D(k+1) | compute(k) | D2H(k-1) on three streams, double buffered.
 // ---------------------------------------------------------------------------------------------
+// ELL rows narrowed to the first `w` slots (post-cleanup degrees are bounded by the largest valence of
+// the element table, e.g. 4 for C/H/O); flags an error if a row holds more
+__global__ void __launch_bounds__(256) k_ell_narrow(const int32_t *__restrict__ ell, int maxb, int w, long long fn,
+                                                    int32_t *__restrict__ out, BondStats *stats) {
+    long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= fn) return;
+    const int4 q = *reinterpret_cast<const int4 *>(ell + a * maxb);
+    if (ell[a * maxb + w] >= 0) atomicExch(&stats->err, MDB_ERR_CSR_OVERFLOW);
+    *reinterpret_cast<int4 *>(out + a * 4) = q;
+}
+
 struct PipeBuf {
     double *pos = nullptr;
     int32_t *ell = nullptr;
+    int32_t *ell4 = nullptr;
     uint64_t *keys = nullptr;
     int32_t *labels = nullptr;
 };
 
 extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
-                                       const uint8_t *h_types, int periodic, int32_t *h_ell, uint64_t *h_keys,
-                                       int32_t *h_labels) {
+                                       const uint8_t *h_types, int periodic, int32_t *h_ell, int ell_width,
+                                       uint64_t *h_keys, int32_t *h_labels) {
     if (check_ctx(c, "mdb_analyze_frames_host")) return -1;
     if (nframes <= 0 || natoms <= 0) return 0;
     const int maxb = c->opt_max_bonds;
@@ -363,7 +375,13 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
     const size_t cn = (size_t)per * natoms;
     const size_t sz_pos = align256(cn * 3 * sizeof(double)), sz_ell = align256(cn * maxb * sizeof(int32_t)),
                  sz_keys = align256(cn * sizeof(uint64_t)), sz_lab = align256(cn * sizeof(int32_t));
-    const size_t need = sz_pos + sz_ell + sz_keys + sz_lab;
+    if (ell_width != 0 && ell_width != 4 && ell_width != maxb) {
+        mdb_set_error("mdb_analyze_frames_host: ell_width must be 0 (= max_bonds), 4 or max_bonds");
+        return -1;
+    }
+    const bool narrow = ell_width == 4 && maxb != 4;
+    const size_t sz_ell4 = narrow ? align256(cn * 4 * sizeof(int32_t)) : 0;
+    const size_t need = sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4;
     PipeBuf b[2];
     for (int k = 0; k < 2; ++k) {
         if (c->pipe_cap[k] < need) {
@@ -379,6 +397,7 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
         b[k].ell = (int32_t *)(m + sz_pos);
         b[k].keys = (uint64_t *)(m + sz_pos + sz_ell);
         b[k].labels = (int32_t *)(m + sz_pos + sz_ell + sz_keys);
+        b[k].ell4 = (int32_t *)(m + sz_pos + sz_ell + sz_keys + sz_lab);
     }
     if (c->pipe_types_cap < (size_t)natoms) {
         MDB_CUDA(cudaDeviceSynchronize());
@@ -406,9 +425,15 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
             cudaDeviceSynchronize();
             return -1;
         }
+        if (h_ell && narrow) {
+            k_ell_narrow<<<cdiv((long long)n, 256), 256, 0, s_c>>>(B.ell, maxb, 4, (long long)n, B.ell4, c->d_stats);
+            c->launches++;
+        }
         MDB_CUDA(cudaEventRecord(c->pipe_comp[k], s_c));
         MDB_CUDA(cudaStreamWaitEvent(s_out, c->pipe_comp[k], 0));
-        if (h_ell)
+        if (h_ell && narrow)
+            MDB_CUDA(cudaMemcpyAsync(h_ell + o * 4, B.ell4, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        else if (h_ell)
             MDB_CUDA(cudaMemcpyAsync(h_ell + o * maxb, B.ell, n * maxb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
         if (h_keys) MDB_CUDA(cudaMemcpyAsync(h_keys + o, B.keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_out));
         if (h_labels)

@@ -10,6 +10,8 @@
 // of either bound is re-evaluated in double with the oracle's operation order
 // (__dmul_rn/__dadd_rn, no FMA contraction), so the bond set is bit-identical to the CPU
 // restatement.  The cleanup runs entirely in double.
+#include <algorithm>
+
 #include "common.cuh"
 
 #define BOND_THREADS 128
@@ -480,6 +482,44 @@ __device__ void resolve_atom(const BondParams &P, const FrameGeom &G, unsigned *
     }
 }
 
+// One round of the same rule with many blocks per frame (large frames: a single block per frame would
+// leave the GPU idle).  Atoms that are still blocked stay pending for the next round / for k_cleanup.
+template <int MAXB>
+__global__ void __launch_bounds__(256) k_cleanup_round(const __grid_constant__ BondParams P) {
+    const int f = blockIdx.y;
+    const int nv = P.nviol[f];
+    const int N = P.N;
+    const FrameGeom &G = P.geom[f];
+    int *viol = P.viol + (size_t)f * N;
+    int *dirty = P.dirty + (size_t)f * N;
+    int *ndirty = P.ndirty + f;
+    unsigned *ell = reinterpret_cast<unsigned *>(P.ell) + (size_t)f * N * MAXB;
+    const double *pos = P.pos + (size_t)f * N * 3;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nv; t += gridDim.x * blockDim.x) {
+        const int v = viol[t];
+        if (v < 0) continue;
+        unsigned e[MAXB];
+        load_row<MAXB>(ell, v, e);
+        unsigned s0[MAXB];
+#pragma unroll
+        for (int s = 0; s < MAXB; ++s) {
+            const int w = (int)(e[s] & MDB_IDX_MASK);
+            const bool look = e[s] != EMPTY_SLOT && !(e[s] & MDB_TOMB) && w < v;
+            s0[s] = look ? __ldcg(&ell[(size_t)w * MAXB]) : EMPTY_SLOT;
+        }
+        bool blocked = false;
+#pragma unroll
+        for (int s = 0; s < MAXB; ++s) blocked |= (s0[s] != EMPTY_SLOT && (s0[s] & MDB_PEND));
+        if (blocked) continue;
+        __threadfence();
+        load_row<MAXB>(ell, v, e);
+        resolve_atom<MAXB>(P, G, ell, pos, v, e, dirty, ndirty);
+        __threadfence();
+        atomicAnd(&ell[(size_t)v * MAXB], ~MDB_PEND);
+        viol[t] = ~v;
+    }
+}
+
 template <int MAXB>
 __global__ void __launch_bounds__(256) k_cleanup(const __grid_constant__ BondParams P) {
     const int f = blockIdx.x;
@@ -514,6 +554,10 @@ __global__ void __launch_bounds__(256) k_cleanup(const __grid_constant__ BondPar
                 ++pending;
                 continue;
             }
+            // a smaller neighbour may have finished between the two loads above: its deletions are
+            // visible once its PEND flag reads clear, so take a fresh copy of the row before resolving
+            __threadfence();
+            load_row<MAXB>(ell, v, e);
             resolve_atom<MAXB>(P, G, ell, pos, v, e, dirty, ndirty);
             __threadfence();
             atomicAnd(&ell[(size_t)v * MAXB], ~MDB_PEND);
@@ -601,6 +645,19 @@ int bonds_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const 
     }
     {
         ProfScope ps(ctx, "k_cleanup", stream);
+        // frames too large for one block each: a few wide rounds first, the single-block kernel then
+        // finishes the (rare) longer dependency chains and compacts the dirty rows
+        const long long per_sm = (long long)nframes * 1;
+        if (per_sm < 148 && natoms >= 50000) {
+            dim3 rg((unsigned)std::min<long long>(128, std::max<long long>(1, 296 / nframes)), nframes);
+            for (int round = 0; round < 3; ++round) {
+                if (maxb == 8)
+                    k_cleanup_round<8><<<rg, 256, 0, stream>>>(P);
+                else
+                    k_cleanup_round<16><<<rg, 256, 0, stream>>>(P);
+                ctx->launches++;
+            }
+        }
         if (maxb == 8)
             k_cleanup<8><<<nframes, 256, 0, stream>>>(P);
         else

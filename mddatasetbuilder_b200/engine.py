@@ -354,7 +354,8 @@ class Engine:
                                             _ptr(wsum), self.stream())
         _lib.check(rc, "mdb_kmeans_apply_update")
 
-    def analyze_host(self, pos, cell, types, periodic=True, want_keys=True, want_labels=True, out=None):
+    def analyze_host(self, pos, cell, types, periodic=True, want_keys=True, want_labels=True, out=None,
+                     ell_width=0):
         """Host-buffer path (e2e): numpy / pinned tensors in, numpy out; H2D and D2H copies
         are pipelined inside the library."""
         torch = _torch()
@@ -370,7 +371,7 @@ class Engine:
         out = out or {}
         ell = out.get("ell")
         if ell is None:
-            ell = np.empty((F, N, self.max_bonds), dtype=np.int32)
+            ell = np.empty((F, N, ell_width or self.max_bonds), dtype=np.int32)
         keys = out.get("keys") if want_keys else None
         if want_keys and keys is None:
             keys = np.empty((F, N), dtype=np.uint64)
@@ -384,7 +385,7 @@ class Engine:
             return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else C.c_void_p(a.ctypes.data)
 
         rc = self.L.mdb_analyze_frames_host(self.ctx, int(F), int(N), p(pos_np), _np_ptr(cells), p(types_np),
-                                            int(bool(periodic)), p(ell), p(keys), p(labels))
+                                            int(bool(periodic)), p(ell), int(ell_width), p(keys), p(labels))
         _lib.check(rc, "mdb_analyze_frames_host")
         return {"ell": ell, "keys": keys, "labels": labels}
 

@@ -143,6 +143,10 @@ def test_host_path_matches_device_path(engine):
     assert np.array_equal(dev["ell"].cpu().numpy(), host["ell"])
     assert np.array_equal(dev["keys"].cpu().numpy().view(np.uint64), host["keys"])
     assert np.array_equal(dev["labels"].cpu().numpy(), host["labels"])
+    # 4-slot rows (C/H/O: degree <= max valence 4 after the cleanup) carry the same bonds
+    narrow = engine.analyze_host(frames, s.cell(), s.types, ell_width=4)
+    full = dev["ell"].cpu().numpy()
+    assert narrow["ell"].shape[-1] == 4 and np.array_equal(narrow["ell"], full[:, :, :4]) and (full[:, :, 4:] < 0).all()
 
 
 def test_bondfile_keys(engine):
