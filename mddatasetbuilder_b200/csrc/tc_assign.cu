@@ -12,10 +12,12 @@
 //
 // One CTA = one 128-row tile against all centroids: A' stays in shared memory (TMA, 128B swizzle),
 // B' tiles of 128 centroids stream through a TMA/mbarrier ring, accumulators are double-buffered
-// in TMEM (2 x 128 columns), 4 epilogue warps read them back with tcgen05.ld.
+// in TMEM (2 x 128 columns), 8 epilogue warps (two per TMEM lane quarter, one column half each) read
+// them back with tcgen05.ld.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -25,7 +27,7 @@
 #define TC_BN 128
 #define TC_KCH 64                      // fp16 elements per 128-byte swizzle row
 #define TC_CHUNK_BYTES (TC_BM * 128)   // one [128 rows][64 elem] slab
-#define TC_THREADS 192
+#define TC_THREADS 320
 #define TC_MAXCH 6                     // 3*Kd <= 384
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,20 +83,36 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+#define TC_TMEM_LD32(R, ADDR)                                                                                         \
+    asm volatile(                                                                                                    \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+        : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), \
+          "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]),      \
+          "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]),     \
+          "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                   \
+        : "r"(ADDR))
+
 struct TcParams {
-    int rows, K, Kin, nch, stages;
+    int rows, K, stages;
     const float *cn;   // [K] squared norm of the centred centroids
     float *best1, *best2;
     int *idx1;
+    long long *trace;   // optional [ntiles][8] clock64 stamps of CTA 0 (tools/tc_trace.py), else nullptr
 };
 
+// KD16 = padded feature width / 16: the inner dimension is 3 * 16 * KD16, i.e. 3 * KD16 MMAs per tile
+template <int KD16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_assign_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve: A slabs | B ring | barriers | cn staging | tmem base
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     unsigned char *gen = smem + (sbase - smem_u32(smem));
-    const int nch = P.nch, S = P.stages;
+    constexpr int nch = (3 * 16 * KD16 + TC_KCH - 1) / TC_KCH;
+    constexpr int NMMA = 3 * KD16;
+    const int S = P.stages;
     const uint32_t sA = sbase;
     const uint32_t sB = sA + (uint32_t)nch * TC_CHUNK_BYTES;
     const uint32_t tail = sB + (uint32_t)S * nch * TC_CHUNK_BYTES;
@@ -105,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t bar_tfull = bar_bempty + 8 * 4;   // [2]
     const uint32_t bar_tempty = bar_tfull + 16;      // [2]
     float *cn_s = reinterpret_cast<float *>(gtail + 128);          // [2][128]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 128 + 1024);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 128 + 1536);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * TC_BM;
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 4);
+            mbar_init(bar_tempty + 8 * a, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -150,83 +168,137 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ===== MMA issuer =====
         // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
         const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        mbar_wait(bar_afull, 0);
-        for (int t = 0; t < ntiles; ++t) {
-            const int s = t % S;
-            const uint32_t ph = (uint32_t)(t / S) & 1u;
-            const int a = t & 1;
-            const uint32_t aph = (uint32_t)(t >> 1) & 1u;
-            mbar_wait(bar_tempty + 8 * a, aph ^ 1u);
-            mbar_wait(bar_bfull + 8 * s, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                uint32_t first = 0;
-                for (int c = 0; c < nch; ++c) {
-                    const int kvalid = min(TC_KCH, P.Kin - c * TC_KCH);
-                    const int ksteps = (kvalid + 15) / 16;
-                    const uint64_t da = umma_desc(sA + c * TC_CHUNK_BYTES);
-                    const uint64_t db = umma_desc(sB + (s * nch + c) * TC_CHUNK_BYTES);
-                    for (int k = 0; k < ksteps; ++k) {
-                        // advance 16 elements = 32 bytes inside the swizzle row
-                        umma_f16(tmem_base + (uint32_t)a * TC_BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first);
-                        first = 1;
-                    }
+        // one thread runs the whole role: no warp-collective work between the issues, and the operand
+        // descriptors of MMA i differ from the slab bases only by compile-time offsets
+        if (lane == 0) {
+            constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
+            const uint32_t alo = ((sA & 0x3FFFFu) >> 4) | (1u << 16);
+            mbar_wait(bar_afull, 0);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int a = t & 1;
+                const uint32_t aph = (uint32_t)(t >> 1) & 1u;
+                const bool tr = P.trace && blockIdx.x == 0;
+                if (tr) P.trace[t * 8 + 0] = clock64();
+                mbar_wait(bar_tempty + 8 * a, aph ^ 1u);
+                if (tr) P.trace[t * 8 + 1] = clock64();
+                mbar_wait(bar_bfull + 8 * s, ph);
+                if (tr) P.trace[t * 8 + 2] = clock64();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t blo = (((sB + (uint32_t)(s * nch) * TC_CHUNK_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+                const uint32_t tacc = tmem_base + (uint32_t)a * TC_BN;
+#pragma unroll
+                for (int i = 0; i < NMMA; ++i) {
+                    // chunk i / 4, then 16 elements = 32 bytes (2 descriptor units) per step inside the swizzle row
+                    const uint32_t off = (uint32_t)((i >> 2) * (TC_CHUNK_BYTES >> 4) + (i & 3) * 2);
+                    const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(alo + off);
+                    const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(blo + off);
+                    umma_f16(tacc, da, db, idesc, (uint32_t)(i > 0));
                 }
                 umma_commit(bar_bempty + 8 * s);
                 umma_commit(bar_tfull + 8 * a);
+                if (tr) P.trace[t * 8 + 3] = clock64();
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        // ===== epilogue: warps 2..9; warp % 4 selects the TMEM lane quarter, (warp - 2) / 4 the column half =====
         const int q = warp & 3;
-        const int e = (warp - 2) * 32 + lane;     // 0..127: staging index for cn
+        const int half = (warp - 2) >> 2;
+        const int e = (warp - 2) * 32 + lane;     // 0..255: staging index for cn (first 128 used)
         const int myrow = row0 + q * 32 + lane;
-        float b1 = FLT_MAX, b2 = FLT_MAX;
-        int i1 = 0;
+        float b1[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX}, b2[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};
+        int i1[4] = {0, 0, 0, 0};
+        // cn of tile t sits in cn_s[t & 1]; the slice for tile t + 1 is fetched into a register while tile t
+        // is processed, so its global-load latency stays off the per-tile critical path
+        if (e < TC_BN) cn_s[e] = (e < P.K) ? P.cn[e] : FLT_MAX;
         for (int t = 0; t < ntiles; ++t) {
             const int a = t & 1;
             const uint32_t aph = (uint32_t)(t >> 1) & 1u;
             const int col0 = t * TC_BN;
-            // the staging buffer `a` was last read two tiles ago; the barrier below orders the reuse
-            cn_s[a * TC_BN + e] = (col0 + e < P.K) ? P.cn[col0 + e] : FLT_MAX;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // orders: cn_s[a] written (previous iteration) -> read below; cn_s[a ^ 1] read (tile t - 1) -> rewritten below
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float cn_next = FLT_MAX;
+            if (e < TC_BN && col0 + TC_BN + e < P.K) cn_next = P.cn[col0 + TC_BN + e];
+            const bool tr = P.trace && blockIdx.x == 0 && threadIdx.x == 64;
+            if (tr) P.trace[t * 8 + 4] = clock64();
             mbar_wait(bar_tfull + 8 * a, aph);
+            if (tr) P.trace[t * 8 + 5] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int j = 0; j < TC_BN / 32; ++j) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + j * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const float *cnp = cn_s + a * TC_BN + j * 32;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float sc = fmaf(-2.0f, __uint_as_float(r[i]), cnp[i]);
-                    if (sc < b1) {
-                        b2 = b1;
-                        b1 = sc;
-                        i1 = col0 + j * 32 + i;
-                    } else if (sc < b2)
-                        b2 = sc;
-                }
-            }
+            // this warp's 32 lanes x 64 columns leave TMEM in one go; the accumulator is handed back to the
+            // MMA warp before any arithmetic
+            uint32_t r[2][32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + half * 64);
+            TC_TMEM_LD32(r[0], taddr);
+            TC_TMEM_LD32(r[1], taddr + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
+            if (tr) P.trace[t * 8 + 6] = clock64();
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const float *cnp = cn_s + a * TC_BN + half * 64 + jj * 32;
+                // four independent running top-2 sets (value i goes to set i & 3) break the serial
+                // dependency through b1 / b2; the updates are branch-free
+                const int cbase = col0 + half * 64 + jj * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float v = fmaf(-2.0f, __uint_as_float(r[jj][i]), cnp[i]);
+                    const int k = i & 3;
+                    b2[k] = fminf(b2[k], fmaxf(b1[k], v));
+                    i1[k] = v < b1[k] ? cbase + i : i1[k];
+                    b1[k] = fminf(b1[k], v);
+                }
+            }
+            if (e < TC_BN) cn_s[(a ^ 1) * TC_BN + e] = cn_next;
+            if (tr) P.trace[t * 8 + 7] = clock64();
         }
-        if (myrow < P.rows) {
-            P.best1[myrow] = b1;
-            P.best2[myrow] = b2;
-            P.idx1[myrow] = i1;
+        // merge the four sets of this thread, then the two column halves of the row; on equal scores the
+        // lower centroid index wins (such rows are re-decided in float64 anyway: their gap is zero)
+        float m1 = b1[0], m2 = b2[0];
+        int mi = i1[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            if (b1[k] < m1 || (b1[k] == m1 && i1[k] < mi)) {
+                m2 = fminf(m1, b2[k]);
+                m1 = b1[k];
+                mi = i1[k];
+            } else {
+                m2 = fminf(m2, b1[k]);
+            }
+        }
+        float *mg = cn_s;  // staging is free after the last tile once every epilogue warp is here
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int slot = q * 32 + lane;
+        if (half == 1) {
+            mg[slot] = m1;
+            mg[128 + slot] = m2;
+            reinterpret_cast<int *>(mg)[256 + slot] = mi;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && myrow < P.rows) {
+            const float c1 = mg[slot], c2 = mg[128 + slot];
+            const int ci = reinterpret_cast<int *>(mg)[256 + slot];
+            float o1, o2;
+            int oi;
+            if (c1 < m1) {
+                o1 = c1;
+                oi = ci;
+                o2 = fminf(m1, c2);
+            } else {
+                o1 = m1;
+                oi = mi;
+                o2 = fminf(m2, c1);
+            }
+            P.best1[myrow] = o1;
+            P.best2[myrow] = o2;
+            P.idx1[myrow] = oi;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -393,10 +465,10 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
         return -1;
     }
     int stages = nch <= 2 ? 4 : (nch <= 3 ? 3 : (nch <= 4 ? 2 : 1));
-    size_t smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1024 + 64;
+    size_t smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1536 + 64;
     while (smem > 227 * 1024 && stages > 1) {
         --stages;
-        smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1024 + 64;
+        smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1536 + 64;
     }
     if (smem > 227 * 1024) {
         mdb_set_error("kmeans_assign_tc: tile does not fit shared memory");
@@ -443,17 +515,34 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     TcParams P;
     P.rows = (int)rows;
     P.K = K;
-    P.Kin = Kin;
-    P.nch = nch;
     P.stages = stages;
+    P.trace = nullptr;
+    if (getenv("MDB_TC_TRACE") && d_diag) {   // developer switch: the stamps go to the start of d_diag
+        P.trace = reinterpret_cast<long long *>(d_diag);
+    }
     P.cn = cn;
     P.best1 = b1;
     P.best2 = b2;
     P.idx1 = i1;
-    MDB_CUDA(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope ps(c, "k_assign_tc", stream);
-        k_assign_tc<<<cdiv(rows, TC_BM), TC_THREADS, smem, stream>>>(tmA, tmB, P);
+        const dim3 grid((unsigned)cdiv(rows, TC_BM));
+#define MDB_TC_LAUNCH(KD)                                                                                          \
+    case KD:                                                                                                       \
+        MDB_CUDA(cudaFuncSetAttribute(k_assign_tc<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_assign_tc<KD><<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, P);                                          \
+        break;
+        switch (Kd / 16) {
+            MDB_TC_LAUNCH(1)
+            MDB_TC_LAUNCH(2)
+            MDB_TC_LAUNCH(3)
+            MDB_TC_LAUNCH(4)
+            MDB_TC_LAUNCH(5)
+            MDB_TC_LAUNCH(6)
+            MDB_TC_LAUNCH(7)
+            MDB_TC_LAUNCH(8)
+        }
+#undef MDB_TC_LAUNCH
     }
     c->launches++;
     // per-product relative error of the split-fp16 contraction with fp32 accumulation over Kin terms
@@ -467,7 +556,7 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, relerr, d_rowidx, d_labels, amb_pos, amb_row,
                                                     namb);
     c->launches++;
-    if (d_diag) {  // diagnostics: best / second-best approximate score, index, ||x'||^2 per row, then max ||c'||^2
+    if (d_diag && !P.trace) {  // diagnostics: best / second-best approximate score, index, ||x'||^2 per row, then max ||c'||^2
         MDB_CUDA(cudaMemcpyAsync(d_diag, b1, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(d_diag + rows, b2, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(d_diag + 2 * rows, i1, rows * sizeof(int), cudaMemcpyDeviceToDevice, stream));
