@@ -408,6 +408,203 @@ __global__ void __launch_bounds__(WARPS * 32) k_tridiag(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6a', clusters of up to 32 atoms: the matrix lives in registers.  LPM lanes own one matrix, lane g
+// holds column g (= row g) as NMAX doubles, so a warp works on 32 / LPM matrices; shared memory
+// carries the member list, a staging copy of the matrix (built pair by pair, each pair once) and the
+// two vectors every lane has to see.  The Householder loop is fully unrolled (every register index
+// is a compile-time constant).  Step k, with x = A[k+1.., k] and T = A[k+1.., k+1..]:
+//     sigma = x.x, alpha = -sign(x1) sqrt(sigma), v = x - alpha e1, H = sigma - alpha x1,
+//     p = T v / H = (T x - alpha T[:, 0]) / H,
+//     K = v.T v / (2 H^2) with v.T v = x.T x - 2 alpha (T x)_0 + alpha^2 T_00,
+//     w = p - K v,  T -= v w^T + w v^T,  d_k = A_kk, e_k = alpha,
+// so one pass over the columns (T x) and ONE fused reduction (sigma, x.T x) give everything.
+// Reciprocal and reciprocal square root are MUFU seeds + Newton steps (a few ulp; the spectrum
+// tolerance is 1e-5): the IEEE sequences would triple the size of the unrolled code.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const double e = fma(-h * y, y, 0.5);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+
+template <int NMAX, int LPM>
+struct RegSmem {
+    double A[NMAX][NMAX + 1];
+    double vec[NMAX][3];
+    double xs[LPM];
+    double2 vw[LPM];
+    int z[NMAX];
+    int t[NMAX];
+    double L[3];
+    int n;
+    int pad;
+};
+
+template <int NMAX, int LPM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg(const __grid_constant__ DescParams P, const int *__restrict__ list,
+                                                            int nlist, int slot0, int nslots, double *__restrict__ dsc,
+                                                            double *__restrict__ esc, int *__restrict__ nsc) {
+    static_assert(NMAX <= LPM, "one column per lane");
+    constexpr int G = 32 / LPM;
+    typedef RegSmem<NMAX, LPM> Sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Sm *Sw = reinterpret_cast<Sm *>(smem_raw) + (threadIdx.x >> 5) * G;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / LPM, gl = lane % LPM;
+    const int sw0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * G;  // first slot of this warp
+    for (int g = 0; g < G; ++g) {
+        const int sg = sw0 + g;
+        Sm *Sg = Sw + g;
+        if (lane == 0) Sg->n = 0;
+        if (sg >= nslots) continue;  // warp-uniform
+        const int ord = list[slot0 + sg];
+        const int gt = P.targets ? P.targets[ord] : ord;
+        const int f = gt / P.N, a = gt - f * P.N;
+        const FrameGeom &G0 = P.geom[f];
+        const double *pos = P.pos + (size_t)f * P.N * 3;
+        __syncwarp();
+        const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
+        const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
+        sphere_scan(P, f, a, [&](int j, int tj) {
+            const int k = atomicAdd(&Sg->n, 1);
+            if (k < NMAX) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double D = pos[(size_t)j * 3 + c] - pa[c];
+                    if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
+                    Sg->vec[k][c] = D;
+                }
+                Sg->z[k] = P.Z[tj];
+                Sg->t[k] = tj;
+            }
+        });
+        if (lane == 0) {
+            Sg->L[0] = Lg[0];
+            Sg->L[1] = Lg[1];
+            Sg->L[2] = Lg[2];
+        }
+    }
+    __syncwarp();
+    Sm *S = Sw + grp;
+    const int s = sw0 + grp;
+    const bool valid = s < nslots;
+    int n = S->n;
+    if (n > NMAX) {
+        if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        n = NMAX;
+    }
+    // Coulomb matrix (datasetbuilder.py:341-348) into the staging copy: the n(n-1)/2 pairs are dealt
+    // evenly to the lanes of the group, pair p -> (i, j), j < i.  Both vectors lie within +-L/2 of the
+    // target, so one conditional shift per axis gives the minimum image.  Rows / columns >= n are zero.
+    for (int q = gl; q < NMAX * NMAX; q += LPM) S->A[q / NMAX][q % NMAX] = 0.0;
+    __syncwarp();
+    for (int i = gl; i < n; i += LPM) S->A[i][i] = P.diag[S->t[i]];
+    if (n > 1) {
+        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
+        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
+        const int npair = n * (n - 1) / 2;
+        for (int p = gl; p < npair; p += LPM) {
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (i * (i - 1) / 2 > p) --i;
+            while ((i + 1) * i / 2 <= p) ++i;
+            const int j = p - i * (i - 1) / 2;
+            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
+            if (P.periodic) {
+                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+            }
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+            S->A[i][j] = mv;
+            S->A[j][i] = mv;
+        }
+    }
+    __syncwarp();
+    double a[NMAX];
+    {
+        const int col = gl < NMAX ? gl : 0;
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) a[i] = gl < NMAX ? S->A[i][col] : 0.0;
+    }
+    double *dptr = dsc + s + (size_t)gl * nslots;
+    double *eptr = esc + s + (size_t)gl * nslots;
+    const bool hi = (lane & (LPM >> 1)) != 0;  // upper half of the lane group
+#pragma unroll
+    for (int k = 0; k < NMAX - 1; ++k) {
+        // keeps the warps of the block within a few steps of each other: the unrolled code is larger
+        // than the instruction cache, and warps that run together share its lines
+        if ((k & 3) == 0) __syncthreads();
+        const double x = (gl > k && gl < n) ? a[k] : 0.0;
+        S->xs[gl] = x;
+        __syncwarp();
+        // (T x)_gl over rows k+1 .. NMAX-1; independent chains hide the DFMA latency
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+        for (int i = k + 1; i < NMAX; ++i) {
+            const double xi = S->xs[i];
+            if (((i - k - 1) & 3) == 0) acc0 = fma(a[i], xi, acc0);
+            if (((i - k - 1) & 3) == 1) acc1 = fma(a[i], xi, acc1);
+            if (((i - k - 1) & 3) == 2) acc2 = fma(a[i], xi, acc2);
+            if (((i - k - 1) & 3) == 3) acc3 = fma(a[i], xi, acc3);
+        }
+        const double pt = (acc0 + acc1) + (acc2 + acc3);
+        // fused reduction of (sigma, tau): the halves of the group first swap one value each, then a
+        // single butterfly runs on the kept value, and a final swap gives every lane both sums
+        const double sg0 = x * x, ta0 = x * pt;
+        double keep = hi ? ta0 : sg0;
+        keep += __shfl_xor_sync(0xffffffffu, hi ? sg0 : ta0, LPM >> 1);
+#pragma unroll
+        for (int o = LPM >> 2; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+        const double other = __shfl_xor_sync(0xffffffffu, keep, LPM >> 1);
+        const double sig = hi ? other : keep, tau = hi ? keep : other;
+        const double x1 = S->xs[k + 1];
+        const double pt1 = __shfl_sync(0xffffffffu, pt, k + 1, LPM);
+        const double t00 = __shfl_sync(0xffffffffu, a[k + 1], k + 1, LPM);
+        const bool doit = sig > 0.0;
+        const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;  // sqrt(sigma)
+        const double alpha = x1 >= 0.0 ? -rs : rs;
+        const double H = sig - alpha * x1;
+        const double iH = doit ? fast_rcp(H) : 0.0;
+        const double K = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
+        const double v = (gl == k + 1) ? x - alpha : x;
+        const double pg = (pt - alpha * a[k + 1]) * iH;
+        const double w = (gl > k) ? pg - K * v : 0.0;
+        if (gl == k && valid && k < n) {
+            *dptr = a[k];
+            if (k + 1 < n) *eptr = alpha;
+        }
+        S->vw[gl] = make_double2(v, w);
+        __syncwarp();
+#pragma unroll
+        for (int i = k + 1; i < NMAX; ++i) {
+            const double2 q = S->vw[i];
+            a[i] = fma(-q.x, w, fma(-q.y, v, a[i]));
+        }
+    }
+    if (valid) {
+        if (gl == NMAX - 1 && n == NMAX) *dptr = a[NMAX - 1];
+        if (gl == 0) nsc[s] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6b: implicit-shift QL on the tridiagonal (d, e), one thread per matrix (EISPACK tql1 / tqli
 // without vectors), ascending sort, then the padded sorted feature row.
 // ---------------------------------------------------------------------------------------------
@@ -508,7 +705,12 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     }
 }
 
-// bucket id by cluster size
+// bucket id by cluster size: classes of 4 up to 32 atoms (register-resident kernel), then 64 and 128
+#define DESC_NB 9
+__device__ __host__ __forceinline__ int desc_bucket(int n) {
+    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 : n <= 128 ? 8 : DESC_NB;
+}
+
 __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ counts, int nt, long long ntargets,
                                                       int *__restrict__ bucket_n, int *__restrict__ nsum) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,8 +718,7 @@ __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ co
     int n = 0;
     for (int k = 0; k < nt; ++k) n += counts[t * nt + k];
     nsum[t] = n;
-    const int b = n <= 16 ? 0 : n <= 32 ? 1 : n <= 64 ? 2 : n <= 128 ? 3 : 4;
-    atomicAdd(&bucket_n[b], 1);
+    atomicAdd(&bucket_n[desc_bucket(n)], 1);
 }
 
 __global__ void __launch_bounds__(256) k_bucket_fill(const int *__restrict__ nsum, long long ntargets,
@@ -525,8 +726,7 @@ __global__ void __launch_bounds__(256) k_bucket_fill(const int *__restrict__ nsu
                                                      int *__restrict__ list) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntargets) return;
-    const int n = nsum[t];
-    const int b = n <= 16 ? 0 : n <= 32 ? 1 : n <= 64 ? 2 : n <= 128 ? 3 : 4;
+    const int b = desc_bucket(nsum[t]);
     const int k = atomicAdd(&cursor[b], 1);
     list[bucket_ofs[b] + k] = (int)t;
 }
@@ -625,23 +825,49 @@ int members_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_c
     return 0;
 }
 
-template <int NMAX, int WARPS, int LPM, int QTHREADS>
+static const char *bucket_name(int nmax, bool tql) {
+    switch (nmax) {
+        case 8: return tql ? "k_tql<8>" : "k_tridiag_reg<8>";
+        case 12: return tql ? "k_tql<12>" : "k_tridiag_reg<12>";
+        case 16: return tql ? "k_tql<16>" : "k_tridiag_reg<16>";
+        case 20: return tql ? "k_tql<20>" : "k_tridiag_reg<20>";
+        case 24: return tql ? "k_tql<24>" : "k_tridiag_reg<24>";
+        case 28: return tql ? "k_tql<28>" : "k_tridiag_reg<28>";
+        case 32: return tql ? "k_tql<32>" : "k_tridiag_reg<32>";
+        case 64: return tql ? "k_tql<64>" : "k_tridiag<64>";
+        default: return tql ? "k_tql<128>" : "k_tridiag<128>";
+    }
+}
+
+template <int NMAX, int WARPS, int LPM, int QTHREADS, bool REG>
 static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int ofs, int cnt, double *dsc, double *esc,
                       int *nsc, int chunk, const int *d_counts, const int *d_padorder, const double *d_padval,
                       const int *d_maxcount, int D, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream) {
     constexpr int G = 32 / LPM;
-    const size_t smem_tri = sizeof(TriSmem<NMAX>) * WARPS * G;
+    size_t smem_tri;
+    if constexpr (REG) smem_tri = sizeof(RegSmem<NMAX, LPM>) * WARPS * G;
+    else smem_tri = sizeof(TriSmem<NMAX>) * WARPS * G;
     const size_t smem_ql = (size_t)2 * NMAX * QTHREADS * sizeof(double);
-    MDB_CUDA(cudaFuncSetAttribute(k_tridiag<NMAX, WARPS, LPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+    if constexpr (REG) {
+        MDB_CUDA(cudaFuncSetAttribute(k_tridiag_reg<NMAX, LPM, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+    } else {
+        MDB_CUDA(cudaFuncSetAttribute(k_tridiag<NMAX, WARPS, LPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+    }
     MDB_CUDA(cudaFuncSetAttribute(k_tql<NMAX, QTHREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ql));
     for (int s0 = 0; s0 < cnt; s0 += chunk) {
         const int ns = std::min(chunk, cnt - s0);
         {
-            ProfScope ps(c, "k_tridiag", stream);
-            k_tridiag<NMAX, WARPS, LPM><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc, esc, nsc);
+            ProfScope ps(c, bucket_name(NMAX, false), stream);
+            if constexpr (REG) {
+                k_tridiag_reg<NMAX, LPM, WARPS><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns,
+                                                                                                   dsc, esc, nsc);
+            } else {
+                k_tridiag<NMAX, WARPS, LPM><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc,
+                                                                                               esc, nsc);
+            }
         }
         {
-            ProfScope ps(c, "k_tql", stream);
+            ProfScope ps(c, bucket_name(NMAX, true), stream);
             k_tql<NMAX, QTHREADS><<<cdiv(ns, QTHREADS), QTHREADS, smem_ql, stream>>>(
                 d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap,
                 d_n, c->d_stats);
@@ -673,7 +899,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     double *dsc = (double *)arena_alloc(c, (size_t)chunk * 128 * sizeof(double));
     double *esc = (double *)arena_alloc(c, (size_t)chunk * 128 * sizeof(double));
     int *nsc = (int *)arena_alloc(c, (size_t)chunk * sizeof(int));
-    int *d_book = (int *)arena_alloc(c, 256);            // bucket_n[5] | cursor[5] | ofs[5]
+    int *d_book = (int *)arena_alloc(c, 256);            // bucket_n[16] | cursor[16] | ofs[16]
     int *d_maxcount = (int *)arena_alloc(c, 256);
     int *d_padorder = (int *)arena_alloc(c, 256);
     double *d_padval = (double *)arena_alloc(c, 256);
@@ -701,28 +927,32 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     MDB_CUDA(cudaMemcpyAsync(d_padval, c->el.diag, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
     k_bucket_count<<<cdiv(T, 256), 256, 0, stream>>>(d_counts, nt, T, d_book, d_nsum);
     c->launches++;
-    int hb[5];
+    int hb[DESC_NB + 1];
     MDB_CUDA(cudaMemcpyAsync(hb, d_book, sizeof(hb), cudaMemcpyDeviceToHost, stream));
     MDB_CUDA(cudaStreamSynchronize(stream));
-    if (hb[4] > 0) {
+    if (hb[DESC_NB] > 0) {
         mdb_set_error("a cutoff sphere holds more than 128 atoms; reduce the cutoff");
         return -1;
     }
-    int ofs[5] = {0, hb[0], hb[0] + hb[1], hb[0] + hb[1] + hb[2], hb[0] + hb[1] + hb[2] + hb[3]};
-    MDB_CUDA(cudaMemcpyAsync(d_book + 10, ofs, sizeof(ofs), cudaMemcpyHostToDevice, stream));
-    k_bucket_fill<<<cdiv(T, 256), 256, 0, stream>>>(d_nsum, T, d_book + 10, d_book + 5, d_list);
+    int ofs[DESC_NB + 1];
+    ofs[0] = 0;
+    for (int b = 0; b < DESC_NB; ++b) ofs[b + 1] = ofs[b] + hb[b];
+    MDB_CUDA(cudaMemcpyAsync(d_book + 32, ofs, sizeof(ofs), cudaMemcpyHostToDevice, stream));
+    k_bucket_fill<<<cdiv(T, 256), 256, 0, stream>>>(d_nsum, T, d_book + 32, d_book + 16, d_list);
     c->launches++;
-    if (hb[0] && run_bucket<16, 8, 8, 128>(c, P, d_list, ofs[0], hb[0], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
-                                       d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
+#define MDB_BUCKET(B, NMAX, WARPS, LPM, QT, REG)                                                                              \
+    if (hb[B] && run_bucket<NMAX, WARPS, LPM, QT, REG>(c, P, d_list, ofs[B], hb[B], dsc, esc, nsc, chunk, d_counts, d_padorder, \
+                                                       d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))               \
         return -1;
-    if (hb[1] && run_bucket<32, 5, 16, 128>(c, P, d_list, ofs[1], hb[1], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
-                                       d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
-        return -1;
-    if (hb[2] && run_bucket<64, 4, 32, 64>(c, P, d_list, ofs[2], hb[2], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
-                                      d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
-        return -1;
-    if (hb[3] && run_bucket<128, 1, 32, 64>(c, P, d_list, ofs[3], hb[3], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
-                                       d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
-        return -1;
+    MDB_BUCKET(0, 8, 8, 8, 128, true)
+    MDB_BUCKET(1, 12, 8, 16, 128, true)
+    MDB_BUCKET(2, 16, 8, 16, 128, true)
+    MDB_BUCKET(3, 20, 8, 32, 128, true)
+    MDB_BUCKET(4, 24, 8, 32, 128, true)
+    MDB_BUCKET(5, 28, 8, 32, 128, true)
+    MDB_BUCKET(6, 32, 8, 32, 128, true)
+    MDB_BUCKET(7, 64, 4, 32, 64, false)
+    MDB_BUCKET(8, 128, 1, 32, 64, false)
+#undef MDB_BUCKET
     return 0;
 }
