@@ -605,6 +605,169 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6a'', clusters of 33..64 atoms: the same register-resident scheme on a pair of warps (lane g of
+// the pair, 0 <= g < 64, holds column g).  The pair meets at a named barrier three times per step:
+// after publishing x, after publishing the per-warp partial sums, and after publishing (v, w).
+// ---------------------------------------------------------------------------------------------
+template <int NMAX>
+struct Reg2Smem {
+    double A[NMAX][NMAX + 1];
+    double vec[NMAX][3];
+    double xs[64];
+    double2 vw[64];
+    double2 red[2];
+    double2 bc;
+    int z[NMAX];
+    int t[NMAX];
+    double L[3];
+    int n;
+    int pad;
+};
+
+template <int NMAX, int PAIRS>
+__global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 : 2)) k_tridiag_reg2(const __grid_constant__ DescParams P, const int *__restrict__ list,
+                                                                int nlist, int slot0, int nslots, double *__restrict__ dsc,
+                                                                double *__restrict__ esc, int *__restrict__ nsc) {
+    static_assert(NMAX > 32 && NMAX <= 56, "one column per lane of a warp pair; 64 rows do not fit the register file");
+    typedef Reg2Smem<NMAX> Sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int pair = threadIdx.x >> 6;
+    Sm *S = reinterpret_cast<Sm *>(smem_raw) + pair;
+    const int lane = threadIdx.x & 31;
+    const int wp = (threadIdx.x >> 5) & 1;  // warp within the pair
+    const int gl = threadIdx.x & 63;
+    const int s = blockIdx.x * PAIRS + pair;
+    const bool valid = s < nslots;
+    const int barid = 1 + pair;
+#define PAIR_SYNC() asm volatile("bar.sync %0, 64;" ::"r"(barid) : "memory")
+    if (wp == 0) {
+        if (lane == 0) S->n = 0;
+        if (valid) {
+            const int ord = list[slot0 + s];
+            const int gt = P.targets ? P.targets[ord] : ord;
+            const int f = gt / P.N, a = gt - f * P.N;
+            const FrameGeom &G0 = P.geom[f];
+            const double *pos = P.pos + (size_t)f * P.N * 3;
+            __syncwarp();
+            const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
+            const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
+            sphere_scan(P, f, a, [&](int j, int tj) {
+                const int k = atomicAdd(&S->n, 1);
+                if (k < NMAX) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        double D = pos[(size_t)j * 3 + c] - pa[c];
+                        if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
+                        S->vec[k][c] = D;
+                    }
+                    S->z[k] = P.Z[tj];
+                    S->t[k] = tj;
+                }
+            });
+            if (lane == 0) {
+                S->L[0] = Lg[0];
+                S->L[1] = Lg[1];
+                S->L[2] = Lg[2];
+            }
+        }
+    }
+    for (int q = gl; q < NMAX * NMAX; q += 64) S->A[q / NMAX][q % NMAX] = 0.0;
+    PAIR_SYNC();
+    int n = S->n;
+    if (n > NMAX) {
+        if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        n = NMAX;
+    }
+    for (int i = gl; i < n; i += 64) S->A[i][i] = P.diag[S->t[i]];
+    if (n > 1) {
+        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
+        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
+        const int npair = n * (n - 1) / 2;
+        for (int p = gl; p < npair; p += 64) {
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (i * (i - 1) / 2 > p) --i;
+            while ((i + 1) * i / 2 <= p) ++i;
+            const int j = p - i * (i - 1) / 2;
+            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
+            if (P.periodic) {
+                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+            }
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+            S->A[i][j] = mv;
+            S->A[j][i] = mv;
+        }
+    }
+    PAIR_SYNC();
+    double a[NMAX];
+    {
+        const int col = gl < NMAX ? gl : 0;
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) a[i] = gl < NMAX ? S->A[i][col] : 0.0;
+    }
+    double *dptr = dsc + s + (size_t)gl * nslots;
+    double *eptr = esc + s + (size_t)gl * nslots;
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < NMAX - 1; ++k) {
+        if ((k & 3) == 0) __syncthreads();  // see k_tridiag_reg
+        const double x = (gl > k && gl < n) ? a[k] : 0.0;
+        S->xs[gl] = x;
+        PAIR_SYNC();
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+        for (int i = k + 1; i < NMAX; ++i) {
+            const double xi = S->xs[i];
+            if (((i - k - 1) & 3) == 0) acc0 = fma(a[i], xi, acc0);
+            if (((i - k - 1) & 3) == 1) acc1 = fma(a[i], xi, acc1);
+            if (((i - k - 1) & 3) == 2) acc2 = fma(a[i], xi, acc2);
+            if (((i - k - 1) & 3) == 3) acc3 = fma(a[i], xi, acc3);
+        }
+        const double pt = (acc0 + acc1) + (acc2 + acc3);
+        const double sg0 = x * x, ta0 = x * pt;
+        double keep = hi ? ta0 : sg0;
+        keep += __shfl_xor_sync(0xffffffffu, hi ? sg0 : ta0, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+        const double other = __shfl_xor_sync(0xffffffffu, keep, 16);
+        if (lane == 0) S->red[wp] = make_double2(keep, other);  // lane 0 is in the lower half: (sigma, tau)
+        if (gl == k + 1) S->bc = make_double2(pt, a[k + 1]);
+        PAIR_SYNC();
+        const double2 r0 = S->red[0], r1 = S->red[1], bc = S->bc;
+        const double sig = r0.x + r1.x, tau = r0.y + r1.y;
+        const double x1 = S->xs[k + 1];
+        const double pt1 = bc.x, t00 = bc.y;
+        const bool doit = sig > 0.0;
+        const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
+        const double alpha = x1 >= 0.0 ? -rs : rs;
+        const double H = sig - alpha * x1;
+        const double iH = doit ? fast_rcp(H) : 0.0;
+        const double K = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
+        const double v = (gl == k + 1) ? x - alpha : x;
+        const double pg = (pt - alpha * a[k + 1]) * iH;
+        const double w = (gl > k) ? pg - K * v : 0.0;
+        if (gl == k && valid && k < n) {
+            *dptr = a[k];
+            if (k + 1 < n) *eptr = alpha;
+        }
+        S->vw[gl] = make_double2(v, w);
+        PAIR_SYNC();
+#pragma unroll
+        for (int i = k + 1; i < NMAX; ++i) {
+            const double2 q = S->vw[i];
+            a[i] = fma(-q.x, w, fma(-q.y, v, a[i]));
+        }
+    }
+#undef PAIR_SYNC
+    if (valid) {
+        if (gl == NMAX - 1 && n == NMAX) *dptr = a[NMAX - 1];
+        if (gl == 0) nsc[s] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6b: implicit-shift QL on the tridiagonal (d, e), one thread per matrix (EISPACK tql1 / tqli
 // without vectors), ascending sort, then the padded sorted feature row.
 // ---------------------------------------------------------------------------------------------
@@ -627,7 +790,10 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     for (int k = 0; k < n; ++k) d[k][tid] = dsc[(size_t)k * nslots + s];
     for (int k = 0; k + 1 < n; ++k) e[k][tid] = esc[(size_t)k * nslots + s];
     if (n > 0) e[n - 1][tid] = 0.0;
-    const double EPS = 2.220446049250313e-16;
+    // off-diagonals below 1e-12 of their neighbours are dropped: that moves an eigenvalue by at most
+    // 1e-12 ||M||, four orders below the floor of the stated tolerance; reciprocals and square roots
+    // are MUFU seeds + Newton steps (fast_rcp / fast_rsqrt), a few ulp
+    const double EPS = 1e-12;
     for (int l = 0; l < n; ++l) {
         int iter = 0, m;
         do {
@@ -640,22 +806,28 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
                     atomicExch(&stats->err, MDB_ERR_EIG_NOCONV);
                     break;
                 }
-                double g = (d[l + 1][tid] - d[l][tid]) / (2.0 * e[l][tid]);
-                double r = sqrt(g * g + 1.0);
-                g = d[m][tid] - d[l][tid] + e[l][tid] / (g + (g >= 0.0 ? fabs(r) : -fabs(r)));
+                const double dl = d[l][tid], el = e[l][tid];
+                double g = (d[l + 1][tid] - dl) * (0.5 * fast_rcp(el));
+                const double t1 = fma(g, g, 1.0);
+                double r = t1 * fast_rsqrt(t1);
+                g = d[m][tid] - dl + el * fast_rcp(g + (g >= 0.0 ? r : -r));
                 double sn = 1.0, c = 1.0, p = 0.0;
                 int i;
                 for (i = m - 1; i >= l; --i) {
-                    double f = sn * e[i][tid];
-                    const double b = c * e[i][tid];
-                    r = sqrt(f * f + g * g);
-                    e[i + 1][tid] = r;
-                    if (r == 0.0) {
+                    const double ei = e[i][tid];
+                    double f = sn * ei;
+                    const double b = c * ei;
+                    const double t2 = fma(f, f, g * g);
+                    if (t2 == 0.0) {
+                        r = 0.0;
+                        e[i + 1][tid] = 0.0;
                         d[i + 1][tid] -= p;
                         e[m][tid] = 0.0;
                         break;
                     }
-                    const double ir = 1.0 / r;
+                    const double ir = fast_rsqrt(t2);
+                    r = t2 * ir;
+                    e[i + 1][tid] = r;
                     sn = f * ir;
                     c = g * ir;
                     g = d[i + 1][tid] - p;
@@ -705,10 +877,10 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     }
 }
 
-// bucket id by cluster size: classes of 4 up to 32 atoms (register-resident kernel), then 64 and 128
-#define DESC_NB 9
+// bucket id by cluster size: classes of 4 up to 32 atoms, of 8 up to 64 (register-resident kernels), then 128
+#define DESC_NB 12
 __device__ __host__ __forceinline__ int desc_bucket(int n) {
-    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 : n <= 128 ? 8 : DESC_NB;
+    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 + ((n - 33) >> 3) : n <= 128 ? 11 : DESC_NB;
 }
 
 __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ counts, int nt, long long ntargets,
@@ -834,22 +1006,28 @@ static const char *bucket_name(int nmax, bool tql) {
         case 24: return tql ? "k_tql<24>" : "k_tridiag_reg<24>";
         case 28: return tql ? "k_tql<28>" : "k_tridiag_reg<28>";
         case 32: return tql ? "k_tql<32>" : "k_tridiag_reg<32>";
+        case 40: return tql ? "k_tql<40>" : "k_tridiag_reg2<40>";
+        case 48: return tql ? "k_tql<48>" : "k_tridiag_reg2<48>";
+        case 56: return tql ? "k_tql<56>" : "k_tridiag_reg2<56>";
         case 64: return tql ? "k_tql<64>" : "k_tridiag<64>";
         default: return tql ? "k_tql<128>" : "k_tridiag<128>";
     }
 }
 
-template <int NMAX, int WARPS, int LPM, int QTHREADS, bool REG>
+template <int NMAX, int WARPS, int LPM, int QTHREADS, int REG>
 static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int ofs, int cnt, double *dsc, double *esc,
                       int *nsc, int chunk, const int *d_counts, const int *d_padorder, const double *d_padval,
                       const int *d_maxcount, int D, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream) {
     constexpr int G = 32 / LPM;
     size_t smem_tri;
-    if constexpr (REG) smem_tri = sizeof(RegSmem<NMAX, LPM>) * WARPS * G;
+    if constexpr (REG == 1) smem_tri = sizeof(RegSmem<NMAX, LPM>) * WARPS * G;
+    else if constexpr (REG == 2) smem_tri = sizeof(Reg2Smem<NMAX>) * (WARPS / 2);
     else smem_tri = sizeof(TriSmem<NMAX>) * WARPS * G;
     const size_t smem_ql = (size_t)2 * NMAX * QTHREADS * sizeof(double);
-    if constexpr (REG) {
+    if constexpr (REG == 1) {
         MDB_CUDA(cudaFuncSetAttribute(k_tridiag_reg<NMAX, LPM, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+    } else if constexpr (REG == 2) {
+        MDB_CUDA(cudaFuncSetAttribute(k_tridiag_reg2<NMAX, WARPS / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
     } else {
         MDB_CUDA(cudaFuncSetAttribute(k_tridiag<NMAX, WARPS, LPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
     }
@@ -858,8 +1036,11 @@ static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int of
         const int ns = std::min(chunk, cnt - s0);
         {
             ProfScope ps(c, bucket_name(NMAX, false), stream);
-            if constexpr (REG) {
+            if constexpr (REG == 1) {
                 k_tridiag_reg<NMAX, LPM, WARPS><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns,
+                                                                                                   dsc, esc, nsc);
+            } else if constexpr (REG == 2) {
+                k_tridiag_reg2<NMAX, WARPS / 2><<<cdiv(ns, WARPS / 2), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns,
                                                                                                    dsc, esc, nsc);
             } else {
                 k_tridiag<NMAX, WARPS, LPM><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc,
@@ -944,15 +1125,18 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     if (hb[B] && run_bucket<NMAX, WARPS, LPM, QT, REG>(c, P, d_list, ofs[B], hb[B], dsc, esc, nsc, chunk, d_counts, d_padorder, \
                                                        d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))               \
         return -1;
-    MDB_BUCKET(0, 8, 8, 8, 128, true)
-    MDB_BUCKET(1, 12, 8, 16, 128, true)
-    MDB_BUCKET(2, 16, 8, 16, 128, true)
-    MDB_BUCKET(3, 20, 8, 32, 128, true)
-    MDB_BUCKET(4, 24, 8, 32, 128, true)
-    MDB_BUCKET(5, 28, 8, 32, 128, true)
-    MDB_BUCKET(6, 32, 8, 32, 128, true)
-    MDB_BUCKET(7, 64, 4, 32, 64, false)
-    MDB_BUCKET(8, 128, 1, 32, 64, false)
+    MDB_BUCKET(0, 8, 8, 8, 128, 1)
+    MDB_BUCKET(1, 12, 8, 16, 128, 1)
+    MDB_BUCKET(2, 16, 8, 16, 128, 1)
+    MDB_BUCKET(3, 20, 8, 32, 128, 1)
+    MDB_BUCKET(4, 24, 8, 32, 128, 1)
+    MDB_BUCKET(5, 28, 8, 32, 128, 1)
+    MDB_BUCKET(6, 32, 8, 32, 128, 1)
+    MDB_BUCKET(7, 40, 4, 32, 64, 2)
+    MDB_BUCKET(8, 48, 4, 32, 64, 2)
+    MDB_BUCKET(9, 56, 4, 32, 64, 2)
+    MDB_BUCKET(10, 64, 4, 32, 64, 0)
+    MDB_BUCKET(11, 128, 1, 32, 64, 0)
 #undef MDB_BUCKET
     return 0;
 }
