@@ -11,8 +11,11 @@
 //
 // Membership is bit-exact (float screen on the 5 A cell list, borderline distances re-evaluated
 // in double with the oracle's operation order); the spectrum is computed in double by Householder
-// tridiagonalisation (one warp per matrix, matrix in shared memory) followed by implicit-shift
-// QL (one thread per matrix), well inside the 1e-5 relative tolerance of the task.
+// tridiagonalisation followed by implicit-shift QL (one thread per matrix), well inside the 1e-5
+// relative tolerance of the task.  Targets are bucketed by cluster size; up to 64 atoms the matrix
+// lives in registers (one column per lane: k_tridiag_reg for <= 32 atoms on LPM lanes of a warp,
+// k_tridiag_reg2 for <= 64 on a warp pair), above that in shared memory (k_tridiag_blk, one block
+// per matrix).
 // Only orthorhombic cells are supported on this path (the reference's wrap at
 // datasetbuilder.py:572-576 is itself exact only for orthorhombic cells).
 #include <algorithm>
@@ -214,100 +217,84 @@ __global__ void __launch_bounds__(256) k_members(const __grid_constant__ DescPar
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6a: gather the cluster, build the Coulomb matrix in shared memory, Householder-tridiagonalise.
-// One warp per target.  Output: diagonal d[0..n) and off-diagonal e[0..n-1) into a scratch laid out
-// [k][slot] so that the QL kernel reads it coalesced.
+// K6a, clusters of 65..128 atoms: one thread block per matrix, matrix in shared memory.  Two threads
+// share a row (even / odd columns), so the matrix-vector product and the rank-2 update are split
+// over 2 n threads; the row stride NMAX + 2 keeps the accesses of a half-warp on distinct banks.
+// Same step as the register kernels below (one fused reduction of (sigma, x.T x) per step); output is
+// the diagonal d[0..n) and the off-diagonal e[0..n-1) in a scratch laid out [k][slot] so that the QL
+// kernel reads it coalesced.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+__device__ __forceinline__ double fast_rcp(double x);
+__device__ __forceinline__ double fast_rsqrt(double x);
 
 template <int NMAX>
-struct TriSmem {
-    double A[NMAX][NMAX + 1];
+struct BlkSmem {
+    double A[NMAX][NMAX + 2];
     double vec[NMAX][3];
-    double v[NMAX];
-    double p[NMAX];
+    double xs[NMAX];
+    double2 vw[NMAX];
+    double2 red[2 * NMAX / 32];
+    double2 bc;
     int z[NMAX];
     int t[NMAX];
     double L[3];
     int n;
+    int pad;
 };
 
-template <int LPM>
-__device__ __forceinline__ double group_sum(double v) {
-#pragma unroll
-    for (int o = LPM / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// LPM lanes cooperate on one matrix, so a warp works on 32 / LPM matrices at once (small clusters
-// would otherwise leave most lanes idle).  The gather is warp-cooperative per target; matrix build
-// and tridiagonalisation run concurrently in the lane groups, in lock step to the largest n.
-template <int NMAX, int WARPS, int LPM>
-__global__ void __launch_bounds__(WARPS * 32) k_tridiag(const __grid_constant__ DescParams P,
-                                                        const int *__restrict__ list,  // target ordinals of this bucket
-                                                        int nlist, int slot0, int nslots, double *__restrict__ dsc,
-                                                        double *__restrict__ esc, int *__restrict__ nsc) {
-    constexpr int G = 32 / LPM;
+template <int NMAX>
+__global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant__ DescParams P, const int *__restrict__ list,
+                                                          int nlist, int slot0, int nslots, double *__restrict__ dsc,
+                                                          double *__restrict__ esc, int *__restrict__ nsc) {
+    constexpr int T = 2 * NMAX, NW = T / 32;
+    typedef BlkSmem<NMAX> Sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TriSmem<NMAX> *Sw = reinterpret_cast<TriSmem<NMAX> *>(smem_raw) + (threadIdx.x >> 5) * G;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / LPM, gl = lane % LPM;
-    const int sw0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * G;  // first slot of this warp
-    if (sw0 >= nslots) return;
-    for (int g = 0; g < G; ++g) {
-        const int sg = sw0 + g;
-        if (sg >= nslots) break;
-        TriSmem<NMAX> *Sg = Sw + g;
-        const int ord = list[slot0 + sg];
+    Sm *S = reinterpret_cast<Sm *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x;  // one slot per block
+    if (tid == 0) S->n = 0;
+    for (int q = tid; q < NMAX * (NMAX + 2); q += T) (&S->A[0][0])[q] = 0.0;
+    __syncthreads();
+    if (warp == 0) {
+        const int ord = list[slot0 + s];
         const int gt = P.targets ? P.targets[ord] : ord;
         const int f = gt / P.N, a = gt - f * P.N;
         const FrameGeom &G0 = P.geom[f];
         const double *pos = P.pos + (size_t)f * P.N * 3;
-        if (lane == 0) Sg->n = 0;
-        __syncwarp();
         const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
         const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
         sphere_scan(P, f, a, [&](int j, int tj) {
-            const int k = atomicAdd(&Sg->n, 1);
+            const int k = atomicAdd(&S->n, 1);
             if (k < NMAX) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     double D = pos[(size_t)j * 3 + c] - pa[c];
                     if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
-                    Sg->vec[k][c] = D;
+                    S->vec[k][c] = D;
                 }
-                Sg->z[k] = P.Z[tj];
-                Sg->t[k] = tj;
+                S->z[k] = P.Z[tj];
+                S->t[k] = tj;
             }
         });
         if (lane == 0) {
-            Sg->L[0] = Lg[0];
-            Sg->L[1] = Lg[1];
-            Sg->L[2] = Lg[2];
+            S->L[0] = Lg[0];
+            S->L[1] = Lg[1];
+            S->L[2] = Lg[2];
         }
-        __syncwarp();
     }
-    TriSmem<NMAX> *S = Sw + grp;
-    const int s = sw0 + grp;
-    const bool valid = s < nslots;
-    int n = valid ? S->n : 0;
+    __syncthreads();
+    int n = S->n;
     if (n > NMAX) {
-        if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        if (tid == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
         n = NMAX;
     }
-    // Coulomb matrix (datasetbuilder.py:341-348).  The n(n-1)/2 pairs are dealt evenly to the lanes of
-    // the group: pair p -> (i, j), j < i.  Both vectors lie within +-L/2 of the target, so one
-    // conditional shift per axis gives the minimum image.
-    for (int i = gl; i < n; i += LPM) S->A[i][i] = P.diag[S->t[i]];
+    // Coulomb matrix (datasetbuilder.py:341-348), each pair once; see k_tridiag_reg for the minimum image
+    for (int i = tid; i < n; i += T) S->A[i][i] = P.diag[S->t[i]];
     if (n > 1) {
         const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
         const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
         const int npair = n * (n - 1) / 2;
-        for (int p = gl; p < npair; p += LPM) {
+        for (int p = tid; p < npair; p += T) {
             int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
             while (i * (i - 1) / 2 > p) --i;
             while ((i + 1) * i / 2 <= p) ++i;
@@ -324,85 +311,70 @@ __global__ void __launch_bounds__(WARPS * 32) k_tridiag(const __grid_constant__ 
             S->A[j][i] = mv;
         }
     }
-    __syncwarp();
-    int nmax = n;
+    __syncthreads();
+    const int row = tid >> 1, hf = tid & 1;
+    double *arow = &S->A[row][0];
+    for (int k = 0; k < n - 1; ++k) {
+        const bool act = row > k && row < n;
+        const double x = act ? arow[k] : 0.0;
+        if (hf == 0) S->xs[row] = x;
+        __syncthreads();
+        // this thread's half of (T x)_row: columns k+1+hf, k+3+hf, ...
+        double acc0 = 0.0, acc1 = 0.0;
+        if (act) {
+            int c = k + 1 + hf;
+            for (; c + 2 < n; c += 4) {
+                acc0 = fma(arow[c], S->xs[c], acc0);
+                acc1 = fma(arow[c + 2], S->xs[c + 2], acc1);
+            }
+            if (c < n) acc0 = fma(arow[c], S->xs[c], acc0);
+        }
+        double pt = acc0 + acc1;
+        pt += __shfl_xor_sync(0xffffffffu, pt, 1);  // both threads of the row hold (T x)_row
+        double sig = hf == 0 ? x * x : 0.0, tau = hf == 0 ? x * pt : 0.0;
 #pragma unroll
-    for (int o = 16; o >= LPM; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-    // Householder tridiagonalisation, column k eliminates A[k+2.., k]
-    double *dout = dsc + s;
-    double *eout = esc + s;
-    for (int k = 0; k < nmax - 1; ++k) {
-        const bool act = k < n - 1;
-        const int m = n - k - 1;  // length of the sub-column x = A[k+1.., k]
-        double sc = 0.0;
-        if (act && m > 1)
-            for (int r = gl; r < m; r += LPM) sc += fabs(S->A[k + 1 + r][k]);
-        sc = group_sum<LPM>(sc);
-        const bool doit = act && m > 1 && sc != 0.0;
-        if (act && !doit && gl == 0) {
-            dout[(size_t)k * nslots] = S->A[k][k];
-            eout[(size_t)k * nslots] = (m == 1) ? S->A[k + 1][k] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            sig += __shfl_xor_sync(0xffffffffu, sig, o);
+            tau += __shfl_xor_sync(0xffffffffu, tau, o);
         }
-        double hh = 0.0;
-        if (doit) {
-            const double isc = 1.0 / sc;
-            for (int r = gl; r < m; r += LPM) {
-                const double x = S->A[k + 1 + r][k] * isc;
-                S->v[r] = x;
-                hh += x * x;
+        if (lane == 0) S->red[warp] = make_double2(sig, tau);
+        if (row == k + 1 && hf == 0) S->bc = make_double2(pt, arow[k + 1]);
+        __syncthreads();
+        sig = 0.0;
+        tau = 0.0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            const double2 r = S->red[q];
+            sig += r.x;
+            tau += r.y;
+        }
+        const double2 bc = S->bc;
+        const double x1 = S->xs[k + 1];
+        const bool doit = sig > 0.0;
+        const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
+        const double alpha = x1 >= 0.0 ? -rs : rs;
+        const double H = sig - alpha * x1;
+        const double iH = doit ? fast_rcp(H) : 0.0;
+        const double Kc = (tau - 2.0 * alpha * bc.x + alpha * alpha * bc.y) * (0.5 * iH * iH);
+        const double v = (row == k + 1) ? x - alpha : x;
+        const double pg = act ? (pt - alpha * arow[k + 1]) * iH : 0.0;
+        const double w = act ? pg - Kc * v : 0.0;
+        if (tid == 0) {
+            dsc[(size_t)k * nslots + s] = S->A[k][k];
+            esc[(size_t)k * nslots + s] = alpha;
+        }
+        if (hf == 0) S->vw[row] = make_double2(v, w);
+        __syncthreads();
+        if (act && doit) {
+            for (int c = k + 1 + hf; c < n; c += 2) {
+                const double2 q = S->vw[c];
+                arow[c] = fma(-q.x, w, fma(-q.y, v, arow[c]));
             }
         }
-        hh = group_sum<LPM>(hh);
-        __syncwarp();
-        double f0 = 0.0, gg = 0.0;
-        if (doit) {
-            f0 = S->v[0];
-            gg = f0 >= 0.0 ? -sqrt(hh) : sqrt(hh);
-            hh -= f0 * gg;
-        }
-        __syncwarp();
-        if (doit && gl == 0) {
-            S->v[0] = f0 - gg;
-            dout[(size_t)k * nslots] = S->A[k][k];
-            eout[(size_t)k * nslots] = sc * gg;
-        }
-        __syncwarp();
-        // p = A22 v / h ; K = v.p / (2h) ; w = p - K v ; A22 -= v w^T + w v^T
-        const double ih = doit ? 1.0 / hh : 0.0;
-        double vp = 0.0;
-        if (doit)
-            for (int r = gl; r < m; r += LPM) {
-                const double *row = &S->A[k + 1 + r][k + 1];
-                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // independent chains hide the DFMA latency
-                int c = 0;
-                for (; c + 4 <= m; c += 4) {
-                    acc0 += row[c] * S->v[c];
-                    acc1 += row[c + 1] * S->v[c + 1];
-                    acc2 += row[c + 2] * S->v[c + 2];
-                    acc3 += row[c + 3] * S->v[c + 3];
-                }
-                for (; c < m; ++c) acc0 += row[c] * S->v[c];
-                const double acc = ((acc0 + acc1) + (acc2 + acc3)) * ih;
-                S->p[r] = acc;
-                vp += acc * S->v[r];
-            }
-        vp = group_sum<LPM>(vp);
-        const double K = vp * 0.5 * ih;
-        __syncwarp();
-        if (doit)
-            for (int r = gl; r < m; r += LPM) S->p[r] -= K * S->v[r];
-        __syncwarp();
-        if (doit)
-            for (int r = gl; r < m; r += LPM) {
-                double *row = &S->A[k + 1 + r][k + 1];
-                const double vr = S->v[r], wr = S->p[r];
-#pragma unroll 4
-                for (int c = 0; c < m; ++c) row[c] -= vr * S->p[c] + wr * S->v[c];
-            }
-        __syncwarp();
     }
-    if (valid && gl == 0) {
-        if (n > 0) dout[(size_t)(n - 1) * nslots] = S->A[n - 1][n - 1];
+    __syncthreads();
+    if (tid == 0) {
+        if (n > 0) dsc[(size_t)(n - 1) * nslots + s] = S->A[n - 1][n - 1];
         nsc[s] = n;
     }
 }
@@ -624,11 +596,89 @@ struct Reg2Smem {
     int pad;
 };
 
+template <int NMAX>
+struct Reg2Ctx {
+    Reg2Smem<NMAX> *S;
+    double *dptr, *eptr;
+    int gl, lane, wp, n, barid;
+    bool valid;
+};
+
+// one Householder step with a compile-time column index (template recursion instead of `#pragma
+// unroll`: the unroller gives up on 63 iterations of this size and would leave a[] in local memory)
+template <int K, int NMAX>
+__device__ __forceinline__ void reg2_step(double (&a)[NMAX], const Reg2Ctx<NMAX> &cx) {
+    Reg2Smem<NMAX> *S = cx.S;
+    const int gl = cx.gl, n = cx.n;
+#define PAIR_SYNC() asm volatile("bar.sync %0, 64;" ::"r"(cx.barid) : "memory")
+    if ((K & 3) == 0) __syncthreads();  // see k_tridiag_reg
+    const double x = (gl > K && gl < n) ? a[K] : 0.0;
+    S->xs[gl] = x;
+    PAIR_SYNC();
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+    for (int i = K + 1; i < NMAX; ++i) {
+        const double xi = S->xs[i];
+        if (((i - K - 1) & 3) == 0) acc0 = fma(a[i], xi, acc0);
+        if (((i - K - 1) & 3) == 1) acc1 = fma(a[i], xi, acc1);
+        if (((i - K - 1) & 3) == 2) acc2 = fma(a[i], xi, acc2);
+        if (((i - K - 1) & 3) == 3) acc3 = fma(a[i], xi, acc3);
+    }
+    const double pt = (acc0 + acc1) + (acc2 + acc3);
+    const bool hi = (cx.lane & 16) != 0;
+    const double sg0 = x * x, ta0 = x * pt;
+    double keep = hi ? ta0 : sg0;
+    keep += __shfl_xor_sync(0xffffffffu, hi ? sg0 : ta0, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    const double other = __shfl_xor_sync(0xffffffffu, keep, 16);
+    if (cx.lane == 0) S->red[cx.wp] = make_double2(keep, other);  // lane 0 is in the lower half: (sigma, tau)
+    if (gl == K + 1) S->bc = make_double2(pt, a[K + 1]);
+    PAIR_SYNC();
+    const double2 r0 = S->red[0], r1 = S->red[1], bc = S->bc;
+    const double sig = r0.x + r1.x, tau = r0.y + r1.y;
+    const double x1 = S->xs[K + 1];
+    const double pt1 = bc.x, t00 = bc.y;
+    const bool doit = sig > 0.0;
+    const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
+    const double alpha = x1 >= 0.0 ? -rs : rs;
+    const double H = sig - alpha * x1;
+    const double iH = doit ? fast_rcp(H) : 0.0;
+    const double Kc = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
+    const double v = (gl == K + 1) ? x - alpha : x;
+    const double pg = (pt - alpha * a[K + 1]) * iH;
+    const double w = (gl > K) ? pg - Kc * v : 0.0;
+    if (gl == K && cx.valid && K < n) {
+        *cx.dptr = a[K];
+        if (K + 1 < n) *cx.eptr = alpha;
+    }
+    S->vw[gl] = make_double2(v, w);
+    PAIR_SYNC();
+#pragma unroll
+    for (int i = K + 1; i < NMAX; ++i) {
+        const double2 q = S->vw[i];
+        a[i] = fma(-q.x, w, fma(-q.y, v, a[i]));
+    }
+#undef PAIR_SYNC
+}
+
+template <int K, int NMAX>
+struct Reg2Steps {
+    static __device__ __forceinline__ void run(double (&a)[NMAX], const Reg2Ctx<NMAX> &cx) {
+        reg2_step<K, NMAX>(a, cx);
+        Reg2Steps<K + 1, NMAX>::run(a, cx);
+    }
+};
+template <int NMAX>
+struct Reg2Steps<NMAX - 1, NMAX> {
+    static __device__ __forceinline__ void run(double (&)[NMAX], const Reg2Ctx<NMAX> &) {}
+};
+
 template <int NMAX, int PAIRS>
 __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 : 2)) k_tridiag_reg2(const __grid_constant__ DescParams P, const int *__restrict__ list,
                                                                 int nlist, int slot0, int nslots, double *__restrict__ dsc,
                                                                 double *__restrict__ esc, int *__restrict__ nsc) {
-    static_assert(NMAX > 32 && NMAX <= 56, "one column per lane of a warp pair; 64 rows do not fit the register file");
+    static_assert(NMAX > 32 && NMAX <= 64, "one column per lane of a warp pair");
     typedef Reg2Smem<NMAX> Sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int pair = threadIdx.x >> 6;
@@ -707,59 +757,18 @@ __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 :
 #pragma unroll
         for (int i = 0; i < NMAX; ++i) a[i] = gl < NMAX ? S->A[i][col] : 0.0;
     }
-    double *dptr = dsc + s + (size_t)gl * nslots;
-    double *eptr = esc + s + (size_t)gl * nslots;
-    const bool hi = (lane & 16) != 0;
-#pragma unroll
-    for (int k = 0; k < NMAX - 1; ++k) {
-        if ((k & 3) == 0) __syncthreads();  // see k_tridiag_reg
-        const double x = (gl > k && gl < n) ? a[k] : 0.0;
-        S->xs[gl] = x;
-        PAIR_SYNC();
-        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll
-        for (int i = k + 1; i < NMAX; ++i) {
-            const double xi = S->xs[i];
-            if (((i - k - 1) & 3) == 0) acc0 = fma(a[i], xi, acc0);
-            if (((i - k - 1) & 3) == 1) acc1 = fma(a[i], xi, acc1);
-            if (((i - k - 1) & 3) == 2) acc2 = fma(a[i], xi, acc2);
-            if (((i - k - 1) & 3) == 3) acc3 = fma(a[i], xi, acc3);
-        }
-        const double pt = (acc0 + acc1) + (acc2 + acc3);
-        const double sg0 = x * x, ta0 = x * pt;
-        double keep = hi ? ta0 : sg0;
-        keep += __shfl_xor_sync(0xffffffffu, hi ? sg0 : ta0, 16);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-        const double other = __shfl_xor_sync(0xffffffffu, keep, 16);
-        if (lane == 0) S->red[wp] = make_double2(keep, other);  // lane 0 is in the lower half: (sigma, tau)
-        if (gl == k + 1) S->bc = make_double2(pt, a[k + 1]);
-        PAIR_SYNC();
-        const double2 r0 = S->red[0], r1 = S->red[1], bc = S->bc;
-        const double sig = r0.x + r1.x, tau = r0.y + r1.y;
-        const double x1 = S->xs[k + 1];
-        const double pt1 = bc.x, t00 = bc.y;
-        const bool doit = sig > 0.0;
-        const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
-        const double alpha = x1 >= 0.0 ? -rs : rs;
-        const double H = sig - alpha * x1;
-        const double iH = doit ? fast_rcp(H) : 0.0;
-        const double K = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
-        const double v = (gl == k + 1) ? x - alpha : x;
-        const double pg = (pt - alpha * a[k + 1]) * iH;
-        const double w = (gl > k) ? pg - K * v : 0.0;
-        if (gl == k && valid && k < n) {
-            *dptr = a[k];
-            if (k + 1 < n) *eptr = alpha;
-        }
-        S->vw[gl] = make_double2(v, w);
-        PAIR_SYNC();
-#pragma unroll
-        for (int i = k + 1; i < NMAX; ++i) {
-            const double2 q = S->vw[i];
-            a[i] = fma(-q.x, w, fma(-q.y, v, a[i]));
-        }
-    }
+    Reg2Ctx<NMAX> cx;
+    cx.S = S;
+    cx.dptr = dsc + s + (size_t)gl * nslots;
+    cx.eptr = esc + s + (size_t)gl * nslots;
+    cx.gl = gl;
+    cx.lane = lane;
+    cx.wp = wp;
+    cx.n = n;
+    cx.barid = barid;
+    cx.valid = valid;
+    Reg2Steps<0, NMAX>::run(a, cx);
+    double *dptr = cx.dptr;
 #undef PAIR_SYNC
     if (valid) {
         if (gl == NMAX - 1 && n == NMAX) *dptr = a[NMAX - 1];
@@ -877,10 +886,10 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     }
 }
 
-// bucket id by cluster size: classes of 4 up to 32 atoms, of 8 up to 64 (register-resident kernels), then 128
-#define DESC_NB 12
+// bucket id by cluster size: classes of 4 up to 32 atoms, of 8 up to 64 (register-resident kernels), then 96 and 128
+#define DESC_NB 13
 __device__ __host__ __forceinline__ int desc_bucket(int n) {
-    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 + ((n - 33) >> 3) : n <= 128 ? 11 : DESC_NB;
+    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 + ((n - 33) >> 3) : n <= 96 ? 11 : n <= 128 ? 12 : DESC_NB;
 }
 
 __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ counts, int nt, long long ntargets,
@@ -1009,8 +1018,9 @@ static const char *bucket_name(int nmax, bool tql) {
         case 40: return tql ? "k_tql<40>" : "k_tridiag_reg2<40>";
         case 48: return tql ? "k_tql<48>" : "k_tridiag_reg2<48>";
         case 56: return tql ? "k_tql<56>" : "k_tridiag_reg2<56>";
-        case 64: return tql ? "k_tql<64>" : "k_tridiag<64>";
-        default: return tql ? "k_tql<128>" : "k_tridiag<128>";
+        case 64: return tql ? "k_tql<64>" : "k_tridiag_reg2<64>";
+        case 96: return tql ? "k_tql<96>" : "k_tridiag_blk<96>";
+        default: return tql ? "k_tql<128>" : "k_tridiag_blk<128>";
     }
 }
 
@@ -1022,14 +1032,14 @@ static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int of
     size_t smem_tri;
     if constexpr (REG == 1) smem_tri = sizeof(RegSmem<NMAX, LPM>) * WARPS * G;
     else if constexpr (REG == 2) smem_tri = sizeof(Reg2Smem<NMAX>) * (WARPS / 2);
-    else smem_tri = sizeof(TriSmem<NMAX>) * WARPS * G;
+    else smem_tri = sizeof(BlkSmem<NMAX>);
     const size_t smem_ql = (size_t)2 * NMAX * QTHREADS * sizeof(double);
     if constexpr (REG == 1) {
         MDB_CUDA(cudaFuncSetAttribute(k_tridiag_reg<NMAX, LPM, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
     } else if constexpr (REG == 2) {
         MDB_CUDA(cudaFuncSetAttribute(k_tridiag_reg2<NMAX, WARPS / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
     } else {
-        MDB_CUDA(cudaFuncSetAttribute(k_tridiag<NMAX, WARPS, LPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+        MDB_CUDA(cudaFuncSetAttribute(k_tridiag_blk<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
     }
     MDB_CUDA(cudaFuncSetAttribute(k_tql<NMAX, QTHREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ql));
     for (int s0 = 0; s0 < cnt; s0 += chunk) {
@@ -1043,8 +1053,7 @@ static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int of
                 k_tridiag_reg2<NMAX, WARPS / 2><<<cdiv(ns, WARPS / 2), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns,
                                                                                                    dsc, esc, nsc);
             } else {
-                k_tridiag<NMAX, WARPS, LPM><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc,
-                                                                                               esc, nsc);
+                k_tridiag_blk<NMAX><<<ns, 2 * NMAX, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc, esc, nsc);
             }
         }
         {
@@ -1135,8 +1144,9 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     MDB_BUCKET(7, 40, 4, 32, 64, 2)
     MDB_BUCKET(8, 48, 4, 32, 64, 2)
     MDB_BUCKET(9, 56, 4, 32, 64, 2)
-    MDB_BUCKET(10, 64, 4, 32, 64, 0)
-    MDB_BUCKET(11, 128, 1, 32, 64, 0)
+    MDB_BUCKET(10, 64, 4, 32, 64, 2)
+    MDB_BUCKET(11, 96, 1, 32, 64, 0)
+    MDB_BUCKET(12, 128, 1, 32, 64, 0)
 #undef MDB_BUCKET
     return 0;
 }

@@ -88,6 +88,19 @@ def test_small_box_single_cell_axes(engine):
     _check(engine, s, s.pos0[None], np.arange(100, dtype=np.int32))
 
 
+def test_large_clusters_every_size_class(engine):
+    # dense phase with a 5.4 A cutoff: cluster sizes run past 96, so the register kernels (<= 64 atoms)
+    # and both block-per-matrix classes (<= 96, <= 128) are all exercised
+    s = synth.make_system(1500, 0.11, seed=synth.BASE_SEED + 47, dense=True)
+    targets = np.arange(0, 1500, 2, dtype=np.int32)
+    engine.set_elements(s.atomname)
+    counts, _ = engine.compositions(s.pos0[None], s.cell(), s.types, 5.4, targets=targets)
+    n = counts.sum(dim=1).cpu().numpy()
+    assert n.max() > 96 and n.max() <= 128 and n.min() <= 64, (n.min(), n.max())
+    worst = _check(engine, s, s.pos0[None], targets, cutoff=5.4)
+    assert worst < 1.0
+
+
 def test_nonperiodic_and_other_cutoff(engine):
     s = synth.make_system(1500, 0.05, seed=synth.BASE_SEED + 43)
     _check(engine, s, s.pos0[None], np.arange(0, 1500, 3, dtype=np.int32), cutoff=4.0, periodic=False)
