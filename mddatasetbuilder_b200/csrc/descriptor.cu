@@ -396,9 +396,8 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // the seed is good to about 2^-20; two Newton steps square that twice
     double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
@@ -408,7 +407,7 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double h = 0.5 * x;
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
+    for (int it = 0; it < 2; ++it) {
         const double e = fma(-h * y, y, 0.5);
         y = fma(y, e, y);
     }
@@ -803,54 +802,69 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     // 1e-12 ||M||, four orders below the floor of the stated tolerance; reciprocals and square roots
     // are MUFU seeds + Newton steps (fast_rcp / fast_rsqrt), a few ulp
     const double EPS = 1e-12;
+    // m = lowest index >= l of a negligible off-diagonal.  The O(n) search for it runs only at the
+    // start (and after an exact-zero stop); afterwards e[l] is tested at the top of every iteration
+    // and every other off-diagonal right when a sweep rewrites it, which is the only time it changes.
+    int m = -1;
     for (int l = 0; l < n; ++l) {
-        int iter = 0, m;
-        do {
-            for (m = l; m < n - 1; ++m) {
-                const double dd = fabs(d[m][tid]) + fabs(d[m + 1][tid]);
-                if (fabs(e[m][tid]) <= EPS * dd) break;
+        int iter = 0;
+        for (;;) {
+            if (m < l) {
+                for (m = l; m < n - 1; ++m) {
+                    const double dd = fabs(d[m][tid]) + fabs(d[m + 1][tid]);
+                    if (fabs(e[m][tid]) <= EPS * dd) break;
+                }
             }
-            if (m != l) {
-                if (iter++ == 80) {
-                    atomicExch(&stats->err, MDB_ERR_EIG_NOCONV);
+            if (m == l) break;
+            // l < m <= n - 1: l has converged when e[l] is negligible; m stays valid for l + 1
+            if (fabs(e[l][tid]) <= EPS * (fabs(d[l][tid]) + fabs(d[l + 1][tid]))) break;
+            if (iter++ == 80) {
+                atomicExch(&stats->err, MDB_ERR_EIG_NOCONV);
+                break;
+            }
+            const double dl = d[l][tid], el = e[l][tid];
+            double g = (d[l + 1][tid] - dl) * (0.5 * fast_rcp(el));
+            const double t1 = fma(g, g, 1.0);
+            double r = t1 * fast_rsqrt(t1);
+            g = d[m][tid] - dl + el * fast_rcp(g + (g >= 0.0 ? r : -r));
+            double sn = 1.0, c = 1.0, p = 0.0;
+            double dup = 0.0;  // d[i + 2] as the sweep left it
+            int i, msplit = -1;
+            for (i = m - 1; i >= l; --i) {
+                const double ei = e[i][tid];
+                double f = sn * ei;
+                const double b = c * ei;
+                const double t2 = fma(f, f, g * g);
+                if (t2 == 0.0) {
+                    r = 0.0;
+                    e[i + 1][tid] = 0.0;
+                    d[i + 1][tid] -= p;
+                    e[m][tid] = 0.0;
                     break;
                 }
-                const double dl = d[l][tid], el = e[l][tid];
-                double g = (d[l + 1][tid] - dl) * (0.5 * fast_rcp(el));
-                const double t1 = fma(g, g, 1.0);
-                double r = t1 * fast_rsqrt(t1);
-                g = d[m][tid] - dl + el * fast_rcp(g + (g >= 0.0 ? r : -r));
-                double sn = 1.0, c = 1.0, p = 0.0;
-                int i;
-                for (i = m - 1; i >= l; --i) {
-                    const double ei = e[i][tid];
-                    double f = sn * ei;
-                    const double b = c * ei;
-                    const double t2 = fma(f, f, g * g);
-                    if (t2 == 0.0) {
-                        r = 0.0;
-                        e[i + 1][tid] = 0.0;
-                        d[i + 1][tid] -= p;
-                        e[m][tid] = 0.0;
-                        break;
-                    }
-                    const double ir = fast_rsqrt(t2);
-                    r = t2 * ir;
-                    e[i + 1][tid] = r;
-                    sn = f * ir;
-                    c = g * ir;
-                    g = d[i + 1][tid] - p;
-                    r = (d[i][tid] - g) * sn + 2.0 * c * b;
-                    p = sn * r;
-                    d[i + 1][tid] = g + p;
-                    g = c * r - b;
-                }
-                if (r == 0.0 && i >= l) continue;
-                d[l][tid] -= p;
-                e[l][tid] = g;
-                e[m][tid] = 0.0;
+                const double ir = fast_rsqrt(t2);
+                r = t2 * ir;
+                e[i + 1][tid] = r;
+                sn = f * ir;
+                c = g * ir;
+                g = d[i + 1][tid] - p;
+                r = (d[i][tid] - g) * sn + 2.0 * c * b;
+                p = sn * r;
+                const double dn = g + p;
+                d[i + 1][tid] = dn;
+                if (i + 1 < m && t2 <= (EPS * EPS) * (fabs(dn) + fabs(dup)) * (fabs(dn) + fabs(dup))) msplit = i + 1;
+                dup = dn;
+                g = c * r - b;
             }
-        } while (m != l);
+            if (r == 0.0 && i >= l) {
+                m = -1;  // the sweep stopped early at an exact zero: search again
+                continue;
+            }
+            d[l][tid] -= p;
+            e[l][tid] = g;
+            e[m][tid] = 0.0;
+            if (msplit >= 0) m = msplit;
+        }
     }
     // ascending insertion sort
     for (int a = 1; a < n; ++a) {
