@@ -32,6 +32,14 @@ __global__ void __launch_bounds__(256) k_cnorm(const double *__restrict__ C, int
     cn[j] = s;
 }
 
+// ||c_j||^2 exactly as the assignment kernel below consumes it (tc_assign.cu re-scores its candidates with it)
+int kmeans_cnorm_run(mdb_ctx *c, const double *d_C, int K, int D, double *d_cn, cudaStream_t stream) {
+    k_cnorm<<<cdiv(K, 256), 256, 0, stream>>>(d_C, K, D, d_cn);
+    c->launches++;
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // grid: (row tiles, centroid splits).  part_val/part_idx: [splits][rows]
 __global__ void __launch_bounds__(AS_THREADS) k_assign(const double *__restrict__ X, long long ldx, long long rows,
                                                        const int *__restrict__ rowidx, const double *__restrict__ C, int K,

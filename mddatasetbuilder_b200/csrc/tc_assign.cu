@@ -100,10 +100,15 @@ struct TcParams {
     float *best1, *best2;
     int *idx1;
     long long *trace;   // optional [ntiles][8] clock64 stamps of CTA 0 (tools/tc_trace.py), else nullptr
+    // candidate mode: every (row, centroid) whose approximate score is <= thr[row] is appended to cand
+    const float *thr;
+    int2 *cand;
+    int *ncand;
+    int candcap;
 };
 
 // KD16 = padded feature width / 16: the inner dimension is 3 * 16 * KD16, i.e. 3 * KD16 MMAs per tile
-template <int KD16>
+template <int KD16, bool CAND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_assign_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int myrow = row0 + q * 32 + lane;
         float b1[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX}, b2[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};
         int i1[4] = {0, 0, 0, 0};
+        const float mythr = (CAND && myrow < P.rows) ? P.thr[myrow] : -FLT_MAX;  // rows past the end never qualify
         // cn of tile t sits in cn_s[t & 1]; the slice for tile t + 1 is fetched into a register while tile t
         // is processed, so its global-load latency stays off the per-tile critical path
         if (e < TC_BN) cn_s[e] = (e < P.K) ? P.cn[e] : FLT_MAX;
@@ -244,16 +250,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const float *cnp = cn_s + a * TC_BN + half * 64 + jj * 32;
-                // four independent running top-2 sets (value i goes to set i & 3) break the serial
-                // dependency through b1 / b2; the updates are branch-free
                 const int cbase = col0 + half * 64 + jj * 32;
+                if (CAND) {
+                    // the same arithmetic as the screening pass, so a row's own best score qualifies again
+                    unsigned hit = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = fmaf(-2.0f, __uint_as_float(r[jj][i]), cnp[i]);
-                    const int k = i & 3;
-                    b2[k] = fminf(b2[k], fmaxf(b1[k], v));
-                    i1[k] = v < b1[k] ? cbase + i : i1[k];
-                    b1[k] = fminf(b1[k], v);
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = fmaf(-2.0f, __uint_as_float(r[jj][i]), cnp[i]);
+                        hit |= (v <= mythr ? 1u : 0u) << i;
+                    }
+                    while (hit) {
+                        const int i = __ffs(hit) - 1;
+                        hit &= hit - 1;
+                        const int slot = atomicAdd(P.ncand, 1);
+                        if (slot < P.candcap) P.cand[slot] = make_int2(myrow, cbase + i);
+                    }
+                } else {
+                    // four independent running top-2 sets (value i goes to set i & 3) break the serial
+                    // dependency through b1 / b2; the updates are branch-free
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = fmaf(-2.0f, __uint_as_float(r[jj][i]), cnp[i]);
+                        const int k = i & 3;
+                        b2[k] = fminf(b2[k], fmaxf(b1[k], v));
+                        i1[k] = v < b1[k] ? cbase + i : i1[k];
+                        b1[k] = fminf(b1[k], v);
+                    }
                 }
             }
             if (e < TC_BN) cn_s[(a ^ 1) * TC_BN + e] = cn_next;
@@ -282,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             reinterpret_cast<int *>(mg)[256 + slot] = mi;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && myrow < P.rows) {
+        if (!CAND && half == 0 && myrow < P.rows) {
             const float c1 = mg[slot], c2 = mg[128 + slot];
             const int ci = reinterpret_cast<int *>(mg)[256 + slot];
             float o1, o2;
@@ -372,7 +394,8 @@ __global__ void __launch_bounds__(256) k_tc_decide(const float *__restrict__ b1,
                                                    const int *__restrict__ i1, const float *__restrict__ xn2,
                                                    const float *__restrict__ cmax2, long long rows, float relerr,
                                                    const int *__restrict__ rowidx, int *__restrict__ labels,
-                                                   int *__restrict__ amb_pos, int *__restrict__ amb_row, int *__restrict__ namb) {
+                                                   int *__restrict__ amb_pos, int *__restrict__ amb_row,
+                                                   float *__restrict__ amb_thr, int *__restrict__ namb) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     // |score error| <= 2 * relerr * ||x|| * max||c||  (Cauchy-Schwarz on the centred operands) + cn rounding
@@ -383,6 +406,10 @@ __global__ void __launch_bounds__(256) k_tc_decide(const float *__restrict__ b1,
         const int k = atomicAdd(namb, 1);
         amb_pos[k] = (int)r;
         amb_row[k] = rowidx ? rowidx[r] : (int)r;
+        // a centroid can only beat the approximate winner if its own approximate score is within
+        // 2 * bound of it (each score is off by at most `bound`); the factor leaves room for the
+        // float rounding of the threshold itself
+        amb_thr[k] = b1[r] + 2.0001f * bound + 1e-30f;
     }
 }
 
@@ -405,6 +432,55 @@ __global__ void __launch_bounds__(256) k_count_mismatch(const int *__restrict__ 
                                                         const int *__restrict__ labels, int *__restrict__ bad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && labels[pos[i]] != lab[i]) atomicAdd(bad, 1);
+}
+
+// ambiguous rows of the split operand, gathered so that the candidate pass reads them through one map
+__global__ void __launch_bounds__(256) k_gather_half_rows(const __half *__restrict__ A, const int *__restrict__ pos, int n,
+                                                          int kin, __half *__restrict__ out) {
+    const int vec = kin / 8;  // 16-byte pieces per row (kin is a multiple of 48)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * vec) return;
+    const int r = (int)(i / vec), v = (int)(i % vec);
+    reinterpret_cast<uint4 *>(out)[(size_t)r * vec + v] = reinterpret_cast<const uint4 *>(A)[(size_t)pos[r] * vec + v];
+}
+
+// doubles in an order-preserving unsigned form (for atomicMin)
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// exact score of one candidate pair, the arithmetic of k_assign (kmeans.cu): a forward chain of
+// fused multiply-adds over the features, then fma(-2, x.c, ||c||^2)
+__global__ void __launch_bounds__(256) k_cand_score(const int2 *__restrict__ cand, int ncand, const int *__restrict__ amb_row,
+                                                    const double *__restrict__ X, long long ldx, const double *__restrict__ C,
+                                                    int D, const double *__restrict__ cn, unsigned long long *__restrict__ key,
+                                                    unsigned long long *__restrict__ best) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ncand) return;
+    const int2 rc = cand[q];
+    const double *x = X + (long long)amb_row[rc.x] * ldx;
+    const double *c = C + (size_t)rc.y * D;
+    double acc = 0.0;
+    for (int k = 0; k < D; ++k) acc = fma(x[k], c[k], acc);
+    const unsigned long long kb = ordered_bits(fma(-2.0, acc, cn[rc.y]));
+    key[q] = kb;
+    atomicMin(&best[rc.x], kb);
+}
+
+// lowest centroid index among the candidates that reach the row minimum (strict <, lowest index on ties)
+__global__ void __launch_bounds__(256) k_cand_pick(const int2 *__restrict__ cand, int ncand,
+                                                   const unsigned long long *__restrict__ key,
+                                                   const unsigned long long *__restrict__ best, unsigned *__restrict__ lab) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ncand) return;
+    const int2 rc = cand[q];
+    if (key[q] == best[rc.x]) atomicMin(&lab[rc.x], (unsigned)rc.y);
+}
+
+__global__ void __launch_bounds__(256) k_count_unset(const unsigned *__restrict__ lab, int n, int *__restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && lab[i] == 0xFFFFFFFFu) atomicAdd(bad, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +524,36 @@ static int make_map(CUtensorMap *m, void *base, long long rows, int kin) {
 int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,
                       const double *d_C, int *d_labels, double *d_mind, double *h_inertia, const double *d_w,
                       cudaStream_t stream);
+int kmeans_cnorm_run(mdb_ctx *c, const double *d_C, int K, int D, double *d_cn, cudaStream_t stream);
+
+template <bool CAND>
+static int tc_launch_mode(int kd16, long long nblocks, size_t smem, const CUtensorMap &tmA, const CUtensorMap &tmB,
+                          const TcParams &P, cudaStream_t stream) {
+    const dim3 grid((unsigned)nblocks);
+#define MDB_TC_LAUNCH(KD)                                                                                               \
+    case KD:                                                                                                            \
+        MDB_CUDA(cudaFuncSetAttribute(k_assign_tc<KD, CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_assign_tc<KD, CAND><<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, P);                                         \
+        break;
+    switch (kd16) {
+        MDB_TC_LAUNCH(1)
+        MDB_TC_LAUNCH(2)
+        MDB_TC_LAUNCH(3)
+        MDB_TC_LAUNCH(4)
+        MDB_TC_LAUNCH(5)
+        MDB_TC_LAUNCH(6)
+        MDB_TC_LAUNCH(7)
+        MDB_TC_LAUNCH(8)
+    }
+#undef MDB_TC_LAUNCH
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+static int tc_launch(bool cand, int kd16, long long nblocks, size_t smem, const CUtensorMap &tmA, const CUtensorMap &tmB,
+                     const TcParams &P, cudaStream_t stream) {
+    return cand ? tc_launch_mode<true>(kd16, nblocks, smem, tmA, tmB, P, stream)
+                : tc_launch_mode<false>(kd16, nblocks, smem, tmA, tmB, P, stream);
+}
 
 // Tensor-core assignment with float64 resolution of near-ties.  *h_namb (optional) receives the
 // number of rows that went through the float64 kernel.
@@ -478,8 +584,15 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     // allocation (kept for the lifetime of the context, grown on demand)
     const size_t needA = align256((size_t)rows * Kin * sizeof(__half)), needB = align256((size_t)K * Kin * sizeof(__half));
     const size_t needf = align256((size_t)rows * sizeof(float));
-    const size_t total = needA + needB + 4 * needf + 3 * align256((size_t)rows * sizeof(int)) + align256((size_t)K * sizeof(float)) +
-                         align256((size_t)D * sizeof(double)) + 4096;
+    // near-ties are re-decided from a candidate list as long as at most a quarter of the rows are ambiguous
+    const long long ambcap = std::max<long long>(rows / 4, 1024);
+    const int candcap = (int)std::min<long long>(16 * ambcap, 1LL << 28);
+    const size_t needAa = align256((size_t)ambcap * Kin * sizeof(__half));
+    const size_t total = needA + needB + needAa + 5 * needf + 3 * align256((size_t)rows * sizeof(int)) +
+                         align256((size_t)K * sizeof(float)) + align256((size_t)K * sizeof(double)) +
+                         align256((size_t)D * sizeof(double)) + align256((size_t)candcap * sizeof(int2)) +
+                         align256((size_t)candcap * sizeof(unsigned long long)) +
+                         align256((size_t)ambcap * sizeof(unsigned long long)) + 8192;
     if (c->tc_bytes < total) {
         MDB_CUDA(cudaDeviceSynchronize());
         if (c->tc_mem) MDB_CUDA(cudaFree(c->tc_mem));
@@ -496,15 +609,21 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     };
     __half *A = (__half *)take(needA);
     __half *B = (__half *)take(needB);
-    float *b1 = (float *)take(needf), *b2 = (float *)take(needf), *xn2 = (float *)take(needf);
+    __half *Aamb = (__half *)take(needAa);
+    float *b1 = (float *)take(needf), *b2 = (float *)take(needf), *xn2 = (float *)take(needf), *amb_thr = (float *)take(needf);
     int *i1 = (int *)take(rows * sizeof(int)), *amb_pos = (int *)take(rows * sizeof(int)), *amb_row = (int *)take(rows * sizeof(int));
     float *cn = (float *)take((size_t)K * sizeof(float));
+    double *cn64 = (double *)take((size_t)K * sizeof(double));
     double *mu = (double *)take((size_t)D * sizeof(double));
     float *cmax2 = (float *)take(256);
     int *namb = (int *)(cmax2 + 8);
+    int *ncand = namb + 1;
     int *amb_lab = (int *)take(needf);
+    int2 *cand = (int2 *)take((size_t)candcap * sizeof(int2));
+    unsigned long long *ckey = (unsigned long long *)take((size_t)candcap * sizeof(unsigned long long));
+    unsigned long long *cbest = (unsigned long long *)take((size_t)ambcap * sizeof(unsigned long long));
 
-    MDB_CUDA(cudaMemsetAsync(namb, 0, sizeof(int), stream));
+    MDB_CUDA(cudaMemsetAsync(namb, 0, 2 * sizeof(int), stream));
     k_col_mean<<<D, 256, 0, stream>>>(d_C, K, D, mu);
     k_split_fp16<<<cdiv(K, 8), 256, 0, stream>>>(d_C, D, nullptr, K, D, Kd, mu, 1, B, cn);
     k_fmax<<<1, 256, 0, stream>>>(cn, K, cmax2);
@@ -517,6 +636,10 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     P.K = K;
     P.stages = stages;
     P.trace = nullptr;
+    P.thr = nullptr;
+    P.cand = nullptr;
+    P.ncand = nullptr;
+    P.candcap = 0;
     if (getenv("MDB_TC_TRACE") && d_diag) {   // developer switch: the stamps go to the start of d_diag
         P.trace = reinterpret_cast<long long *>(d_diag);
     }
@@ -526,23 +649,7 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     P.idx1 = i1;
     {
         ProfScope ps(c, "k_assign_tc", stream);
-        const dim3 grid((unsigned)cdiv(rows, TC_BM));
-#define MDB_TC_LAUNCH(KD)                                                                                          \
-    case KD:                                                                                                       \
-        MDB_CUDA(cudaFuncSetAttribute(k_assign_tc<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_assign_tc<KD><<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, P);                                          \
-        break;
-        switch (Kd / 16) {
-            MDB_TC_LAUNCH(1)
-            MDB_TC_LAUNCH(2)
-            MDB_TC_LAUNCH(3)
-            MDB_TC_LAUNCH(4)
-            MDB_TC_LAUNCH(5)
-            MDB_TC_LAUNCH(6)
-            MDB_TC_LAUNCH(7)
-            MDB_TC_LAUNCH(8)
-        }
-#undef MDB_TC_LAUNCH
+        if (tc_launch(false, Kd / 16, cdiv(rows, TC_BM), smem, tmA, tmB, P, stream)) return -1;
     }
     c->launches++;
     // per-product relative error of the split-fp16 contraction with fp32 accumulation over Kin terms
@@ -554,7 +661,7 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     // 1.5e-6 (Kin = 144) to 3.5e-6 (Kin = 384) in these units, i.e. 2.7x to 4x below this bound.
     const float relerr = 2.0f * (4.0f * 2.3841858e-7f + (float)(Kin / 16) * 1.1920929e-7f + 16.0f * 5.9604645e-8f);
     k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, relerr, d_rowidx, d_labels, amb_pos, amb_row,
-                                                    namb);
+                                                    amb_thr, namb);
     c->launches++;
     if (d_diag && !P.trace) {  // diagnostics: best / second-best approximate score, index, ||x'||^2 per row, then max ||c'||^2
         MDB_CUDA(cudaMemcpyAsync(d_diag, b1, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -569,7 +676,49 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     MDB_CUDA(cudaGetLastError());
     if (h_namb) *h_namb = h;
     if (h > 0) {
-        if (kmeans_assign_run(c, h, D, K, d_X, ldx, amb_row, d_C, amb_lab, nullptr, nullptr, nullptr, stream)) return -1;
+        // near-ties: a second tensor-core pass over just these rows lists every centroid whose
+        // approximate score is within the error bound of the row's best; those few pairs are then
+        // scored in float64 with the arithmetic of k_assign.  Too many ambiguous rows or candidates
+        // (degenerate data) fall back to the full float64 kernel for the ambiguous rows.
+        bool done = false;
+        if (h <= ambcap) {
+            k_gather_half_rows<<<cdiv((long long)h * (Kin / 8), 256), 256, 0, stream>>>(A, amb_pos, h, Kin, Aamb);
+            CUtensorMap tmAa;
+            if (make_map(&tmAa, Aamb, h, Kin)) return -1;
+            TcParams Pc = P;
+            Pc.rows = h;
+            Pc.thr = amb_thr;
+            Pc.cand = cand;
+            Pc.ncand = ncand;
+            Pc.candcap = candcap;
+            Pc.trace = nullptr;
+            {
+                ProfScope ps(c, "k_assign_tc<cand>", stream);
+                if (tc_launch(true, Kd / 16, cdiv(h, TC_BM), smem, tmAa, tmB, Pc, stream)) return -1;
+            }
+            c->launches += 2;
+            int nc = 0;
+            MDB_CUDA(cudaMemcpyAsync(&nc, ncand, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaStreamSynchronize(stream));
+            if (nc >= h && nc <= candcap) {
+                if (kmeans_cnorm_run(c, d_C, K, D, cn64, stream)) return -1;
+                MDB_CUDA(cudaMemsetAsync(cbest, 0xFF, (size_t)h * sizeof(unsigned long long), stream));
+                MDB_CUDA(cudaMemsetAsync(amb_lab, 0xFF, (size_t)h * sizeof(int), stream));
+                MDB_CUDA(cudaMemsetAsync(ncand, 0, sizeof(int), stream));
+                {
+                    ProfScope ps(c, "k_cand_score", stream);
+                    k_cand_score<<<cdiv(nc, 256), 256, 0, stream>>>(cand, nc, amb_row, d_X, ldx, d_C, D, cn64, ckey, cbest);
+                }
+                k_cand_pick<<<cdiv(nc, 256), 256, 0, stream>>>(cand, nc, ckey, cbest, (unsigned *)amb_lab);
+                k_count_unset<<<cdiv(h, 256), 256, 0, stream>>>((const unsigned *)amb_lab, h, ncand);
+                c->launches += 3;
+                int unset = 0;
+                MDB_CUDA(cudaMemcpyAsync(&unset, ncand, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                MDB_CUDA(cudaStreamSynchronize(stream));
+                done = unset == 0;  // every ambiguous row must have found its own best again
+            }
+        }
+        if (!done && kmeans_assign_run(c, h, D, K, d_X, ldx, amb_row, d_C, amb_lab, nullptr, nullptr, nullptr, stream)) return -1;
         k_scatter_labels<<<cdiv(h, 256), 256, 0, stream>>>(amb_pos, amb_lab, h, d_labels);
         c->launches++;
         MDB_CUDA(cudaGetLastError());
