@@ -352,12 +352,13 @@ def main():
         h_pos.copy_(pos)
         # C/H/O: every element's max valence is <= 4, so the 4-slot rows are lossless (checked on device)
         h_out = {"ell": torch.empty((frames, natoms, 4), dtype=torch.int32, pin_memory=True),
-                 "keys": torch.empty((frames, natoms), dtype=torch.int64, pin_memory=True),
+                 "keycode": torch.empty((frames, natoms), dtype=torch.uint8, pin_memory=True),
+                 "keytable": torch.empty(256, dtype=torch.int64, pin_memory=True),
                  "labels": torch.empty((frames, natoms), dtype=torch.int32, pin_memory=True)}
         torch.cuda.synchronize()
 
         def e2e_step():
-            eng.analyze_host(h_pos, cell, sysm.types, True, out=h_out, ell_width=4)
+            eng.analyze_host(h_pos, cell, sysm.types, True, out=h_out, ell_width=4, key_codes=True)
 
         for _ in range(min(args.warmup, 2) or 1):
             e2e_step()
@@ -372,14 +373,16 @@ def main():
         e_ms = max_over_ranks((t1 - t0) * 1e3) / args.steps
         # spot-check: the host path returned the same results as the device path
         same = bool(torch.equal(h_out["labels"][:2], out["labels"][:2].cpu()) and
+                    torch.equal(h_out["keytable"][h_out["keycode"][:2].long()], out["keys"][:2].cpu()) and
                     torch.equal(h_out["ell"][:2], out["ell"][:2, :, :4].cpu()) and
                     bool((out["ell"][:2, :, 4:] < 0).all().item()))
         e2e = {"value": units_per_step / (e_ms / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(h_pos.numel() * 8 + natoms),
                "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_out.values())),
                "ms_per_step": e_ms, "matches_device_path": same,
-               "api": "Engine.analyze_host -> mdb_analyze_frames_host (pinned host buffers, pipelined H2D/compute/D2H); "
-                      "results returned: bond rows [F,N,4] int32, keys [F,N] uint64, molecule labels [F,N] int32"}
+               "api": "Engine.analyze_host -> mdb_analyze_frames_host_coded (pinned host buffers, pipelined "
+                      "H2D/compute/D2H); results returned: bond rows [F,N,4] int32, bond-type key codes [F,N] uint8 + "
+                      "dictionary [256] uint64, molecule labels [F,N] int32"}
         del h_pos, h_out
 
     # ---- the other two stages of the metric, on the same frames (reported beside the headline) ----

@@ -129,6 +129,16 @@ int mdb_analyze_frames_host(mdb_ctx *ctx, int nframes, int natoms, const double 
  * [F][N][4] (lossless whenever every element's max valence is <= 4, e.g. C/H/O/N: the cleanup
  * guarantees degree <= MaxBonds; a longer row is an error). */
 
+/* Same, with the bond-type keys returned as one byte per atom: h_keycode[f][i] indexes h_keytable
+ * (256 entries, unused = all ones), a dictionary of the distinct 64-bit keys of the whole call.  What
+ * the caller of readatombondtype (reference detect.py:196-226) groups by is the key, of which a frame
+ * has a few dozen at most; 8 -> 1 byte per atom takes the device-to-host copy off the critical path.
+ * More than 256 distinct keys is an error (use mdb_analyze_frames_host). */
+int mdb_analyze_frames_host_coded(mdb_ctx *ctx, int nframes, int natoms, const double *h_pos,
+                                  const double *h_cell, const uint8_t *h_types, int periodic,
+                                  int32_t *h_ell, int ell_width, uint8_t *h_keycode,
+                                  uint64_t *h_keytable, int32_t *h_labels);
+
 /* ---- K5: element composition of the cutoff sphere -----------------------------
  * Replaces, per target atom, `distances = get_distances(a, all, mic=True);
  * Counter(symbols[distances < cutoff])` (datasetbuilder.py:312-322): d_counts

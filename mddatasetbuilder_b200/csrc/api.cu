@@ -32,6 +32,8 @@ static const char *err_text(int e) {
             return "atom type index outside the element table";
         case MDB_ERR_EIG_NOCONV:
             return "QL eigenvalue iteration did not converge";
+        case MDB_ERR_KEY_TABLE_FULL:
+            return "more than 256 distinct bond-type keys: use the 64-bit key output";
         default:
             return "unknown device-side error";
     }
@@ -363,25 +365,51 @@ struct PipeBuf {
     int32_t *ell4 = nullptr;
     uint64_t *keys = nullptr;
     int32_t *labels = nullptr;
+    uint8_t *code = nullptr;
 };
 
-extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
-                                       const uint8_t *h_types, int periodic, int32_t *h_ell, int ell_width,
-                                       uint64_t *h_keys, int32_t *h_labels) {
-    if (check_ctx(c, "mdb_analyze_frames_host")) return -1;
+// keys -> one-byte codes through a 256-slot open-addressing dictionary shared by the whole call
+#define KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+__global__ void __launch_bounds__(256) k_key_encode(const uint64_t *__restrict__ keys, long long n,
+                                                    unsigned long long *__restrict__ table, uint8_t *__restrict__ code,
+                                                    BondStats *stats) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i];
+    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 56);
+    for (int probe = 0; probe < 256; ++probe, h = (h + 1) & 255u) {
+        unsigned long long cur = table[h];
+        if (cur == KEY_EMPTY) cur = atomicCAS(&table[h], KEY_EMPTY, key);
+        if (cur == KEY_EMPTY || cur == key) {
+            code[i] = (uint8_t)h;
+            return;
+        }
+    }
+    atomicExch(&stats->err, MDB_ERR_KEY_TABLE_FULL);
+}
+
+static int analyze_host_impl(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
+                             const uint8_t *h_types, int periodic, int32_t *h_ell, int ell_width, uint64_t *h_keys,
+                             uint8_t *h_keycode, uint64_t *h_keytable, int32_t *h_labels) {
     if (nframes <= 0 || natoms <= 0) return 0;
     const int maxb = c->opt_max_bonds;
-    const int per = frames_per_chunk(c, nframes, natoms);
+    // the host path pipelines copies against compute, so it wants more, smaller chunks than the device
+    // path (measured on B200, 100k-atom frames: 160 / 80 / 40 / 20 / 10 frames per chunk = 68.9 / 63.1 /
+    // 61.6 / 63.1 / 67.5 ms per 1e8 atom-frames)
+    int per = frames_per_chunk(c, nframes, natoms);
+    if (c->opt_frames_per_launch <= 0) per = std::max(1, std::min(per, (4 << 20) / std::max(natoms, 1)));
+    const bool want_keys = h_keys || h_keycode;
     const size_t cn = (size_t)per * natoms;
     const size_t sz_pos = align256(cn * 3 * sizeof(double)), sz_ell = align256(cn * maxb * sizeof(int32_t)),
-                 sz_keys = align256(cn * sizeof(uint64_t)), sz_lab = align256(cn * sizeof(int32_t));
+                 sz_keys = align256(cn * sizeof(uint64_t)), sz_lab = align256(cn * sizeof(int32_t)),
+                 sz_code = h_keycode ? align256(cn) + 256 * sizeof(uint64_t) : 0;
     if (ell_width != 0 && ell_width != 4 && ell_width != maxb) {
         mdb_set_error("mdb_analyze_frames_host: ell_width must be 0 (= max_bonds), 4 or max_bonds");
         return -1;
     }
     const bool narrow = ell_width == 4 && maxb != 4;
     const size_t sz_ell4 = narrow ? align256(cn * 4 * sizeof(int32_t)) : 0;
-    const size_t need = sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4;
+    const size_t need = sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4 + sz_code;
     PipeBuf b[2];
     for (int k = 0; k < 2; ++k) {
         if (c->pipe_cap[k] < need) {
@@ -398,7 +426,10 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
         b[k].keys = (uint64_t *)(m + sz_pos + sz_ell);
         b[k].labels = (int32_t *)(m + sz_pos + sz_ell + sz_keys);
         b[k].ell4 = (int32_t *)(m + sz_pos + sz_ell + sz_keys + sz_lab);
+        b[k].code = (uint8_t *)(m + sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4);
     }
+    // the dictionary lives behind the code bytes of buffer 0
+    unsigned long long *d_table = h_keycode ? (unsigned long long *)(b[0].code + align256(cn)) : nullptr;
     if (c->pipe_types_cap < (size_t)natoms) {
         MDB_CUDA(cudaDeviceSynchronize());
         if (c->pipe_types) MDB_CUDA(cudaFree(c->pipe_types));
@@ -409,6 +440,7 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
     cudaStream_t s_in = c->pipe[0], s_c = c->pipe[1], s_out = c->pipe[2];
     MDB_CUDA(cudaMemcpyAsync(c->pipe_types, h_types, natoms, cudaMemcpyHostToDevice, s_c));
     MDB_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(BondStats), s_c));
+    if (d_table) MDB_CUDA(cudaMemsetAsync(d_table, 0xFF, 256 * sizeof(uint64_t), s_c));
     int chunk = 0;
     for (int f0 = 0; f0 < nframes; f0 += per, ++chunk) {
         const int F = std::min(per, nframes - f0);
@@ -421,9 +453,13 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
         MDB_CUDA(cudaStreamWaitEvent(s_c, c->pipe_in[k], 0));
         if (chunk >= 2) MDB_CUDA(cudaStreamWaitEvent(s_c, c->pipe_out[k], 0));
         if (analyze_chunk(c, F, natoms, B.pos, h_cell ? h_cell + (size_t)f0 * 9 : nullptr, c->pipe_types, periodic, B.ell,
-                          h_keys ? B.keys : nullptr, h_labels ? B.labels : nullptr, s_c)) {
+                          want_keys ? B.keys : nullptr, h_labels ? B.labels : nullptr, s_c)) {
             cudaDeviceSynchronize();
             return -1;
+        }
+        if (h_keycode) {
+            k_key_encode<<<cdiv((long long)n, 256), 256, 0, s_c>>>(B.keys, (long long)n, d_table, B.code, c->d_stats);
+            c->launches++;
         }
         if (h_ell && narrow) {
             k_ell_narrow<<<cdiv((long long)n, 256), 256, 0, s_c>>>(B.ell, maxb, 4, (long long)n, B.ell4, c->d_stats);
@@ -436,6 +472,7 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
         else if (h_ell)
             MDB_CUDA(cudaMemcpyAsync(h_ell + o * maxb, B.ell, n * maxb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
         if (h_keys) MDB_CUDA(cudaMemcpyAsync(h_keys + o, B.keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_out));
+        if (h_keycode) MDB_CUDA(cudaMemcpyAsync(h_keycode + o, B.code, n, cudaMemcpyDeviceToHost, s_out));
         if (h_labels)
             MDB_CUDA(cudaMemcpyAsync(h_labels + o, B.labels, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
         MDB_CUDA(cudaEventRecord(c->pipe_out[k], s_out));
@@ -443,6 +480,7 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
     MDB_CUDA(cudaStreamSynchronize(s_in));
     MDB_CUDA(cudaStreamSynchronize(s_c));
     MDB_CUDA(cudaStreamSynchronize(s_out));
+    if (h_keycode && h_keytable) MDB_CUDA(cudaMemcpy(h_keytable, d_table, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     BondStats hs;
     MDB_CUDA(cudaMemcpy(&hs, c->d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
     if (hs.err) {
@@ -450,4 +488,24 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
         return hs.err;
     }
     return 0;
+}
+
+extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
+                                       const uint8_t *h_types, int periodic, int32_t *h_ell, int ell_width,
+                                       uint64_t *h_keys, int32_t *h_labels) {
+    if (check_ctx(c, "mdb_analyze_frames_host")) return -1;
+    return analyze_host_impl(c, nframes, natoms, h_pos, h_cell, h_types, periodic, h_ell, ell_width, h_keys, nullptr, nullptr,
+                             h_labels);
+}
+
+extern "C" int mdb_analyze_frames_host_coded(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
+                                             const uint8_t *h_types, int periodic, int32_t *h_ell, int ell_width,
+                                             uint8_t *h_keycode, uint64_t *h_keytable, int32_t *h_labels) {
+    if (check_ctx(c, "mdb_analyze_frames_host_coded")) return -1;
+    if (!h_keycode || !h_keytable) {
+        mdb_set_error("mdb_analyze_frames_host_coded: h_keycode and h_keytable are required");
+        return -1;
+    }
+    return analyze_host_impl(c, nframes, natoms, h_pos, h_cell, h_types, periodic, h_ell, ell_width, nullptr, h_keycode,
+                             h_keytable, h_labels);
 }

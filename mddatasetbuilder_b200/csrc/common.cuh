@@ -21,6 +21,7 @@
 #define MDB_ERR_CSR_OVERFLOW 3
 #define MDB_ERR_TYPE_RANGE 4
 #define MDB_ERR_EIG_NOCONV 5  // QL iteration did not converge
+#define MDB_ERR_KEY_TABLE_FULL 6  // more than 256 distinct bond-type keys in one coded call
 
 struct FrameGeom {
     double ortho[9];    // fractional -> cartesian (lattice vectors as columns), OB's _mOrtho

@@ -355,9 +355,11 @@ class Engine:
         _lib.check(rc, "mdb_kmeans_apply_update")
 
     def analyze_host(self, pos, cell, types, periodic=True, want_keys=True, want_labels=True, out=None,
-                     ell_width=0):
+                     ell_width=0, key_codes=False):
         """Host-buffer path (e2e): numpy / pinned tensors in, numpy out; H2D and D2H copies
-        are pipelined inside the library."""
+        are pipelined inside the library.  key_codes=True returns the bond-type keys as one byte per
+        atom ("keycode") plus the dictionary "keytable" (256 x uint64, unused = all ones) instead of
+        "keys"."""
         torch = _torch()
         if isinstance(pos, torch.Tensor):
             pos_np = pos.numpy()
@@ -372,9 +374,6 @@ class Engine:
         ell = out.get("ell")
         if ell is None:
             ell = np.empty((F, N, ell_width or self.max_bonds), dtype=np.int32)
-        keys = out.get("keys") if want_keys else None
-        if want_keys and keys is None:
-            keys = np.empty((F, N), dtype=np.uint64)
         labels = out.get("labels") if want_labels else None
         if want_labels and labels is None:
             labels = np.empty((F, N), dtype=np.int32)
@@ -384,6 +383,21 @@ class Engine:
                 return C.c_void_p(0)
             return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else C.c_void_p(a.ctypes.data)
 
+        if key_codes:
+            code = out.get("keycode")
+            if code is None:
+                code = np.empty((F, N), dtype=np.uint8)
+            table = out.get("keytable")
+            if table is None:
+                table = np.empty(256, dtype=np.uint64)
+            rc = self.L.mdb_analyze_frames_host_coded(self.ctx, int(F), int(N), p(pos_np), _np_ptr(cells), p(types_np),
+                                                      int(bool(periodic)), p(ell), int(ell_width), p(code), p(table),
+                                                      p(labels))
+            _lib.check(rc, "mdb_analyze_frames_host_coded")
+            return {"ell": ell, "keycode": code, "keytable": table, "labels": labels}
+        keys = out.get("keys") if want_keys else None
+        if want_keys and keys is None:
+            keys = np.empty((F, N), dtype=np.uint64)
         rc = self.L.mdb_analyze_frames_host(self.ctx, int(F), int(N), p(pos_np), _np_ptr(cells), p(types_np),
                                             int(bool(periodic)), p(ell), int(ell_width), p(keys), p(labels))
         _lib.check(rc, "mdb_analyze_frames_host")

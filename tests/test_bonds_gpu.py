@@ -147,6 +147,17 @@ def test_host_path_matches_device_path(engine):
     narrow = engine.analyze_host(frames, s.cell(), s.types, ell_width=4)
     full = dev["ell"].cpu().numpy()
     assert narrow["ell"].shape[-1] == 4 and np.array_equal(narrow["ell"], full[:, :, :4]) and (full[:, :, 4:] < 0).all()
+    # one-byte key codes + dictionary decode to the same 64-bit keys
+    engine.set_option("frames_per_launch", 3)
+    try:
+        coded = engine.analyze_host(frames, s.cell(), s.types, ell_width=4, key_codes=True)
+    finally:
+        engine.set_option("frames_per_launch", 0)
+    table = coded["keytable"]
+    assert np.array_equal(table[coded["keycode"]], host["keys"])
+    used = table != np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert set(table[used].tolist()) == set(np.unique(host["keys"]).tolist())
+    assert np.array_equal(coded["labels"], host["labels"]) and np.array_equal(coded["ell"], narrow["ell"])
 
 
 def test_bondfile_keys(engine):
