@@ -198,7 +198,7 @@ int mdb_kmeans_assign(mdb_ctx *ctx, long long rows, int D, int K, const double *
 
 /* Same labels as mdb_kmeans_assign, computed with a tcgen05 (tensor-core) screening pass on
  * split-fp16 operands; rows whose best / second-best gap is inside the error bound are
- * re-decided by the float64 kernel (*h_nrecheck = how many).  D <= 128.  Synchronises. */
+ * re-decided in float64 (*h_nrecheck = how many).  D <= 112.  Synchronises. */
 int mdb_kmeans_assign_tc(mdb_ctx *ctx, long long rows, int D, int K, const double *d_X,
                          long long ldx, const int32_t *d_rowidx, const double *d_centers,
                          int32_t *d_labels, long long *h_nrecheck, float *d_diag, void *stream);

@@ -2,13 +2,15 @@
 //
 // The reference's assignment (scikit-learn lloyd_iter_chunked_dense, cluster/_k_means_lloyd.pyx:168-213,
 // driven from datasetbuilder.py:371-376) compares float64 scores ||c_j||^2 - 2 x.c_j.  Here the
-// contraction runs as tcgen05.mma (kind::f16, fp32 accumulation in TMEM) on split-fp16 operands
-//     x ~ x_hi + x_lo,  c ~ c_hi + c_lo,   x.c ~ x_hi.c_hi + x_hi.c_lo + x_lo.c_hi
-// (one GEMM with the inner dimension tripled: A' = [x_hi | x_hi | x_lo], B' = [c_hi | c_lo | c_hi]),
-// after centring both operands on the centroid mean so that the products stay small.  The epilogue
-// keeps, per row, the best and second-best approximate score.  A row whose gap exceeds its error
-// bound takes the tensor-core label; the others (near-ties) are re-decided by the exact float64
-// kernel (kmeans.cu: k_assign), so the final labels are those of the float64 comparison.
+// equivalent quantity s_j = x.c_j - ||c_j||^2 / 2 (to be MAXIMISED) comes out of one tcgen05.mma GEMM
+// (kind::f16, fp32 accumulation in TMEM) on split-fp16 operands
+//     x ~ x_hi + x_lo,  c ~ c_hi + c_lo,   x.c ~ x_hi.c_hi + x_hi.c_lo + x_lo.c_hi,
+// i.e. the inner dimension tripled (A' = [x_hi | x_hi | x_lo], B' = [c_hi | c_lo | c_hi]) after centring
+// both operands on the centroid mean so that the products stay small, plus one more 16-wide block that
+// carries the norm: A' gets (1, 1, 1, 0...), B' gets -||c||^2/2 split over three fp16 values.  The
+// epilogue therefore only keeps, per row, the best and second-best accumulator value.  A row whose gap
+// exceeds its error bound takes the tensor-core label; the others (near-ties) are re-decided in float64
+// (see kmeans_assign_tc_run), so the final labels are those of the float64 comparison.
 //
 // One CTA = one 128-row tile against all centroids: A' stays in shared memory (TMA, 128B swizzle),
 // B' tiles of 128 centroids stream through a TMA/mbarrier ring, accumulators are double-buffered
@@ -28,7 +30,7 @@
 #define TC_KCH 64                      // fp16 elements per 128-byte swizzle row
 #define TC_CHUNK_BYTES (TC_BM * 128)   // one [128 rows][64 elem] slab
 #define TC_THREADS 320
-#define TC_MAXCH 6                     // 3*Kd <= 384
+#define TC_MAXCH 6                     // 3*Kd + 16 <= 384
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -96,7 +98,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 struct TcParams {
     int rows, K, stages;
-    const float *cn;   // [K] squared norm of the centred centroids
     float *best1, *best2;
     int *idx1;
     long long *trace;   // optional [ntiles][8] clock64 stamps of CTA 0 (tools/tc_trace.py), else nullptr
@@ -107,16 +108,16 @@ struct TcParams {
     int candcap;
 };
 
-// KD16 = padded feature width / 16: the inner dimension is 3 * 16 * KD16, i.e. 3 * KD16 MMAs per tile
+// KD16 = padded feature width / 16: the inner dimension is 3 * 16 * KD16 + 16, i.e. 3 * KD16 + 1 MMAs per tile
 template <int KD16, bool CAND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_assign_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // carve: A slabs | B ring | barriers | cn staging | tmem base
+    // carve: A slabs | B ring | barriers | merge staging | tmem base
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     unsigned char *gen = smem + (sbase - smem_u32(smem));
-    constexpr int nch = (3 * 16 * KD16 + TC_KCH - 1) / TC_KCH;
-    constexpr int NMMA = 3 * KD16;
+    constexpr int nch = (3 * 16 * KD16 + 16 + TC_KCH - 1) / TC_KCH;
+    constexpr int NMMA = 3 * KD16 + 1;
     const int S = P.stages;
     const uint32_t sA = sbase;
     const uint32_t sB = sA + (uint32_t)nch * TC_CHUNK_BYTES;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t bar_bempty = bar_bfull + 8 * 4;   // [S] (S <= 4)
     const uint32_t bar_tfull = bar_bempty + 8 * 4;   // [2]
     const uint32_t bar_tempty = bar_tfull + 16;      // [2]
-    float *cn_s = reinterpret_cast<float *>(gtail + 128);          // [2][128]
+    float *mrg_s = reinterpret_cast<float *>(gtail + 128);         // [3][128]: merge of the two column halves
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 128 + 1536);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,22 +216,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ===== epilogue: warps 2..9; warp % 4 selects the TMEM lane quarter, (warp - 2) / 4 the column half =====
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        const int e = (warp - 2) * 32 + lane;     // 0..255: staging index for cn (first 128 used)
         const int myrow = row0 + q * 32 + lane;
-        float b1[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX}, b2[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};
-        int i1[4] = {0, 0, 0, 0};
-        const float mythr = (CAND && myrow < P.rows) ? P.thr[myrow] : -FLT_MAX;  // rows past the end never qualify
-        // cn of tile t sits in cn_s[t & 1]; the slice for tile t + 1 is fetched into a register while tile t
-        // is processed, so its global-load latency stays off the per-tile critical path
-        if (e < TC_BN) cn_s[e] = (e < P.K) ? P.cn[e] : FLT_MAX;
+        // running best / second best (largest) score and the index of the best, in four independent sets
+        // (value i goes to set i & 3) so that the updates do not serialise; all updates are branch-free
+        float b1[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}, b2[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+        int il[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};  // best index = chunk base + position inside the chunk
+        const float mythr = (CAND && myrow < P.rows) ? P.thr[myrow] : FLT_MAX;  // rows past the end never qualify
         for (int t = 0; t < ntiles; ++t) {
             const int a = t & 1;
             const uint32_t aph = (uint32_t)(t >> 1) & 1u;
             const int col0 = t * TC_BN;
-            // orders: cn_s[a] written (previous iteration) -> read below; cn_s[a ^ 1] read (tile t - 1) -> rewritten below
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            float cn_next = FLT_MAX;
-            if (e < TC_BN && col0 + TC_BN + e < P.K) cn_next = P.cn[col0 + TC_BN + e];
             const bool tr = P.trace && blockIdx.x == 0 && threadIdx.x == 64;
             if (tr) P.trace[t * 8 + 4] = clock64();
             mbar_wait(bar_tfull + 8 * a, aph);
@@ -249,54 +244,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (tr) P.trace[t * 8 + 6] = clock64();
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
-                const float *cnp = cn_s + a * TC_BN + half * 64 + jj * 32;
                 const int cbase = col0 + half * 64 + jj * 32;
                 if (CAND) {
                     // the same arithmetic as the screening pass, so a row's own best score qualifies again
                     unsigned hit = 0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float v = fmaf(-2.0f, __uint_as_float(r[jj][i]), cnp[i]);
-                        hit |= (v <= mythr ? 1u : 0u) << i;
-                    }
+                    for (int i = 0; i < 32; ++i) hit |= (__uint_as_float(r[jj][i]) >= mythr ? 1u : 0u) << i;
                     while (hit) {
                         const int i = __ffs(hit) - 1;
                         hit &= hit - 1;
-                        const int slot = atomicAdd(P.ncand, 1);
-                        if (slot < P.candcap) P.cand[slot] = make_int2(myrow, cbase + i);
+                        if (cbase + i < P.K) {  // padding centroids never count
+                            const int slot = atomicAdd(P.ncand, 1);
+                            if (slot < P.candcap) P.cand[slot] = make_int2(myrow, cbase + i);
+                        }
                     }
                 } else {
-                    // four independent running top-2 sets (value i goes to set i & 3) break the serial
-                    // dependency through b1 / b2; the updates are branch-free
+                    // per score: three min/max, one compare, one select with an immediate; the 32-column
+                    // chunk of the current best is noted once per chunk and set
+                    float o1[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o1[k] = b1[k];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float v = fmaf(-2.0f, __uint_as_float(r[jj][i]), cnp[i]);
+                        const float v = __uint_as_float(r[jj][i]);
                         const int k = i & 3;
-                        b2[k] = fminf(b2[k], fmaxf(b1[k], v));
-                        i1[k] = v < b1[k] ? cbase + i : i1[k];
-                        b1[k] = fminf(b1[k], v);
+                        b2[k] = fmaxf(b2[k], fminf(b1[k], v));
+                        il[k] = v > b1[k] ? i : il[k];
+                        b1[k] = fmaxf(b1[k], v);
                     }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ib[k] = b1[k] > o1[k] ? cbase : ib[k];
                 }
             }
-            if (e < TC_BN) cn_s[(a ^ 1) * TC_BN + e] = cn_next;
             if (tr) P.trace[t * 8 + 7] = clock64();
         }
         // merge the four sets of this thread, then the two column halves of the row; on equal scores the
         // lower centroid index wins (such rows are re-decided in float64 anyway: their gap is zero)
         float m1 = b1[0], m2 = b2[0];
-        int mi = i1[0];
+        int mi = ib[0] + il[0];
 #pragma unroll
         for (int k = 1; k < 4; ++k) {
-            if (b1[k] < m1 || (b1[k] == m1 && i1[k] < mi)) {
-                m2 = fminf(m1, b2[k]);
+            const int ik = ib[k] + il[k];
+            if (b1[k] > m1 || (b1[k] == m1 && ik < mi)) {
+                m2 = fmaxf(m1, b2[k]);
                 m1 = b1[k];
-                mi = i1[k];
+                mi = ik;
             } else {
-                m2 = fminf(m2, b1[k]);
+                m2 = fmaxf(m2, b1[k]);
             }
         }
-        float *mg = cn_s;  // staging is free after the last tile once every epilogue warp is here
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float *mg = mrg_s;
         const int slot = q * 32 + lane;
         if (half == 1) {
             mg[slot] = m1;
@@ -309,14 +306,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int ci = reinterpret_cast<int *>(mg)[256 + slot];
             float o1, o2;
             int oi;
-            if (c1 < m1) {
+            if (c1 > m1 || (c1 == m1 && ci < mi)) {
                 o1 = c1;
                 oi = ci;
-                o2 = fminf(m1, c2);
+                o2 = fmaxf(m1, c2);
             } else {
                 o1 = m1;
                 oi = mi;
-                o2 = fminf(m2, c1);
+                o2 = fmaxf(m2, c1);
             }
             P.best1[myrow] = o1;
             P.best2[myrow] = o2;
@@ -348,16 +345,32 @@ __global__ void __launch_bounds__(256) k_col_mean(const double *__restrict__ C, 
     if (threadIdx.x == 0) mu[k] = s[0] / K;
 }
 
-// rows of X (or of C when is_c) -> split fp16, tripled inner dimension
-//   X:  [hi | hi | lo]      C:  [hi | lo | hi]
+// power of two S with max||c||^2 / 2 <= 32768 S: the norm block holds -||c||^2 / (2 S) on the centroid
+// side and S on the row side, so it stays inside the fp16 range whatever the magnitude of the data
+__device__ __forceinline__ float norm_scale(float cmax2) {
+    float s = 1.f;
+    while (s < 32768.f && cmax2 > 65536.f * s) s *= 2.f;
+    return s;
+}
+
+// rows of X (or of C when is_c) -> split fp16, tripled inner dimension + the 16-wide norm block
+//   X:  [hi | hi | lo | S S S 0...]      C:  [hi | lo | hi | h0 h1 h2 0...],  S (h0 + h1 + h2) ~ -||c'||^2 / 2
+// The C side is written in two steps (the scale needs the largest norm): features and norms here,
+// the block by k_norm_block; rows_out > rows pads B' to whole 128-centroid tiles with centroids that
+// never win (zero features, block -60000).
 __global__ void __launch_bounds__(256) k_split_fp16(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
-                                                    long long rows, int D, int Kd, const double *__restrict__ mu, int is_c,
+                                                    long long rows, long long rows_out, int D, int Kd,
+                                                    const double *__restrict__ mu, int is_c, const float *__restrict__ cmax2,
                                                     __half *__restrict__ out, float *__restrict__ norm2) {
     const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= rows) return;
+    if (r >= rows_out) return;
     const int lane = threadIdx.x & 31;
+    __half *o = out + (size_t)r * (3 * Kd + 16);
+    if (r >= rows) {  // padding centroid
+        for (int k = lane; k < 3 * Kd + 16; k += 32) o[k] = __float2half(k == 3 * Kd ? -60000.f : 0.f);
+        return;
+    }
     const double *x = X + (rowidx ? (long long)rowidx[r] : r) * ldx;
-    __half *o = out + (size_t)r * 3 * Kd;
     double n2 = 0.0;
     for (int k = lane; k < Kd; k += 32) {
         __half hi = __float2half(0.f), lo = hi;
@@ -373,7 +386,31 @@ __global__ void __launch_bounds__(256) k_split_fp16(const double *__restrict__ X
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, s);
+    if (!is_c && lane < 16) o[3 * Kd + lane] = __float2half(lane < 3 ? norm_scale(*cmax2) : 0.f);
     if (lane == 0) norm2[r] = (float)n2;
+}
+
+__global__ void __launch_bounds__(256) k_norm_block(const double *__restrict__ C, int K, int D, int Kd,
+                                                    const double *__restrict__ mu, const float *__restrict__ cmax2,
+                                                    __half *__restrict__ out) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= K) return;
+    const int lane = threadIdx.x & 31;
+    double n2 = 0.0;
+    for (int k = lane; k < D; k += 32) {
+        const double v = C[(size_t)r * D + k] - mu[k];
+        n2 += v * v;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, s);
+    if (lane < 16) {
+        const double h = -0.5 * n2 / (double)norm_scale(*cmax2);
+        const __half h0 = __double2half(h);
+        const double r1 = h - (double)__half2float(h0);
+        const __half h1 = __double2half(r1);
+        const __half h2 = __double2half(r1 - (double)__half2float(h1));
+        out[(size_t)r * (3 * Kd + 16) + 3 * Kd + lane] = lane == 0 ? h0 : lane == 1 ? h1 : lane == 2 ? h2 : __float2half(0.f);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_fmax(const float *__restrict__ v, int n, float *__restrict__ out) {
@@ -392,15 +429,18 @@ __global__ void __launch_bounds__(256) k_fmax(const float *__restrict__ v, int n
 // accept the tensor-core label when the gap beats the error bound; list the rest for float64
 __global__ void __launch_bounds__(256) k_tc_decide(const float *__restrict__ b1, const float *__restrict__ b2,
                                                    const int *__restrict__ i1, const float *__restrict__ xn2,
-                                                   const float *__restrict__ cmax2, long long rows, float relerr,
+                                                   const float *__restrict__ cmax2, long long rows, int K, float relerr,
                                                    const int *__restrict__ rowidx, int *__restrict__ labels,
                                                    int *__restrict__ amb_pos, int *__restrict__ amb_row,
                                                    float *__restrict__ amb_thr, int *__restrict__ namb) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
-    // |score error| <= 2 * relerr * ||x|| * max||c||  (Cauchy-Schwarz on the centred operands) + cn rounding
-    const float bound = 2.f * relerr * sqrtf(xn2[r] * (*cmax2)) + 2.4e-7f * (*cmax2) + 1e-30f;
-    if (b2[r] - b1[r] > 2.f * bound) {
+    // |score error| <= relerr * ||x|| * max||c||  (Cauchy-Schwarz on the centred operands)
+    //                  + 2^-22 max||c||^2 (the norm block is built from the unsplit centroid)
+    //                  + one fp32 rounding of the final sum, 2^-23 (||x|| ||c|| + ||c||^2 / 2)
+    const float xc = sqrtf(xn2[r] * (*cmax2));
+    const float bound = (relerr + 1.2e-7f) * xc + 3.0e-7f * (*cmax2) + 1e-30f;
+    if (b1[r] - b2[r] > 2.f * bound && i1[r] < K) {
         labels[r] = i1[r];
     } else {
         const int k = atomicAdd(namb, 1);
@@ -409,7 +449,7 @@ __global__ void __launch_bounds__(256) k_tc_decide(const float *__restrict__ b1,
         // a centroid can only beat the approximate winner if its own approximate score is within
         // 2 * bound of it (each score is off by at most `bound`); the factor leaves room for the
         // float rounding of the threshold itself
-        amb_thr[k] = b1[r] + 2.0001f * bound + 1e-30f;
+        amb_thr[k] = b1[r] - 2.0001f * bound - 1e-30f;
     }
 }
 
@@ -437,7 +477,7 @@ __global__ void __launch_bounds__(256) k_count_mismatch(const int *__restrict__ 
 // ambiguous rows of the split operand, gathered so that the candidate pass reads them through one map
 __global__ void __launch_bounds__(256) k_gather_half_rows(const __half *__restrict__ A, const int *__restrict__ pos, int n,
                                                           int kin, __half *__restrict__ out) {
-    const int vec = kin / 8;  // 16-byte pieces per row (kin is a multiple of 48)
+    const int vec = kin / 8;  // 16-byte pieces per row (kin is a multiple of 16)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n * vec) return;
     const int r = (int)(i / vec), v = (int)(i % vec);
@@ -543,7 +583,6 @@ static int tc_launch_mode(int kd16, long long nblocks, size_t smem, const CUtens
         MDB_TC_LAUNCH(5)
         MDB_TC_LAUNCH(6)
         MDB_TC_LAUNCH(7)
-        MDB_TC_LAUNCH(8)
     }
 #undef MDB_TC_LAUNCH
     MDB_CUDA(cudaGetLastError());
@@ -564,10 +603,10 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
         return 0;
     }
     const int Kd = (D + 15) / 16 * 16;
-    const int Kin = 3 * Kd;
+    const int Kin = 3 * Kd + 16;
     const int nch = (Kin + TC_KCH - 1) / TC_KCH;
     if (nch > TC_MAXCH || rows >= (1LL << 31) || K < 1) {
-        mdb_set_error("kmeans_assign_tc: D must be <= 128 and rows < 2^31");
+        mdb_set_error("kmeans_assign_tc: D must be <= 112 and rows < 2^31");
         return -1;
     }
     int stages = nch <= 2 ? 4 : (nch <= 3 ? 3 : (nch <= 4 ? 2 : 1));
@@ -582,7 +621,8 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     }
     // the exact kernel below re-uses the arena, so everything that must survive it lives in its own
     // allocation (kept for the lifetime of the context, grown on demand)
-    const size_t needA = align256((size_t)rows * Kin * sizeof(__half)), needB = align256((size_t)K * Kin * sizeof(__half));
+    const long long Kpad = cdiv((long long)K, TC_BN) * TC_BN;
+    const size_t needA = align256((size_t)rows * Kin * sizeof(__half)), needB = align256((size_t)Kpad * Kin * sizeof(__half));
     const size_t needf = align256((size_t)rows * sizeof(float));
     // near-ties are re-decided from a candidate list as long as at most a quarter of the rows are ambiguous
     const long long ambcap = std::max<long long>(rows / 4, 1024);
@@ -625,12 +665,13 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
 
     MDB_CUDA(cudaMemsetAsync(namb, 0, 2 * sizeof(int), stream));
     k_col_mean<<<D, 256, 0, stream>>>(d_C, K, D, mu);
-    k_split_fp16<<<cdiv(K, 8), 256, 0, stream>>>(d_C, D, nullptr, K, D, Kd, mu, 1, B, cn);
+    k_split_fp16<<<cdiv(Kpad, 8), 256, 0, stream>>>(d_C, D, nullptr, K, Kpad, D, Kd, mu, 1, nullptr, B, cn);
     k_fmax<<<1, 256, 0, stream>>>(cn, K, cmax2);
-    k_split_fp16<<<cdiv(rows, 8), 256, 0, stream>>>(d_X, ldx, d_rowidx, rows, D, Kd, mu, 0, A, xn2);
-    c->launches += 4;
+    k_norm_block<<<cdiv(K, 8), 256, 0, stream>>>(d_C, K, D, Kd, mu, cmax2, B);
+    k_split_fp16<<<cdiv(rows, 8), 256, 0, stream>>>(d_X, ldx, d_rowidx, rows, rows, D, Kd, mu, 0, cmax2, A, xn2);
+    c->launches += 5;
     CUtensorMap tmA, tmB;
-    if (make_map(&tmA, A, rows, Kin) || make_map(&tmB, B, K, Kin)) return -1;
+    if (make_map(&tmA, A, rows, Kin) || make_map(&tmB, B, Kpad, Kin)) return -1;
     TcParams P;
     P.rows = (int)rows;
     P.K = K;
@@ -643,7 +684,6 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     if (getenv("MDB_TC_TRACE") && d_diag) {   // developer switch: the stamps go to the start of d_diag
         P.trace = reinterpret_cast<long long *>(d_diag);
     }
-    P.cn = cn;
     P.best1 = b1;
     P.best2 = b2;
     P.idx1 = i1;
@@ -660,7 +700,7 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     // times a safety factor of 2.  Measured on B200 (tools/tc_error_probe.py): the largest observed error is
     // 1.5e-6 (Kin = 144) to 3.5e-6 (Kin = 384) in these units, i.e. 2.7x to 4x below this bound.
     const float relerr = 2.0f * (4.0f * 2.3841858e-7f + (float)(Kin / 16) * 1.1920929e-7f + 16.0f * 5.9604645e-8f);
-    k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, relerr, d_rowidx, d_labels, amb_pos, amb_row,
+    k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, K, relerr, d_rowidx, d_labels, amb_pos, amb_row,
                                                     amb_thr, namb);
     c->launches++;
     if (d_diag && !P.trace) {  // diagnostics: best / second-best approximate score, index, ||x'||^2 per row, then max ||c'||^2

@@ -227,7 +227,7 @@ class MiniBatchKMeansB200:
         self.counts_ = weight_sums
         self.n_steps_ = i + 1
         # final full-data assignment: tensor-core screening + float64 re-check (same labels as float64)
-        if D <= 128 and n_local >= 4096:
+        if D <= 112 and n_local >= 4096:
             self.labels_, self.n_rechecked_ = eng.kmeans_assign_tc(X, centers)
             self.inertia_ = eng.kmeans_inertia(X, centers, self.labels_)
         else:

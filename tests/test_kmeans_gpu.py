@@ -78,7 +78,8 @@ def test_minibatch_update_matches_sklearn(engine, B, D, K):
     assert np.allclose(dW.cpu().numpy(), ref_w, rtol=1e-14, atol=0)
 
 
-@pytest.mark.parametrize("rows,D,K", [(5000, 37, 1000), (4096, 35, 10000), (777, 121, 130), (300, 5, 3), (20000, 64, 2500)])
+@pytest.mark.parametrize("rows,D,K", [(5000, 37, 1000), (4096, 35, 10000), (777, 110, 130), (900, 100, 260), (300, 5, 3),
+                                      (20000, 64, 2500)])
 def test_tensor_core_assign_matches_sklearn(engine, rows, D, K):
     """tcgen05 screening pass + float64 re-check of near-ties: identical labels to sklearn."""
     rng = np.random.default_rng(rows * 7 + D)
