@@ -29,7 +29,10 @@
 #define TC_BN 128
 #define TC_KCH 64                      // fp16 elements per 128-byte swizzle row
 #define TC_CHUNK_BYTES (TC_BM * 128)   // one [128 rows][64 elem] slab
-#define TC_THREADS 320
+#define TC_PARTS 2                     // column parts per TMEM lane quarter: 4 * TC_PARTS epilogue warps
+#define TC_PCOLS (TC_BN / TC_PARTS)
+#define TC_THREADS (64 + 128 * TC_PARTS)
+#define TC_TAIL (128 + 1536 * (TC_PARTS - 1) + 64)
 #define TC_MAXCH 6                     // 3*Kd + 16 <= 384
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,8 +131,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t bar_bempty = bar_bfull + 8 * 4;   // [S] (S <= 4)
     const uint32_t bar_tfull = bar_bempty + 8 * 4;   // [2]
     const uint32_t bar_tempty = bar_tfull + 16;      // [2]
-    float *mrg_s = reinterpret_cast<float *>(gtail + 128);         // [3][128]: merge of the two column halves
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 128 + 1536);
+    float *mrg_s = reinterpret_cast<float *>(gtail + 128);         // [TC_PARTS - 1][3][128]: merge of the column parts
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 128 + 1536 * (TC_PARTS - 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * TC_BM;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 8);
+            mbar_init(bar_tempty + 8 * a, 4 * TC_PARTS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -213,14 +216,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 2..9; warp % 4 selects the TMEM lane quarter, (warp - 2) / 4 the column half =====
+        // ===== epilogue: warps 2..; warp % 4 selects the TMEM lane quarter, (warp - 2) / 4 the column part =====
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;
         const int myrow = row0 + q * 32 + lane;
         // running best / second best (largest) score and the index of the best, in four independent sets
         // (value i goes to set i & 3) so that the updates do not serialise; all updates are branch-free
         float b1[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}, b2[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-        int il[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};  // best index = chunk base + position inside the chunk
+        int ib[4] = {0, 1, 2, 3};  // first of the eight columns (stride 4) that hold the best of the set
         const float mythr = (CAND && myrow < P.rows) ? P.thr[myrow] : FLT_MAX;  // rows past the end never qualify
         for (int t = 0; t < ntiles; ++t) {
             const int a = t & 1;
@@ -231,20 +234,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_wait(bar_tfull + 8 * a, aph);
             if (tr) P.trace[t * 8 + 5] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // this warp's 32 lanes x 64 columns leave TMEM in one go; the accumulator is handed back to the
-            // MMA warp before any arithmetic
-            uint32_t r[2][32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + half * 64);
-            TC_TMEM_LD32(r[0], taddr);
-            TC_TMEM_LD32(r[1], taddr + 32);
+            // this warp's 32 lanes x TC_PCOLS columns leave TMEM in one go; the accumulator is handed back to
+            // the MMA warp before any arithmetic
+            uint32_t r[TC_PCOLS / 32][32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + part * TC_PCOLS);
+#pragma unroll
+            for (int jj = 0; jj < TC_PCOLS / 32; ++jj) TC_TMEM_LD32(r[jj], taddr + 32 * jj);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
             if (tr) P.trace[t * 8 + 6] = clock64();
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int cbase = col0 + half * 64 + jj * 32;
+            for (int jj = 0; jj < TC_PCOLS / 32; ++jj) {
+                const int cbase = col0 + part * TC_PCOLS + jj * 32;
                 if (CAND) {
                     // the same arithmetic as the screening pass, so a row's own best score qualifies again
                     unsigned hit = 0;
@@ -259,8 +262,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         }
                     }
                 } else {
-                    // per score: three min/max, one compare, one select with an immediate; the 32-column
-                    // chunk of the current best is noted once per chunk and set
+                    // per score: three min/max and nothing else.  Where the best sits is noted per 32-column
+                    // chunk and set only (one compare + select per set and chunk); the winner among the eight
+                    // columns base + k, base + k + 4, ... is found later, in float64, by k_tc_decide
                     float o1[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) o1[k] = b1[k];
@@ -269,22 +273,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         const float v = __uint_as_float(r[jj][i]);
                         const int k = i & 3;
                         b2[k] = fmaxf(b2[k], fminf(b1[k], v));
-                        il[k] = v > b1[k] ? i : il[k];
                         b1[k] = fmaxf(b1[k], v);
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) ib[k] = b1[k] > o1[k] ? cbase : ib[k];
+                    for (int k = 0; k < 4; ++k) ib[k] = b1[k] > o1[k] ? cbase + k : ib[k];
                 }
             }
             if (tr) P.trace[t * 8 + 7] = clock64();
         }
-        // merge the four sets of this thread, then the two column halves of the row; on equal scores the
+        // merge the four sets of this thread, then the column parts of the row; on equal scores the
         // lower centroid index wins (such rows are re-decided in float64 anyway: their gap is zero)
         float m1 = b1[0], m2 = b2[0];
-        int mi = ib[0] + il[0];
+        int mi = ib[0];
 #pragma unroll
         for (int k = 1; k < 4; ++k) {
-            const int ik = ib[k] + il[k];
+            const int ik = ib[k];
             if (b1[k] > m1 || (b1[k] == m1 && ik < mi)) {
                 m2 = fmaxf(m1, b2[k]);
                 m1 = b1[k];
@@ -293,31 +296,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 m2 = fmaxf(m2, b1[k]);
             }
         }
-        float *mg = mrg_s;
+        // parts 1.. hand their (best, second, index) to part 0 of the same lane quarter
         const int slot = q * 32 + lane;
-        if (half == 1) {
+        if (part > 0) {
+            float *mg = mrg_s + (part - 1) * 384;
             mg[slot] = m1;
             mg[128 + slot] = m2;
             reinterpret_cast<int *>(mg)[256 + slot] = mi;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (!CAND && half == 0 && myrow < P.rows) {
-            const float c1 = mg[slot], c2 = mg[128 + slot];
-            const int ci = reinterpret_cast<int *>(mg)[256 + slot];
-            float o1, o2;
-            int oi;
-            if (c1 > m1 || (c1 == m1 && ci < mi)) {
-                o1 = c1;
-                oi = ci;
-                o2 = fmaxf(m1, c2);
-            } else {
-                o1 = m1;
-                oi = mi;
-                o2 = fmaxf(m2, c1);
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_PARTS) : "memory");
+        if (!CAND && part == 0 && myrow < P.rows) {
+#pragma unroll
+            for (int pp = 0; pp < TC_PARTS - 1; ++pp) {
+                const float *mg = mrg_s + pp * 384;
+                const float c1 = mg[slot], c2 = mg[128 + slot];
+                const int ci = reinterpret_cast<const int *>(mg)[256 + slot];
+                if (c1 > m1 || (c1 == m1 && ci < mi)) {
+                    m2 = fmaxf(m1, c2);
+                    m1 = c1;
+                    mi = ci;
+                } else {
+                    m2 = fmaxf(m2, c1);
+                }
             }
-            P.best1[myrow] = o1;
-            P.best2[myrow] = o2;
-            P.idx1[myrow] = oi;
+            P.best1[myrow] = m1;
+            P.best2[myrow] = m2;
+            P.idx1[myrow] = mi;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -427,25 +431,55 @@ __global__ void __launch_bounds__(256) k_fmax(const float *__restrict__ v, int n
 }
 
 // accept the tensor-core label when the gap beats the error bound; list the rest for float64
+// accept the tensor-core decision when the gap beats the error bound; list the rest for float64.
+// i1[r] is the first of eight columns (stride 4) one of which holds the row's best approximate score:
+// for an accepted row that one beats every other centroid by more than the error bound, so the
+// float64 scores of just these eight name it (any summation order will do at that margin).
+// One warp per row: 4 lanes per candidate column (features dealt round-robin), 8 candidates.
 __global__ void __launch_bounds__(256) k_tc_decide(const float *__restrict__ b1, const float *__restrict__ b2,
                                                    const int *__restrict__ i1, const float *__restrict__ xn2,
                                                    const float *__restrict__ cmax2, long long rows, int K, float relerr,
-                                                   const int *__restrict__ rowidx, int *__restrict__ labels,
-                                                   int *__restrict__ amb_pos, int *__restrict__ amb_row,
-                                                   float *__restrict__ amb_thr, int *__restrict__ namb) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                                   const int *__restrict__ rowidx, const double *__restrict__ X, long long ldx,
+                                                   const double *__restrict__ C, int D, const double *__restrict__ cn64,
+                                                   int *__restrict__ labels, int *__restrict__ amb_pos,
+                                                   int *__restrict__ amb_row, float *__restrict__ amb_thr,
+                                                   int *__restrict__ namb) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
     // |score error| <= relerr * ||x|| * max||c||  (Cauchy-Schwarz on the centred operands)
     //                  + 2^-22 max||c||^2 (the norm block is built from the unsplit centroid)
     //                  + one fp32 rounding of the final sum, 2^-23 (||x|| ||c|| + ||c||^2 / 2)
     const float xc = sqrtf(xn2[r] * (*cmax2));
     const float bound = (relerr + 1.2e-7f) * xc + 3.0e-7f * (*cmax2) + 1e-30f;
-    if (b1[r] - b2[r] > 2.f * bound && i1[r] < K) {
-        labels[r] = i1[r];
-    } else {
+    const int first = i1[r];
+    const long long xr = rowidx ? (long long)rowidx[r] : r;
+    if (b1[r] - b2[r] > 2.f * bound && first < K) {
+        const double *x = X + xr * ldx;
+        const int j = first + 4 * (lane >> 2), sub = lane & 3;
+        double acc = 0.0;
+        if (j < K) {
+            const double *c = C + (size_t)j * D;
+            for (int k = sub; k < D; k += 4) acc = fma(x[k], c[k], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        double sc = j < K ? fma(-2.0, acc, cn64[j]) : DBL_MAX;
+        int lab = j;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, sc, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, lab, o);
+            if (os < sc || (os == sc && ol < lab)) {
+                sc = os;
+                lab = ol;
+            }
+        }
+        if (lane == 0) labels[r] = lab;
+    } else if (lane == 0) {
         const int k = atomicAdd(namb, 1);
         amb_pos[k] = (int)r;
-        amb_row[k] = rowidx ? rowidx[r] : (int)r;
+        amb_row[k] = (int)xr;
         // a centroid can only beat the approximate winner if its own approximate score is within
         // 2 * bound of it (each score is off by at most `bound`); the factor leaves room for the
         // float rounding of the threshold itself
@@ -610,10 +644,10 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
         return -1;
     }
     int stages = nch <= 2 ? 4 : (nch <= 3 ? 3 : (nch <= 4 ? 2 : 1));
-    size_t smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1536 + 64;
+    size_t smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + TC_TAIL;
     while (smem > 227 * 1024 && stages > 1) {
         --stages;
-        smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + 128 + 1536 + 64;
+        smem = 1024 + (size_t)nch * TC_CHUNK_BYTES * (1 + stages) + TC_TAIL;
     }
     if (smem > 227 * 1024) {
         mdb_set_error("kmeans_assign_tc: tile does not fit shared memory");
@@ -700,8 +734,12 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     // times a safety factor of 2.  Measured on B200 (tools/tc_error_probe.py): the largest observed error is
     // 1.5e-6 (Kin = 144) to 3.5e-6 (Kin = 384) in these units, i.e. 2.7x to 4x below this bound.
     const float relerr = 2.0f * (4.0f * 2.3841858e-7f + (float)(Kin / 16) * 1.1920929e-7f + 16.0f * 5.9604645e-8f);
-    k_tc_decide<<<cdiv(rows, 256), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, K, relerr, d_rowidx, d_labels, amb_pos, amb_row,
-                                                    amb_thr, namb);
+    if (kmeans_cnorm_run(c, d_C, K, D, cn64, stream)) return -1;
+    {
+        ProfScope ps(c, "k_tc_decide", stream);
+        k_tc_decide<<<cdiv(rows, 8), 256, 0, stream>>>(b1, b2, i1, xn2, cmax2, rows, K, relerr, d_rowidx, d_X, ldx, d_C, D, cn64,
+                                                        d_labels, amb_pos, amb_row, amb_thr, namb);
+    }
     c->launches++;
     if (d_diag && !P.trace) {  // diagnostics: best / second-best approximate score, index, ||x'||^2 per row, then max ||c'||^2
         MDB_CUDA(cudaMemcpyAsync(d_diag, b1, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -741,7 +779,6 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
             MDB_CUDA(cudaMemcpyAsync(&nc, ncand, sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));
             if (nc >= h && nc <= candcap) {
-                if (kmeans_cnorm_run(c, d_C, K, D, cn64, stream)) return -1;
                 MDB_CUDA(cudaMemsetAsync(cbest, 0xFF, (size_t)h * sizeof(unsigned long long), stream));
                 MDB_CUDA(cudaMemsetAsync(amb_lab, 0xFF, (size_t)h * sizeof(int), stream));
                 MDB_CUDA(cudaMemsetAsync(ncand, 0, sizeof(int), stream));

@@ -7,10 +7,12 @@ def run(X, C, name):
     lab,nre,dg=eng.kmeans_assign_tc(torch.as_tensor(X,device='cuda'), torch.as_tensor(C,device='cuda'), diag=True)
     dg=dg.cpu().numpy(); b1=dg[:rows].astype(np.float64); b2=dg[rows:2*rows]; i1=dg[2*rows:3*rows].view(np.int32); xn2=dg[3*rows:4*rows]; cmax2=dg[4*rows]
     mu=C.mean(0); Xc=X-mu; Cc=C-mu
-    exact=(Xc*Cc[i1]).sum(1)-0.5*(Cc[i1]**2).sum(1)   # the score the kernel maximises: x.c - ||c||^2/2, centred
+    # the score the kernel maximises: x.c - ||c||^2/2 (centred); i1 is the first of 8 columns (stride 4) holding the best
+    cand=np.minimum(i1[:,None]+4*np.arange(8)[None,:],len(C)-1)
+    exact=((Xc[:,None,:]*Cc[cand]).sum(2)-0.5*(Cc[cand]**2).sum(2)).max(1)
     err=np.abs(b1-exact)
     norm=np.sqrt(xn2.astype(np.float64)*cmax2)
-    sxc=(np.abs(Xc)*np.abs(Cc[i1])).sum(1)
+    sxc=(np.abs(Xc)*np.abs(Cc[np.minimum(i1,len(C)-1)])).sum(1)
     print(f"{name:28s} rows={rows} D={X.shape[1]} K={len(C)} recheck={nre} ({100*nre/rows:.2f}%) max|err|={err.max():.3e} max err/(|x||c|max)={np.max(err/norm):.3e} max err/sum|xc|={np.max(err/np.maximum(sxc,1e-300)):.3e}")
 rng=np.random.default_rng(0)
 for D,K in [(35,10000),(64,2500),(110,1000),(16,5000)]:
