@@ -227,6 +227,35 @@ __global__ void __launch_bounds__(256) k_members(const __grid_constant__ DescPar
 __device__ __forceinline__ double fast_rcp(double x);
 __device__ __forceinline__ double fast_rsqrt(double x);
 
+// Members arrive in the order of the cell scan (atomic slots); the matrix is built in ascending
+// atom index, the order of the reference's np.where (datasetbuilder.py:315), so that the spectrum
+// does not depend on how the cell list happened to be filled.  Entry e (one per participating
+// thread, e < n) moves to the rank of its atom index; `sync` separates the read and write phases.
+template <class Sm, class Sync>
+__device__ __forceinline__ void canonical_member_order(Sm *S, int n, int e, Sync sync) {
+    const bool has = e < n;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    int zz = 0, tt = 0, rank = 0;
+    if (has) {
+        v0 = S->vec[e][0];
+        v1 = S->vec[e][1];
+        v2 = S->vec[e][2];
+        zz = S->z[e];
+        tt = S->t[e];
+        const int ii = S->idx[e];
+        for (int q = 0; q < n; ++q) rank += S->idx[q] < ii;
+    }
+    sync();
+    if (has) {
+        S->vec[rank][0] = v0;
+        S->vec[rank][1] = v1;
+        S->vec[rank][2] = v2;
+        S->z[rank] = zz;
+        S->t[rank] = tt;
+    }
+    sync();
+}
+
 template <int NMAX>
 struct BlkSmem {
     double A[NMAX][NMAX + 2];
@@ -237,6 +266,7 @@ struct BlkSmem {
     double2 bc;
     int z[NMAX];
     int t[NMAX];
+    int idx[NMAX];  // atom index of each member (canonical order = ascending index)
     double L[3];
     int n;
     int pad;
@@ -274,6 +304,7 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
                 }
                 S->z[k] = P.Z[tj];
                 S->t[k] = tj;
+                S->idx[k] = j;
             }
         });
         if (lane == 0) {
@@ -288,6 +319,7 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
         if (tid == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
         n = NMAX;
     }
+    canonical_member_order(S, n, tid, [] { __syncthreads(); });
     // Coulomb matrix (datasetbuilder.py:341-348), each pair once; see k_tridiag_reg for the minimum image
     for (int i = tid; i < n; i += T) S->A[i][i] = P.diag[S->t[i]];
     if (n > 1) {
@@ -422,6 +454,7 @@ struct RegSmem {
     double2 vw[LPM];
     int z[NMAX];
     int t[NMAX];
+    int idx[NMAX];  // atom index of each member (canonical order = ascending index)
     double L[3];
     int n;
     int pad;
@@ -463,6 +496,7 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
                 }
                 Sg->z[k] = P.Z[tj];
                 Sg->t[k] = tj;
+                Sg->idx[k] = j;
             }
         });
         if (lane == 0) {
@@ -480,6 +514,7 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
         if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
         n = NMAX;
     }
+    canonical_member_order(S, n, gl, [] { __syncwarp(); });
     // Coulomb matrix (datasetbuilder.py:341-348) into the staging copy: the n(n-1)/2 pairs are dealt
     // evenly to the lanes of the group, pair p -> (i, j), j < i.  Both vectors lie within +-L/2 of the
     // target, so one conditional shift per axis gives the minimum image.  Rows / columns >= n are zero.
@@ -590,6 +625,7 @@ struct Reg2Smem {
     double2 bc;
     int z[NMAX];
     int t[NMAX];
+    int idx[NMAX];  // atom index of each member (canonical order = ascending index)
     double L[3];
     int n;
     int pad;
@@ -711,6 +747,7 @@ __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 :
                     }
                     S->z[k] = P.Z[tj];
                     S->t[k] = tj;
+                    S->idx[k] = j;
                 }
             });
             if (lane == 0) {
@@ -727,6 +764,7 @@ __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 :
         if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
         n = NMAX;
     }
+    canonical_member_order(S, n, gl, [barid] { asm volatile("bar.sync %0, 64;" ::"r"(barid) : "memory"); });
     for (int i = gl; i < n; i += 64) S->A[i][i] = P.diag[S->t[i]];
     if (n > 1) {
         const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];

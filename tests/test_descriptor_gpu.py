@@ -101,6 +101,21 @@ def test_large_clusters_every_size_class(engine):
     assert worst < 1.0
 
 
+def test_descriptors_are_reproducible_bit_for_bit(engine):
+    # the matrix is built in ascending atom index whatever order the cell scan delivered the members in,
+    # so two runs (whose cell lists are filled in different atomic orders) give identical rows
+    import torch
+
+    s = synth.make_system(3000, 0.05, seed=synth.BASE_SEED + 49)
+    engine.set_elements(s.atomname)
+    pos = synth.frame_positions(s, 3)
+    rows = []
+    for _ in range(3):
+        counts, maxc = engine.compositions(pos, s.cell(), s.types, 5.0)
+        rows.append(engine.descriptors(pos, s.cell(), s.types, 5.0, counts, maxc)["X"].clone())
+    assert torch.equal(rows[0], rows[1]) and torch.equal(rows[0], rows[2])
+
+
 def test_nonperiodic_and_other_cutoff(engine):
     s = synth.make_system(1500, 0.05, seed=synth.BASE_SEED + 43)
     _check(engine, s, s.pos0[None], np.arange(0, 1500, 3, dtype=np.int32), cutoff=4.0, periodic=False)
