@@ -209,8 +209,45 @@ def measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_
     res["kmeans_assign_tc"] = {"atom_frames_per_s": world * rows / (t_tc / 1e3), "ms": t_tc, "rows": rows, "K": K, "D": D,
                                "rechecked_in_float64": nre, "labels_equal_float64_path": bool(torch.equal(labels, labels_tc)),
                                "effective_tflops": 2.0 * rows * K * D / (t_tc / 1e3) / 1e12,
-                               "tensor_tflops_issued": 2.0 * rows * K * (3 * ((D + 15) // 16 * 16)) / (t_tc / 1e3) / 1e12}
+                               "tensor_tflops_issued": 2.0 * rows * K * (3 * ((D + 15) // 16 * 16) + 16) / (t_tc / 1e3) / 1e12}
     return res
+
+
+def measure_text_reader(sysm, natoms, args):
+    """LAMMPS dump text -> float64 positions through the library's reader (csrc/textio.cpp, host threads):
+    what feeds the GPU when the input is a trajectory file rather than arrays (measured
+    separately, on a 1e5-atom slice)."""
+    import shutil
+    import tempfile
+
+    from mddatasetbuilder_b200 import synth
+    from mddatasetbuilder_b200.reader import KIND_DUMP, TextReader
+
+    nf = 8
+    d = tempfile.mkdtemp(prefix="mdb_bench_")
+    try:
+        fn = os.path.join(d, "dump.bench")
+        synth.write_lammps_dump(fn, sysm, synth.frame_positions(sysm, nf))
+        size = os.path.getsize(fn)
+        best = None
+        buf = np.empty((nf, natoms, 3), dtype=np.float64)
+        for _ in range(3):
+            r = TextReader(KIND_DUMP, fn, nthreads=0)
+            t0 = time.perf_counter()
+            got = 0
+            while True:
+                pos, _cell = r.read(nf, pinned=buf)
+                if len(pos) == 0:
+                    break
+                got += len(pos)
+            dt = time.perf_counter() - t0
+            r.close()
+            best = dt if best is None else min(best, dt)
+        return {"atom_frames_per_s": got * natoms / best, "mb_per_s": size / 1e6 / best, "frames": got,
+                "file_mb": size / 1e6, "host_threads": len(os.sched_getaffinity(0)),
+                "note": "host-side parse (mmap + from_chars), page-cached file; not part of `value` or `e2e`"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 # --------------------------------------------------------------------------------------
@@ -389,6 +426,8 @@ def main():
     stages = None
     if not args.no_stages:
         stages = measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_ranks, world, peaks)
+        if rank == 0:
+            stages["text_reader"] = measure_text_reader(sysm, natoms, args)
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
