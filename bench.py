@@ -213,7 +213,7 @@ def measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_
     return res
 
 
-def measure_text_reader(sysm, natoms, args):
+def measure_text_reader(sysm, natoms, args, eng=None):
     """LAMMPS dump text -> float64 positions through the library's reader (csrc/textio.cpp, host threads):
     what feeds the GPU when the input is a trajectory file rather than arrays (measured
     separately, on a 1e5-atom slice)."""
@@ -243,9 +243,33 @@ def measure_text_reader(sysm, natoms, args):
             dt = time.perf_counter() - t0
             r.close()
             best = dt if best is None else min(best, dt)
-        return {"atom_frames_per_s": got * natoms / best, "mb_per_s": size / 1e6 / best, "frames": got,
-                "file_mb": size / 1e6, "host_threads": len(os.sched_getaffinity(0)),
-                "note": "host-side parse (mmap + from_chars), page-cached file; not part of `value` or `e2e`"}
+        res = {"atom_frames_per_s": got * natoms / best, "mb_per_s": size / 1e6 / best, "frames": got,
+               "file_mb": size / 1e6, "host_threads": len(os.sched_getaffinity(0)),
+               "note": "host-side parse (mmap + from_chars), page-cached file; not part of `value` or `e2e`"}
+        if eng is not None:
+            # the same file through the device parser: host slices frames into page-locked memory, H2D, k_parse_dump
+            import torch
+
+            bestd, fb = None, 0
+            for _ in range(3):
+                r = TextReader(KIND_DUMP, fn, nthreads=0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                got = 0
+                while True:
+                    pos, _cell = r.read_device(nf, eng)
+                    if pos.shape[0] == 0:
+                        break
+                    got += int(pos.shape[0])
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                fb = getattr(r, "device_fallback_frames", 0)
+                r.close()
+                bestd = dt if bestd is None else min(bestd, dt)
+            res["device_parser"] = {"atom_frames_per_s": got * natoms / bestd, "mb_per_s": size / 1e6 / bestd,
+                                    "frames_handed_back_to_host": fb,
+                                    "note": "text -> float64 positions in HBM (csrc/textparse.cu), bit-identical to the host parser"}
+        return res
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
@@ -427,7 +451,7 @@ def main():
     if not args.no_stages:
         stages = measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_ranks, world, peaks)
         if rank == 0:
-            stages["text_reader"] = measure_text_reader(sysm, natoms, args)
+            stages["text_reader"] = measure_text_reader(sysm, natoms, args, eng)
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

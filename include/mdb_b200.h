@@ -256,6 +256,25 @@ int mdb_reader_rewind(mdb_reader *r);
  * neighbours in file order (0-based, -1 padded), h_bo same shape (optional). */
 int mdb_reader_next(mdb_reader *r, int stride, int max_frames, double *h_pos, double *h_cell,
                     int32_t *h_nbr, double *h_bo, int width, int *nread);
+/* Raw text of the next kept dump frames, packed back to back into h_buf (page-locked), for the
+ * device parser below: frame k occupies [frame_begin[k], frame_end[k]), its atom lines start at
+ * atoms_begin[k] (-1: no "ITEM: ATOMS" section found, parse it with mdb_reader_parse_buffer),
+ * h_cell [k][9] is its cell.  Stops early when the next frame would not fit cap. */
+int mdb_reader_next_raw(mdb_reader *r, int stride, int max_frames, char *h_buf, size_t cap,
+                        long long *frame_begin, long long *atoms_begin, long long *frame_end,
+                        double *h_cell, int *nread);
+/* Device-side parse of the atom lines delivered by mdb_reader_next_raw (after the caller copied
+ * h_buf to d_text): what the per-line split()/float() of DetectDump.readcrd (reference
+ * detect.py:294-345) produces, positions sorted by id into d_pos [F][N][3].  Decimal strings are
+ * converted exactly (significand <= 2^53 and |exponent| <= 22, one correctly rounded multiply or
+ * divide); a frame holding anything else -- longer numbers, inf/nan, a malformed line, a wrong
+ * atom count, a type that differs from the first frame -- gets d_status[k] != 0 and must be parsed
+ * on the host.  cols5 = column indices of id, type, x, y, z (mdb_reader_info); d_types = LAMMPS
+ * types by id-1 (mdb_reader_types); d_count [F] is scratch. */
+int mdb_parse_dump_text(mdb_ctx *ctx, const char *d_text, int nframes, int natoms,
+                        const long long *d_atoms_begin, const long long *d_frame_end,
+                        long long max_frame_bytes, const int *cols5, const int32_t *d_types,
+                        double *d_pos, int *d_status, int *d_count, void *stream);
 /* One frame already in memory (the lines a per-frame drop-in method receives). */
 int mdb_reader_parse_buffer(const mdb_reader *r, const char *buf, size_t len, double *h_pos,
                             double *h_cell, int32_t *h_nbr, double *h_bo, int width);

@@ -89,6 +89,94 @@ const char *advance_lines(const char *p, const char *e, long lines) {
     return p;
 }
 
+// The same walk for `nframes` groups of `lines` lines at once, with the newline counting spread
+// over `nthreads` threads: ends[k] = pointer after group k.  Returns the number of COMPLETE groups
+// found (<= nframes); a trailing partial group is not reported.  est = a guess of the bytes one
+// group takes (the window of the first counting round).
+int advance_groups(const char *p, const char *e, long lines, int nframes, int nthreads, size_t est,
+                   std::vector<const char *> &ends) {
+    ends.clear();
+    if (nframes <= 0 || p >= e) return 0;
+    if (nthreads <= 1 || nframes * (size_t)lines < 4096) {
+        for (int k = 0; k < nframes; ++k) {
+            const char *nx = advance_lines(p, e, lines);
+            if (!nx) break;
+            ends.push_back(nx);
+            p = nx;
+        }
+        return (int)ends.size();
+    }
+    const size_t BLK = 1 << 18;
+    const bool tail_line = e[-1] != '\n';  // a final line without '\n' counts as a line
+    std::vector<size_t> cnt;               // newlines per block, blocks start at p
+    size_t covered = 0;                    // bytes of [p, e) counted so far
+    const long long need = (long long)nframes * lines;
+    long long have = 0;
+    size_t window = std::max<size_t>(BLK, (size_t)((double)std::max<size_t>(est, 1) * nframes * 1.02));
+    while (have < need && p + covered < e) {
+        const size_t lim = std::min<size_t>((size_t)(e - p), covered + window);
+        const size_t b0 = cnt.size(), b1 = (lim + BLK - 1) / BLK;
+        cnt.resize(b1, 0);
+        std::atomic<size_t> next(b0);
+        auto work = [&]() {
+            for (;;) {
+                const size_t b = next.fetch_add(1);
+                if (b >= b1) break;
+                const char *a = p + b * BLK, *z = p + std::min(lim, (b + 1) * BLK);
+                cnt[b] = (size_t)std::count(a, z, '\n');
+            }
+        };
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<size_t>((size_t)nthreads, b1 - b0);
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        for (size_t b = b0; b < b1; ++b) have += (long long)cnt[b];
+        covered = lim;
+        // a window that stopped inside a block recounts that block next round
+        if (covered < (size_t)(e - p) && covered % BLK != 0) {
+            have -= (long long)cnt.back();
+            cnt.pop_back();
+            covered = cnt.size() * BLK;
+        }
+        window *= 2;
+    }
+    const bool at_end = p + covered >= e;
+    long long total = have + ((at_end && tail_line) ? 1 : 0);
+    const int nfull = (int)std::min<long long>(nframes, total / lines);
+    ends.assign((size_t)nfull, nullptr);
+    // block prefix sums, then every boundary is located inside its block independently
+    std::vector<long long> pre(cnt.size() + 1, 0);
+    for (size_t b = 0; b < cnt.size(); ++b) pre[b + 1] = pre[b] + (long long)cnt[b];
+    std::atomic<int> nextk(0);
+    auto locate = [&]() {
+        for (;;) {
+            const int k = nextk.fetch_add(1);
+            if (k >= nfull) break;
+            const long long target = (long long)(k + 1) * lines;  // the target-th newline ends group k
+            if (target > have) {  // only possible for the unterminated last line
+                ends[k] = e;
+                continue;
+            }
+            const size_t b = (size_t)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin()) - 1;
+            long long left = target - pre[b];
+            const char *q = p + b * BLK;
+            const char *z = p + std::min((size_t)(e - p), (b + 1) * BLK);
+            while (left > 0) {
+                q = (const char *)memchr(q, '\n', (size_t)(z - q)) + 1;
+                --left;
+            }
+            ends[k] = q;
+        }
+    };
+    std::vector<std::thread> th;
+    const int nt = std::min(nthreads, nfull);
+    for (int t = 1; t < nt; ++t) th.emplace_back(locate);
+    locate();
+    for (auto &t : th) t.join();
+    return nfull;
+}
+
 enum Section { S_NONE, S_TIMESTEP, S_NUMBER, S_BOX, S_ATOMS, S_OTHER };
 Section section_of(const char *p, const char *e) {
     // LineType.linecontent (detect.py:356-367)
@@ -114,6 +202,7 @@ struct mdb_reader {
     const char *cur = nullptr;
     long frame_in_file = 0;
     int nthreads = 1;
+    size_t est_frame_bytes = 0;  // size of the last frame seen (sizes the newline-counting window)
 };
 
 static int fail(const std::string &m) {
@@ -254,6 +343,23 @@ static int bonds_readN(mdb_reader *r) {
 
 // ---- one frame ---------------------------------------------------------------------------------
 // dump frame (readcrd, detect.py:294-345): positions placed at id-1, 3x3 cell incl. tilt
+// lower-triangular cell from the `xlo xhi [tilt]` bounds, tilt correction included (detect.py:326-341)
+static void box_to_cell(const double box[3][3], int boxcols, double *cell) {
+    double xy = 0, xz = 0, yz = 0;
+    if (boxcols > 2) {
+        xy = box[0][2];
+        xz = box[1][2];
+        yz = box[2][2];
+    }
+    const double xlo = box[0][0] - std::min({0.0, xy, xz, xy + xz});
+    const double xhi = box[0][1] - std::max({0.0, xy, xz, xy + xz});
+    const double ylo = box[1][0] - std::min(0.0, yz);
+    const double yhi = box[1][1] - std::max(0.0, yz);
+    const double zlo = box[2][0], zhi = box[2][1];
+    const double c9[9] = {xhi - xlo, 0.0, 0.0, xy, yhi - ylo, 0.0, xz, yz, zhi - zlo};
+    memcpy(cell, c9, sizeof(c9));
+}
+
 static int parse_dump_frame(const mdb_reader *r, const char *p, const char *e, double *pos, double *cell, int *type_mismatch,
                             std::string *err) {
     const int N = r->natoms;
@@ -323,20 +429,7 @@ static int parse_dump_frame(const mdb_reader *r, const char *p, const char *e, d
                std::to_string(natom_lines) + " and " + std::to_string(nbox);
         return -1;
     }
-    // detect.py:326-341
-    double xy = 0, xz = 0, yz = 0;
-    if (boxcols > 2) {
-        xy = box[0][2];
-        xz = box[1][2];
-        yz = box[2][2];
-    }
-    const double xlo = box[0][0] - std::min({0.0, xy, xz, xy + xz});
-    const double xhi = box[0][1] - std::max({0.0, xy, xz, xy + xz});
-    const double ylo = box[1][0] - std::min(0.0, yz);
-    const double yhi = box[1][1] - std::max(0.0, yz);
-    const double zlo = box[2][0], zhi = box[2][1];
-    const double c9[9] = {xhi - xlo, 0.0, 0.0, xy, yhi - ylo, 0.0, xz, yz, zhi - zlo};
-    memcpy(cell, c9, sizeof(c9));
+    box_to_cell(box, boxcols, cell);
     return 0;
 }
 
@@ -468,6 +561,25 @@ extern "C" int mdb_reader_rewind(mdb_reader *r) {
     return 0;
 }
 
+// Frame boundaries are found in batches (advance_groups counts newlines on all reader threads); this
+// hands them out one by one as long as the caller consumes the file contiguously.
+struct GroupCursor {
+    std::vector<const char *> ends;
+    size_t i = 0;
+    const char *expect = nullptr;
+    const char *next(mdb_reader *r, const char *cur, const char *e, int want) {
+        if (i >= ends.size() || expect != cur) {
+            advance_groups(cur, e, r->steplinenum, std::max(want, 1), r->nthreads, r->est_frame_bytes, ends);
+            i = 0;
+            if (ends.empty()) return nullptr;
+        }
+        const char *nx = ends[i++];
+        expect = nx;
+        r->est_frame_bytes = (size_t)(nx - cur);
+        return nx;
+    }
+};
+
 // Reads up to max_frames KEPT frames (every `stride`-th group of steplinenum lines of each file,
 // like itertools.islice(zip_longest(*[f]*steplinenum), 0, None, stride) at datasetbuilder.py:632-637).
 // dump: pos [max_frames][N][3], cell [max_frames][9].  bonds: nbr [max_frames][N][width] (file
@@ -479,6 +591,7 @@ extern "C" int mdb_reader_next(mdb_reader *r, int stride, int max_frames, double
         const char *a, *b;
     };
     std::vector<Span> spans;
+    GroupCursor gc;
     while ((int)spans.size() < max_frames && r->cur_file < r->files.size()) {
         const Mapped &f = r->files[r->cur_file];
         const char *e = f.p + f.n;
@@ -490,7 +603,7 @@ extern "C" int mdb_reader_next(mdb_reader *r, int stride, int max_frames, double
             }
             continue;
         }
-        const char *nx = advance_lines(r->cur, e, r->steplinenum);
+        const char *nx = gc.next(r, r->cur, e, (max_frames - (int)spans.size()) * stride);
         const bool complete = nx != nullptr;
         if (!complete) nx = e;  // trailing partial group
         if (r->frame_in_file % stride == 0) {
@@ -540,6 +653,116 @@ extern "C" int mdb_reader_next(mdb_reader *r, int stride, int max_frames, double
         return fail("frame parse error");
     }
     if (mismatch) return fail("dump file: atom types change between frames (not supported)");
+    return 0;
+}
+
+// Header of one dump frame: the cell from the BOX section and the offset of the first line after
+// "ITEM: ATOMS" (the atom lines run from there to the end of the frame).  Returns -1 if the frame
+// does not have that shape (the caller then parses the frame on the host).
+static long long dump_header(const char *p, const char *e, double *cell) {
+    Section sec = S_NONE;
+    double box[3][3];
+    int nbox = 0, boxcols = 0;
+    const char *p0 = p;
+    while (p < e) {
+        const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+        const char *le = q ? q : e;
+        const char *t = skip_ws(p, le);
+        const char *next = q ? q + 1 : e;
+        if (t < le) {
+            if (starts(p, le, "ITEM:")) {
+                sec = section_of(p, le);
+                if (sec == S_ATOMS) {
+                    if (nbox != 3) return -1;
+                    box_to_cell(box, boxcols, cell);
+                    return (long long)(next - p0);
+                }
+            } else if (sec == S_BOX && nbox < 3) {
+                int c = 0;
+                while (t < le && c < 3) {
+                    t = skip_ws(t, le);
+                    const char *te = token_end(t, le);
+                    if (te == t) break;
+                    if (!parse_double(t, te, box[nbox][c])) return -1;
+                    ++c;
+                    t = te;
+                }
+                boxcols = std::max(boxcols, c);
+                ++nbox;
+            } else if (sec == S_NONE) {
+                return -1;
+            }
+        }
+        p = next;
+    }
+    return -1;
+}
+
+// Raw text of the next kept dump frames, packed back to back into buf (page-locked memory of the
+// caller), for the device parser (csrc/textparse.cu).  frame_begin[k] / frame_end[k] bracket frame
+// k inside buf, atoms_begin[k] is its first atom line (or -1: parse that frame on the host), cell
+// [k][9] comes from its BOX section.  Stops early when the next frame would not fit `cap`.
+extern "C" int mdb_reader_next_raw(mdb_reader *r, int stride, int max_frames, char *buf, size_t cap, long long *frame_begin,
+                                   long long *atoms_begin, long long *frame_end, double *cell, int *nread) {
+    if (!r || r->kind != 0 || stride < 1 || max_frames < 0 || !buf) return fail("mdb_reader_next_raw: bad arguments");
+    struct Span {
+        const char *a, *b;
+    };
+    std::vector<Span> spans;
+    size_t used = 0;
+    GroupCursor gc;
+    while ((int)spans.size() < max_frames && r->cur_file < r->files.size()) {
+        const Mapped &f = r->files[r->cur_file];
+        const char *e = f.p + f.n;
+        if (r->cur >= e) {
+            ++r->cur_file;
+            if (r->cur_file < r->files.size()) {
+                r->cur = r->files[r->cur_file].p;
+                r->frame_in_file = 0;
+            }
+            continue;
+        }
+        const char *nx = gc.next(r, r->cur, e, (max_frames - (int)spans.size()) * stride);
+        const bool complete = nx != nullptr;
+        if (!complete) nx = e;
+        if (r->frame_in_file % stride == 0) {
+            if (!complete) {
+                r->cur = e;  // truncated final frame: dropped (see mdb_reader_next)
+                continue;
+            }
+            const size_t sz = (size_t)(nx - r->cur);
+            if (used + sz > cap) {
+                if (spans.empty()) return fail("mdb_reader_next_raw: one frame does not fit the staging buffer");
+                break;  // this frame stays for the next call
+            }
+            used += sz;
+            spans.push_back({r->cur, nx});
+        }
+        r->cur = nx;
+        ++r->frame_in_file;
+    }
+    const int nf = (int)spans.size();
+    *nread = nf;
+    if (nf == 0) return 0;
+    std::vector<size_t> off((size_t)nf + 1, 0);
+    for (int k = 0; k < nf; ++k) off[k + 1] = off[k] + (size_t)(spans[k].b - spans[k].a);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= nf) break;
+            memcpy(buf + off[k], spans[k].a, off[k + 1] - off[k]);
+            frame_begin[k] = (long long)off[k];
+            frame_end[k] = (long long)off[k + 1];
+            const long long h = dump_header(spans[k].a, spans[k].b, cell + (size_t)k * 9);
+            atoms_begin[k] = h < 0 ? -1 : (long long)off[k] + h;
+        }
+    };
+    const int nt = std::min(r->nthreads, nf);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
     return 0;
 }
 

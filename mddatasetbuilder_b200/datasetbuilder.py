@@ -188,12 +188,13 @@ class DatasetBuilder:
         step0, b, cache, used = 0, 0, [], 0
         while True:
             if b % world == rank:
-                pos, cell = rd.read(B, self.stepinterval)
+                # text -> positions on the GPU (csrc/textparse.cu); the host only slices frames
+                pos, cell = rd.read_device(B, self.engine, self.stepinterval, prefetch=(world == 1))
                 if len(pos) == 0:
                     break
-                item = (step0, torch.from_numpy(pos).to(self.engine.device), cell.copy())
+                item = (step0, pos, cell.copy())
                 if cache is not None:
-                    used += pos.nbytes
+                    used += pos.numel() * 8
                     if used <= self._cache_bytes:
                         cache.append(item)
                     else:
