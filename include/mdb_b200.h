@@ -256,10 +256,11 @@ int mdb_reader_rewind(mdb_reader *r);
  * neighbours in file order (0-based, -1 padded), h_bo same shape (optional). */
 int mdb_reader_next(mdb_reader *r, int stride, int max_frames, double *h_pos, double *h_cell,
                     int32_t *h_nbr, double *h_bo, int width, int *nread);
-/* Raw text of the next kept dump frames, packed back to back into h_buf (page-locked), for the
- * device parser below: frame k occupies [frame_begin[k], frame_end[k]), its atom lines start at
- * atoms_begin[k] (-1: no "ITEM: ATOMS" section found, parse it with mdb_reader_parse_buffer),
- * h_cell [k][9] is its cell.  Stops early when the next frame would not fit cap. */
+/* Raw text of the next kept frames, packed back to back into h_buf (page-locked), for the device
+ * parsers below: frame k occupies [frame_begin[k], frame_end[k]).  Dump readers: its atom lines
+ * start at atoms_begin[k] (-1: no "ITEM: ATOMS" section found, parse it with
+ * mdb_reader_parse_buffer) and h_cell [k][9] is its cell.  Bonds readers: atoms_begin = frame_begin,
+ * h_cell is not written.  Stops early when the next frame would not fit cap. */
 int mdb_reader_next_raw(mdb_reader *r, int stride, int max_frames, char *h_buf, size_t cap,
                         long long *frame_begin, long long *atoms_begin, long long *frame_end,
                         double *h_cell, int *nread);
@@ -275,6 +276,14 @@ int mdb_parse_dump_text(mdb_ctx *ctx, const char *d_text, int nframes, int natom
                         const long long *d_atoms_begin, const long long *d_frame_end,
                         long long max_frame_bytes, const int *cols5, const int32_t *d_types,
                         double *d_pos, int *d_status, int *d_count, void *stream);
+/* The same for fix reaxff/bonds tables (mdb_reader_next_raw on a bonds reader; frame k =
+ * [frame_begin[k], frame_end[k])): neighbours in file order, 0-based, -1 padded, into d_nbr
+ * [F][N][width], bond orders into d_bo (same shape, optional) -- DetectBond.readatombondtype /
+ * readmolecule, reference detect.py:105-119, 137-142.  d_status[k] != 0: parse frame k on the host. */
+int mdb_parse_bonds_text(mdb_ctx *ctx, const char *d_text, int nframes, int natoms,
+                         const long long *d_frame_begin, const long long *d_frame_end,
+                         long long max_frame_bytes, int width, int32_t *d_nbr, double *d_bo,
+                         int *d_status, int *d_count, void *stream);
 /* One frame already in memory (the lines a per-frame drop-in method receives). */
 int mdb_reader_parse_buffer(const mdb_reader *r, const char *buf, size_t len, double *h_pos,
                             double *h_cell, int32_t *h_nbr, double *h_bo, int width);

@@ -64,6 +64,8 @@ SIGNATURES = {
     "mdb_reader_next": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "mdb_reader_next_raw": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp, C.POINTER(C.c_int)]),
     "mdb_parse_dump_text": (C.c_int, [c_ctx, _vp, C.c_int, C.c_int, _vp, _vp, C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mdb_parse_bonds_text": (C.c_int, [c_ctx, _vp, C.c_int, C.c_int, _vp, _vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp,
+                                       _vp]),
     "mdb_reader_parse_buffer": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _vp, _vp, _vp, _vp, C.c_int]),
     "mdb_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "mdb_profile_read": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),

@@ -698,13 +698,14 @@ static long long dump_header(const char *p, const char *e, double *cell) {
     return -1;
 }
 
-// Raw text of the next kept dump frames, packed back to back into buf (page-locked memory of the
-// caller), for the device parser (csrc/textparse.cu).  frame_begin[k] / frame_end[k] bracket frame
-// k inside buf, atoms_begin[k] is its first atom line (or -1: parse that frame on the host), cell
-// [k][9] comes from its BOX section.  Stops early when the next frame would not fit `cap`.
+// Raw text of the next kept frames, packed back to back into buf (page-locked memory of the
+// caller), for the device parsers (csrc/textparse.cu).  frame_begin[k] / frame_end[k] bracket frame
+// k inside buf.  dump: atoms_begin[k] is its first atom line (or -1: parse that frame on the host)
+// and cell [k][9] comes from its BOX section; bonds: atoms_begin[k] = frame_begin[k], cell unused.
+// Stops early when the next frame would not fit `cap`.
 extern "C" int mdb_reader_next_raw(mdb_reader *r, int stride, int max_frames, char *buf, size_t cap, long long *frame_begin,
                                    long long *atoms_begin, long long *frame_end, double *cell, int *nread) {
-    if (!r || r->kind != 0 || stride < 1 || max_frames < 0 || !buf) return fail("mdb_reader_next_raw: bad arguments");
+    if (!r || stride < 1 || max_frames < 0 || !buf) return fail("mdb_reader_next_raw: bad arguments");
     struct Span {
         const char *a, *b;
     };
@@ -754,8 +755,12 @@ extern "C" int mdb_reader_next_raw(mdb_reader *r, int stride, int max_frames, ch
             memcpy(buf + off[k], spans[k].a, off[k + 1] - off[k]);
             frame_begin[k] = (long long)off[k];
             frame_end[k] = (long long)off[k + 1];
-            const long long h = dump_header(spans[k].a, spans[k].b, cell + (size_t)k * 9);
-            atoms_begin[k] = h < 0 ? -1 : (long long)off[k] + h;
+            if (r->kind == 0) {
+                const long long h = dump_header(spans[k].a, spans[k].b, cell + (size_t)k * 9);
+                atoms_begin[k] = h < 0 ? -1 : (long long)off[k] + h;
+            } else {
+                atoms_begin[k] = (long long)off[k];  // bonds tables: '#' lines are skipped by the parser
+            }
         }
     };
     const int nt = std::min(r->nthreads, nf);

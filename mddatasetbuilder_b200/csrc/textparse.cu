@@ -203,6 +203,134 @@ __global__ void k_parse_finish(const long long *__restrict__ abeg, const int *__
     if (abeg[f] < 0 || count[f] != N) status[f] |= 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fix reaxff/bonds tables: "id type nb id_1..id_nb mol bo_1..bo_nb abo nlp q" (reference
+// detect.py:105-119, 137-142) -> neighbours in file order (0-based) and bond orders, rows by id-1.
+// Lines that start with '#' and blank lines are skipped; nbr / bo are pre-filled with -1 / 0.
+// ---------------------------------------------------------------------------------------------
+struct BondTextParams {
+    const char *text;
+    const long long *fbeg;
+    const long long *fend;
+    int32_t *nbr;  // [F][N][width]
+    double *bo;    // [F][N][width] or nullptr
+    int *status;
+    int *count;
+    int N, width;
+};
+
+__device__ __forceinline__ bool tp_token(const char *&q, const char *e, const char *&te) {
+    while (q < e && tp_space(*q)) ++q;
+    if (q >= e || *q == '\n') return false;
+    te = q;
+    while (te < e && !tp_space(*te) && *te != '\n') ++te;
+    return true;
+}
+
+__global__ void __launch_bounds__(TP_THREADS) k_parse_bonds(const __grid_constant__ BondTextParams P) {
+    const int f = blockIdx.y;
+    const long long begin = P.fbeg[f], end = P.fend[f];
+    const long long a = begin + ((long long)blockIdx.x * TP_THREADS + threadIdx.x) * TP_PIECE;
+    const long long b = min(a + (long long)TP_PIECE, end);
+    const char *__restrict__ tx = P.text;
+    __shared__ int s_lines[TP_THREADS / 32];
+    int nlines = 0;
+    bool bad = false;
+    unsigned long long starts = 0;
+    for (long long p = a; p < b; ++p)
+        if (p == begin || tx[p - 1] == '\n') starts |= 1ull << (int)(p - a);
+    while (starts) {
+        const long long p = a + (__ffsll((long long)starts) - 1);
+        starts &= starts - 1;
+        if (tx[p] == '#') continue;
+        const char *q = tx + p, *e = tx + end, *te;
+        if (!tp_token(q, e, te)) continue;  // blank line
+        long long id = -1, ty = -1, nb = -1;
+        bool ok = tp_int(q, te, id);
+        q = te;
+        ok = ok && tp_token(q, e, te) && tp_int(q, te, ty);
+        q = te;
+        ok = ok && tp_token(q, e, te) && tp_int(q, te, nb);
+        q = te;
+        if (!ok || id < 1 || id > P.N || nb < 0 || nb > P.width) {
+            bad = true;
+            continue;
+        }
+        int32_t *row = P.nbr + ((size_t)f * P.N + (size_t)(id - 1)) * P.width;
+        for (int k = 0; k < (int)nb && ok; ++k) {
+            long long j = -1;
+            ok = tp_token(q, e, te) && tp_int(q, te, j) && j >= 1 && j <= P.N;
+            q = te;
+            if (ok) row[k] = (int32_t)(j - 1);
+        }
+        // s[3 + nb] is the molecule id; the bond orders follow at s[4 + nb : 4 + 2 nb]
+        if (ok) {
+            ok = tp_token(q, e, te);
+            q = te;
+        }
+        if (ok && P.bo) {
+            double *brow = P.bo + ((size_t)f * P.N + (size_t)(id - 1)) * P.width;
+            for (int k = 0; k < (int)nb && ok; ++k) {
+                double v = 0.0;
+                ok = tp_token(q, e, te) && tp_double(q, te, v);
+                q = te;
+                if (ok) brow[k] = v;
+            }
+        }
+        if (!ok) {
+            bad = true;
+            continue;
+        }
+        ++nlines;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nlines += __shfl_xor_sync(0xffffffffu, nlines, o);
+    if ((threadIdx.x & 31) == 0) s_lines[threadIdx.x >> 5] = nlines;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < TP_THREADS / 32; ++w) tot += s_lines[w];
+        if (tot) atomicAdd(&P.count[f], tot);
+    }
+    if (bad) atomicOr(&P.status[f], 1);
+}
+
+extern "C" int mdb_parse_bonds_text(mdb_ctx *c, const char *d_text, int nframes, int natoms, const long long *d_frame_begin,
+                                    const long long *d_frame_end, long long max_frame_bytes, int width, int32_t *d_nbr,
+                                    double *d_bo, int *d_status, int *d_count, void *stream_) {
+    if (!c) {
+        mdb_set_error("mdb_parse_bonds_text: context is NULL");
+        return -1;
+    }
+    if (nframes <= 0 || natoms <= 0 || width <= 0) return 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BondTextParams P;
+    P.text = d_text;
+    P.fbeg = d_frame_begin;
+    P.fend = d_frame_end;
+    P.nbr = d_nbr;
+    P.bo = d_bo;
+    P.status = d_status;
+    P.count = d_count;
+    P.N = natoms;
+    P.width = width;
+    const size_t cells = (size_t)nframes * natoms * width;
+    MDB_CUDA(cudaMemsetAsync(d_nbr, 0xFF, cells * sizeof(int32_t), stream));
+    if (d_bo) MDB_CUDA(cudaMemsetAsync(d_bo, 0, cells * sizeof(double), stream));
+    MDB_CUDA(cudaMemsetAsync(d_status, 0, (size_t)nframes * sizeof(int), stream));
+    MDB_CUDA(cudaMemsetAsync(d_count, 0, (size_t)nframes * sizeof(int), stream));
+    const long long pieces = cdiv(std::max<long long>(max_frame_bytes, 1), TP_PIECE);
+    dim3 grid((unsigned)cdiv(pieces, TP_THREADS), (unsigned)nframes);
+    {
+        ProfScope ps(c, "k_parse_bonds", stream);
+        k_parse_bonds<<<grid, TP_THREADS, 0, stream>>>(P);
+    }
+    k_parse_finish<<<cdiv(nframes, 128), 128, 0, stream>>>(d_frame_begin, d_count, nframes, natoms, d_status);
+    c->launches += 2;
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // d_status [F] (int) and d_count [F] (int) are scratch of the caller; d_status is the result.
 extern "C" int mdb_parse_dump_text(mdb_ctx *c, const char *d_text, int nframes, int natoms, const long long *d_atoms_begin,
                                    const long long *d_frame_end, long long max_frame_bytes, const int *cols5,

@@ -218,7 +218,8 @@ class DatasetBuilder:
         width = self.engine.max_bonds
         while True:
             if b % world == rank:
-                nbr, bo = rd.read(B, self.stepinterval, width=width)
+                # text -> neighbour / bond-order tables on the GPU (csrc/textparse.cu)
+                nbr, bo = rd.read_device(B, self.engine, self.stepinterval, prefetch=(world == 1), width=width)
                 nf = len(nbr)
                 if nf == 0:
                     break
@@ -314,7 +315,7 @@ class DatasetBuilder:
                 collect(step0, out["keys"].cpu().numpy().view(np.uint64))
         else:
             for step0, nbr, bo in self._bond_batches():
-                keys = eng.bond_keys_bo(torch.from_numpy(nbr).to(eng.device), torch.from_numpy(bo).to(eng.device), d_types)
+                keys = eng.bond_keys_bo(nbr, bo, d_types)
                 collect(step0, keys.cpu().numpy().view(np.uint64))
         counts = {t: sum(len(ids) for _, ids in rows) for t, rows in typerows.items()}
         d = _dist()
@@ -480,7 +481,7 @@ class DatasetBuilder:
                 # bond file and dump are matched by frame index (datasetbuilder.py:428-433)
                 for f in range(min(pos.shape[0], nbr.shape[0])):
                     if (step0 + f) in self.dstep:
-                        written += self._writestepxyzfile((step0 + f, (pos[f], cell[f], nbr[f])))
+                        written += self._writestepxyzfile((step0 + f, (pos[f], cell[f], nbr[f].cpu().numpy())))
         return written
 
     @staticmethod

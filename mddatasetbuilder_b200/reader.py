@@ -117,10 +117,13 @@ class TextReader:
             self._pf_thread = None
             self._pf_result = None
 
-    def read_device(self, max_frames: int, engine, stride: int = 1, prefetch: bool = False):
-        """Next batch of kept dump frames, parsed ON THE GPU: the raw text goes through a page-locked
-        staging buffer to the device, `mdb_parse_dump_text` turns the atom lines into positions.
-        Returns (pos [F,N,3] float64 device tensor, cell [F,9] numpy); F == 0 at end of input.
+    def read_device(self, max_frames: int, engine, stride: int = 1, prefetch: bool = False, width: int = 8,
+                    want_bo: bool = True):
+        """Next batch of kept frames, parsed ON THE GPU: the raw text goes through a page-locked
+        staging buffer to the device, `mdb_parse_dump_text` / `mdb_parse_bonds_text` turn the atom
+        lines into arrays.  dump -> (pos [F,N,3] float64 device tensor, cell [F,9] numpy); bonds ->
+        (nbr [F,N,width] int32 device tensor, bo [F,N,width] float64 device tensor or None).
+        F == 0 at end of input.
         Frames the device parser hands back (numbers outside its exact fast path, malformed lines)
         are parsed by the host parser, which also owns the error messages.
         prefetch=True promises that the next call on this reader is the same read_device call: the
@@ -130,8 +133,6 @@ class TextReader:
 
         import torch
 
-        if self.kind != KIND_DUMP:
-            raise RuntimeError("read_device is for dump files")
         N = self.natoms
         slot = getattr(self, "_slot", 0)
         batch = None
@@ -151,6 +152,9 @@ class TextReader:
         F = batch["F"]
         dev = engine.device
         if F == 0:
+            if self.kind == KIND_BOND:
+                return (torch.empty((0, N, width), dtype=torch.int32, device=dev),
+                        torch.empty((0, N, width), dtype=torch.float64, device=dev) if want_bo else None)
             return torch.empty((0, N, 3), dtype=torch.float64, device=dev), batch["cell"][:0]
         if prefetch:
             def work(s=self._slot):
@@ -164,11 +168,37 @@ class TextReader:
         d_text[:total].copy_(stage[:total], non_blocking=True)
         d_ab = torch.from_numpy(ab[:F]).to(dev)
         d_fe = torch.from_numpy(fe[:F]).to(dev)
+        status = torch.empty(F, dtype=torch.int32, device=dev)
+        count = torch.empty(F, dtype=torch.int32, device=dev)
+        if self.kind == KIND_BOND:
+            nbr = torch.empty((F, N, width), dtype=torch.int32, device=dev)
+            bo = torch.empty((F, N, width), dtype=torch.float64, device=dev) if want_bo else None
+            rc = self.L.mdb_parse_bonds_text(engine.ctx, C.c_void_p(d_text.data_ptr()), F, N, C.c_void_p(d_ab.data_ptr()),
+                                             C.c_void_p(d_fe.data_ptr()), C.c_longlong(int((fe[:F] - fb[:F]).max())),
+                                             int(width), C.c_void_p(nbr.data_ptr()),
+                                             C.c_void_p(bo.data_ptr()) if bo is not None else None,
+                                             C.c_void_p(status.data_ptr()), C.c_void_p(count.data_ptr()), engine.stream())
+            _lib.check(rc, "mdb_parse_bonds_text")
+            st = status.cpu().numpy()  # synchronises: this staging buffer is free again after this
+            self.device_fallback_frames = getattr(self, "device_fallback_frames", 0) + int((st != 0).sum())
+            for k in np.nonzero(st)[0]:
+                hn = np.empty((N, width), dtype=np.int32)
+                hb = np.empty((N, width), dtype=np.float64) if want_bo else None
+                base = stage.data_ptr() + int(fb[k])
+                rc = self.L.mdb_reader_parse_buffer(self.h, C.cast(C.c_void_p(base), C.c_char_p), int(fe[k] - fb[k]), None,
+                                                    None, C.c_void_p(hn.ctypes.data),
+                                                    C.c_void_p(hb.ctypes.data) if hb is not None else None, int(width))
+                if rc != 0:
+                    msg = _lib.last_error()
+                    self._drop_prefetch()
+                    raise RuntimeError(msg)
+                nbr[k].copy_(torch.from_numpy(hn))
+                if bo is not None:
+                    bo[k].copy_(torch.from_numpy(hb))
+            return nbr, bo
         if getattr(self, "_d_types", None) is None or self._d_types.device != dev:
             self._d_types = torch.from_numpy(self.atomtype.astype(np.int32)).to(dev)
         pos = torch.empty((F, N, 3), dtype=torch.float64, device=dev)
-        status = torch.empty(F, dtype=torch.int32, device=dev)
-        count = torch.empty(F, dtype=torch.int32, device=dev)
         cols = (C.c_int * 5)(*self.cols)
         rc = self.L.mdb_parse_dump_text(engine.ctx, C.c_void_p(d_text.data_ptr()), F, N, C.c_void_p(d_ab.data_ptr()),
                                         C.c_void_p(d_fe.data_ptr()), C.c_longlong(int((fe[:F] - fb[:F]).max())), cols,

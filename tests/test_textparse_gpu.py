@@ -169,3 +169,67 @@ def test_prefetch_double_buffering(engine):
     pos2, _ = r.read_device(2, engine)
     assert _same_bits(pos.cpu().numpy(), pos2.cpu().numpy())
     r.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# fix reaxff/bonds tables
+# --------------------------------------------------------------------------------------------------
+BONDS = os.path.join(HERE, "golden", "traj", "bonds.small")
+
+
+def _bonds_host(path, stride, batch, width=8):
+    from mddatasetbuilder_b200.reader import KIND_BOND
+
+    r = TextReader(KIND_BOND, path, nthreads=2)
+    A, B = [], []
+    while True:
+        nbr, bo = r.read(batch, stride, width=width)
+        if len(nbr) == 0:
+            break
+        A.append(nbr.copy())
+        B.append(bo.copy())
+    r.close()
+    return np.concatenate(A), np.concatenate(B)
+
+
+def _bonds_device(engine, path, stride, batch, width=8, prefetch=False):
+    from mddatasetbuilder_b200.reader import KIND_BOND
+
+    r = TextReader(KIND_BOND, path, nthreads=2)
+    A, B = [], []
+    while True:
+        nbr, bo = r.read_device(batch, engine, stride, prefetch=prefetch, width=width)
+        if nbr.shape[0] == 0:
+            break
+        A.append(nbr.cpu().numpy())
+        B.append(bo.cpu().numpy())
+    fb = getattr(r, "device_fallback_frames", 0)
+    r.close()
+    return np.concatenate(A), np.concatenate(B), fb
+
+
+@pytest.mark.parametrize("stride,batch,prefetch", [(1, 3, False), (2, 5, True), (7, 1, False)])
+def test_golden_bonds_table_bit_exact(engine, stride, batch, prefetch):
+    hn, hb = _bonds_host(BONDS, stride, batch)
+    dn, db, fb = _bonds_device(engine, BONDS, stride, batch, prefetch=prefetch)
+    assert np.array_equal(hn, dn) and _same_bits(hb, db)
+    assert fb == 0
+
+
+def test_synthetic_bonds_table_and_errors(engine, tmp_path):
+    from mddatasetbuilder_b200 import synth
+    from mddatasetbuilder_b200.reader import KIND_BOND
+
+    s = synth.make_system(4000, 0.05, seed=synth.BASE_SEED + 61)
+    path = str(tmp_path / "bonds.syn")
+    rng = np.random.default_rng(5)
+    bo_frames = [np.abs(s.bo + rng.uniform(-0.3, 0.3, s.bo.shape)) for _ in range(4)]
+    synth.write_lammps_bonds(path, s, 4, bo_frames=bo_frames)
+    hn, hb = _bonds_host(path, 1, 3, width=6)
+    dn, db, fb = _bonds_device(engine, path, 1, 3, width=6)
+    assert np.array_equal(hn, dn) and _same_bits(hb, db) and fb == 0
+    # a row wider than `width`: the device parser flags the frame, the host parser names the problem
+    r = TextReader(KIND_BOND, path)
+    with pytest.raises(RuntimeError, match="raise max_bonds"):
+        r.read_device(2, engine, width=2)
+    r.close()
