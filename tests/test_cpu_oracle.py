@@ -277,3 +277,37 @@ def test_distributed_selection_bookkeeping_gloo_world2():
     assert len(merged) == 25 and sorted(k for k, _, _ in merged) == list(range(25))
     assert all(k == lab for k, _, lab in merged), "every pick must belong to the cluster it was drawn for"
     assert mn == [0.0, 4.0]
+
+
+def test_frame_boundary_search_parallel_equals_sequential(tmp_path):
+    """The multi-threaded newline counting that slices frames (textio.cpp: advance_groups) delivers the
+    same frames as the line-by-line walk, for every stride / batch size, with and without a final
+    newline, and drops a truncated last frame (datasetbuilder.py:616-638 semantics)."""
+    from mddatasetbuilder_b200 import synth
+    from mddatasetbuilder_b200.reader import KIND_DUMP, TextReader
+
+    s = synth.make_system(2500, 0.05, seed=synth.BASE_SEED + 71)
+    base = str(tmp_path / "dump.full")
+    synth.write_lammps_dump(base, s, synth.frame_positions(s, 9))
+    data = open(base, "rb").read()
+
+    def read_all(path, nt, stride, batch):
+        r = TextReader(KIND_DUMP, path, nthreads=nt)
+        out = []
+        while True:
+            pos, _ = r.read(batch, stride)
+            if len(pos) == 0:
+                break
+            out.append(pos.copy())
+        r.close()
+        return np.concatenate(out)
+
+    for name, blob, nframes in (("full", data, 9), ("nonl", data[:-1], 9), ("trunc", data[:-4000], 8)):
+        path = str(tmp_path / ("dump." + name))
+        open(path, "wb").write(blob)
+        for stride in (1, 2, 4):
+            for batch in (1, 3, 20):
+                a = read_all(path, 1, stride, batch)
+                b = read_all(path, 4, stride, batch)
+                assert a.shape == b.shape == ((nframes + stride - 1) // stride, 2500, 3)
+                assert np.array_equal(a, b)
