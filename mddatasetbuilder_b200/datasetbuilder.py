@@ -426,6 +426,36 @@ class DatasetBuilder:
         Xd = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64), device=eng.device).clone()
         return clusterdatas(eng, Xd, n_clusters, n_each, seed=seed)
 
+    def _writestepmatrix(self, item):
+        """Calculate Coulumb atoms for each atom of this bond type in one frame (datasetbuilder.py:283-325).
+
+        item = (step, lines).  Returns a list of (numpy array [step, atom id], ascending eigenvalues of
+        the Coulomb matrix of the cutoff sphere, Counter of the element symbols in the sphere), one per
+        atom id in ``self.dstep[step]`` -- the per-frame unit the reference hands to its worker pool.  The
+        batched path (``_writecoulumbmatrix``) runs the same kernels over many frames at once."""
+        step, lines = item
+        results = []
+        if step not in self.dstep:
+            return results
+        eng = self.engine
+        pos, cell = self.crddetector.reader.parse_lines(lines)
+        types = (self.crddetector.atomtype - 1).astype(np.uint8)
+        ids = np.asarray(self.dstep[step], dtype=np.int64)
+        targets = (ids - 1).astype(np.int32)
+        periodic = bool(self.pbc)
+        counts, maxc = eng.compositions(pos[None], cell.reshape(9), types, self.cutoff, targets=targets,
+                                        periodic=periodic)
+        c = counts.cpu().numpy()
+        out = eng.descriptors(pos[None], cell.reshape(9), types, self.cutoff, counts, maxc, targets=targets,
+                              periodic=periodic, want_X=False, want_eig=True, eigcap=max(int(c.sum(axis=1).max()), 1))
+        eng.check()
+        eig = out["eig"].cpu().numpy()
+        for k, atoma in enumerate(ids):
+            n = int(c[k].sum())
+            symbols = Counter({str(self.atomname[t]): int(v) for t, v in enumerate(c[k]) if v})
+            results.append((np.array([step, int(atoma)]), eig[k, :n].copy(), symbols))
+        return results
+
     def _calcoulumbmatrix(self, atoms):
         """Eigenvalues of the Coulomb matrix of `atoms` (datasetbuilder.py:327-349): the cluster
         is treated as given (every atom a member), orthorhombic cell."""
