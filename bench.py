@@ -170,13 +170,19 @@ def measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     res = {}
     maxc = None
+    _, mc0 = eng.compositions(sub[:1], cell, types, 5.0, periodic=True)
+    memcap = int(mc0.sum()) + 8                           # list capacity: a bound on the largest sphere
+    eng.check()
     for it in range(2):                                   # pass 0 warms up
+        # the one-pass flow of DatasetBuilder: the composition scan leaves the membership lists behind and
+        # the descriptor pass gathers from them (no second cell scan)
         ev[0].record()
-        counts, maxc = eng.compositions(sub, cell, types, 5.0, periodic=True)
+        counts, maxc, members = eng.compositions(sub, cell, types, 5.0, periodic=True, members_cap=memcap)
         ev[1].record()
-        out = eng.descriptors(sub, cell, types, 5.0, counts, maxc, periodic=True)
+        out = eng.descriptors(sub, cell, types, 5.0, counts, maxc, periodic=True, members=members)
         ev[2].record()
         torch.cuda.synchronize()
+        del members
     X = out["X"]
     rows, D = int(X.shape[0]), int(X.shape[1])
     n_mean = float(out["n"].double().mean().item())

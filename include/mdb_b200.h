@@ -175,6 +175,29 @@ int mdb_descriptors(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
                     const int32_t *h_maxcount, double *d_X, double *d_eig, int eigcap,
                     int32_t *d_n, void *stream);
 
+/* One-pass variant for callers that visit every frame once (the reference visits them once per
+ * bond type, datasetbuilder.py:236-276, but needs max_counter over ALL rows before it can pad):
+ *   mdb_compositions_members   = mdb_compositions + the sphere membership of every target into
+ *                                d_members [ntargets][cap] (-1 padded, any order);
+ *   mdb_descriptors_members    = mdb_descriptors with the membership taken from those lists instead
+ *                                of a second cell scan (no cutoff argument; d_X may be NULL and the
+ *                                spectra kept in d_eig / d_n);
+ *   mdb_feature_rows           = the padded sorted rows d_X [ntargets][D] from stored spectra once
+ *                                the final h_maxcount is known (the same merge mdb_descriptors does). */
+int mdb_compositions_members(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                             const double *h_cell, const uint8_t *d_types, int periodic,
+                             double cutoff, const int32_t *d_targets, long long ntargets,
+                             int32_t *d_counts, int32_t *h_maxcount, int cap, int32_t *d_members,
+                             void *stream);
+int mdb_descriptors_members(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                            const double *h_cell, const uint8_t *d_types, int periodic,
+                            const int32_t *d_targets, long long ntargets, const int32_t *d_counts,
+                            const int32_t *h_maxcount, const int32_t *d_members, int cap,
+                            double *d_X, double *d_eig, int eigcap, int32_t *d_n, void *stream);
+int mdb_feature_rows(mdb_ctx *ctx, long long ntargets, const double *d_eig, int eigcap,
+                     const int32_t *d_n, const int32_t *d_counts, const int32_t *h_maxcount,
+                     double *d_X, void *stream);
+
 /* ---- MinMaxScaler (datasetbuilder.py:369-370; sklearn preprocessing/_data.py) ------
  * fit: column minima / maxima of d_X [rows][D] (row stride ldx doubles) into d_min /
  * d_max [D] (device).  transform: X = X * scale + min_ in place with scale = 1/range
@@ -235,7 +258,8 @@ int mdb_kpp_step(mdb_ctx *ctx, long long n, int D, const double *d_X, long long 
                  const double *d_closest, const double *d_weights, double *d_dist, double *d_pot,
                  void *stream);
 
-/* Diagnostics of the last bond batch: counts summed over frames (synchronises). */
+/* Diagnostics of the last bond batch: counts summed over frames (synchronises).  A device-side error
+ * flag raised by any kernel since the last call is returned (non-zero) and cleared. */
 int mdb_bond_stats(mdb_ctx *ctx, long long *n_violators, long long *n_exact_tests,
                    long long *n_overflow);
 

@@ -195,6 +195,8 @@ extern "C" int mdb_bond_stats(mdb_ctx *c, long long *n_violators, long long *n_e
     if (n_exact) *n_exact = (long long)h.exact_tests;
     if (n_overflow) *n_overflow = (long long)h.overflow;
     if (h.err) {
+        // read and clear: the flag is reported once (a caller may retry with other capacities)
+        MDB_CUDA(cudaMemset(&c->d_stats->err, 0, sizeof(int)));
         mdb_set_error(std::string("device-side error: ") + err_text(h.err));
         return h.err;
     }
@@ -236,6 +238,47 @@ extern "C" int mdb_descriptors(mdb_ctx *c, int nframes, int natoms, const double
     }
     return descriptors_run(c, nframes, natoms, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, d_counts,
                            h_maxcount, d_X, d_eig, eigcap, d_n, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_compositions_members(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                        const uint8_t *d_types, int periodic, double cutoff, const int32_t *d_targets,
+                                        long long ntargets, int32_t *d_counts, int32_t *h_maxcount, int cap,
+                                        int32_t *d_members, void *stream) {
+    if (check_ctx(c, "mdb_compositions_members")) return -1;
+    if ((long long)nframes * natoms >= (1LL << 31) - 64) {
+        mdb_set_error("mdb_compositions_members: batch too large, split the frames");
+        return -1;
+    }
+    if (!d_members) {
+        mdb_set_error("mdb_compositions_members: d_members is required");
+        return -1;
+    }
+    return compositions_run(c, nframes, natoms, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, d_counts,
+                            h_maxcount, (cudaStream_t)stream, cap, d_members);
+}
+
+extern "C" int mdb_descriptors_members(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                       const uint8_t *d_types, int periodic, const int32_t *d_targets, long long ntargets,
+                                       const int32_t *d_counts, const int32_t *h_maxcount, const int32_t *d_members, int cap,
+                                       double *d_X, double *d_eig, int eigcap, int32_t *d_n, void *stream) {
+    if (check_ctx(c, "mdb_descriptors_members")) return -1;
+    if ((long long)nframes * natoms >= (1LL << 31) - 64) {
+        mdb_set_error("mdb_descriptors_members: batch too large, split the frames");
+        return -1;
+    }
+    if (!d_members || cap < 1) {
+        mdb_set_error("mdb_descriptors_members: d_members / cap are required");
+        return -1;
+    }
+    // the cutoff only sizes the (unused) cell geometry here: membership comes from the lists
+    return descriptors_run(c, nframes, natoms, d_pos, h_cell, d_types, periodic, 5.0, d_targets, ntargets, d_counts,
+                           h_maxcount, d_X, d_eig, eigcap, d_n, (cudaStream_t)stream, d_members, cap);
+}
+
+extern "C" int mdb_feature_rows(mdb_ctx *c, long long ntargets, const double *d_eig, int eigcap, const int32_t *d_n,
+                                const int32_t *d_counts, const int32_t *h_maxcount, double *d_X, void *stream) {
+    if (check_ctx(c, "mdb_feature_rows")) return -1;
+    return feature_rows_run(c, ntargets, d_eig, eigcap, d_n, d_counts, h_maxcount, d_X, (cudaStream_t)stream);
 }
 
 extern "C" int mdb_kmeans_assign(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx,

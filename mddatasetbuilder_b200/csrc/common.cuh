@@ -169,10 +169,13 @@ int ell_to_csr_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, 
 // descriptor.cu
 int compositions_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                      int periodic, double cutoff, const int *d_targets, long long ntargets, int *d_counts,
-                     int *h_maxcount, cudaStream_t stream);
+                     int *h_maxcount, cudaStream_t stream, int memcap = 0, int *d_members_out = nullptr);
 int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                     int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
-                    const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream);
+                    const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream,
+                    const int *d_members = nullptr, int memcap = 0);
+int feature_rows_run(mdb_ctx *c, long long T, const double *d_eig, int eigcap, const int *d_n, const int *d_counts,
+                     const int *h_maxcount, double *d_X, cudaStream_t stream);
 
 // kmeans.cu
 int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,

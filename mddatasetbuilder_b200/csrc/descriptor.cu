@@ -40,6 +40,11 @@ struct DescParams {
     double diag[MDB_MAXT];
     int Z[MDB_MAXT];
     BondStats *stats;
+    // optional sphere membership lists [ntargets][memcap] (-1 padded, any order): written by the
+    // composition pass (members_out), read instead of a second cell scan by the descriptor pass
+    const int *members;
+    int *members_out;
+    int memcap;
 };
 
 // ASE general_find_mic along one axis of an orthorhombic cell (oracle.c: ase_axis_general)
@@ -156,6 +161,26 @@ __device__ __forceinline__ void sphere_scan(const DescParams &P, int f, int a, V
     }
 }
 
+// The same visit over a stored membership list (written by k_composition) instead of the cell scan.
+template <class Visit>
+__device__ __forceinline__ void member_scan(const DescParams &P, long long ord, Visit visit) {
+    const int lane = threadIdx.x & 31;
+    const int *m = P.members + (size_t)ord * P.memcap;
+    for (int k0 = 0; k0 < P.memcap; k0 += 32) {
+        const int k = k0 + lane;
+        const int j = k < P.memcap ? m[k] : -1;
+        if (j >= 0) visit(j, (int)P.types[j]);
+        if (__all_sync(0xffffffffu, j < 0)) break;
+    }
+}
+template <class Visit>
+__device__ __forceinline__ void gather_scan(const DescParams &P, int f, int a, long long ord, Visit visit) {
+    if (P.members)
+        member_scan(P, ord, visit);
+    else
+        sphere_scan(P, f, a, visit);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K5: element composition of every target's sphere; running per-element maximum
 // ---------------------------------------------------------------------------------------------
@@ -163,6 +188,7 @@ __global__ void __launch_bounds__(256) k_composition(const __grid_constant__ Des
                                                      int *__restrict__ maxcount) {
     __shared__ int s_cnt[8][MDB_MAXT];
     __shared__ int s_max[MDB_MAXT];
+    __shared__ int s_n[8];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < MDB_MAXT) s_max[threadIdx.x] = 0;
     __syncthreads();
@@ -171,9 +197,22 @@ __global__ void __launch_bounds__(256) k_composition(const __grid_constant__ Des
         const int g = P.targets ? P.targets[t] : (int)t;
         const int f = g / P.N, a = g - f * P.N;
         if (lane < MDB_MAXT) s_cnt[w][lane] = 0;
+        if (lane == 0) s_n[w] = 0;
         __syncwarp();
-        sphere_scan(P, f, a, [&](int, int tj) { atomicAdd(&s_cnt[w][tj], 1); });
+        int *mo = P.members_out ? P.members_out + (size_t)t * P.memcap : nullptr;
+        sphere_scan(P, f, a, [&](int j, int tj) {
+            atomicAdd(&s_cnt[w][tj], 1);
+            if (mo) {
+                const int k = atomicAdd(&s_n[w], 1);
+                if (k < P.memcap) mo[k] = j;
+            }
+        });
         __syncwarp();
+        if (mo) {
+            const int n = s_n[w];
+            if (n > P.memcap && lane == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+            for (int k = min(n, P.memcap) + lane; k < P.memcap; k += 32) mo[k] = -1;
+        }
         if (lane < P.nt) {
             const int c = s_cnt[w][lane];
             counts[t * P.nt + lane] = c;
@@ -293,7 +332,7 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
         const double *pos = P.pos + (size_t)f * P.N * 3;
         const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
         const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
-        sphere_scan(P, f, a, [&](int j, int tj) {
+        gather_scan(P, f, a, ord, [&](int j, int tj) {
             const int k = atomicAdd(&S->n, 1);
             if (k < NMAX) {
 #pragma unroll
@@ -485,7 +524,7 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
         __syncwarp();
         const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
         const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
-        sphere_scan(P, f, a, [&](int j, int tj) {
+        gather_scan(P, f, a, ord, [&](int j, int tj) {
             const int k = atomicAdd(&Sg->n, 1);
             if (k < NMAX) {
 #pragma unroll
@@ -736,7 +775,7 @@ __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 :
             __syncwarp();
             const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
             const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
-            sphere_scan(P, f, a, [&](int j, int tj) {
+            gather_scan(P, f, a, ord, [&](int j, int tj) {
                 const int k = atomicAdd(&S->n, 1);
                 if (k < NMAX) {
 #pragma unroll
@@ -969,7 +1008,7 @@ __global__ void __launch_bounds__(256) k_bucket_fill(const int *__restrict__ nsu
 // ---------------------------------------------------------------------------------------------
 static int desc_setup(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                       int periodic, double cutoff, const int *d_targets, long long ntargets, cudaStream_t stream,
-                      DescParams *P, size_t extra_bytes) {
+                      DescParams *P, size_t extra_bytes, bool need_cells = true) {
     std::vector<double> bbox;
     if (!periodic) {
         bbox.resize((size_t)F * 6);
@@ -990,18 +1029,24 @@ static int desc_setup(mdb_ctx *c, int F, int N, const double *d_pos, const doubl
         }
         for (int v = 0; v < 3; ++v) lmax = std::max(lmax, fabs(g.ortho[v * 4]));
     }
-    size_t need = align256(geom.size() * sizeof(FrameGeom)) + cells_workspace_bytes(F, N, total_cells) + extra_bytes + 4096;
+    size_t need = align256(geom.size() * sizeof(FrameGeom)) + (need_cells ? cells_workspace_bytes(F, N, total_cells) : 0) +
+                  extra_bytes + 4096;
     if (arena_reserve(c, need, stream)) return -1;
     arena_reset(c);
     FrameGeom *d_geom = (FrameGeom *)arena_alloc(c, geom.size() * sizeof(FrameGeom));
     if (!d_geom) return -1;
     if (upload_geometry(c, geom, d_geom, stream)) return -1;
     CellList cl;
-    if (cells_build(c, F, N, d_pos, d_types, d_geom, total_cells, periodic, 1, &cl, &c->d_stats->err, stream)) return -1;
+    memset(&cl, 0, sizeof(cl));
+    if (need_cells && cells_build(c, F, N, d_pos, d_types, d_geom, total_cells, periodic, 1, &cl, &c->d_stats->err, stream))
+        return -1;
     P->rec = cl.rec;
     P->ccell = cl.ccell;
     P->cr = cl.cr;
     P->cell_start = cl.cell_start;
+    P->members = nullptr;
+    P->members_out = nullptr;
+    P->memcap = 0;
     P->geom = d_geom;
     P->pos = d_pos;
     P->types = d_types;
@@ -1021,11 +1066,84 @@ static int desc_setup(mdb_ctx *c, int F, int N, const double *d_pos, const doubl
     return 0;
 }
 
+// Padded sorted feature rows from stored spectra (the closed form of the parent loop,
+// datasetbuilder.py:236-276): row = sort(eig U {pad_el repeated (max_el - count_el) times}).  One
+// thread per row; the same merge as at the end of k_tql, for callers that keep the eigenvalues of a
+// batch until the per-element maxima over ALL rows are known.
+__global__ void __launch_bounds__(128) k_feature_rows(long long T, const double *__restrict__ eig, int eigcap,
+                                                      const int *__restrict__ nn, const int *__restrict__ counts, int nt,
+                                                      const int *__restrict__ padorder, const double *__restrict__ padval,
+                                                      const int *__restrict__ maxcount, int D, double *__restrict__ X) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int n = min(nn[t], eigcap);
+    const double *d = eig + (size_t)t * eigcap;
+    double *o = X + (size_t)t * D;
+    int w = 0, k = 0;
+    for (int q = 0; q < nt; ++q) {
+        const int el = padorder[q];
+        const int reps = maxcount[el] - counts[(size_t)t * nt + el];
+        const double pv = padval[el];
+        for (int r = 0; r < reps; ++r) {
+            while (k < n && d[k] <= pv && w < D) o[w++] = d[k++];
+            if (w < D) o[w++] = pv;
+        }
+    }
+    while (k < n && w < D) o[w++] = d[k++];
+    while (w < D) o[w++] = 0.0;
+}
+
+int feature_rows_run(mdb_ctx *c, long long T, const double *d_eig, int eigcap, const int *d_n, const int *d_counts,
+                     const int *h_maxcount, double *d_X, cudaStream_t stream) {
+    if (T <= 0) return 0;
+    const int nt = c->el.nt;
+    int D = 0;
+    int order[MDB_MAXT];
+    for (int k = 0; k < nt; ++k) {
+        D += h_maxcount[k];
+        order[k] = k;
+    }
+    for (int x = 1; x < nt; ++x) {  // elements by ascending pad value
+        int v = order[x], y = x - 1;
+        while (y >= 0 && c->el.diag[order[y]] > c->el.diag[v]) {
+            order[y + 1] = order[y];
+            --y;
+        }
+        order[y + 1] = v;
+    }
+    if (arena_reserve(c, 4096, stream)) return -1;
+    arena_reset(c);
+    int *d_maxcount = (int *)arena_alloc(c, 256);
+    int *d_padorder = (int *)arena_alloc(c, 256);
+    double *d_padval = (double *)arena_alloc(c, 256);
+    if (!d_maxcount || !d_padorder || !d_padval) return -1;
+    MDB_CUDA(cudaMemcpyAsync(d_maxcount, h_maxcount, nt * sizeof(int), cudaMemcpyHostToDevice, stream));
+    MDB_CUDA(cudaMemcpyAsync(d_padorder, order, nt * sizeof(int), cudaMemcpyHostToDevice, stream));
+    MDB_CUDA(cudaMemcpyAsync(d_padval, c->el.diag, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
+    {
+        ProfScope ps(c, "k_feature_rows", stream);
+        k_feature_rows<<<cdiv(T, 128), 128, 0, stream>>>(T, d_eig, eigcap, d_n, d_counts, nt, d_padorder, d_padval, d_maxcount,
+                                                        D, d_X);
+    }
+    c->launches++;
+    MDB_CUDA(cudaGetLastError());
+    MDB_CUDA(cudaStreamSynchronize(stream));  // the host arrays above live on the stack
+    return 0;
+}
+
 int compositions_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                      int periodic, double cutoff, const int *d_targets, long long ntargets, int *d_counts,
-                     int *h_maxcount, cudaStream_t stream) {
+                     int *h_maxcount, cudaStream_t stream, int memcap, int *d_members_out) {
     DescParams P;
     if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, 1024)) return -1;
+    if (d_members_out) {
+        if (memcap < 1) {
+            mdb_set_error("mdb_compositions_members: cap must be positive");
+            return -1;
+        }
+        P.members_out = d_members_out;
+        P.memcap = memcap;
+    }
     int *d_max = (int *)arena_alloc(c, MDB_MAXT * sizeof(int));
     if (!d_max) return -1;
     MDB_CUDA(cudaMemcpyAsync(d_max, h_maxcount, c->el.nt * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1122,7 +1240,8 @@ static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int of
 
 int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                     int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
-                    const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream) {
+                    const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream,
+                    const int *d_members, int memcap) {
     const int nt = c->el.nt;
     const long long T = d_targets ? ntargets : (long long)F * N;
     if (T == 0) return 0;
@@ -1135,7 +1254,10 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     size_t extra = align256(T * sizeof(int)) * 2 + align256((size_t)chunk * 128 * sizeof(double)) * 2 +
                    align256((size_t)chunk * sizeof(int)) + 16 * 256;
     DescParams P;
-    if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, extra)) return -1;
+    if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, extra, d_members == nullptr))
+        return -1;
+    P.members = d_members;  // membership from the composition pass: no cell list, no second scan
+    P.memcap = d_members ? memcap : 0;
     int *d_nsum = (int *)arena_alloc(c, T * sizeof(int));
     int *d_list = (int *)arena_alloc(c, T * sizeof(int));
     double *dsc = (double *)arena_alloc(c, (size_t)chunk * 128 * sizeof(double));

@@ -364,9 +364,13 @@ class DatasetBuilder:
             N = self.crddetector._N
             d_types = eng.to_device_types((self.crddetector.atomtype - 1).astype(np.uint8))
             nt = len(self.atomname)
-            # pass A: sphere compositions -> max_counter over every row of this type
+            # ONE pass over the frames: sphere compositions (-> max_counter over every row of this type) and,
+            # from the membership lists the same scan leaves behind, the Coulomb-matrix spectra.  The padded
+            # sorted rows need the final max_counter, so they are assembled from the stored spectra afterwards
+            # (the reference makes the same two steps inside its parent loop, datasetbuilder.py:253-272).
             maxc = np.zeros(nt, dtype=np.int32)
             per_batch = []
+            cap = getattr(self, "_memcap", 32)
             for step0, pos, cell in self._dump_batches():
                 tg, sa = [], []
                 for f in range(pos.shape[0]):
@@ -377,26 +381,35 @@ class DatasetBuilder:
                 if not tg:
                     continue
                 targets = np.concatenate(tg).astype(np.int32)
-                counts, maxc = eng.compositions(pos, cell, d_types, self.cutoff, targets=targets, periodic=self.pbc,
-                                                maxcount=maxc)
-                per_batch.append((step0, targets, counts, np.concatenate(sa)))
+                while True:
+                    counts, maxc_new, members = eng.compositions(pos, cell, d_types, self.cutoff, targets=targets,
+                                                                 periodic=self.pbc, maxcount=maxc, members_cap=cap)
+                    try:
+                        eng.check()
+                        break
+                    except RuntimeError as e:
+                        if "(2)" not in str(e) or cap >= 128:   # 2 = a list overflowed its capacity
+                            raise
+                        cap = min(128, cap * 2)
+                maxc = maxc_new
+                nmax = max(int(counts.sum(dim=1).max().item()), 1)
+                out = eng.descriptors(pos, cell, d_types, self.cutoff, counts, maxc, targets=targets, periodic=self.pbc,
+                                      want_X=False, want_eig=True, eigcap=nmax, members=members)
+                per_batch.append((out["eig"], out["n"], counts, np.concatenate(sa)))
+                del members
+            self._memcap = cap
+            eng.check()
             if d is not None:
                 t = torch.as_tensor(maxc, device=eng.device)
                 d.all_reduce(t, op=d.ReduceOp.MAX)
                 maxc = t.cpu().numpy().astype(np.int32)
             logger.info(f"Max counter of {trajatomfilename} is "
                         f"{Counter({str(a): int(c) for a, c in zip(self.atomname, maxc) if c})}")
-            # pass B: Coulomb-matrix spectra -> padded sorted feature rows
-            todo = {step0: (targets, counts, sa) for step0, targets, counts, sa in per_batch}
             Xs, stepatoms = [], []
-            for step0, pos, cell in self._dump_batches():
-                if step0 not in todo:
-                    continue
-                targets, counts, sa = todo[step0]
-                out = eng.descriptors(pos, cell, d_types, self.cutoff, counts, maxc, targets=targets, periodic=self.pbc)
-                Xs.append(out["X"])
+            for eig, nn, counts, sa in per_batch:
+                Xs.append(eng.feature_rows(eig, nn, counts, maxc))
                 stepatoms.append(sa)
-            eng.check()
+            todo = None
             D = int(maxc.sum())
             X = torch.cat(Xs) if Xs else torch.zeros((0, D), dtype=torch.float64, device=eng.device)
             stepatom = np.concatenate(stepatoms) if stepatoms else np.zeros((0, 2), dtype=np.int64)

@@ -199,9 +199,11 @@ class Engine:
         _lib.check(rc, "mdb_dps")
         return mol_atoms[:N], mol_ptr[: nm.value + 1]
 
-    def compositions(self, pos, cell, types, cutoff, targets=None, periodic=True, maxcount=None):
+    def compositions(self, pos, cell, types, cutoff, targets=None, periodic=True, maxcount=None, members_cap=0):
         """Element composition of every target's cutoff sphere (datasetbuilder.py:312-322).
-        Returns (counts [T, ntypes] int32 device tensor, maxcount numpy [ntypes] running max)."""
+        Returns (counts [T, ntypes] int32 device tensor, maxcount numpy [ntypes] running max); with
+        members_cap > 0 also the membership lists [T, members_cap] (int32, -1 padded, any order) that
+        `descriptors(members=...)` can use instead of scanning the cells again."""
         torch = _torch()
         pos = self.to_device_pos(pos)
         types = self.to_device_types(types)
@@ -215,6 +217,13 @@ class Engine:
             T = F * N
         counts = torch.zeros((T, nt), dtype=torch.int32, device=self.device)
         mc = np.zeros(nt, dtype=np.int32) if maxcount is None else np.ascontiguousarray(maxcount, dtype=np.int32).copy()
+        if members_cap > 0:
+            members = torch.empty((T, int(members_cap)), dtype=torch.int32, device=self.device)
+            rc = self.L.mdb_compositions_members(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                                 float(cutoff), _ptr(targets), T, _ptr(counts), _np_ptr(mc),
+                                                 int(members_cap), _ptr(members), self.stream())
+            _lib.check(rc, "mdb_compositions_members")
+            return counts, mc, members
         rc = self.L.mdb_compositions(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
                                      float(cutoff), _ptr(targets), T, _ptr(counts), _np_ptr(mc), self.stream())
         _lib.check(rc, "mdb_compositions")
@@ -244,8 +253,10 @@ class Engine:
         return [m[k, : min(n[k], cap)] for k in range(T)]
 
     def descriptors(self, pos, cell, types, cutoff, counts, maxcount, targets=None, periodic=True, want_X=True,
-                    want_eig=False, eigcap=128):
-        """Coulomb-matrix spectrum + padded sorted feature rows (datasetbuilder.py:236-349)."""
+                    want_eig=False, eigcap=128, members=None):
+        """Coulomb-matrix spectrum + padded sorted feature rows (datasetbuilder.py:236-349).
+        members = the lists from `compositions(members_cap=...)` for the same targets: the cluster is
+        then gathered from them (no cell list, `cutoff` unused)."""
         torch = _torch()
         pos = self.to_device_pos(pos)
         types = self.to_device_types(types)
@@ -261,11 +272,30 @@ class Engine:
         X = torch.empty((T, D), dtype=torch.float64, device=self.device) if want_X else None
         eig = torch.empty((T, eigcap), dtype=torch.float64, device=self.device) if want_eig else None
         n = torch.empty((T,), dtype=torch.int32, device=self.device)
+        if members is not None:
+            rc = self.L.mdb_descriptors_members(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                                _ptr(targets), T, _ptr(counts), _np_ptr(mc), _ptr(members),
+                                                int(members.shape[1]), _ptr(X), _ptr(eig), int(eigcap), _ptr(n),
+                                                self.stream())
+            _lib.check(rc, "mdb_descriptors_members")
+            return {"X": X, "eig": eig, "n": n}
         rc = self.L.mdb_descriptors(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
                                     float(cutoff), _ptr(targets), T, _ptr(counts), _np_ptr(mc), _ptr(X), _ptr(eig),
                                     int(eigcap), _ptr(n), self.stream())
         _lib.check(rc, "mdb_descriptors")
         return {"X": X, "eig": eig, "n": n}
+
+    def feature_rows(self, eig, n, counts, maxcount):
+        """Padded sorted feature rows [T, D] from stored spectra (eig [T, eigcap], n [T]) and compositions once
+        the final per-element maxima are known (closed form of datasetbuilder.py:236-276)."""
+        torch = _torch()
+        mc = np.ascontiguousarray(maxcount, dtype=np.int32)
+        T = int(eig.shape[0])
+        X = torch.empty((T, int(mc.sum())), dtype=torch.float64, device=self.device)
+        rc = self.L.mdb_feature_rows(self.ctx, T, _ptr(eig), int(eig.shape[1]), _ptr(n), _ptr(counts), _np_ptr(mc), _ptr(X),
+                                     self.stream())
+        _lib.check(rc, "mdb_feature_rows")
+        return X
 
     # ------------------------------------------------------------------ clustering
     def minmax_fit(self, X):

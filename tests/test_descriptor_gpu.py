@@ -141,3 +141,36 @@ def test_reference_feature_assembly_closed_form():
     ref, maxc = O.reference_feature_assembly(results, diag)
     X, mx = O.feature_rows(eigs, np.array(comp), np.array([diag[n] for n in names]))
     assert np.array_equal(ref, X)
+
+
+def test_one_pass_path_members_and_feature_rows(engine):
+    """compositions(members) -> descriptors(members, spectra only) -> feature_rows gives bit for bit the rows
+    of the two-scan path, also when the final per-element maxima are larger than this batch's."""
+    import torch
+
+    s = synth.make_system(4000, 0.05, seed=synth.BASE_SEED + 53)
+    engine.set_elements(s.atomname)
+    pos = synth.frame_positions(s, 2)
+    targets = np.arange(0, 2 * 4000, 3, dtype=np.int32)
+    counts, maxc = engine.compositions(pos, s.cell(), s.types, 5.0, targets=targets)
+    ref = engine.descriptors(pos, s.cell(), s.types, 5.0, counts, maxc, targets=targets, want_eig=True, eigcap=64)
+    nmax = int(counts.sum(dim=1).max().item())
+    counts2, maxc2, members = engine.compositions(pos, s.cell(), s.types, 5.0, targets=targets, members_cap=nmax)
+    engine.check()
+    assert torch.equal(counts, counts2) and np.array_equal(maxc, maxc2)
+    m = members.cpu().numpy()
+    assert np.array_equal((m >= 0).sum(axis=1), counts.sum(dim=1).cpu().numpy())
+    out = engine.descriptors(pos, s.cell(), s.types, 5.0, counts, maxc, targets=targets, want_X=False, want_eig=True,
+                             eigcap=nmax, members=members)
+    engine.check()
+    assert torch.equal(out["n"], ref["n"])
+    assert torch.equal(out["eig"].nan_to_num(0.0), ref["eig"][:, :nmax].nan_to_num(0.0))
+    X = engine.feature_rows(out["eig"], out["n"], counts, maxc)
+    assert torch.equal(X, ref["X"])
+    bigger = maxc + np.array([2, 0, 1], dtype=np.int32)
+    ref2 = engine.descriptors(pos, s.cell(), s.types, 5.0, counts, bigger, targets=targets)
+    assert torch.equal(engine.feature_rows(out["eig"], out["n"], counts, bigger), ref2["X"])
+    # a list that is too short is reported
+    with pytest.raises(RuntimeError):
+        engine.compositions(pos, s.cell(), s.types, 5.0, targets=targets, members_cap=max(nmax - 3, 1))
+        engine.check()
