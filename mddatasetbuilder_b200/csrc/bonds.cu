@@ -100,11 +100,13 @@ __device__ __forceinline__ bool nbr_cell(int c, int d, int n, int reduce, int pe
 // Phase 1 streams the candidates of the (pruned) 3x3 rows and keeps the few that pass the coarse
 // float test in a per-thread pending list; phase 2 decides them (type-specific cutoff, borderline
 // cases in double) and phase 3 sorts, flags and writes the row.
-#define BOND_PEND 12
+// pending candidates per atom (coarse float test passed): a few more than the row holds
+#define BOND_PEND(MAXB) ((MAXB) + ((MAXB) >> 1))
 template <int MAXB, int MODE>
 __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ BondParams P) {
     __shared__ float4 s_nb[MAXB][BOND_THREADS];
-    __shared__ int s_pend[BOND_PEND][BOND_THREADS];
+    constexpr int PEND = BOND_PEND(MAXB);
+    __shared__ int s_pend[PEND][BOND_THREADS];
     __shared__ float s_cut2f[MDB_MAXT * MDB_MAXT];
     const int tid = threadIdx.x;
     if (tid < MDB_MAXT * MDB_MAXT) s_cut2f[tid] = P.el.cut2f[tid];
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
             }
             const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             if (d2 <= cmax && d2 >= dmin) {
-                if (np < BOND_PEND) s_pend[np][tid] = q;
+                if (np < PEND) s_pend[np][tid] = q;
                 ++np;
             }
         }
@@ -254,10 +256,10 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
             scan(cs[rowbase + xw], cs[rowbase + xw + 1], xws - me.x, sy - me.y, sz - me.z);
         }
     }
-    if (np > BOND_PEND) {
+    if (np > PEND) {
         atomicAdd(&P.stats->overflow, 1ull);
         atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
-        np = BOND_PEND;
+        np = PEND;
     }
 
     // phase 2: decide the pending candidates

@@ -8,9 +8,9 @@ for natoms,dens,dense in [(100000,0.02,False),(200000,0.05,False),(100000,0.11,T
     pos=synth.frame_positions_device(s,4,torch.device('cuda'))
     types=eng.to_device_types(s.types)
     for it in range(2):
-        counts,maxc=eng.compositions(pos,s.cell(),types,5.0)
         eng.profile(True)
-        out=eng.descriptors(pos,s.cell(),types,5.0,counts,maxc)
+        counts,maxc,members=eng.compositions(pos,s.cell(),types,5.0,members_cap=128)
+        out=eng.descriptors(pos,s.cell(),types,5.0,counts,maxc,members=members)
         torch.cuda.synchronize()
         pr=eng.profile_read(); eng.profile(False)
     n=out['n'].double()
