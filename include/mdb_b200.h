@@ -258,6 +258,14 @@ int mdb_kpp_step(mdb_ctx *ctx, long long n, int D, const double *d_X, long long 
                  const double *d_closest, const double *d_weights, double *d_dist, double *d_pot,
                  void *stream);
 
+/* The whole k-means++ seeding (sklearn cluster/_kmeans.py:180-279, unit sample weights) on the device:
+ * K centres out of the n rows X[rowidx] (or X itself), n_local_trials candidates per step.  h_rand holds
+ * the (K-1) x n_local_trials uniform variates in the order sklearn draws them, first_center the first
+ * centre; d_indices [K] receives the chosen positions (0..n-1).  Synchronises. */
+int mdb_kmeans_plusplus(mdb_ctx *ctx, long long n, int D, const double *d_X, long long ldx,
+                        const int32_t *d_rowidx, int K, int n_local_trials, const double *h_rand,
+                        int first_center, int32_t *d_indices, void *stream);
+
 /* Diagnostics of the last bond batch: counts summed over frames (synchronises).  A device-side error
  * flag raised by any kernel since the last call is returned (non-zero) and cleared. */
 int mdb_bond_stats(mdb_ctx *ctx, long long *n_violators, long long *n_exact_tests,

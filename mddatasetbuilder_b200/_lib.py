@@ -61,6 +61,8 @@ SIGNATURES = {
     "mdb_kmeans_apply_update": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdb_kpp_step": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
                                _vp]),
+    "mdb_kmeans_plusplus": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, C.c_int, C.c_int, _vp, C.c_int,
+                                      _vp, _vp]),
     "mdb_reader_open": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(_vp)]),
     "mdb_reader_close": (None, [_vp]),
     "mdb_reader_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_int)]),

@@ -335,6 +335,17 @@ extern "C" int mdb_kpp_step(mdb_ctx *c, long long n, int D, const double *d_X, l
                         (cudaStream_t)stream);
 }
 
+int kmeans_plusplus_run(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, int K, int T,
+                        const double *h_rand, int first, int *d_indices, cudaStream_t stream);
+
+extern "C" int mdb_kmeans_plusplus(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int32_t *d_rowidx,
+                                   int K, int n_local_trials, const double *h_rand, int first_center, int32_t *d_indices,
+                                   void *stream) {
+    if (check_ctx(c, "mdb_kmeans_plusplus", false)) return -1;
+    return kmeans_plusplus_run(c, n, D, d_X, ldx, d_rowidx, K, n_local_trials, h_rand, first_center, d_indices,
+                               (cudaStream_t)stream);
+}
+
 extern "C" int mdb_minmax_fit(mdb_ctx *c, long long rows, int D, const double *d_X, long long ldx, double *d_min,
                               double *d_max, void *stream) {
     if (check_ctx(c, "mdb_minmax_fit", false)) return -1;

@@ -421,6 +421,221 @@ int kpp_step_run(mdb_ctx *c, long long n, int D, const double *d_X, long long ld
 }
 
 // ---------------------------------------------------------------------------------------------
+// The whole k-means++ seeding loop on the device (sklearn cluster/_kmeans.py:180-279, unit sample
+// weights): K - 1 steps of { draw T candidates in proportion to the closest squared distance,
+// score each by the potential it would leave, keep the best }.  The uniform variates come from the
+// caller ((K-1) x T of them, drawn in sklearn's order), everything else -- cumulative sum, the
+// searchsorted draw, candidate distances, argmin, the update of `closest` -- stays on the GPU, two
+// launches per step and no host round trip (the Python loop with its three .item() syncs per step
+// took 230 us per step; K = 10,000 with n_init = 3 is 30,000 steps).
+// Sums are taken in a fixed order (per-thread run, block scan, per-block partials combined serially),
+// so the seeding is reproducible bit for bit.
+// ---------------------------------------------------------------------------------------------
+struct KppState {
+    int best;  // winning candidate of the previous step: dist[best] is the current `closest`
+    int pad;
+};
+
+// Finish step c-1 (potential of each candidate from the per-block partials, argmin with the lowest
+// index on ties like np.argmin) and draw the T candidates of step c: searchsorted(cumsum(closest),
+// u * pot), side = left, clipped to n - 1 (:241-245).  The cumulative sum is taken hierarchically --
+// the per-block partial sums of dist[best] that k_kpp_dist already produced, then the 256 rows of
+// the block that holds the target -- so nothing of length n is touched here.  One warp per candidate.
+__global__ void __launch_bounds__(1024) k_kpp_select_pick(long long n, int T, int Tprev, int c, int K,
+                                                          const double *__restrict__ rnd,  // [(K-1)][T]
+                                                          const double *__restrict__ partial, int nblk,
+                                                          const double *__restrict__ dist, int *__restrict__ cand,
+                                                          int *__restrict__ indices, KppState *st) {
+    extern __shared__ double s_dyn[];  // [nblk + 1] prefix of the block sums of dist[best] | [nblk][KPP_MAXT] partials
+    double *s_pre = s_dyn;
+    double *s_par = s_dyn + (nblk + 1);
+    __shared__ double s_pot[KPP_MAXT];
+    __shared__ int s_best;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int q = tid; q < nblk * KPP_MAXT; q += 1024) s_par[q] = partial[q];
+    __syncthreads();
+    // potential of candidate `warp`: lane-strided runs over the blocks, then a fixed shuffle tree
+    if (warp < Tprev) {
+        double p = 0.0;
+        for (int b = lane; b < nblk; b += 32) p += s_par[b * KPP_MAXT + warp];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) s_pot[warp] = p;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int t = 1; t < Tprev; ++t)
+            if (s_pot[t] < s_pot[best]) best = t;
+        s_best = best;
+        st->best = best;
+        indices[c - 1] = cand[best];
+        double acc = 0.0;
+        s_pre[0] = 0.0;
+        for (int b = 0; b < nblk; ++b) {
+            acc += s_par[b * KPP_MAXT + best];
+            s_pre[b + 1] = acc;
+        }
+    }
+    __syncthreads();
+    if (c >= K) return;  // the last call only selects
+    const int best = s_best;
+    if (warp < T) {
+        const double r = rnd[(size_t)(c - 1) * T + warp] * s_pot[best];
+        // block whose cumulative range holds r: first b with pre[b + 1] >= r
+        int lo = 0, hi = nblk;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_pre[mid + 1] < r) lo = mid + 1;
+            else hi = mid;
+        }
+        long long pick = n - 1;
+        if (lo < nblk) {
+            const double *d = dist + (size_t)best * n;
+            const long long i0 = (long long)lo * 256;
+            double base = s_pre[lo];
+            bool found = false;
+            for (int q = 0; q < 256 && !found; q += 32) {
+                const long long i = i0 + q + lane;
+                double v = i < n ? d[i] : 0.0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {  // inclusive warp scan
+                    const double u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, i < n && base + v >= r);
+                if (hit) {
+                    pick = i0 + q + (__ffs(hit) - 1);
+                    found = true;
+                }
+                base += __shfl_sync(0xffffffffu, v, 31);
+            }
+            if (!found) pick = min(n - 1, i0 + 256);  // rounding left r just past this block's rows
+        }
+        if (lane == 0) cand[warp] = (int)pick;
+    }
+}
+
+// distances of the T candidate rows to every row, clipped against the current closest distance
+// (= dist[best] of the previous step, read before it is overwritten; nothing to clip in step 0);
+// one thread per row, candidates staged in shared memory; per-block partial potentials
+template <int TMAX>
+__global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
+                                                  long long n, int D, const int *__restrict__ cand, int T, int first_step,
+                                                  const KppState *__restrict__ st, double *__restrict__ dist,
+                                                  double *__restrict__ partial) {
+    extern __shared__ double s_c[];  // [T][D] candidate rows, then [8][KPP_MAXT] warp partials
+    double *s_w = s_c + (size_t)T * D;
+    for (int q = threadIdx.x; q < T * D; q += 256) {
+        const int t = q / D, k = q - t * D;
+        const int ci = cand[t];
+        s_c[q] = X[(rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx + k];
+    }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    double acc[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) acc[t] = 0.0;
+    if (i < n) {
+        const double cl = first_step ? DBL_MAX : dist[(size_t)st->best * n + i];
+        const double *x = X + (rowidx ? (long long)rowidx[i] : i) * ldx;
+#pragma unroll 5
+        for (int k = 0; k < D; ++k) {
+            const double xv = x[k];
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t)
+                if (t < T) {
+                    const double df = xv - s_c[t * D + k];
+                    acc[t] = fma(df, df, acc[t]);
+                }
+        }
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+            if (t < T) {
+                acc[t] = fmin(acc[t], cl);
+                dist[(size_t)t * n + i] = acc[t];
+            }
+    }
+    // block potentials in a fixed order: lanes by shuffle tree, warps serially
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+        if (t < T) {
+            double v = acc[t];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_w[warp * KPP_MAXT + t] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < T) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += s_w[w * KPP_MAXT + threadIdx.x];
+        partial[(size_t)blockIdx.x * KPP_MAXT + threadIdx.x] = v;
+    }
+}
+
+int kmeans_plusplus_run(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, int K, int T,
+                        const double *h_rand, int first, int *d_indices, cudaStream_t stream) {
+    if (n < 1 || K < 1 || K > n || T < 1 || T > KPP_MAXT || first < 0 || first >= n) {
+        mdb_set_error("kmeans_plusplus: need 1 <= K <= n, 1 <= T <= 32 and a valid first centre");
+        return -1;
+    }
+    const int nblk = (int)cdiv(n, 256);
+    const size_t nrand = (size_t)std::max(K - 1, 1) * T;
+    size_t need = align256((size_t)T * n * sizeof(double)) + align256((size_t)nblk * KPP_MAXT * sizeof(double)) +
+                  align256(nrand * sizeof(double)) + 4 * 256 + 1024;
+    if (arena_reserve(c, need, stream)) return -1;
+    arena_reset(c);
+    double *dist = (double *)arena_alloc(c, (size_t)T * n * sizeof(double));
+    double *partial = (double *)arena_alloc(c, (size_t)nblk * KPP_MAXT * sizeof(double));
+    double *rnd = (double *)arena_alloc(c, nrand * sizeof(double));
+    int *cand = (int *)arena_alloc(c, 256);
+    KppState *st = (KppState *)arena_alloc(c, 256);
+    if (!dist || !partial || !rnd || !cand || !st) {
+        mdb_set_error("kmeans_plusplus: arena too small (internal sizing error)");
+        return -1;
+    }
+    if (K > 1) MDB_CUDA(cudaMemcpyAsync(rnd, h_rand, nrand * sizeof(double), cudaMemcpyHostToDevice, stream));
+    MDB_CUDA(cudaMemcpyAsync(cand, &first, sizeof(int), cudaMemcpyHostToDevice, stream));
+    const size_t smem = ((size_t)T * D + 8 * KPP_MAXT) * sizeof(double);
+    const size_t smem_sel = ((size_t)(nblk + 1) + (size_t)nblk * KPP_MAXT) * sizeof(double);
+    if (smem > 200 * 1024 || smem_sel > 200 * 1024) {
+        mdb_set_error("kmeans_plusplus: too many features or seeding rows for the shared-memory staging");
+        return -1;
+    }
+    MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MDB_CUDA(cudaFuncSetAttribute(k_kpp_select_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+    auto launch_dist = [&](int Tn, int first_step) {
+        if (Tn <= 16)
+            k_kpp_dist<16><<<nblk, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, first_step, st, dist, partial);
+        else
+            k_kpp_dist<32><<<nblk, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, first_step, st, dist, partial);
+    };
+    {
+        // step 0: the first centre alone (T = 1, nothing to clip against)
+        launch_dist(1, 1);
+        int Tprev = 1;
+        for (int step = 1; step <= K; ++step) {
+            {
+                ProfScope ps(c, "k_kpp_select_pick", stream);
+                k_kpp_select_pick<<<1, 1024, smem_sel, stream>>>(n, T, Tprev, step, K, rnd, partial, nblk, dist, cand, d_indices,
+                                                                 st);
+            }
+            if (step < K) {
+                ProfScope ps(c, "k_kpp_dist", stream);
+                launch_dist(T, 0);
+            }
+            Tprev = T;
+        }
+    }
+    c->launches += 2ull * K;
+    MDB_CUDA(cudaGetLastError());
+    MDB_CUDA(cudaStreamSynchronize(stream));  // `first` and h_rand are the caller's
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host wrappers
 // ---------------------------------------------------------------------------------------------
 int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,

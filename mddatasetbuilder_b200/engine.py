@@ -378,6 +378,19 @@ class Engine:
                                  self.stream())
         _lib.check(rc, "mdb_kpp_step")
 
+    def kmeans_plusplus(self, X, K, rand, first_center, rowidx=None):
+        """k-means++ seeding on the device (sklearn _kmeans_plusplus): `rand` = the (K-1, n_local_trials)
+        uniform variates in drawing order (host), returns the K chosen positions (int32 device tensor)."""
+        torch = _torch()
+        n = int(rowidx.numel()) if rowidx is not None else int(X.shape[0])
+        rand = np.ascontiguousarray(rand, dtype=np.float64).reshape(max(K - 1, 1) if rand.size else 1, -1)
+        T = int(rand.shape[1])
+        idx = torch.empty(K, dtype=torch.int32, device=self.device)
+        rc = self.L.mdb_kmeans_plusplus(self.ctx, n, int(X.shape[1]), _ptr(X), int(X.stride(0)), _ptr(rowidx), int(K), T,
+                                        _np_ptr(rand), int(first_center), _ptr(idx), self.stream())
+        _lib.check(rc, "mdb_kmeans_plusplus")
+        return idx
+
     def kmeans_apply_update(self, centers, weight_sums, sums, wsum):
         K, D = centers.shape
         rc = self.L.mdb_kmeans_apply_update(self.ctx, int(K), int(D), _ptr(centers), _ptr(weight_sums), _ptr(sums),

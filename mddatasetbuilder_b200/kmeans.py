@@ -75,25 +75,11 @@ class MiniBatchKMeansB200:
         K = self.n_clusters
         n_local_trials = 2 + int(np.log(K))
         center_id = int(rs.choice(n, p=np.full(n, 1.0 / n)))
-        indices = np.full(K, -1, dtype=np.int64)
-        indices[0] = center_id
-        dist = torch.empty((n_local_trials, n), dtype=torch.float64, device=eng.device)
-        pot = torch.empty(n_local_trials, dtype=torch.float64, device=eng.device)
-        cand = torch.tensor([center_id], dtype=torch.int32, device=eng.device)
-        eng.kpp_step(X, cand, None, dist, pot, rowidx=rowidx)
-        closest = dist[0].clone()
-        current_pot = float(pot[0].item())
-        for c in range(1, K):
-            rand_vals = rs.uniform(size=n_local_trials) * current_pot
-            csum = torch.cumsum(closest, dim=0)
-            cand = torch.searchsorted(csum, torch.as_tensor(rand_vals, device=eng.device)).clamp_(max=n - 1).to(torch.int32)
-            eng.kpp_step(X, cand, closest, dist, pot, rowidx=rowidx)
-            best = int(torch.argmin(pot).item())
-            current_pot = float(pot[best].item())
-            closest = dist[best].clone()
-            indices[c] = int(cand[best].item())
-        idx_t = torch.as_tensor(indices, device=eng.device)
-        return X[rowidx.long()[idx_t]].clone()
+        # sklearn draws n_local_trials uniforms per step from the same RandomState; drawing them all at once
+        # gives the identical stream, and the loop itself runs on the device (two launches per step)
+        rand = rs.uniform(size=(max(K - 1, 0), n_local_trials))
+        idx = eng.kmeans_plusplus(X, K, rand if K > 1 else np.zeros((1, n_local_trials)), center_id, rowidx=rowidx)
+        return X[rowidx.long()[idx.long()]].clone()
 
     def _init_centroids(self, X, rs, init_size):
         import torch

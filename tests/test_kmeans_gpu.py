@@ -107,3 +107,30 @@ def test_tensor_core_assign_clustered_data(engine):
     labels, _ = O.kmeans_labels(X, centers)
     got, nre = engine.kmeans_assign_tc(_t(engine, X), _t(engine, centers))
     assert np.array_equal(got.cpu().numpy(), labels), f"{(got.cpu().numpy() != labels).sum()} differ; {nre} re-checked"
+
+
+@pytest.mark.parametrize("n,D,K,seed", [(500, 7, 20, 0), (3000, 35, 150, 1), (1200, 3, 1, 2), (64, 5, 64, 3)])
+def test_device_kmeans_plusplus_matches_sklearn(engine, n, D, K, seed):
+    """The device-resident seeding loop picks the centres scikit-learn's _kmeans_plusplus picks from the
+    same RandomState stream (cluster/_kmeans.py:180-279)."""
+    import torch
+    from sklearn.cluster._kmeans import _kmeans_plusplus
+    from sklearn.utils.extmath import row_norms
+
+    rng = np.random.default_rng(100 + seed)
+    X = rng.random((n, D))
+    rs = np.random.RandomState(seed)
+    _, want = _kmeans_plusplus(X, K, row_norms(X, squared=True), np.ones(n), rs, None)
+    rs = np.random.RandomState(seed)
+    T = 2 + int(np.log(K))
+    first = int(rs.choice(n, p=np.full(n, 1.0 / n)))
+    rand = rs.uniform(size=(max(K - 1, 0), T))
+    got = engine.kmeans_plusplus(_t(engine, X), K, rand if K > 1 else np.zeros((1, T)), first).cpu().numpy()
+    assert np.array_equal(got, want)
+    # rows addressed through an index list give the same answer in positions of that list
+    perm = rng.permutation(n).astype(np.int32)
+    Xp = np.empty_like(X)
+    Xp[perm] = X
+    got2 = engine.kmeans_plusplus(_t(engine, Xp), K, rand if K > 1 else np.zeros((1, T)), first,
+                                  rowidx=torch.as_tensor(perm, device=engine.device)).cpu().numpy()
+    assert np.array_equal(got2, want)
