@@ -258,13 +258,15 @@ int mdb_kpp_step(mdb_ctx *ctx, long long n, int D, const double *d_X, long long 
                  const double *d_closest, const double *d_weights, double *d_dist, double *d_pot,
                  void *stream);
 
-/* The whole k-means++ seeding (sklearn cluster/_kmeans.py:180-279, unit sample weights) on the device:
- * K centres out of the n rows X[rowidx] (or X itself), n_local_trials candidates per step.  h_rand holds
- * the (K-1) x n_local_trials uniform variates in the order sklearn draws them, first_center the first
- * centre; d_indices [K] receives the chosen positions (0..n-1).  Synchronises. */
-int mdb_kmeans_plusplus(mdb_ctx *ctx, long long n, int D, const double *d_X, long long ldx,
+/* The whole k-means++ seeding (sklearn cluster/_kmeans.py:180-279, unit sample weights) on the device,
+ * for nbatch independent runs at once (MiniBatchKMeans' n_init seedings share nothing but X): K centres
+ * out of the n rows X[rowidx[b]] (d_rowidx [nbatch][n], or NULL = X itself), n_local_trials candidates
+ * per step.  h_rand [nbatch][(K-1) * n_local_trials] holds the uniform variates in the order sklearn
+ * draws them, h_first_center [nbatch] the first centres; d_indices [nbatch][K] receives the chosen
+ * positions (0..n-1).  Synchronises. */
+int mdb_kmeans_plusplus(mdb_ctx *ctx, int nbatch, long long n, int D, const double *d_X, long long ldx,
                         const int32_t *d_rowidx, int K, int n_local_trials, const double *h_rand,
-                        int first_center, int32_t *d_indices, void *stream);
+                        const int32_t *h_first_center, int32_t *d_indices, void *stream);
 
 /* Diagnostics of the last bond batch: counts summed over frames (synchronises).  A device-side error
  * flag raised by any kernel since the last call is returned (non-zero) and cleared. */
@@ -319,6 +321,12 @@ int mdb_parse_bonds_text(mdb_ctx *ctx, const char *d_text, int nframes, int nato
 /* One frame already in memory (the lines a per-frame drop-in method receives). */
 int mdb_reader_parse_buffer(const mdb_reader *r, const char *buf, size_t len, double *h_pos,
                             double *h_cell, int32_t *h_nbr, double *h_bo, int width);
+
+/* Output side: many ASE "simple xyz" files in one call (the per-structure ase.io.write of reference
+ * datasetbuilder.py:577-585): "<n>\n\n" then "%-2s %22.15f %22.15f %22.15f\n" per atom.  File k holds
+ * atoms [offsets[k], offsets[k+1]) of the flat arrays; symbols4 = 4-byte NUL-padded strings. */
+int mdb_write_xyz_batch(int nfiles, const char *const *paths, const long long *offsets,
+                        const char *symbols4, const double *h_pos, int nthreads);
 
 /* Per-launch CUDA-event timing on the launching stream (bench.py's live roofline
  * measurement).  mdb_profile_read synchronises and writes "name count total_ms" lines

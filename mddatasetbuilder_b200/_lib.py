@@ -61,8 +61,8 @@ SIGNATURES = {
     "mdb_kmeans_apply_update": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdb_kpp_step": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
                                _vp]),
-    "mdb_kmeans_plusplus": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, C.c_int, C.c_int, _vp, C.c_int,
-                                      _vp, _vp]),
+    "mdb_kmeans_plusplus": (C.c_int, [c_ctx, C.c_int, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, C.c_int, C.c_int, _vp,
+                                      _vp, _vp, _vp]),
     "mdb_reader_open": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(_vp)]),
     "mdb_reader_close": (None, [_vp]),
     "mdb_reader_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_int)]),
@@ -74,6 +74,7 @@ SIGNATURES = {
     "mdb_parse_bonds_text": (C.c_int, [c_ctx, _vp, C.c_int, C.c_int, _vp, _vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp,
                                        _vp]),
     "mdb_reader_parse_buffer": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _vp, _vp, _vp, _vp, C.c_int]),
+    "mdb_write_xyz_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), _vp, _vp, _vp, C.c_int]),
     "mdb_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "mdb_profile_read": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),
     "mdb_bond_stats": (C.c_int, [c_ctx, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

@@ -335,14 +335,14 @@ extern "C" int mdb_kpp_step(mdb_ctx *c, long long n, int D, const double *d_X, l
                         (cudaStream_t)stream);
 }
 
-int kmeans_plusplus_run(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, int K, int T,
-                        const double *h_rand, int first, int *d_indices, cudaStream_t stream);
+int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, int K,
+                        int T, const double *h_rand, const int *h_first, int *d_indices, cudaStream_t stream);
 
-extern "C" int mdb_kmeans_plusplus(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int32_t *d_rowidx,
-                                   int K, int n_local_trials, const double *h_rand, int first_center, int32_t *d_indices,
-                                   void *stream) {
+extern "C" int mdb_kmeans_plusplus(mdb_ctx *c, int nbatch, long long n, int D, const double *d_X, long long ldx,
+                                   const int32_t *d_rowidx, int K, int n_local_trials, const double *h_rand,
+                                   const int32_t *h_first_center, int32_t *d_indices, void *stream) {
     if (check_ctx(c, "mdb_kmeans_plusplus", false)) return -1;
-    return kmeans_plusplus_run(c, n, D, d_X, ldx, d_rowidx, K, n_local_trials, h_rand, first_center, d_indices,
+    return kmeans_plusplus_run(c, nbatch, n, D, d_X, ldx, d_rowidx, K, n_local_trials, h_rand, h_first_center, d_indices,
                                (cudaStream_t)stream);
 }
 

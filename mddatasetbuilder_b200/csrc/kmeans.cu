@@ -446,6 +446,13 @@ __global__ void __launch_bounds__(1024) k_kpp_select_pick(long long n, int T, in
                                                           const double *__restrict__ partial, int nblk,
                                                           const double *__restrict__ dist, int *__restrict__ cand,
                                                           int *__restrict__ indices, KppState *st) {
+    // blockIdx.y = independent seeding problem (sklearn's n_init runs share nothing but X)
+    rnd += (size_t)blockIdx.y * (size_t)max(K - 1, 1) * T;
+    partial += (size_t)blockIdx.y * nblk * KPP_MAXT;
+    dist += (size_t)blockIdx.y * T * n;
+    cand += blockIdx.y * KPP_MAXT;
+    indices += (size_t)blockIdx.y * K;
+    st += blockIdx.y;
     extern __shared__ double s_dyn[];  // [nblk + 1] prefix of the block sums of dist[best] | [nblk][KPP_MAXT] partials
     double *s_pre = s_dyn;
     double *s_par = s_dyn + (nblk + 1);
@@ -521,9 +528,14 @@ __global__ void __launch_bounds__(1024) k_kpp_select_pick(long long n, int T, in
 // one thread per row, candidates staged in shared memory; per-block partial potentials
 template <int TMAX>
 __global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
-                                                  long long n, int D, const int *__restrict__ cand, int T, int first_step,
-                                                  const KppState *__restrict__ st, double *__restrict__ dist,
-                                                  double *__restrict__ partial) {
+                                                  long long n, int D, const int *__restrict__ cand, int T, int Tfull,
+                                                  int first_step, const KppState *__restrict__ st,
+                                                  double *__restrict__ dist, double *__restrict__ partial) {
+    if (rowidx) rowidx += (size_t)blockIdx.y * n;
+    cand += blockIdx.y * KPP_MAXT;
+    st += blockIdx.y;
+    dist += (size_t)blockIdx.y * Tfull * n;
+    partial += (size_t)blockIdx.y * gridDim.x * KPP_MAXT;
     extern __shared__ double s_c[];  // [T][D] candidate rows, then [8][KPP_MAXT] warp partials
     double *s_w = s_c + (size_t)T * D;
     for (int q = threadIdx.x; q < T * D; q += 256) {
@@ -574,29 +586,37 @@ __global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, 
     }
 }
 
-int kmeans_plusplus_run(mdb_ctx *c, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, int K, int T,
-                        const double *h_rand, int first, int *d_indices, cudaStream_t stream) {
-    if (n < 1 || K < 1 || K > n || T < 1 || T > KPP_MAXT || first < 0 || first >= n) {
-        mdb_set_error("kmeans_plusplus: need 1 <= K <= n, 1 <= T <= 32 and a valid first centre");
+int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X, long long ldx, const int *d_rowidx, int K,
+                        int T, const double *h_rand, const int *h_first, int *d_indices, cudaStream_t stream) {
+    if (B < 1 || B > 64 || n < 1 || K < 1 || K > n || T < 1 || T > KPP_MAXT) {
+        mdb_set_error("kmeans_plusplus: need 1 <= K <= n, 1 <= T <= 32, 1 <= batch <= 64");
         return -1;
     }
+    for (int b = 0; b < B; ++b)
+        if (h_first[b] < 0 || h_first[b] >= n) {
+            mdb_set_error("kmeans_plusplus: first centre out of range");
+            return -1;
+        }
     const int nblk = (int)cdiv(n, 256);
     const size_t nrand = (size_t)std::max(K - 1, 1) * T;
-    size_t need = align256((size_t)T * n * sizeof(double)) + align256((size_t)nblk * KPP_MAXT * sizeof(double)) +
-                  align256(nrand * sizeof(double)) + 4 * 256 + 1024;
+    size_t need = align256((size_t)B * T * n * sizeof(double)) + align256((size_t)B * nblk * KPP_MAXT * sizeof(double)) +
+                  align256((size_t)B * nrand * sizeof(double)) + align256((size_t)B * KPP_MAXT * sizeof(int)) +
+                  align256((size_t)B * sizeof(KppState)) + 1024;
     if (arena_reserve(c, need, stream)) return -1;
     arena_reset(c);
-    double *dist = (double *)arena_alloc(c, (size_t)T * n * sizeof(double));
-    double *partial = (double *)arena_alloc(c, (size_t)nblk * KPP_MAXT * sizeof(double));
-    double *rnd = (double *)arena_alloc(c, nrand * sizeof(double));
-    int *cand = (int *)arena_alloc(c, 256);
-    KppState *st = (KppState *)arena_alloc(c, 256);
+    double *dist = (double *)arena_alloc(c, (size_t)B * T * n * sizeof(double));
+    double *partial = (double *)arena_alloc(c, (size_t)B * nblk * KPP_MAXT * sizeof(double));
+    double *rnd = (double *)arena_alloc(c, (size_t)B * nrand * sizeof(double));
+    int *cand = (int *)arena_alloc(c, (size_t)B * KPP_MAXT * sizeof(int));
+    KppState *st = (KppState *)arena_alloc(c, (size_t)B * sizeof(KppState));
     if (!dist || !partial || !rnd || !cand || !st) {
         mdb_set_error("kmeans_plusplus: arena too small (internal sizing error)");
         return -1;
     }
-    if (K > 1) MDB_CUDA(cudaMemcpyAsync(rnd, h_rand, nrand * sizeof(double), cudaMemcpyHostToDevice, stream));
-    MDB_CUDA(cudaMemcpyAsync(cand, &first, sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (K > 1) MDB_CUDA(cudaMemcpyAsync(rnd, h_rand, (size_t)B * nrand * sizeof(double), cudaMemcpyHostToDevice, stream));
+    std::vector<int> hc((size_t)B * KPP_MAXT, 0);
+    for (int b = 0; b < B; ++b) hc[(size_t)b * KPP_MAXT] = h_first[b];
+    MDB_CUDA(cudaMemcpyAsync(cand, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     const size_t smem = ((size_t)T * D + 8 * KPP_MAXT) * sizeof(double);
     const size_t smem_sel = ((size_t)(nblk + 1) + (size_t)nblk * KPP_MAXT) * sizeof(double);
     if (smem > 200 * 1024 || smem_sel > 200 * 1024) {
@@ -606,11 +626,12 @@ int kmeans_plusplus_run(mdb_ctx *c, long long n, int D, const double *d_X, long 
     MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MDB_CUDA(cudaFuncSetAttribute(k_kpp_select_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+    const dim3 gd((unsigned)nblk, (unsigned)B), gs(1, (unsigned)B);
     auto launch_dist = [&](int Tn, int first_step) {
         if (Tn <= 16)
-            k_kpp_dist<16><<<nblk, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, first_step, st, dist, partial);
+            k_kpp_dist<16><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial);
         else
-            k_kpp_dist<32><<<nblk, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, first_step, st, dist, partial);
+            k_kpp_dist<32><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial);
     };
     {
         // step 0: the first centre alone (T = 1, nothing to clip against)
@@ -619,8 +640,8 @@ int kmeans_plusplus_run(mdb_ctx *c, long long n, int D, const double *d_X, long 
         for (int step = 1; step <= K; ++step) {
             {
                 ProfScope ps(c, "k_kpp_select_pick", stream);
-                k_kpp_select_pick<<<1, 1024, smem_sel, stream>>>(n, T, Tprev, step, K, rnd, partial, nblk, dist, cand, d_indices,
-                                                                 st);
+                k_kpp_select_pick<<<gs, 1024, smem_sel, stream>>>(n, T, Tprev, step, K, rnd, partial, nblk, dist, cand, d_indices,
+                                                                  st);
             }
             if (step < K) {
                 ProfScope ps(c, "k_kpp_dist", stream);
@@ -631,7 +652,7 @@ int kmeans_plusplus_run(mdb_ctx *c, long long n, int D, const double *d_X, long 
     }
     c->launches += 2ull * K;
     MDB_CUDA(cudaGetLastError());
-    MDB_CUDA(cudaStreamSynchronize(stream));  // `first` and h_rand are the caller's
+    MDB_CUDA(cudaStreamSynchronize(stream));  // the host arrays are the caller's
     return 0;
 }
 

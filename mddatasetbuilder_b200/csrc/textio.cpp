@@ -787,3 +787,46 @@ extern "C" int mdb_reader_parse_buffer(const mdb_reader *r, const char *buf, siz
     if (rc) return fail(err);
     return 0;
 }
+
+// ---- output: ASE "simple xyz" files, many at once ----------------------------------------------
+// The per-structure writer of the reference (ase.io.write(..., format="xyz") at
+// datasetbuilder.py:577-585): "<n>\n\n" then one "%-2s %22.15f %22.15f %22.15f\n" line per atom.
+// File k holds atoms [offsets[k], offsets[k+1]) of the flat arrays; symbols are 4-byte NUL-padded
+// strings.  Files are written by `nthreads` threads (<= 0: the hardware concurrency).
+extern "C" int mdb_write_xyz_batch(int nfiles, const char *const *paths, const long long *offsets, const char *symbols4,
+                                   const double *pos, int nthreads) {
+    if (nfiles < 0 || (nfiles > 0 && (!paths || !offsets || !symbols4 || !pos))) return fail("mdb_write_xyz_batch: bad arguments");
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<int> next(0), bad(-1);
+    auto work = [&]() {
+        std::string buf;
+        char line[128];
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= nfiles) break;
+            const long long a = offsets[k], b = offsets[k + 1];
+            buf.clear();
+            int m = snprintf(line, sizeof(line), "%lld\n\n", b - a);
+            buf.append(line, (size_t)m);
+            for (long long i = a; i < b; ++i) {
+                char sym[5] = {0, 0, 0, 0, 0};
+                memcpy(sym, symbols4 + 4 * i, 4);
+                m = snprintf(line, sizeof(line), "%-2s %22.15f %22.15f %22.15f\n", sym, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+                buf.append(line, (size_t)m);
+            }
+            FILE *f = fopen(paths[k], "wb");
+            if (!f || fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+                int expect = -1;
+                bad.compare_exchange_strong(expect, k);
+            }
+            if (f) fclose(f);
+        }
+    };
+    std::vector<std::thread> th;
+    const int nt = std::min(nthreads, std::max(nfiles, 1));
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (bad.load() >= 0) return fail(std::string("cannot write ") + paths[bad.load()]);
+    return 0;
+}

@@ -40,7 +40,7 @@ from .atoms import atomic_numbers
 from .detect import Detect, DetectDump, unpack_key
 from .utils import must_be_list
 from .writer import detect_multiplicity as _detect_multiplicity
-from .writer import wrap_positions, write_gjf, write_xyz
+from .writer import wrap_positions, write_gjf, write_xyz, write_xyz_batch  # noqa: F401
 
 
 def _dist():
@@ -564,6 +564,7 @@ class DatasetBuilder:
         symbols_all = np.asarray(self.crddetector.atomnames)
         lengths = np.linalg.norm(cell3, axis=1)
         results = 0
+        xyz_paths, xyz_symbols, xyz_positions = [], [], []
         for (atoma, trajatomfilename, itype, itotal), cutoffatomid in zip(sel, members):
             folder = str(itotal // 1000).zfill(self.foldermaxlength)
             atomtypenum = str(itype).zfill(self.maxlength)
@@ -580,13 +581,17 @@ class DatasetBuilder:
             tags[np.nonzero(idx == atoma - 1)[0][0]] = 1
             positions = wrap_positions(pos_h[idx], cell3, pos_h[atoma - 1] / lengths, self.pbc)
             name = f"{self.xyzfilename}_{trajatomfilename}_{atomtypenum}"
-            write_xyz(os.path.join(self.dataset_dir, folder, name + ".xyz"), symbols, positions)
+            xyz_paths.append(os.path.join(self.dataset_dir, folder, name + ".xyz"))
+            xyz_symbols.append(symbols)
+            xyz_positions.append(positions)
             if self.writegjf:
                 write_gjf(os.path.join(self.gjfdir, folder, name + ".gjf"), takenatomidindex, symbols, positions,
                           self.qmkeywords, self.fragment)
             if self.atom_pref:
                 np.save(os.path.join(self.gjfdir, folder, name + ".atom_pref.npy"), np.array([tags]))
             results += 1
+        # the xyz files of the frame in one native call (formatting + I/O on several threads)
+        write_xyz_batch(xyz_paths, xyz_symbols, xyz_positions)
         return results
 
     def lineiter(self, detector):

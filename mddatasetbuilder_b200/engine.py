@@ -379,17 +379,27 @@ class Engine:
         _lib.check(rc, "mdb_kpp_step")
 
     def kmeans_plusplus(self, X, K, rand, first_center, rowidx=None):
-        """k-means++ seeding on the device (sklearn _kmeans_plusplus): `rand` = the (K-1, n_local_trials)
-        uniform variates in drawing order (host), returns the K chosen positions (int32 device tensor)."""
+        """k-means++ seeding on the device (sklearn _kmeans_plusplus).  Single run: `rand` = the
+        (K-1, n_local_trials) uniform variates in drawing order (host), first_center an int, rowidx [n] or
+        None; returns the K chosen positions (int32 device tensor).  Batch of independent runs: rand
+        [B, K-1, T], first_center [B], rowidx [B, n] or None; returns [B, K]."""
         torch = _torch()
-        n = int(rowidx.numel()) if rowidx is not None else int(X.shape[0])
-        rand = np.ascontiguousarray(rand, dtype=np.float64).reshape(max(K - 1, 1) if rand.size else 1, -1)
-        T = int(rand.shape[1])
-        idx = torch.empty(K, dtype=torch.int32, device=self.device)
-        rc = self.L.mdb_kmeans_plusplus(self.ctx, n, int(X.shape[1]), _ptr(X), int(X.stride(0)), _ptr(rowidx), int(K), T,
-                                        _np_ptr(rand), int(first_center), _ptr(idx), self.stream())
+        rand = np.asarray(rand, dtype=np.float64)
+        batched = np.ndim(first_center) > 0
+        B = len(first_center) if batched else 1
+        T = int(rand.shape[-1])
+        rand = np.ascontiguousarray(rand.reshape(B, -1))
+        first = np.ascontiguousarray(np.atleast_1d(first_center), dtype=np.int32)
+        if rowidx is not None:
+            rowidx = rowidx.contiguous()
+            n = int(rowidx.shape[-1])
+        else:
+            n = int(X.shape[0])
+        idx = torch.empty((B, K), dtype=torch.int32, device=self.device)
+        rc = self.L.mdb_kmeans_plusplus(self.ctx, B, n, int(X.shape[1]), _ptr(X), int(X.stride(0)), _ptr(rowidx), int(K), T,
+                                        _np_ptr(rand), _np_ptr(first), _ptr(idx), self.stream())
         _lib.check(rc, "mdb_kmeans_plusplus")
-        return idx
+        return idx if batched else idx[0]
 
     def kmeans_apply_update(self, centers, weight_sums, sums, wsum):
         K, D = centers.shape

@@ -66,31 +66,31 @@ class MiniBatchKMeansB200:
         self.verbose = verbose
 
     # ------------------------------------------------------------------ seeding
-    def _kmeans_plusplus(self, X, rowidx, rs):
-        """sklearn _kmeans_plusplus on the rows X[rowidx] (unit sample weights)."""
+    def _init_centroids_all(self, X, rs, init_size):
+        """The n_init seedings of sklearn's MiniBatchKMeans.fit (init_indices, then _kmeans_plusplus on
+        those rows), run as ONE batched device loop.  Each seeding consumes a fixed number of variates
+        (randint for the rows, one choice, (K-1) x n_local_trials uniforms) and nothing else touches the
+        RandomState in between, so drawing them up front reproduces sklearn's stream."""
         import torch
 
         eng = self.eng
-        n = int(rowidx.numel())
+        n = int(X.shape[0])
         K = self.n_clusters
-        n_local_trials = 2 + int(np.log(K))
-        center_id = int(rs.choice(n, p=np.full(n, 1.0 / n)))
-        # sklearn draws n_local_trials uniforms per step from the same RandomState; drawing them all at once
-        # gives the identical stream, and the loop itself runs on the device (two launches per step)
-        rand = rs.uniform(size=(max(K - 1, 0), n_local_trials))
-        idx = eng.kmeans_plusplus(X, K, rand if K > 1 else np.zeros((1, n_local_trials)), center_id, rowidx=rowidx)
-        return X[rowidx.long()[idx.long()]].clone()
-
-    def _init_centroids(self, X, rs, init_size):
-        import torch
-
-        n = X.shape[0]
-        if init_size is not None and init_size < n:
-            init_indices = rs.randint(0, n, init_size)
-        else:
-            init_indices = np.arange(n)
-        rowidx = torch.as_tensor(init_indices, dtype=torch.int32, device=self.eng.device)
-        return self._kmeans_plusplus(X, rowidx, rs)
+        T = 2 + int(np.log(K))
+        rows, firsts, rands = [], [], []
+        for _ in range(self.n_init):
+            if init_size is not None and init_size < n:
+                init_indices = rs.randint(0, n, init_size)
+            else:
+                init_indices = np.arange(n)
+            m = len(init_indices)
+            rows.append(init_indices.astype(np.int32))
+            firsts.append(int(rs.choice(m, p=np.full(m, 1.0 / m))))
+            rands.append(rs.uniform(size=(max(K - 1, 0), T)) if K > 1 else np.zeros((0, T)))
+        rowidx = torch.as_tensor(np.stack(rows), dtype=torch.int32, device=eng.device)
+        rand = np.stack(rands) if K > 1 else np.zeros((self.n_init, 1, T))
+        idx = eng.kmeans_plusplus(X, K, rand, np.array(firsts, dtype=np.int32), rowidx=rowidx)
+        return [X[rowidx[b].long()[idx[b].long()]].clone() for b in range(self.n_init)]
 
     # ------------------------------------------------------------------ one mini-batch step
     def _mini_batch_step(self, X, batch_idx, centers, weight_sums, rs, random_reassign):
@@ -170,8 +170,7 @@ class MiniBatchKMeansB200:
         validation_indices = rs.randint(0, n_pool, init_size)
         valid_idx = torch.as_tensor(validation_indices, dtype=torch.int32, device=eng.device)
         best_inertia, centers = None, None
-        for _ in range(self.n_init):
-            c = self._init_centroids(pool, rs, init_size if pool_is_all else None)
+        for c in self._init_centroids_all(pool, rs, init_size if pool_is_all else None):
             _, inertia, _ = eng.kmeans_assign(pool, c, rowidx=valid_idx, want_inertia=True)
             if best_inertia is None or inertia < best_inertia:
                 centers, best_inertia = c, inertia
@@ -179,6 +178,7 @@ class MiniBatchKMeansB200:
         weight_sums = torch.zeros(K, dtype=torch.float64, device=eng.device)
         ewa, ewa_min, no_improvement = None, None, 0
         n_since_last_reassign = 0
+        counts_zero = True
         n_steps = (self.max_iter * n_samples) // batch_size
         local_batch = batch_size if d is None else max(1, batch_size // world)
         rs_local = rs if d is None else np.random.RandomState(self.seed + 104729 * (rank + 1))
@@ -187,7 +187,9 @@ class MiniBatchKMeansB200:
             idx = rs_local.randint(0, max(n_local, 1), local_batch)
             batch_idx = torch.as_tensor(idx, dtype=torch.int32, device=eng.device)
             n_since_last_reassign += batch_size
-            counts_zero = bool((weight_sums == 0).any().item())
+            # weights only grow, so once no centre has a zero count the test never fires again (one sync less per step)
+            if counts_zero:
+                counts_zero = bool((weight_sums == 0).any().item())
             random_reassign = counts_zero or n_since_last_reassign >= 10 * K
             if random_reassign:
                 n_since_last_reassign = 0

@@ -311,3 +311,30 @@ def test_frame_boundary_search_parallel_equals_sequential(tmp_path):
                 b = read_all(path, 4, stride, batch)
                 assert a.shape == b.shape == ((nframes + stride - 1) // stride, 2500, 3)
                 assert np.array_equal(a, b)
+
+
+def test_native_xyz_batch_writer_is_byte_identical(tmp_path):
+    """mdb_write_xyz_batch writes the bytes of the reference's per-structure writer (ASE simple xyz,
+    datasetbuilder.py:577-585; the Python restatement in writer.write_xyz is pinned by the golden files)."""
+    from mddatasetbuilder_b200.writer import write_xyz, write_xyz_batch
+
+    rng = np.random.default_rng(0)
+    pa, pb, syms, poss = [], [], [], []
+    for k in range(120):
+        n = int(rng.integers(1, 50))
+        s = rng.choice(np.array(["H", "C", "O", "Cl", "Na"]), n)
+        p = rng.normal(0, 10.0 ** rng.integers(-3, 4), (n, 3))
+        if k == 0:
+            p[0] = [0.0, -0.0, 1e-17]
+        if k == 1:
+            p[0] = [123456789.123456789, -1e15, 5e-16]
+        pa.append(str(tmp_path / f"a{k}.xyz"))
+        pb.append(str(tmp_path / f"b{k}.xyz"))
+        syms.append(s)
+        poss.append(p)
+        write_xyz(pa[-1], s, p)
+    write_xyz_batch(pb, syms, poss, nthreads=3)
+    for a, b in zip(pa, pb):
+        assert open(a, "rb").read() == open(b, "rb").read()
+    with pytest.raises(RuntimeError):
+        write_xyz_batch([str(tmp_path / "no_such_dir" / "x.xyz")], syms[:1], poss[:1])

@@ -134,3 +134,13 @@ def test_device_kmeans_plusplus_matches_sklearn(engine, n, D, K, seed):
     got2 = engine.kmeans_plusplus(_t(engine, Xp), K, rand if K > 1 else np.zeros((1, T)), first,
                                   rowidx=torch.as_tensor(perm, device=engine.device)).cpu().numpy()
     assert np.array_equal(got2, want)
+    # a batch of independent seedings (MiniBatchKMeans' n_init) in one device loop
+    wants, firsts, rands = [], [], []
+    for b in range(3):
+        rs = np.random.RandomState(seed + 10 * b)
+        wants.append(_kmeans_plusplus(X, K, row_norms(X, squared=True), np.ones(n), rs, None)[1])
+        rs = np.random.RandomState(seed + 10 * b)
+        firsts.append(int(rs.choice(n, p=np.full(n, 1.0 / n))))
+        rands.append(rs.uniform(size=(max(K - 1, 0), T)) if K > 1 else np.zeros((1, T)))
+    got3 = engine.kmeans_plusplus(_t(engine, X), K, np.stack(rands), np.array(firsts)).cpu().numpy()
+    assert np.array_equal(got3, np.stack(wants))
