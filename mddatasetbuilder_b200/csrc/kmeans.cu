@@ -439,8 +439,88 @@ struct KppState {
 // Finish step c-1 (potential of each candidate from the per-block partials, argmin with the lowest
 // index on ties like np.argmin) and draw the T candidates of step c: searchsorted(cumsum(closest),
 // u * pot), side = left, clipped to n - 1 (:241-245).  The cumulative sum is taken hierarchically --
-// the per-block partial sums of dist[best] that k_kpp_dist already produced, then the 256 rows of
-// the block that holds the target -- so nothing of length n is touched here.  One warp per candidate.
+// the per-block partial sums of dist[best] that the distance pass already produced, then the 256
+// rows of the block that holds the target -- so nothing of length n is touched here.  One warp per
+// candidate (in turns).  Everything another block wrote is read with __ldcg (the persistent kernel
+// below runs this inside one launch, where L1 is not coherent across SMs).
+__device__ __forceinline__ void kpp_select_pick_body(long long n, int T, int Tprev, int c, int K,
+                                                     const double *__restrict__ rnd, const double *partial, int nblk,
+                                                     const double *dist, int *cand, int *indices, KppState *st, double *s_dyn,
+                                                     double *s_pot, int *s_best) {
+    double *s_pre = s_dyn;               // [nblk + 1] prefix of the block sums of dist[best]
+    double *s_par = s_dyn + (nblk + 1);  // [nblk][KPP_MAXT] partials
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int q = tid; q < nblk * KPP_MAXT; q += blockDim.x) s_par[q] = __ldcg(partial + q);
+    __syncthreads();
+    // potential of candidate t: lane-strided runs over the blocks, then a fixed shuffle tree
+    for (int t = warp; t < Tprev; t += nwarps) {
+        double p = 0.0;
+        for (int b = lane; b < nblk; b += 32) p += s_par[b * KPP_MAXT + t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) s_pot[t] = p;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int t = 1; t < Tprev; ++t)
+            if (s_pot[t] < s_pot[best]) best = t;
+        *s_best = best;
+        st->best = best;
+        indices[c - 1] = __ldcg(cand + best);
+        double acc = 0.0;
+        s_pre[0] = 0.0;
+        for (int b = 0; b < nblk; ++b) {
+            acc += s_par[b * KPP_MAXT + best];
+            s_pre[b + 1] = acc;
+        }
+    }
+    __syncthreads();
+    if (c >= K) return;  // the last call only selects
+    const int best = *s_best;
+    for (int t = warp; t < T; t += nwarps) {
+        const double r = rnd[(size_t)(c - 1) * T + t] * s_pot[best];
+        // block whose cumulative range holds r: first b with pre[b + 1] >= r
+        int lo = 0, hi = nblk;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_pre[mid + 1] < r) lo = mid + 1;
+            else hi = mid;
+        }
+        long long pick = n - 1;
+        if (lo < nblk) {
+            // the 256 rows of that block in one round trip: 8 consecutive rows per lane, a running sum
+            // inside the lane, a warp scan over the lane totals, then the first row that reaches r
+            const double *d = dist + (size_t)best * n;
+            const long long i0 = (long long)lo * 256 + 8 * lane;
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = (i0 + q < n) ? __ldcg(d + i0 + q) : 0.0;
+#pragma unroll
+            for (int q = 1; q < 8; ++q) v[q] += v[q - 1];
+            double incl = v[7];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const double base = s_pre[lo] + (incl - v[7]);  // everything before this lane's rows
+            int first = 8;
+#pragma unroll
+            for (int q = 7; q >= 0; --q)
+                if (i0 + q < n && base + v[q] >= r) first = q;
+            const unsigned hit = __ballot_sync(0xffffffffu, first < 8);
+            if (hit) {
+                const int src = __ffs(hit) - 1;
+                pick = (long long)lo * 256 + 8 * src + __shfl_sync(0xffffffffu, first, src);
+            } else {
+                pick = min(n - 1, (long long)lo * 256 + 256);  // rounding left r just past this block's rows
+            }
+        }
+        if (lane == 0) cand[t] = (int)pick;
+    }
+}
+
 __global__ void __launch_bounds__(1024) k_kpp_select_pick(long long n, int T, int Tprev, int c, int K,
                                                           const double *__restrict__ rnd,  // [(K-1)][T]
                                                           const double *__restrict__ partial, int nblk,
@@ -453,103 +533,34 @@ __global__ void __launch_bounds__(1024) k_kpp_select_pick(long long n, int T, in
     cand += blockIdx.y * KPP_MAXT;
     indices += (size_t)blockIdx.y * K;
     st += blockIdx.y;
-    extern __shared__ double s_dyn[];  // [nblk + 1] prefix of the block sums of dist[best] | [nblk][KPP_MAXT] partials
-    double *s_pre = s_dyn;
-    double *s_par = s_dyn + (nblk + 1);
+    extern __shared__ double s_dyn[];
     __shared__ double s_pot[KPP_MAXT];
     __shared__ int s_best;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int q = tid; q < nblk * KPP_MAXT; q += 1024) s_par[q] = partial[q];
-    __syncthreads();
-    // potential of candidate `warp`: lane-strided runs over the blocks, then a fixed shuffle tree
-    if (warp < Tprev) {
-        double p = 0.0;
-        for (int b = lane; b < nblk; b += 32) p += s_par[b * KPP_MAXT + warp];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (lane == 0) s_pot[warp] = p;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int best = 0;
-        for (int t = 1; t < Tprev; ++t)
-            if (s_pot[t] < s_pot[best]) best = t;
-        s_best = best;
-        st->best = best;
-        indices[c - 1] = cand[best];
-        double acc = 0.0;
-        s_pre[0] = 0.0;
-        for (int b = 0; b < nblk; ++b) {
-            acc += s_par[b * KPP_MAXT + best];
-            s_pre[b + 1] = acc;
-        }
-    }
-    __syncthreads();
-    if (c >= K) return;  // the last call only selects
-    const int best = s_best;
-    if (warp < T) {
-        const double r = rnd[(size_t)(c - 1) * T + warp] * s_pot[best];
-        // block whose cumulative range holds r: first b with pre[b + 1] >= r
-        int lo = 0, hi = nblk;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_pre[mid + 1] < r) lo = mid + 1;
-            else hi = mid;
-        }
-        long long pick = n - 1;
-        if (lo < nblk) {
-            const double *d = dist + (size_t)best * n;
-            const long long i0 = (long long)lo * 256;
-            double base = s_pre[lo];
-            bool found = false;
-            for (int q = 0; q < 256 && !found; q += 32) {
-                const long long i = i0 + q + lane;
-                double v = i < n ? d[i] : 0.0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {  // inclusive warp scan
-                    const double u = __shfl_up_sync(0xffffffffu, v, o);
-                    if (lane >= o) v += u;
-                }
-                const unsigned hit = __ballot_sync(0xffffffffu, i < n && base + v >= r);
-                if (hit) {
-                    pick = i0 + q + (__ffs(hit) - 1);
-                    found = true;
-                }
-                base += __shfl_sync(0xffffffffu, v, 31);
-            }
-            if (!found) pick = min(n - 1, i0 + 256);  // rounding left r just past this block's rows
-        }
-        if (lane == 0) cand[warp] = (int)pick;
-    }
+    kpp_select_pick_body(n, T, Tprev, c, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best);
 }
 
 // distances of the T candidate rows to every row, clipped against the current closest distance
 // (= dist[best] of the previous step, read before it is overwritten; nothing to clip in step 0);
 // one thread per row, candidates staged in shared memory; per-block partial potentials
 template <int TMAX>
-__global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
-                                                  long long n, int D, const int *__restrict__ cand, int T, int Tfull,
-                                                  int first_step, const KppState *__restrict__ st,
-                                                  double *__restrict__ dist, double *__restrict__ partial) {
-    if (rowidx) rowidx += (size_t)blockIdx.y * n;
-    cand += blockIdx.y * KPP_MAXT;
-    st += blockIdx.y;
-    dist += (size_t)blockIdx.y * Tfull * n;
-    partial += (size_t)blockIdx.y * gridDim.x * KPP_MAXT;
-    extern __shared__ double s_c[];  // [T][D] candidate rows, then [8][KPP_MAXT] warp partials
-    double *s_w = s_c + (size_t)T * D;
-    for (int q = threadIdx.x; q < T * D; q += 256) {
-        const int t = q / D, k = q - t * D;
-        const int ci = cand[t];
-        s_c[q] = X[(rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx + k];
+__device__ __forceinline__ void kpp_dist_body(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
+                                              long long n, int D, const int *cand, int T, int first_step, const KppState *st,
+                                              double *dist, double *partial_blk, double *s_c, int chunk, bool stage) {
+    double *s_w = s_c + (size_t)T * D;  // [8][KPP_MAXT] warp partials
+    if (stage) {
+        for (int q = threadIdx.x; q < T * D; q += 256) {
+            const int t = q / D, k = q - t * D;
+            const int ci = __ldcg(cand + t);
+            s_c[q] = X[(rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx + k];
+        }
     }
     __syncthreads();
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long i = (long long)chunk * 256 + threadIdx.x;
     double acc[TMAX];
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) acc[t] = 0.0;
     if (i < n) {
-        const double cl = first_step ? DBL_MAX : dist[(size_t)st->best * n + i];
+        const double cl = first_step ? DBL_MAX : dist[(size_t)__ldcg(&st->best) * n + i];  // this thread's own write
         const double *x = X + (rowidx ? (long long)rowidx[i] : i) * ldx;
 #pragma unroll 5
         for (int k = 0; k < D; ++k) {
@@ -582,7 +593,75 @@ __global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, 
     if (threadIdx.x < T) {
         double v = 0.0;
         for (int w = 0; w < 8; ++w) v += s_w[w * KPP_MAXT + threadIdx.x];
-        partial[(size_t)blockIdx.x * KPP_MAXT + threadIdx.x] = v;
+        partial_blk[threadIdx.x] = v;
+    }
+    __syncthreads();  // s_w is reused by the next chunk of a persistent block
+}
+
+template <int TMAX>
+__global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
+                                                  long long n, int D, const int *__restrict__ cand, int T, int Tfull,
+                                                  int first_step, const KppState *__restrict__ st,
+                                                  double *__restrict__ dist, double *__restrict__ partial) {
+    if (rowidx) rowidx += (size_t)blockIdx.y * n;
+    cand += blockIdx.y * KPP_MAXT;
+    st += blockIdx.y;
+    dist += (size_t)blockIdx.y * Tfull * n;
+    partial += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * KPP_MAXT;
+    extern __shared__ double s_c[];
+    kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, first_step, st, dist, partial, s_c, blockIdx.x, true);
+}
+
+// All K - 1 steps in ONE launch: the blocks of a seeding problem meet at a counter barrier between
+// the distance pass (every block) and the select / pick (block 0).  Launched co-operatively, so
+// every block is resident; the spin is bounded (a protocol bug traps instead of hanging the GPU).
+__device__ __forceinline__ void kpp_grid_barrier(unsigned *counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        volatile unsigned *vc = counter;
+        unsigned spins = 0;
+        while (*vc < target) {
+            if (++spins > (1u << 28)) __trap();
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int TMAX>
+__global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict__ X, long long ldx,
+                                                        const int *__restrict__ rowidx, long long n, int D, int T, int K,
+                                                        const double *__restrict__ rnd, int *cand, KppState *st, double *dist,
+                                                        double *partial, int *indices, unsigned *barrier, int nblk) {
+    const int nb = gridDim.x;  // blocks per problem; each takes the 256-row chunks blockIdx.x, + nb, ...
+    if (rowidx) rowidx += (size_t)blockIdx.y * n;
+    rnd += (size_t)blockIdx.y * (size_t)max(K - 1, 1) * T;
+    cand += blockIdx.y * KPP_MAXT;
+    st += blockIdx.y;
+    dist += (size_t)blockIdx.y * T * n;
+    partial += (size_t)blockIdx.y * nblk * KPP_MAXT;
+    indices += (size_t)blockIdx.y * K;
+    barrier += blockIdx.y * 32;  // one counter per problem, a cache line apart
+    extern __shared__ double s_dyn[];
+    __shared__ double s_pot[KPP_MAXT];
+    __shared__ int s_best;
+    unsigned epoch = 0;
+    for (int ch = blockIdx.x; ch < nblk; ch += nb)
+        kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, 1, 1, st, dist, partial + (size_t)ch * KPP_MAXT, s_dyn, ch,
+                            ch == (int)blockIdx.x);
+    int Tprev = 1;
+    for (int step = 1; step <= K; ++step) {
+        kpp_grid_barrier(barrier, (unsigned)nb * ++epoch);
+        if (blockIdx.x == 0)
+            kpp_select_pick_body(n, T, Tprev, step, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best);
+        if (step == K) break;
+        kpp_grid_barrier(barrier, (unsigned)nb * ++epoch);
+        for (int ch = blockIdx.x; ch < nblk; ch += nb)
+            kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, 0, st, dist, partial + (size_t)ch * KPP_MAXT, s_dyn, ch,
+                                ch == (int)blockIdx.x);
+        Tprev = T;
     }
 }
 
@@ -601,7 +680,7 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
     const size_t nrand = (size_t)std::max(K - 1, 1) * T;
     size_t need = align256((size_t)B * T * n * sizeof(double)) + align256((size_t)B * nblk * KPP_MAXT * sizeof(double)) +
                   align256((size_t)B * nrand * sizeof(double)) + align256((size_t)B * KPP_MAXT * sizeof(int)) +
-                  align256((size_t)B * sizeof(KppState)) + 1024;
+                  align256((size_t)B * sizeof(KppState)) + align256((size_t)B * 32 * sizeof(unsigned)) + 1024;
     if (arena_reserve(c, need, stream)) return -1;
     arena_reset(c);
     double *dist = (double *)arena_alloc(c, (size_t)B * T * n * sizeof(double));
@@ -627,6 +706,42 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
     MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MDB_CUDA(cudaFuncSetAttribute(k_kpp_select_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
     const dim3 gd((unsigned)nblk, (unsigned)B), gs(1, (unsigned)B);
+    // one co-operative launch for the whole loop when every block can be resident at once
+    {
+        const size_t smem_p = std::max(smem, smem_sel);
+        void *fn = T <= 16 ? (void *)k_kpp_persistent<16> : (void *)k_kpp_persistent<32>;
+        int per_sm = 0, coop = 0;
+        cudaDeviceProp prop;
+        MDB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+        MDB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+        MDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+        MDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem_p));
+        // blocks per problem: as many as fit at once, each taking several 256-row chunks if need be
+        const int nb = (int)std::min<long long>(nblk, (long long)per_sm * prop.multiProcessorCount / B);
+        if (coop && nb >= 1 && nblk <= 16 * nb && !getenv("MDB_KPP_NO_PERSISTENT")) {
+            unsigned *bar = (unsigned *)arena_alloc(c, (size_t)B * 32 * sizeof(unsigned));
+            if (!bar) {
+                mdb_set_error("kmeans_plusplus: arena too small (internal sizing error)");
+                return -1;
+            }
+            MDB_CUDA(cudaMemsetAsync(bar, 0, (size_t)B * 32 * sizeof(unsigned), stream));
+            const double *aX = d_X;
+            long long aldx = ldx, an = n;
+            const int *arow = d_rowidx;
+            int aD = D, aT = T, aK = K;
+            const double *arnd = rnd;
+            int anblk = nblk;
+            void *args[] = {&aX, &aldx, &arow, &an, &aD, &aT, &aK, &arnd, &cand, &st, &dist, &partial, &d_indices, &bar, &anblk};
+            {
+                ProfScope ps(c, "k_kpp_persistent", stream);
+                MDB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)nb, (unsigned)B), dim3(256), args, smem_p, stream));
+            }
+            c->launches += 1;
+            MDB_CUDA(cudaGetLastError());
+            MDB_CUDA(cudaStreamSynchronize(stream));
+            return 0;
+        }
+    }
     auto launch_dist = [&](int Tn, int first_step) {
         if (Tn <= 16)
             k_kpp_dist<16><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial);
