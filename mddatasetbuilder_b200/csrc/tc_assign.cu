@@ -31,7 +31,8 @@
 #define TC_CHUNK_BYTES (TC_BM * 128)   // one [128 rows][64 elem] slab
 #define TC_PARTS 2                     // column parts per TMEM lane quarter: 4 * TC_PARTS epilogue warps
 #define TC_PCOLS (TC_BN / TC_PARTS)
-#define TC_THREADS (64 + 128 * TC_PARTS)
+#define TC_EPI_END (2 + 4 * TC_PARTS)   // warps 2 .. TC_EPI_END-1 are epilogue warps, warp TC_EPI_END the second MMA issuer
+#define TC_THREADS (64 + 128 * TC_PARTS + 32)
 #define TC_TAIL (128 + 1536 * (TC_PARTS - 1) + 64)
 #define TC_MAXCH 6                     // 3*Kd + 16 <= 384
 
@@ -101,6 +102,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 struct TcParams {
     int rows, K, stages;
+    int two_issuers;   // 1: even / odd centroid tiles go to two MMA threads, each with its own half of the B ring
     float *best1, *best2;
     int *idx1;
     long long *trace;   // optional [ntiles][8] clock64 stamps of CTA 0 (tools/tc_trace.py), else nullptr
@@ -110,6 +112,21 @@ struct TcParams {
     int *ncand;
     int candcap;
 };
+
+// Ring stage and mbarrier phase of centroid tile t.  With two MMA threads every stage belongs to one of
+// them (even tiles: stages 0, 2, ...; odd tiles: 1, 3, ...), so each thread meets the phases of its
+// stages in order -- a thread that waited on a stage the OTHER thread consumed last could run a whole
+// phase ahead, and a parity wait cannot tell phase k from phase k - 2.
+__device__ __forceinline__ void tc_stage(int t, int S, int two, int &s, uint32_t &ph) {
+    if (two) {
+        const int h = S >> 1, u = t >> 1;
+        s = (t & 1) + 2 * (u % h);
+        ph = (uint32_t)(u / h) & 1u;
+    } else {
+        s = t % S;
+        ph = (uint32_t)(t / S) & 1u;
+    }
+}
 
 // KD16 = padded feature width / 16: the inner dimension is 3 * 16 * KD16 + 16, i.e. 3 * KD16 + 1 MMAs per tile
 template <int KD16, bool CAND>
@@ -165,16 +182,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_expect_tx(bar_afull, (uint32_t)nch * TC_CHUNK_BYTES);
             for (int c = 0; c < nch; ++c) tma_load_2d(sA + c * TC_CHUNK_BYTES, &tmA, c * TC_KCH, row0, bar_afull);
             for (int t = 0; t < ntiles; ++t) {
-                const int s = t % S;
-                const uint32_t ph = (uint32_t)(t / S) & 1u;
+                int s;
+                uint32_t ph;
+                tc_stage(t, S, P.two_issuers, s, ph);
                 mbar_wait(bar_bempty + 8 * s, ph ^ 1u);
                 mbar_expect_tx(bar_bfull + 8 * s, (uint32_t)nch * TC_CHUNK_BYTES);
                 for (int c = 0; c < nch; ++c)
                     tma_load_2d(sB + (s * nch + c) * TC_CHUNK_BYTES, &tmB, c * TC_KCH, t * TC_BN, bar_bfull + 8 * s);
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 1 || warp == TC_EPI_END) {
+        // ===== MMA issuers: warp 1 takes the even centroid tiles (TMEM buffer 0), warp TC_EPI_END the odd
+        // ones (buffer 1).  While one thread issues its tile the other is already through the barrier
+        // waits of the next one, so the tensor pipe does not idle across the per-tile handshake. =====
         // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
         const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         // one thread runs the whole role: no warp-collective work between the issues, and the operand
@@ -182,10 +202,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) {
             constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
             const uint32_t alo = ((sA & 0x3FFFFu) >> 4) | (1u << 16);
+            const int first = warp == 1 ? 0 : (P.two_issuers ? 1 : ntiles), step = P.two_issuers ? 2 : 1;
             mbar_wait(bar_afull, 0);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = 0; t < ntiles; ++t) {
+            for (int t = first; t < ntiles; t += step) {
+                int s;
+                uint32_t ph;
+                tc_stage(t, S, P.two_issuers, s, ph);
                 const int a = t & 1;
                 const uint32_t aph = (uint32_t)(t >> 1) & 1u;
                 const bool tr = P.trace && blockIdx.x == 0;
@@ -208,10 +230,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 umma_commit(bar_bempty + 8 * s);
                 umma_commit(bar_tfull + 8 * a);
                 if (tr) P.trace[t * 8 + 3] = clock64();
-                if (++s == S) {
-                    s = 0;
-                    ph ^= 1u;
-                }
             }
         }
         __syncwarp();
@@ -709,6 +727,8 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     TcParams P;
     P.rows = (int)rows;
     P.K = K;
+    P.two_issuers = stages >= 2 ? 1 : 0;
+    if (P.two_issuers) stages &= ~1;  // an even ring: half of it per MMA thread
     P.stages = stages;
     P.trace = nullptr;
     P.thr = nullptr;
