@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdb_b200.so")
+LIB_PATH = os.environ.get("MDB_B200_LIB", os.path.join(_HERE, "libmdb_b200.so"))  # override: A/B runs of two builds
 _lib = None
 
 c_ctx = C.c_void_p
