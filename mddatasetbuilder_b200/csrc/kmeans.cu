@@ -448,14 +448,17 @@ __device__ __forceinline__ void kpp_select_pick_body(long long n, int T, int Tpr
                                                      const double *dist, int *cand, int *indices, KppState *st, double *s_dyn,
                                                      double *s_pot, int *s_best) {
     double *s_pre = s_dyn;               // [nblk + 1] prefix of the block sums of dist[best]
-    double *s_par = s_dyn + (nblk + 1);  // [nblk][KPP_MAXT] partials
+    double *s_par = s_dyn + (nblk + 1);  // [Tprev][nblk] partials, one row per candidate
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    for (int q = tid; q < nblk * KPP_MAXT; q += blockDim.x) s_par[q] = __ldcg(partial + q);
+    for (int q = tid; q < nblk * Tprev; q += blockDim.x) {
+        const int t = q / nblk, b = q - t * nblk;
+        s_par[q] = __ldcg(partial + (size_t)b * KPP_MAXT + t);
+    }
     __syncthreads();
     // potential of candidate t: lane-strided runs over the blocks, then a fixed shuffle tree
     for (int t = warp; t < Tprev; t += nwarps) {
         double p = 0.0;
-        for (int b = lane; b < nblk; b += 32) p += s_par[b * KPP_MAXT + t];
+        for (int b = lane; b < nblk; b += 32) p += s_par[t * nblk + b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
         if (lane == 0) s_pot[t] = p;
@@ -468,11 +471,22 @@ __device__ __forceinline__ void kpp_select_pick_body(long long n, int T, int Tpr
         *s_best = best;
         st->best = best;
         indices[c - 1] = __ldcg(cand + best);
-        double acc = 0.0;
         s_pre[0] = 0.0;
-        for (int b = 0; b < nblk; ++b) {
-            acc += s_par[b * KPP_MAXT + best];
-            s_pre[b + 1] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {  // inclusive prefix of the winner's block sums, 32 at a time in a fixed order
+        const int best = *s_best;
+        double base = 0.0;
+        for (int b0 = 0; b0 < nblk; b0 += 32) {
+            const int b = b0 + lane;
+            double v = b < nblk ? s_par[best * nblk + b] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            if (b < nblk) s_pre[b + 1] = base + v;
+            base += __shfl_sync(0xffffffffu, v, 31);
         }
     }
     __syncthreads();
@@ -539,19 +553,38 @@ __global__ void __launch_bounds__(1024) k_kpp_select_pick(long long n, int T, in
     kpp_select_pick_body(n, T, Tprev, c, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best);
 }
 
-// distances of the T candidate rows to every row, clipped against the current closest distance
-// (= dist[best] of the previous step, read before it is overwritten; nothing to clip in step 0);
-// one thread per row, candidates staged in shared memory; per-block partial potentials
+// squared distances of the T candidate rows to every row as scikit-learn takes them in
+// _kmeans_plusplus (euclidean_distances with precomputed norms: ||x||^2 - 2 x.c + ||c||^2, clipped at
+// 0), then clipped against the current closest distance (= dist[best] of the previous step, read
+// before it is overwritten; nothing to clip in step 0).  One thread per row, one DFMA per (candidate,
+// feature); candidates staged in shared memory feature-major so that two of them come per LDS.128;
+// ||x||^2 is computed in step 0 and kept in xn; per-block partial potentials in a fixed order.
 template <int TMAX>
 __device__ __forceinline__ void kpp_dist_body(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
                                               long long n, int D, const int *cand, int T, int first_step, const KppState *st,
-                                              double *dist, double *partial_blk, double *s_c, int chunk, bool stage) {
-    double *s_w = s_c + (size_t)T * D;  // [8][KPP_MAXT] warp partials
+                                              double *dist, double *partial_blk, double *s_c, int chunk, bool stage,
+                                              double *xn, const double *crows = nullptr) {
+    double *s_cn = s_c + (size_t)D * TMAX;  // [TMAX] squared norms of the candidates
+    double *s_w = s_cn + TMAX;              // [8][KPP_MAXT] warp partials
     if (stage) {
-        for (int q = threadIdx.x; q < T * D; q += 256) {
+        for (int q = threadIdx.x; q < TMAX * D; q += 256) {
             const int t = q / D, k = q - t * D;
-            const int ci = __ldcg(cand + t);
-            s_c[q] = X[(rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx + k];
+            double v = 0.0;
+            if (t < T) {
+                if (crows) {  // rows already gathered by the block that picked them: one hop instead of two
+                    v = __ldcg(crows + q);
+                } else {
+                    const int ci = __ldcg(cand + t);
+                    v = X[(rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx + k];
+                }
+            }
+            s_c[k * TMAX + t] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < TMAX) {
+            double a2 = 0.0;
+            for (int k = 0; k < D; ++k) a2 = fma(s_c[k * TMAX + threadIdx.x], s_c[k * TMAX + threadIdx.x], a2);
+            s_cn[threadIdx.x] = a2;
         }
     }
     __syncthreads();
@@ -562,33 +595,37 @@ __device__ __forceinline__ void kpp_dist_body(const double *__restrict__ X, long
     if (i < n) {
         const double cl = first_step ? DBL_MAX : dist[(size_t)__ldcg(&st->best) * n + i];  // this thread's own write
         const double *x = X + (rowidx ? (long long)rowidx[i] : i) * ldx;
+        double x2 = 0.0;
 #pragma unroll 5
         for (int k = 0; k < D; ++k) {
             const double xv = x[k];
+            if (first_step) x2 = fma(xv, xv, x2);
+            const double2 *cr = reinterpret_cast<const double2 *>(s_c + k * TMAX);
 #pragma unroll
-            for (int t = 0; t < TMAX; ++t)
-                if (t < T) {
-                    const double df = xv - s_c[t * D + k];
-                    acc[t] = fma(df, df, acc[t]);
-                }
-        }
-#pragma unroll
-        for (int t = 0; t < TMAX; ++t)
-            if (t < T) {
-                acc[t] = fmin(acc[t], cl);
-                dist[(size_t)t * n + i] = acc[t];
+            for (int t = 0; t < TMAX; t += 2) {
+                const double2 cv = cr[t >> 1];
+                acc[t] = fma(xv, cv.x, acc[t]);
+                acc[t + 1] = fma(xv, cv.y, acc[t + 1]);
             }
+        }
+        if (first_step) xn[i] = x2;
+        else x2 = xn[i];
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t) {
+            const double dsq = fmax(fma(-2.0, acc[t], x2 + s_cn[t]), 0.0);
+            acc[t] = fmin(dsq, cl);
+            if (t < T) dist[(size_t)t * n + i] = acc[t];
+        }
     }
     // block potentials in a fixed order: lanes by shuffle tree, warps serially
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int t = 0; t < TMAX; ++t)
-        if (t < T) {
-            double v = acc[t];
+    for (int t = 0; t < TMAX; ++t) {
+        double v = acc[t];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_w[warp * KPP_MAXT + t] = v;
-        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_w[warp * KPP_MAXT + t] = v;
+    }
     __syncthreads();
     if (threadIdx.x < T) {
         double v = 0.0;
@@ -602,39 +639,30 @@ template <int TMAX>
 __global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
                                                   long long n, int D, const int *__restrict__ cand, int T, int Tfull,
                                                   int first_step, const KppState *__restrict__ st,
-                                                  double *__restrict__ dist, double *__restrict__ partial) {
+                                                  double *__restrict__ dist, double *__restrict__ partial,
+                                                  double *__restrict__ xn) {
+    xn += (size_t)blockIdx.y * n;
     if (rowidx) rowidx += (size_t)blockIdx.y * n;
     cand += blockIdx.y * KPP_MAXT;
     st += blockIdx.y;
     dist += (size_t)blockIdx.y * Tfull * n;
     partial += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * KPP_MAXT;
     extern __shared__ double s_c[];
-    kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, first_step, st, dist, partial, s_c, blockIdx.x, true);
+    kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, first_step, st, dist, partial, s_c, blockIdx.x, true, xn);
 }
 
-// All K - 1 steps in ONE launch: the blocks of a seeding problem meet at a counter barrier between
-// the distance pass (every block) and the select / pick (block 0).  Launched co-operatively, so
-// every block is resident; the spin is bounded (a protocol bug traps instead of hanging the GPU).
-__device__ __forceinline__ void kpp_grid_barrier(unsigned *counter, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        volatile unsigned *vc = counter;
-        unsigned spins = 0;
-        while (*vc < target) {
-            if (++spins > (1u << 28)) __trap();
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
+// All K - 1 steps in ONE launch.  After its distance pass every block of a seeding problem takes a
+// ticket; the block that draws the last ticket of the step runs the select / pick, gathers the rows
+// of the new candidates and raises the step flag the others spin on -- one wait per step instead of
+// two full barriers, and the candidates' coordinates travel with the flag.  Launched co-operatively,
+// so every block is resident; the spin is bounded (a protocol bug traps instead of hanging the GPU).
 template <int TMAX>
 __global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict__ X, long long ldx,
                                                         const int *__restrict__ rowidx, long long n, int D, int T, int K,
                                                         const double *__restrict__ rnd, int *cand, KppState *st, double *dist,
-                                                        double *partial, int *indices, unsigned *barrier, int nblk) {
+                                                        double *partial, int *indices, unsigned *sync, int nblk,
+                                                        double *crows, long long *trace, double *xn) {
+    xn += (size_t)blockIdx.y * n;
     const int nb = gridDim.x;  // blocks per problem; each takes the 256-row chunks blockIdx.x, + nb, ...
     if (rowidx) rowidx += (size_t)blockIdx.y * n;
     rnd += (size_t)blockIdx.y * (size_t)max(K - 1, 1) * T;
@@ -643,25 +671,70 @@ __global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict
     dist += (size_t)blockIdx.y * T * n;
     partial += (size_t)blockIdx.y * nblk * KPP_MAXT;
     indices += (size_t)blockIdx.y * K;
-    barrier += blockIdx.y * 32;  // one counter per problem, a cache line apart
+    crows += (size_t)blockIdx.y * KPP_MAXT * D;
+    unsigned *tickets = sync + blockIdx.y * 64;   // per problem: ticket counter and step flag, a cache line apart
+    unsigned *flag = tickets + 32;
     extern __shared__ double s_dyn[];
     __shared__ double s_pot[KPP_MAXT];
     __shared__ int s_best;
-    unsigned epoch = 0;
+    __shared__ int s_last;
     for (int ch = blockIdx.x; ch < nblk; ch += nb)
         kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, 1, 1, st, dist, partial + (size_t)ch * KPP_MAXT, s_dyn, ch,
-                            ch == (int)blockIdx.x);
+                            ch == (int)blockIdx.x, xn);
     int Tprev = 1;
+    long long tr0 = 0, tr1 = 0, tr2 = 0, trt = clock64();
     for (int step = 1; step <= K; ++step) {
-        kpp_grid_barrier(barrier, (unsigned)nb * ++epoch);
-        if (blockIdx.x == 0)
+        __syncthreads();
+        if (trace && blockIdx.x == 1 && blockIdx.y == 0 && threadIdx.x == 0) {
+            const long long now = clock64();
+            tr0 += now - trt;  // distance pass
+            trt = now;
+        }
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(tickets, 1u) == (unsigned)nb * (unsigned)step - 1u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
             kpp_select_pick_body(n, T, Tprev, step, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best);
+            __syncthreads();
+            if (step < K)
+                for (int q = threadIdx.x; q < T * D; q += 256) {
+                    const int t = q / D, k = q - t * D;
+                    const int ci = __ldcg(cand + t);
+                    crows[q] = X[(rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx + k];
+                }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicExch(flag, (unsigned)step);
+            }
+        }
         if (step == K) break;
-        kpp_grid_barrier(barrier, (unsigned)nb * ++epoch);
+        if (threadIdx.x == 0) {
+            volatile unsigned *vf = flag;
+            unsigned spins = 0;
+            while (*vf < (unsigned)step) {
+                if (++spins > (1u << 28)) __trap();
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (trace && blockIdx.x == 1 && blockIdx.y == 0 && threadIdx.x == 0) {
+            const long long now = clock64();
+            if (s_last) tr2 += now - trt; else tr1 += now - trt;  // select by this block / wait for the flag
+            trt = now;
+        }
         for (int ch = blockIdx.x; ch < nblk; ch += nb)
             kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, 0, st, dist, partial + (size_t)ch * KPP_MAXT, s_dyn, ch,
-                                ch == (int)blockIdx.x);
+                                ch == (int)blockIdx.x, xn, crows);
         Tprev = T;
+    }
+    if (trace && blockIdx.x == 1 && blockIdx.y == 0 && threadIdx.x == 0) {
+        trace[0] = tr0;
+        trace[1] = tr1;
+        trace[2] = tr2;
     }
 }
 
@@ -678,17 +751,19 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
         }
     const int nblk = (int)cdiv(n, 256);
     const size_t nrand = (size_t)std::max(K - 1, 1) * T;
-    size_t need = align256((size_t)B * T * n * sizeof(double)) + align256((size_t)B * nblk * KPP_MAXT * sizeof(double)) +
+    size_t need = align256((size_t)B * T * n * sizeof(double)) + align256((size_t)B * n * sizeof(double)) + align256((size_t)B * nblk * KPP_MAXT * sizeof(double)) +
                   align256((size_t)B * nrand * sizeof(double)) + align256((size_t)B * KPP_MAXT * sizeof(int)) +
-                  align256((size_t)B * sizeof(KppState)) + align256((size_t)B * 32 * sizeof(unsigned)) + 1024;
+                  align256((size_t)B * sizeof(KppState)) + align256((size_t)B * 64 * sizeof(unsigned)) +
+                  align256((size_t)B * KPP_MAXT * D * sizeof(double)) + 256 + 1024;
     if (arena_reserve(c, need, stream)) return -1;
     arena_reset(c);
     double *dist = (double *)arena_alloc(c, (size_t)B * T * n * sizeof(double));
+    double *xn = (double *)arena_alloc(c, (size_t)B * n * sizeof(double));
     double *partial = (double *)arena_alloc(c, (size_t)B * nblk * KPP_MAXT * sizeof(double));
     double *rnd = (double *)arena_alloc(c, (size_t)B * nrand * sizeof(double));
     int *cand = (int *)arena_alloc(c, (size_t)B * KPP_MAXT * sizeof(int));
     KppState *st = (KppState *)arena_alloc(c, (size_t)B * sizeof(KppState));
-    if (!dist || !partial || !rnd || !cand || !st) {
+    if (!dist || !xn || !partial || !rnd || !cand || !st) {
         mdb_set_error("kmeans_plusplus: arena too small (internal sizing error)");
         return -1;
     }
@@ -696,20 +771,29 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
     std::vector<int> hc((size_t)B * KPP_MAXT, 0);
     for (int b = 0; b < B; ++b) hc[(size_t)b * KPP_MAXT] = h_first[b];
     MDB_CUDA(cudaMemcpyAsync(cand, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-    const size_t smem = ((size_t)T * D + 8 * KPP_MAXT) * sizeof(double);
-    const size_t smem_sel = ((size_t)(nblk + 1) + (size_t)nblk * KPP_MAXT) * sizeof(double);
+    // candidate width of the instantiation (multiple of 2: candidates are read two per LDS.128)
+    const int TW = T <= 4 ? 4 : T <= 8 ? 8 : T <= 12 ? 12 : T <= 16 ? 16 : T <= 24 ? 24 : 32;
+    const size_t smem = ((size_t)TW * D + TW + 8 * KPP_MAXT) * sizeof(double);
+    const size_t smem_sel = ((size_t)(nblk + 1) + (size_t)nblk * T) * sizeof(double);
     if (smem > 200 * 1024 || smem_sel > 200 * 1024) {
         mdb_set_error("kmeans_plusplus: too many features or seeding rows for the shared-memory staging");
         return -1;
     }
-    MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define MDB_KPP_WIDTHS(M) M(4) M(8) M(12) M(16) M(24) M(32)
+#define MDB_KPP_ATTR(W) \
+    if (TW == W) MDB_CUDA(cudaFuncSetAttribute(k_kpp_dist<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MDB_KPP_WIDTHS(MDB_KPP_ATTR)
+#undef MDB_KPP_ATTR
     MDB_CUDA(cudaFuncSetAttribute(k_kpp_select_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
     const dim3 gd((unsigned)nblk, (unsigned)B), gs(1, (unsigned)B);
     // one co-operative launch for the whole loop when every block can be resident at once
     {
         const size_t smem_p = std::max(smem, smem_sel);
-        void *fn = T <= 16 ? (void *)k_kpp_persistent<16> : (void *)k_kpp_persistent<32>;
+        void *fn = nullptr;
+#define MDB_KPP_FN(W) \
+    if (TW == W) fn = (void *)k_kpp_persistent<W>;
+        MDB_KPP_WIDTHS(MDB_KPP_FN)
+#undef MDB_KPP_FN
         int per_sm = 0, coop = 0;
         cudaDeviceProp prop;
         MDB_CUDA(cudaGetDeviceProperties(&prop, c->device));
@@ -719,19 +803,26 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
         // blocks per problem: as many as fit at once, each taking several 256-row chunks if need be
         const int nb = (int)std::min<long long>(nblk, (long long)per_sm * prop.multiProcessorCount / B);
         if (coop && nb >= 1 && nblk <= 16 * nb && !getenv("MDB_KPP_NO_PERSISTENT")) {
-            unsigned *bar = (unsigned *)arena_alloc(c, (size_t)B * 32 * sizeof(unsigned));
-            if (!bar) {
+            unsigned *bar = (unsigned *)arena_alloc(c, (size_t)B * 64 * sizeof(unsigned));
+            double *crows = (double *)arena_alloc(c, (size_t)B * KPP_MAXT * D * sizeof(double));
+            if (!bar || !crows) {
                 mdb_set_error("kmeans_plusplus: arena too small (internal sizing error)");
                 return -1;
             }
-            MDB_CUDA(cudaMemsetAsync(bar, 0, (size_t)B * 32 * sizeof(unsigned), stream));
+            MDB_CUDA(cudaMemsetAsync(bar, 0, (size_t)B * 64 * sizeof(unsigned), stream));
             const double *aX = d_X;
             long long aldx = ldx, an = n;
             const int *arow = d_rowidx;
             int aD = D, aT = T, aK = K;
             const double *arnd = rnd;
             int anblk = nblk;
-            void *args[] = {&aX, &aldx, &arow, &an, &aD, &aT, &aK, &arnd, &cand, &st, &dist, &partial, &d_indices, &bar, &anblk};
+            long long *trace = nullptr;
+            if (getenv("MDB_KPP_TRACE")) {  // developer switch: cycles of block 1 in the distance pass / waiting / selecting
+                trace = (long long *)arena_alloc(c, 256);
+                if (trace) MDB_CUDA(cudaMemsetAsync(trace, 0, 256, stream));
+            }
+            void *args[] = {&aX,   &aldx, &arow,    &an,        &aD,  &aT,    &aK,    &arnd,
+                            &cand, &st,   &dist,    &partial,   &d_indices, &bar, &anblk, &crows, &trace, &xn};
             {
                 ProfScope ps(c, "k_kpp_persistent", stream);
                 MDB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)nb, (unsigned)B), dim3(256), args, smem_p, stream));
@@ -739,14 +830,20 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
             c->launches += 1;
             MDB_CUDA(cudaGetLastError());
             MDB_CUDA(cudaStreamSynchronize(stream));
+            if (trace) {
+                long long h[3];
+                MDB_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+                fprintf(stderr, "k_kpp_persistent block 1, cycles per step: distance pass %.0f, waiting %.0f, selecting %.0f\n",
+                        (double)h[0] / K, (double)h[1] / K, (double)h[2] / K);
+            }
             return 0;
         }
     }
     auto launch_dist = [&](int Tn, int first_step) {
-        if (Tn <= 16)
-            k_kpp_dist<16><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial);
-        else
-            k_kpp_dist<32><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial);
+#define MDB_KPP_LAUNCH(W) \
+    if (TW == W) k_kpp_dist<W><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial, xn);
+        MDB_KPP_WIDTHS(MDB_KPP_LAUNCH)
+#undef MDB_KPP_LAUNCH
     };
     {
         // step 0: the first centre alone (T = 1, nothing to clip against)
