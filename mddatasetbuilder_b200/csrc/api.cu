@@ -80,6 +80,8 @@ static int analyze_chunk(mdb_ctx *c, int F, int N, const double *d_pos, const do
     size_t need = align256(geom.size() * sizeof(FrameGeom)) + cells_workspace_bytes(F, N, total_cells) +
                   bonds_workspace_bytes(F, N) + (d_ell ? 0 : align256(fn * maxb * sizeof(int32_t))) +
                   (d_labels ? 0 : align256(fn * sizeof(int32_t))) + 4096;
+    const bool perceive = c->opt_perceive && d_keys;
+    if (perceive) need += perceive_workspace_bytes(F, N, maxb, true);
     if (arena_reserve(c, need, stream)) return -1;
     arena_reset(c);
     FrameGeom *d_geom = (FrameGeom *)arena_alloc(c, geom.size() * sizeof(FrameGeom));
@@ -95,10 +97,12 @@ static int analyze_chunk(mdb_ctx *c, int F, int N, const double *d_pos, const do
         return -1;
     if (bonds_run(c, F, N, d_pos, d_types, cl, periodic, d_ell, d_labels, stream)) return -1;
     if (d_labels) {
-        if (keys_components_run(c, F, N, d_ell, d_types, d_keys, d_labels, stream)) return -1;
-    } else if (d_keys) {
+        if (keys_components_run(c, F, N, d_ell, d_types, perceive ? nullptr : d_keys, d_labels, stream)) return -1;
+    } else if (d_keys && !perceive) {
         if (keys_run(c, F, N, d_ell, d_types, d_keys, nullptr, stream)) return -1;
     }
+    // dump-only keys with perceived bond orders (reference detect.py:279-280)
+    if (perceive && perceive_run(c, F, N, d_pos, d_geom, d_types, periodic, d_ell, d_labels, nullptr, d_keys, stream)) return -1;
     return 0;
 }
 
@@ -200,6 +204,48 @@ extern "C" int mdb_bond_stats(mdb_ctx *c, long long *n_violators, long long *n_e
         mdb_set_error(std::string("device-side error: ") + err_text(h.err));
         return h.err;
     }
+    return 0;
+}
+
+extern "C" int mdb_perceive_bond_orders(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                        const uint8_t *d_types, int periodic, const int32_t *d_ell,
+                                        const int32_t *d_labels, uint8_t *d_orders, uint64_t *d_keys, void *stream) {
+    if (check_ctx(c, "mdb_perceive_bond_orders")) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!d_pos || !d_ell || !d_types || (!d_orders && !d_keys)) {
+        mdb_set_error("mdb_perceive_bond_orders: positions, types, ELL rows and one output are required");
+        return -1;
+    }
+    if (nframes <= 0 || natoms <= 0) return 0;
+    std::vector<FrameGeom> geom((size_t)nframes);
+    if (periodic) {
+        if (!h_cell) {
+            mdb_set_error("periodic frames need a cell");
+            return -1;
+        }
+        long long total_cells = 0;
+        if (build_geometry(c, nframes, natoms, h_cell, 1, nullptr, (double)c->el.rc_max * 1.0005, c->opt_cell_edge, geom,
+                           &total_cells))
+            return -1;
+    } else {
+        memset(geom.data(), 0, geom.size() * sizeof(FrameGeom));
+    }
+    const int maxb = c->opt_max_bonds;
+    size_t need = align256(geom.size() * sizeof(FrameGeom)) + perceive_workspace_bytes(nframes, natoms, maxb, !d_orders) + 1024;
+    if (arena_reserve(c, need, s)) return -1;
+    arena_reset(c);
+    FrameGeom *d_geom = (FrameGeom *)arena_alloc(c, geom.size() * sizeof(FrameGeom));
+    if (upload_geometry(c, geom, d_geom, s)) return -1;
+    MDB_CUDA(cudaMemsetAsync(&c->d_stats->ring_molecules, 0, sizeof(unsigned long long), s));
+    return perceive_run(c, nframes, natoms, d_pos, d_geom, d_types, periodic, d_ell, d_labels, d_orders, d_keys, s);
+}
+
+extern "C" int mdb_perceive_stats(mdb_ctx *c, long long *n_ring_molecules) {
+    if (check_ctx(c, "mdb_perceive_stats", false)) return -1;
+    MDB_CUDA(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    MDB_CUDA(cudaMemcpy(&v, &c->d_stats->ring_molecules, sizeof(v), cudaMemcpyDeviceToHost));
+    if (n_ring_molecules) *n_ring_molecules = (long long)v;
     return 0;
 }
 

@@ -10,7 +10,7 @@ pids=()
 for f in "$HERE"/*.cu "$HERE"/*.cpp; do
   b="$(basename "$f")"
   o="$HERE/build/${b%.*}.o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/../../include/mdb_b200.h" -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/geom.cuh" -nt "$o" ] || [ "$HERE/../../include/mdb_b200.h" -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
     pids+=($!)
   fi

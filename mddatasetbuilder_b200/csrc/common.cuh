@@ -48,6 +48,7 @@ struct ElemTables {
 
 struct BondStats {
     unsigned long long violators, exact_tests, overflow;
+    unsigned long long ring_molecules;  // perceive.cu: molecules with a cycle (ring passes not restated)
     int err;
 };
 
@@ -58,6 +59,7 @@ struct mdb_ctx {
     double opt_cell_edge = 0.0;
     int opt_max_bonds = 8;
     int opt_frames_per_launch = 0;
+    int opt_perceive = 0;  // dump-only keys carry perceived bond orders (perceive.cu)
     uint64_t launches = 0;
     // arena
     char *arena = nullptr;
@@ -198,6 +200,11 @@ int keys_bo_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, con
 int components_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, int32_t *d_labels, int seeded,
                    cudaStream_t stream);
 // keys + union-find hooks in one pass over the ELL rows (d_labels must hold the seed), then flatten
+// perceive.cu
+size_t perceive_workspace_bytes(int nframes, int natoms, int maxb, bool own_orders);
+int perceive_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, const FrameGeom *d_geom, const uint8_t *d_types,
+                 int periodic, const int32_t *d_ell, const int32_t *d_labels, uint8_t *d_orders, uint64_t *d_keys,
+                 cudaStream_t stream);
 int keys_components_run(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell, const uint8_t *d_types,
                         uint64_t *d_keys, int32_t *d_labels, cudaStream_t stream);
 int dps_run(mdb_ctx *ctx, int natoms, const int32_t *d_rowptr, const int32_t *d_col, int32_t *d_mol_atoms,

@@ -133,6 +133,8 @@ extern "C" int mdb_set_option(mdb_ctx *c, const char *key, double v) {
         c->opt_max_bonds = (int)v;
     } else if (k == "frames_per_launch")
         c->opt_frames_per_launch = (int)v;
+    else if (k == "perceive_bond_orders")
+        c->opt_perceive = v != 0.0;
     else {
         mdb_set_error("unknown option " + k);
         return -1;

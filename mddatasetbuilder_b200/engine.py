@@ -159,6 +159,27 @@ class Engine:
         _lib.check(self.L.mdb_bond_stats(self.ctx, C.byref(v), C.byref(e), C.byref(o)), "device check")
         return {"violators": v.value, "exact_tests": e.value, "overflow": o.value}
 
+    def perceive(self, pos, cell, types, ell, periodic=True, labels=None, want_keys=True):
+        """Bond orders of the final bonds (Open Babel PerceiveBondOrders, reference detect.py:279-280,
+        C/H/O subset): orders [F,N,max_bonds] uint8 per ELL slot (0 = empty) and, optionally, the
+        64-bit keys built from them."""
+        torch = _torch()
+        pos = self.to_device_pos(pos)
+        types = self.to_device_types(types)
+        F, N = int(pos.shape[0]), int(pos.shape[1])
+        cells = self._cells(cell, F) if periodic else None
+        orders = torch.empty((F, N, self.max_bonds), dtype=torch.uint8, device=self.device)
+        keys = torch.empty((F, N), dtype=torch.int64, device=self.device) if want_keys else None
+        rc = self.L.mdb_perceive_bond_orders(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                             _ptr(ell), _ptr(labels), _ptr(orders), _ptr(keys), self.stream())
+        _lib.check(rc, "mdb_perceive_bond_orders")
+        return {"orders": orders, "keys": keys}
+
+    def perceive_stats(self):
+        v = C.c_longlong()
+        _lib.check(self.L.mdb_perceive_stats(self.ctx, C.byref(v)), "mdb_perceive_stats")
+        return {"ring_molecules": v.value}
+
     def ell_to_csr(self, ell, order=0, pos=None, colcap=None):
         torch = _torch()
         F, N, _ = ell.shape

@@ -1,10 +1,10 @@
 """openbabel.openbabel stand-in: the API surface touched at reference detect.py:255-291.
 
 Pure-Python/numpy restatement of Open Babel 3.1.x OBMol::ConnectTheDots,
-written independently of oracle/oracle.c so the two can be cross-checked.  PerceiveBondOrders is
-NOT restated (all surviving bonds keep order 1): the documented tier-1 deviation; the
-reference's only known answer for it (O2 -> [[1],[1]], tests/test_bond.py:19-20) holds.
-Test infrastructure only -- PARITY UNPINNED beyond tests/test_bond.py."""
+written independently of oracle/oracle.c so the two can be cross-checked.  PerceiveBondOrders is the
+C/H/O-subset restatement in oracle/perceive.py (ring passes and most bondtyp.txt patterns left out,
+see its header); the reference's only known answer for it (O2 -> [[1],[1]], tests/test_bond.py:19-20)
+holds.  Test infrastructure only -- PARITY UNPINNED beyond tests/test_bond.py."""
 import math
 
 import numpy as np
@@ -107,6 +107,21 @@ class OBMol:
         self.periodic = bool(v)
 
     def PerceiveBondOrders(self):
+        from oracle.perceive import perceive_bond_orders
+
+        n = len(self.atoms)
+        if n == 0 or not self.bonds:
+            return None
+        P = np.array([a.pos for a in self.atoms], dtype=float)
+        nbrs = [[] for _ in range(n)]
+        for b in self.bonds:  # creation order = every atom's own bond order
+            nbrs[b.a.idx].append(b.b.idx)
+            nbrs[b.b.idx].append(b.a.idx)
+        orders, info = perceive_bond_orders([a.z for a in self.atoms], nbrs,
+                                            lambda a, b: tuple(float(x) for x in self._delta(P, a, b)))
+        for b in self.bonds:
+            b.order = orders[b.a.idx][nbrs[b.a.idx].index(b.b.idx)]
+        self.perceive_info = info
         return None
 
     def _delta(self, P, a, b):
