@@ -112,8 +112,11 @@ class DatasetBuilder:
         errorlimit=0.0,
         atom_pref=False,
         seed=0,
+        perceive_bond_orders=True,
     ):
-        """Init the builder."""
+        """Init the builder.  ``seed`` and ``perceive_bond_orders`` are additions: the latter switches the
+        dump-only keys between perceived bond orders (the reference's behaviour, detect.py:279-280) and
+        all-single levels."""
         print(__doc__)
         print(f"Author:{__author__}  Email:{__email__}")
         atomname = np.array(atomname) if atomname is not None and len(atomname) else np.array(["C", "H", "O"])
@@ -128,6 +131,7 @@ class DatasetBuilder:
         self.xyzfilename = dataset_name
         self.clusteratom = clusteratom if clusteratom else atomname
         self.atombondtype = []
+        self.perceive_bond_orders = bool(perceive_bond_orders)
         self.stepinterval = stepinterval
         if nproc:
             self.nproc = nproc
@@ -309,10 +313,18 @@ class DatasetBuilder:
                 nstep += 1
 
         if self.bonddetector is self.crddetector:
-            for step0, pos, cell in self._dump_batches():
-                out = eng.analyze(pos, cell, d_types, self.pbc, want_ell=False, want_keys=True, want_labels=False)
-                eng.check()
-                collect(step0, out["keys"].cpu().numpy().view(np.uint64))
+            eng.set_option("perceive_bond_orders", 1 if self.perceive_bond_orders else 0)
+            try:
+                for step0, pos, cell in self._dump_batches():
+                    out = eng.analyze(pos, cell, d_types, self.pbc, want_ell=False, want_keys=True, want_labels=False)
+                    eng.check()
+                    collect(step0, out["keys"].cpu().numpy().view(np.uint64))
+                self._ring_molecules = eng.perceive_stats()["ring_molecules"] if self.perceive_bond_orders else 0
+                if self._ring_molecules:
+                    logger.warning(f"{self._ring_molecules} molecule-frames contain a ring: their bond orders come "
+                                   "without Open Babel's ring passes (planar-ring sp2, aromatic Kekule)")
+            finally:
+                eng.set_option("perceive_bond_orders", 0)
         else:
             for step0, nbr, bo in self._bond_batches():
                 keys = eng.bond_keys_bo(nbr, bo, d_types)

@@ -13,10 +13,10 @@ method                       reference                              kernel path
 ``DetectDump.readcrd``       detect.py:294-345                      C++ parser (textio.cpp)
 ===========================  =====================================  ===========================
 
-Deviation (documented in DESIGN.md): Open Babel's ``PerceiveBondOrders`` is not restated, so in
-dump-only mode every surviving bond has order 1 (``_crd2bond(atoms, readlevel=True)`` returns
-``[1] * degree`` per atom); the reference's only known answer for it (tests/test_bond.py:19-20)
-holds.
+Open Babel's ``PerceiveBondOrders`` (dump-only keys, ``_crd2bond(atoms, readlevel=True)``) is the
+C/H/O-subset restatement of csrc/perceive.cu / oracle/perceive.py: ring passes and most
+bondtyp.txt patterns are left out, parity with Open Babel itself is unpinned; the
+reference's only known answer for it (tests/test_bond.py:19-20) holds.
 """
 
 from __future__ import annotations
@@ -200,7 +200,15 @@ class DetectDump(Detect):
         rowptr = rowptr.cpu().numpy()[0]
         col = col.cpu().numpy()[0]
         if readlevel:
-            return [[1] * int(rowptr[i + 1] - rowptr[i]) for i in range(atomnumber)]
+            orders = eng.perceive(out["pos"], cell.reshape(9), types, out["ell"], periodic, want_keys=False)["orders"]
+            eng.check()
+            orders = orders.cpu().numpy()[0]
+            ell = out["ell"].cpu().numpy()[0]
+            level = []
+            for i in range(atomnumber):
+                by_partner = {int(j): int(o) for j, o in zip(ell[i], orders[i]) if j >= 0}
+                level.append([by_partner[int(j)] for j in col[rowptr[i]:rowptr[i + 1]]])
+            return level
         return [col[rowptr[i]:rowptr[i + 1]].tolist() for i in range(atomnumber)]
 
     def readcrd(self, item):
