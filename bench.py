@@ -193,6 +193,18 @@ def measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_
                          "mean_cluster_size": n_mean, "D": D,
                          "hbm_frac_algorithmic": (16 + 8 * D) * rows / (t_desc / 1e3) / 1e9 / peaks["hbm_gbs"],
                          "note": "FP64-pipe bound (Householder + QL), not HBM bound; see DESIGN.md"}
+    # bond-order perception of the dump-only key (detect.py:279-280) on the same frames
+    an = eng.analyze(sub, cell, types)
+    for it in range(2):
+        ev[3].record()
+        pb = eng.perceive(sub, cell, types, an["ell"], labels=an["labels"])
+        ev[4].record()
+        torch.cuda.synchronize()
+    t_po = max_over_ranks(ev[3].elapsed_time(ev[4]))
+    res["bond_orders"] = {"atom_frames_per_s": world * rows / (t_po / 1e3), "ms": t_po, "atom_frames": rows,
+                          "multiple_bonds": int((pb["orders"] > 1).sum().item()) // 2,
+                          "rings": eng.perceive_stats()["rings"]}
+    del an, pb
     mn, mx = eng.minmax_fit(X)
     eng.minmax_transform(X, mn.cpu().numpy(), mx.cpu().numpy())
     K = 10000

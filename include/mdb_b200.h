@@ -273,7 +273,7 @@ int mdb_kmeans_plusplus(mdb_ctx *ctx, int nbatch, long long n, int D, const doub
  * OBMol::PerceiveBondOrders, third-party) for the C/H/O(/N) subset restated in oracle/perceive.py:
  * hybridisation from the average bond angle, the carboxylic / CO2 / allene patterns of bondtyp.txt
  * and the coded carbonyl rule, then the electronegativity-ordered double / triple assignment.  The
- * ring passes are not restated (molecules with a cycle are counted, mdb_perceive_stats).  PARITY
+ * ring passes are not restated (independent cycles are counted, mdb_perceive_stats).  PARITY
  * UNPINNED against Open Babel itself.
  * d_ell [F][N][max_bonds] final rows (after the cleanup), d_labels [F][N] molecule roots or NULL (no
  * ring statistics); outputs, either may be NULL: d_orders [F][N][max_bonds] one byte per ELL slot
@@ -283,8 +283,9 @@ int mdb_perceive_bond_orders(mdb_ctx *ctx, int nframes, int natoms, const double
                              const double *h_cell, const uint8_t *d_types, int periodic,
                              const int32_t *d_ell, const int32_t *d_labels, uint8_t *d_orders,
                              uint64_t *d_keys, void *stream);
-/* Molecules with a cycle seen by the perception since the last analyze / perceive call (synchronises). */
-int mdb_perceive_stats(mdb_ctx *ctx, long long *n_ring_molecules);
+/* Independent cycles (bonds - atoms + molecules, summed over frames) seen by the perception since the
+ * last analyze / perceive call, which needs d_labels for it (synchronises). */
+int mdb_perceive_stats(mdb_ctx *ctx, long long *n_rings);
 
 /* Diagnostics of the last bond batch: counts summed over frames (synchronises).  A device-side error
  * flag raised by any kernel since the last call is returned (non-zero) and cleared. */

@@ -240,12 +240,12 @@ extern "C" int mdb_perceive_bond_orders(mdb_ctx *c, int nframes, int natoms, con
     return perceive_run(c, nframes, natoms, d_pos, d_geom, d_types, periodic, d_ell, d_labels, d_orders, d_keys, s);
 }
 
-extern "C" int mdb_perceive_stats(mdb_ctx *c, long long *n_ring_molecules) {
+extern "C" int mdb_perceive_stats(mdb_ctx *c, long long *n_rings) {
     if (check_ctx(c, "mdb_perceive_stats", false)) return -1;
     MDB_CUDA(cudaDeviceSynchronize());
     unsigned long long v = 0;
     MDB_CUDA(cudaMemcpy(&v, &c->d_stats->ring_molecules, sizeof(v), cudaMemcpyDeviceToHost));
-    if (n_ring_molecules) *n_ring_molecules = (long long)v;
+    if (n_rings) *n_rings = (long long)v / 2;  // the kernel sums deg - 2 + 2 [root] = 2 (bonds - atoms + molecules)
     return 0;
 }
 

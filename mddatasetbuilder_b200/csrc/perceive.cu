@@ -7,16 +7,20 @@
 // against Open Babel itself; bit-for-bit against the restatement (tests/test_perceive_gpu.py).
 //
 //   k_po_hyb      per atom: neighbours in Open Babel's bond order (ascending partner z-rank),
-//                 average bond angle -> hybridisation (pass 1), pass-6 sort key, ring tally
+//                 average bond angle -> hybridisation (pass 1), pass-6 sort key and candidate lists, cycle count
 //   k_po_groups   per carbon: carboxylic / CO2 / allene patterns of bondtyp.txt (pass 4)
 //   k_po_carbonyl per carbon: the coded carbonyl rule of OBBondTyper::AssignFunctionalGroupBonds
-//   k_po_assign   pass 6, one block per frame: an atom takes its turn once no atom within two
-//                 bonds with a smaller (key, index) is still waiting -- the sequential semantics of
-//                 the sorted loop, since a turn reads and writes nothing beyond that radius
+//   k_po_round    pass 6 in rounds over the list of atoms that can act: an atom takes its turn once
+//   k_po_finish   no atom within two bonds with a smaller (key, index) is still waiting -- the
+//                 sequential semantics of the sorted loop, since a turn reads and writes nothing
+//                 beyond that radius; a few grid-wide rounds, then one block finishes long chains
 //   k_po_keys     64-bit key (element, degree, sorted orders) like k_keys_bo
 #include "common.cuh"
 #include "geom.cuh"
 
+#define PO_ROUNDS 3
+#define PO_NC 8
+#define PO_NQ 9
 #define PO_MAXD 8  // degree after the valence cleanup is <= MaxBonds(Z) <= 6
 
 struct PoParams {
@@ -30,8 +34,10 @@ struct PoParams {
     uint32_t *perm;         // [F][N] degree in bits 28.., ELL slots in OB order 3-4 bits each
     double *key;            // [F][N]
     uint8_t *st;            // [F][N] 1 = waiting for its pass-6 turn
-    int *plist;             // [F][N]
-    int *tally;             // [F][N] per root: sum(deg - 2) = 2 (bonds - atoms)
+    int *plist;             // [F][N] atom-frames waiting for their turn (round 0)
+    int *plist2;            // [F][N] ping-pong partner; before round 0 the pass-6 candidates of k_po_hyb
+    int *clist;             // [F][N] carbons the pass-4 patterns can match
+    int *counters;          // [0..PO_ROUNDS] list lengths per round, [PO_NC] carbons, [PO_NQ] pass-6 candidates
     uint64_t *keys;
     BondStats *stats;
     int N, periodic;
@@ -69,15 +75,19 @@ __device__ __forceinline__ void po_load_nb(const PoParams &P, size_t fbase, int 
 // degree, valence (sum of orders) and "has a non-single bond" of one atom from its order bytes
 template <int MAXB>
 __device__ __forceinline__ void po_rowstat(const uint8_t *orders, size_t a, int &deg, int &val, bool &nonsingle) {
-    const volatile uint8_t *r = orders + a * MAXB;
+    const volatile unsigned long long *r = reinterpret_cast<const volatile unsigned long long *>(orders + a * MAXB);
     deg = val = 0;
     nonsingle = false;
 #pragma unroll
-    for (int k = 0; k < MAXB; ++k) {
-        const int o = r[k];
-        deg += o != 0;
-        val += o;
-        nonsingle = nonsingle || o > 1;
+    for (int w = 0; w < MAXB / 8; ++w) {
+        const unsigned long long q = r[w];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int o = (int)((q >> (8 * k)) & 0xFFull);
+            deg += o != 0;
+            val += o;
+            nonsingle = nonsingle || o > 1;
+        }
     }
 }
 
@@ -157,6 +167,13 @@ __global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams
     }
 #pragma unroll
     for (int k = 0; k < MAXB; ++k) P.orders[(fbase + i) * MAXB + k] = ord[k];
+    if (P.labels) {
+        // independent cycles of the batch = bonds - atoms + molecules = sum(deg - 2 + 2 [root]) / 2
+        const int r = nb.n - 2 + 2 * (P.labels[fbase + i] == i);
+        const unsigned m = __activemask();
+        const int sum = __reduce_add_sync(m, r);
+        if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&P.stats->ring_molecules, (unsigned long long)(long long)sum);
+    }
     // Open Babel's per-atom bond order: ascending z-rank of the partner (ties: index)
     for (int a = 1; a < nb.n; ++a) {
         const int n0 = nb.idx[a], s0 = nb.slot[a];
@@ -177,25 +194,33 @@ __global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams
     P.perm[fbase + i] = pm;
     const int ti = P.types[i];
     const int Zi = P.Z[ti];
-    // pass 1
-    const double ang = po_avg_angle(P, G, fbase, i, nb);
+    // pass 1 (an atom with fewer than two bonds has no angle)
+    const double ang = nb.n >= 2 ? po_avg_angle(P, G, fbase, i, nb) : 0.0;
     int h = 0;
     if (ang > 155.0)
         h = 1;
     else if (ang > 115.0)
         h = 2;
-    double shortest = 1.0e5;
-    int nh = 0;
+    int nh = 0, no = 0;
     for (int k = 0; k < nb.n; ++k) {
         const int Zj = P.Z[P.types[nb.idx[k]]];
         nh += Zj == 1;
-        if (Zj != 1) shortest = fmin(shortest, po_length(P, G, fbase, i, nb.idx[k]));
+        no += Zj == 8;
     }
     if (Zi == 7 && nb.n == 2 && nh == 1 && ang > 109.5) h = 2;
     P.hyb[fbase + i] = (uint8_t)h;
-    P.key[fbase + i] = P.elneg[ti] * 1e6 + shortest;
     P.st[fbase + i] = 0;
-    if (P.labels) atomicAdd(&P.tally[fbase + P.labels[fbase + i]], nb.n - 2);
+    // who can take a pass-6 turn at all: valences only rise from here, so test with every bond single
+    const int mx = P.maxb[ti];
+    if (nb.n > 0 && (((h == 1 || nb.n == 1) && nb.n + 2 <= mx) || ((h == 2 || nb.n == 1) && nb.n + 1 <= mx))) {
+        double shortest = 1.0e5;
+        for (int k = 0; k < nb.n; ++k)
+            if (P.Z[P.types[nb.idx[k]]] != 1) shortest = fmin(shortest, po_length(P, G, fbase, i, nb.idx[k]));
+        P.key[fbase + i] = P.elneg[ti] * 1e6 + shortest;
+        P.plist2[atomicAdd(P.counters + PO_NQ, 1)] = (int)(fbase + i);
+    }
+    // carbons the pass-4 patterns can match: sp centre of CO2 / allene, or an oxygen on a carbon with >= 3 bonds
+    if (Zi == 6 && ((nb.n == 2 && h == 1) || (nb.n >= 3 && no > 0))) P.clist[atomicAdd(P.counters + PO_NC, 1)] = (int)(fbase + i);
 }
 
 // pass 3 ("antialiasing") only acts on atoms all of whose neighbours already hold hyb 3, which no
@@ -203,10 +228,9 @@ __global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams
 
 template <int MAXB>
 __global__ void __launch_bounds__(256) k_po_groups(const __grid_constant__ PoParams P) {
-    const int f = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.N) return;
-    if (P.Z[P.types[c]] != 6) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.counters[PO_NC]) return;
+    const int f = P.clist[q] / P.N, c = P.clist[q] - f * P.N;
     const size_t fbase = (size_t)f * P.N;
     const int h = P.hyb[fbase + c];
     const uint32_t pm = P.perm[fbase + c];
@@ -244,10 +268,9 @@ __global__ void __launch_bounds__(256) k_po_groups(const __grid_constant__ PoPar
 // carbonyl:  [#8D1;!-][#6](*)(*) matched on the state k_po_groups left, 115 < angle(C) < 150, d < 1.28
 template <int MAXB>
 __global__ void __launch_bounds__(256) k_po_carbonyl(const __grid_constant__ PoParams P) {
-    const int f = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.N) return;
-    if (P.Z[P.types[c]] != 6) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.counters[PO_NC]) return;
+    const int f = P.clist[q] / P.N, c = P.clist[q] - f * P.N;
     const size_t fbase = (size_t)f * P.N;
     const int deg = (int)(P.perm[fbase + c] >> 28);
     if (deg < 3) return;
@@ -276,9 +299,9 @@ __global__ void __launch_bounds__(256) k_po_carbonyl(const __grid_constant__ PoP
 // which atoms can ever act in pass 6: the branch conditions only get harder to meet as orders rise
 template <int MAXB>
 __global__ void __launch_bounds__(256) k_po_pending(const __grid_constant__ PoParams P) {
-    const int f = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.counters[PO_NQ]) return;
+    const int f = P.plist2[q] / P.N, i = P.plist2[q] - f * P.N;
     const size_t fbase = (size_t)f * P.N;
     int deg, val;
     bool ns;
@@ -294,8 +317,7 @@ __global__ void __launch_bounds__(256) k_po_pending(const __grid_constant__ PoPa
             act = true;
     }
     P.st[fbase + i] = act ? 1 : 0;
-    if (P.labels && P.labels[fbase + i] == i && P.tally[fbase + i] >= 0 && deg > 0)
-        atomicAdd(&P.stats->ring_molecules, 1ull);
+    if (act) P.plist[atomicAdd(P.counters, 1)] = (int)(fbase + i);
 }
 
 __device__ __forceinline__ double po_corrected_rad(double r, int h) { return h == 2 ? r * 0.95 : (h == 1 ? r * 0.90 : r); }
@@ -395,56 +417,74 @@ __device__ void po_turn(const PoParams &P, const FrameGeom &G, size_t fbase, int
     if (c >= 0) po_put<MAXB>(P, fbase, a, nb.slot[c], nb.idx[c], bump == 2 ? 3 : 2);
 }
 
+// is any atom within two bonds of `a` still waiting with a smaller (key, index)?
 template <int MAXB>
-__global__ void __launch_bounds__(1024) k_po_assign(const __grid_constant__ PoParams P) {
-    __shared__ int s_n, s_left;
-    const int f = blockIdx.x;
-    const size_t fbase = (size_t)f * P.N;
-    const FrameGeom &G = P.geom[f];
-    volatile uint8_t *st = P.st + fbase;
-    int *plist = P.plist + fbase;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < P.N; i += blockDim.x)
-        if (st[i]) plist[atomicAdd(&s_n, 1)] = i;
-    __syncthreads();
-    const int n = s_n;
+__device__ bool po_blocked(const PoParams &P, size_t fbase, int a) {
+    const volatile uint8_t *st = P.st + fbase;
     const double *key = P.key + fbase;
-    for (int it = 0; it <= n; ++it) {
-        if (threadIdx.x == 0) s_left = 0;
+    const double ka = key[a];
+    PoNb nb;
+    po_load_nb<MAXB>(P, fbase, a, nb);
+    for (int k = 0; k < nb.n; ++k) {
+        const int b = nb.idx[k];
+        if (st[b] && (key[b] < ka || (key[b] == ka && b < a))) return true;
+        PoNb n2;
+        po_load_nb<MAXB>(P, fbase, b, n2);
+        for (int m = 0; m < n2.n; ++m) {
+            const int x = n2.idx[m];
+            if (x != a && st[x] && (key[x] < ka || (key[x] == ka && x < a))) return true;
+        }
+    }
+    return false;
+}
+
+// one round of pass 6 over the list of waiting atom-frames: whoever is not blocked takes its turn,
+// the others go to the next round's list
+template <int MAXB>
+__global__ void __launch_bounds__(256) k_po_round(const __grid_constant__ PoParams P, const int *__restrict__ lin,
+                                                  const int *__restrict__ nin, int *__restrict__ lout, int *nout) {
+    const int n = *nin;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int af = lin[q];
+        const int f = af / P.N, a = af - f * P.N;
+        const size_t fbase = (size_t)f * P.N;
+        if (po_blocked<MAXB>(P, fbase, a)) {
+            lout[atomicAdd(nout, 1)] = af;
+            continue;
+        }
+        po_turn<MAXB>(P, P.geom[f], fbase, a);
+        __threadfence();
+        ((volatile uint8_t *)P.st)[fbase + a] = 0;
+    }
+}
+
+// whatever is still waiting after the fixed rounds (long chains): one block iterates to the end
+template <int MAXB>
+__global__ void __launch_bounds__(1024) k_po_finish(const __grid_constant__ PoParams P, int *la, const int *na, int *lb) {
+    __shared__ int s_next;
+    int n = *na;
+    int *lin = la, *lout = lb;
+    while (n > 0) {
+        if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
-        int left = 0;
         for (int q = threadIdx.x; q < n; q += blockDim.x) {
-            const int a = plist[q];
-            if (!st[a]) continue;
-            // anybody within two bonds who is still waiting and comes earlier in the sorted order?
-            const double ka = key[a];
-            bool blocked = false;
-            PoNb nb;
-            po_load_nb<MAXB>(P, fbase, a, nb);
-            for (int k = 0; k < nb.n && !blocked; ++k) {
-                const int b = nb.idx[k];
-                if (st[b] && (key[b] < ka || (key[b] == ka && b < a))) blocked = true;
-                PoNb n2;
-                po_load_nb<MAXB>(P, fbase, b, n2);
-                for (int m = 0; m < n2.n && !blocked; ++m) {
-                    const int x = n2.idx[m];
-                    if (x != a && st[x] && (key[x] < ka || (key[x] == ka && x < a))) blocked = true;
-                }
-            }
-            if (blocked) {
-                ++left;
+            const int af = lin[q];
+            const int f = af / P.N, a = af - f * P.N;
+            const size_t fbase = (size_t)f * P.N;
+            if (po_blocked<MAXB>(P, fbase, a)) {
+                lout[atomicAdd(&s_next, 1)] = af;
                 continue;
             }
-            po_turn<MAXB>(P, G, fbase, a);
-            __threadfence_block();
-            st[a] = 0;
+            po_turn<MAXB>(P, P.geom[f], fbase, a);
+            __threadfence();
+            ((volatile uint8_t *)P.st)[fbase + a] = 0;
         }
-        if (left) atomicAdd(&s_left, left);
         __syncthreads();
-        const int remaining = s_left;
+        n = s_next;
         __syncthreads();
-        if (!remaining) break;
+        int *t = lin;
+        lin = lout;
+        lout = t;
     }
 }
 
@@ -476,17 +516,33 @@ __global__ void __launch_bounds__(256) k_po_keys(const uint8_t *__restrict__ ord
 
 size_t perceive_workspace_bytes(int nframes, int natoms, int maxb, bool own_orders) {
     const size_t fn = (size_t)nframes * natoms;
-    return (own_orders ? align256(fn * maxb) : 0) + align256(fn) * 2 + align256(fn * 4) * 3 + align256(fn * 8) + 2048;
+    return (own_orders ? align256(fn * maxb) : 0) + align256(fn) * 2 + align256(fn * 4) * 4 + align256(fn * 8) + 4096;
 }
 
 template <int MAXB>
-static void po_launch(const PoParams &P, int F, int N, cudaStream_t stream) {
+static void po_launch(mdb_ctx *ctx, const PoParams &P, int F, int N, cudaStream_t stream) {
     dim3 grid(cdiv(N, 256), F);
-    k_po_hyb<MAXB><<<grid, 256, 0, stream>>>(P);
-    k_po_groups<MAXB><<<grid, 256, 0, stream>>>(P);
-    k_po_carbonyl<MAXB><<<grid, 256, 0, stream>>>(P);
-    k_po_pending<MAXB><<<grid, 256, 0, stream>>>(P);
-    k_po_assign<MAXB><<<F, 1024, 0, stream>>>(P);
+    {
+        ProfScope ps(ctx, "k_po_hyb", stream);
+        k_po_hyb<MAXB><<<grid, 256, 0, stream>>>(P);
+    }
+    {
+        ProfScope ps(ctx, "k_po_groups+carbonyl+pending", stream);
+        const int lgrid = (int)cdiv((long long)F * N, 256);  // list kernels: sized for the worst case, most blocks leave at once
+        k_po_groups<MAXB><<<lgrid, 256, 0, stream>>>(P);
+        k_po_carbonyl<MAXB><<<lgrid, 256, 0, stream>>>(P);
+        k_po_pending<MAXB><<<lgrid, 256, 0, stream>>>(P);
+    }
+    ProfScope ps(ctx, "k_po_round+finish+keys", stream);
+    // pass 6: a few grid-wide rounds (pairs like O=O or C=C need two), then a one-block tail
+    int *la = P.plist, *lb = P.plist2;
+    for (int r = 0; r < PO_ROUNDS; ++r) {
+        k_po_round<MAXB><<<148 * 8, 256, 0, stream>>>(P, la, P.counters + r, lb, P.counters + r + 1);
+        int *t = la;
+        la = lb;
+        lb = t;
+    }
+    k_po_finish<MAXB><<<1, 1024, 0, stream>>>(P, la, P.counters + PO_ROUNDS, lb);
     if (P.keys) k_po_keys<MAXB><<<cdiv((long long)F * N, 256), 256, 0, stream>>>(P.orders, P.types, N, (long long)F * N, P.keys);
 }
 
@@ -508,9 +564,15 @@ int perceive_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, con
     P.st = (uint8_t *)arena_alloc(ctx, fn);
     P.perm = (uint32_t *)arena_alloc(ctx, fn * 4);
     P.plist = (int *)arena_alloc(ctx, fn * 4);
-    P.tally = (int *)arena_alloc(ctx, fn * 4);
+    P.plist2 = (int *)arena_alloc(ctx, fn * 4);
+    P.counters = (int *)arena_alloc(ctx, 256);
+    P.clist = (int *)arena_alloc(ctx, fn * 4);
     P.key = (double *)arena_alloc(ctx, fn * 8);
-    if (!P.orders || !P.hyb || !P.st || !P.perm || !P.plist || !P.tally || !P.key) {
+    if (fn >= (1ull << 31)) {
+        mdb_set_error("perceive_run: batch too large, split the frames");
+        return -1;
+    }
+    if (!P.orders || !P.hyb || !P.st || !P.perm || !P.plist || !P.plist2 || !P.counters || !P.clist || !P.key) {
         mdb_set_error("perceive_run: arena too small (internal sizing error)");
         return -1;
     }
@@ -525,13 +587,12 @@ int perceive_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, con
         P.rcov[t] = kRcovP[Z];
         P.elneg[t] = kElNeg[Z];
     }
-    if (d_labels) MDB_CUDA(cudaMemsetAsync(P.tally, 0, fn * 4, stream));
-    ProfScope ps(ctx, "k_po_*", stream);
+    MDB_CUDA(cudaMemsetAsync(P.counters, 0, 256, stream));
     if (maxb == 8)
-        po_launch<8>(P, nframes, natoms, stream);
+        po_launch<8>(ctx, P, nframes, natoms, stream);
     else
-        po_launch<16>(P, nframes, natoms, stream);
-    ctx->launches += d_keys ? 6 : 5;
+        po_launch<16>(ctx, P, nframes, natoms, stream);
+    ctx->launches += (d_keys ? 6 : 5) + PO_ROUNDS;
     MDB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -319,9 +319,9 @@ class DatasetBuilder:
                     out = eng.analyze(pos, cell, d_types, self.pbc, want_ell=False, want_keys=True, want_labels=False)
                     eng.check()
                     collect(step0, out["keys"].cpu().numpy().view(np.uint64))
-                self._ring_molecules = eng.perceive_stats()["ring_molecules"] if self.perceive_bond_orders else 0
-                if self._ring_molecules:
-                    logger.warning(f"{self._ring_molecules} molecule-frames contain a ring: their bond orders come "
+                self._rings = eng.perceive_stats()["rings"] if self.perceive_bond_orders else 0
+                if self._rings:
+                    logger.warning(f"{self._rings} molecule-frames contain a ring: their bond orders come "
                                    "without Open Babel's ring passes (planar-ring sp2, aromatic Kekule)")
             finally:
                 eng.set_option("perceive_bond_orders", 0)

@@ -178,7 +178,7 @@ class Engine:
     def perceive_stats(self):
         v = C.c_longlong()
         _lib.check(self.L.mdb_perceive_stats(self.ctx, C.byref(v)), "mdb_perceive_stats")
-        return {"ring_molecules": v.value}
+        return {"rings": v.value}
 
     def ell_to_csr(self, ell, order=0, pos=None, colcap=None):
         torch = _torch()

@@ -16,7 +16,7 @@ restatement against itself, not against Open Babel.
 Scope (stated deviations, the same on the device, csrc/perceive.cu):
   * pass 2 (planar 5/6-rings -> sp2) and pass 5 (aromatic candidates -> Kekule) are NOT restated:
     molecules that contain a cycle go through passes 1, 3, 4, 6 only (``IsInRing`` treated as
-    false) and are counted in ``ring_molecules``;
+    false); ``rings`` reports how many independent cycles the frame holds;
   * pass 4 keeps the bondtyp.txt patterns that can match C/H/O molecules and are needed because
     pass 6 cannot reach them -- carboxylic acid / ester, carbon dioxide, allene -- and the coded
     carbonyl rule of AssignFunctionalGroupBonds; patterns that need N, P, S, Se or metals, and the
@@ -71,7 +71,7 @@ def perceive_bond_orders(Z, nbrs, delta):
     delta  delta(a, b) -> minimum-image vector(a) - vector(b) as a 3-tuple of floats
 
     Returns (orders, info): orders[i][k] is the order of the bond from atom i to nbrs[i][k];
-    info = {"hyb": [...], "ring_molecules": n}.
+    info = {"hyb": [...], "rings": n}.
     """
     n = len(Z)
     order = [[1] * len(nb) for nb in nbrs]
@@ -276,5 +276,6 @@ def perceive_bond_orders(Z, nbrs, delta):
     for i in range(n):
         r = root(i)
         tally[r] = tally.get(r, 0) + deg[i] - 2
-    rings = sum(1 for v in tally.values() if v >= 0)
-    return order, {"hyb": hyb, "ring_molecules": rings}
+    # independent cycles = bonds - atoms + molecules (what the device sums, csrc/perceive.cu)
+    rings = sum(v + 2 for v in tally.values()) // 2
+    return order, {"hyb": hyb, "rings": rings}

@@ -132,10 +132,18 @@ def test_oracle_bonds_and_molecules_match_reference_through_shims(golden):
             adj = O.crd2bond(Z, pos[k], cell[k].reshape(3, 3), True, mode=mode)
             assert adj == fr["dump_adjacency"]
         assert O.dps_lists(adj) == fr["dump_molecules"]
+        # keys: the adjacency above (Open Babel's bond order) through the PerceiveBondOrders restatement
+        from tests.test_perceive_gpu import _uc
+        from oracle.perceive import perceive_bond_orders
+
+        uc = _uc(cell[k])
+        P = pos[k]
+        orders, _ = perceive_bond_orders([int(z) for z in Z], adj,
+                                         lambda a, b: tuple(float(x) for x in uc.mic((P[a] - P[b]).reshape(1, 3))[0]))
         want = {(n, tuple(lv)): ids for n, lv, ids in fr["dump_keys"]}
         got = {}
         for i, a in enumerate(adj):
-            got.setdefault((golden["atomname"][golden["atomtype"][i] - 1], tuple([1] * len(a))), []).append(i + 1)
+            got.setdefault((golden["atomname"][golden["atomtype"][i] - 1], tuple(sorted(orders[i]))), []).append(i + 1)
         assert got == want
 
 

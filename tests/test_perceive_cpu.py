@@ -124,10 +124,10 @@ def test_butadiene_and_ring_count():
     bonds = [(0, 1), (1, 2), (2, 3), (0, 4), (0, 5), (1, 6), (2, 7), (3, 8), (3, 9)]
     lv, info = levels(spec, bonds)
     assert lv[0] == [1, 1, 2] and lv[1] == [1, 1, 2] and lv[2] == [1, 1, 2] and lv[3] == [1, 1, 2]
-    assert info["ring_molecules"] == 0
+    assert info["rings"] == 0
     # cyclopropane skeleton counts as a ring molecule
     lv, info = levels([("C", 0, 0, 0), ("C", 1.5, 0, 0), ("C", 0.75, 1.3, 0)], [(0, 1), (1, 2), (0, 2)])
-    assert info["ring_molecules"] == 1
+    assert info["rings"] == 1
 
 
 def test_shim_uses_it():

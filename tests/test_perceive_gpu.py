@@ -71,7 +71,7 @@ def test_synthetic_frames_match_the_restatement(engine, natoms, density, sigma, 
     out = engine.analyze(frames, cell, types)
     engine.check()
     got = engine.perceive(frames, cell, types, out["ell"], labels=out["labels"])
-    ring = engine.perceive_stats()["ring_molecules"]
+    ring = engine.perceive_stats()["rings"]
     engine.check()
     ell = out["ell"].cpu().numpy()
     orders = got["orders"].cpu().numpy()
@@ -80,7 +80,7 @@ def test_synthetic_frames_match_the_restatement(engine, natoms, density, sigma, 
     nmult = 0
     for f in range(frames.shape[0]):
         want, info = _oracle_orders(ell[f], frames[f], Z, cell, True)
-        rings += info["ring_molecules"]
+        rings += info["rings"]
         bad = np.argwhere(want != orders[f])
         assert bad.size == 0, f"frame {f}: {len(bad)} slots differ, first at atom {bad[0][0]}"
         nmult += int((want > 1).sum())
