@@ -51,6 +51,17 @@ static const double kRcovP[19] = {0.0, 0.31, 0.28, 1.28, 0.96, 0.84, 0.76, 0.71,
 static const double kElNeg[19] = {0.0, 2.20, 0.0, 0.98, 1.57, 2.04, 2.55, 3.04, 3.44, 3.98, 0.0, 0.93, 1.31, 1.61, 1.90,
                                   2.19, 2.58, 3.16, 0.0};
 
+// warp-aggregated list append: one atomic per group of threads that arrive together
+__device__ __forceinline__ int po_append(int *counter) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
 struct PoNb {
     int n;
     int idx[PO_MAXD];
@@ -59,17 +70,25 @@ struct PoNb {
 
 template <int MAXB>
 __device__ __forceinline__ void po_load_nb(const PoParams &P, size_t fbase, int i, PoNb &o) {
+    // row and permutation are fetched together (the live slots are among the first eight, k_po_hyb checks)
+    const int4 *row4 = reinterpret_cast<const int4 *>(P.ell + (fbase + i) * MAXB);
+    const int4 q0 = row4[0], q1 = row4[1];
     const uint32_t pm = P.perm[fbase + i];
     o.n = (int)(pm >> 28);
-    if (MAXB == 8) {
-        for (int k = 0; k < o.n; ++k) o.slot[k] = (int)((pm >> (3 * k)) & 7u);
-    } else {
-        // 16 slots: the live ones are the first `deg` after the cleanup's compaction, so 3 bits hold
-        // them whenever deg <= 8 (k_po_hyb raises an error otherwise)
-        for (int k = 0; k < o.n; ++k) o.slot[k] = (int)((pm >> (3 * k)) & 7u);
+#pragma unroll
+    for (int k = 0; k < PO_MAXD; ++k) {
+        const int sl = (int)((pm >> (3 * k)) & 7u);
+        int v = q0.x;
+        v = sl == 1 ? q0.y : v;
+        v = sl == 2 ? q0.z : v;
+        v = sl == 3 ? q0.w : v;
+        v = sl == 4 ? q1.x : v;
+        v = sl == 5 ? q1.y : v;
+        v = sl == 6 ? q1.z : v;
+        v = sl == 7 ? q1.w : v;
+        o.slot[k] = sl;
+        o.idx[k] = v;
     }
-    const int32_t *row = P.ell + (fbase + i) * MAXB;
-    for (int k = 0; k < o.n; ++k) o.idx[k] = row[o.slot[k]];
 }
 
 // degree, valence (sum of orders) and "has a non-single bond" of one atom from its order bytes
@@ -138,11 +157,9 @@ __device__ __forceinline__ double po_length(const PoParams &P, const FrameGeom &
     return sqrt(len2_rn(v));
 }
 
+// generic path of k_po_hyb: any degree up to PO_MAXD, everything in double
 template <int MAXB>
-__global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams P) {
-    const int f = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N) return;
+__device__ __noinline__ void po_hyb_slow(const PoParams &P, int f, int i) {
     const size_t fbase = (size_t)f * P.N;
     const FrameGeom &G = P.geom[f];
     const int32_t *row = P.ell + (fbase + i) * MAXB;
@@ -164,15 +181,6 @@ __global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams
                 atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
             }
         }
-    }
-#pragma unroll
-    for (int k = 0; k < MAXB; ++k) P.orders[(fbase + i) * MAXB + k] = ord[k];
-    if (P.labels) {
-        // independent cycles of the batch = bonds - atoms + molecules = sum(deg - 2 + 2 [root]) / 2
-        const int r = nb.n - 2 + 2 * (P.labels[fbase + i] == i);
-        const unsigned m = __activemask();
-        const int sum = __reduce_add_sync(m, r);
-        if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&P.stats->ring_molecules, (unsigned long long)(long long)sum);
     }
     // Open Babel's per-atom bond order: ascending z-rank of the partner (ties: index)
     for (int a = 1; a < nb.n; ++a) {
@@ -217,10 +225,175 @@ __global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams
         for (int k = 0; k < nb.n; ++k)
             if (P.Z[P.types[nb.idx[k]]] != 1) shortest = fmin(shortest, po_length(P, G, fbase, i, nb.idx[k]));
         P.key[fbase + i] = P.elneg[ti] * 1e6 + shortest;
-        P.plist2[atomicAdd(P.counters + PO_NQ, 1)] = (int)(fbase + i);
+        P.plist2[po_append(P.counters + PO_NQ)] = (int)(fbase + i);
     }
     // carbons the pass-4 patterns can match: sp centre of CO2 / allene, or an oxygen on a carbon with >= 3 bonds
-    if (Zi == 6 && ((nb.n == 2 && h == 1) || (nb.n >= 3 && no > 0))) P.clist[atomicAdd(P.counters + PO_NC, 1)] = (int)(fbase + i);
+    if (Zi == 6 && ((nb.n == 2 && h == 1) || (nb.n >= 3 && no > 0))) P.clist[po_append(P.counters + PO_NC)] = (int)(fbase + i);
+}
+
+// shared tail of both paths: hybridisation byte, pass-6 candidate (with its sort key), pass-4 candidate
+__device__ __forceinline__ void po_hyb_finish(const PoParams &P, size_t fbase, int i, int n, int h, int no, double shortest) {
+    const int ti = P.types[i];
+    P.hyb[fbase + i] = (uint8_t)h;
+    P.st[fbase + i] = 0;
+    const int mx = P.maxb[ti];
+    if (shortest >= 0.0) {
+        P.key[fbase + i] = P.elneg[ti] * 1e6 + shortest;
+        P.plist2[po_append(P.counters + PO_NQ)] = (int)(fbase + i);
+    }
+    (void)mx;
+    if (P.Z[ti] == 6 && ((n == 2 && h == 1) || (n >= 3 && no > 0))) P.clist[po_append(P.counters + PO_NC)] = (int)(fbase + i);
+}
+
+// who can take a pass-6 turn at all: valences only rise from here, so test with every bond single
+__device__ __forceinline__ bool po_can_act(int n, int h, int mx) {
+    return n > 0 && (((h == 1 || n == 1) && n + 2 <= mx) || ((h == 2 || n == 1) && n + 1 <= mx));
+}
+
+template <int MAXB>
+__global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams P) {
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    const size_t fbase = (size_t)f * P.N;
+    const FrameGeom &G = P.geom[f];
+    int e[MAXB];
+    const int4 *row4 = reinterpret_cast<const int4 *>(P.ell + (fbase + i) * MAXB);
+#pragma unroll
+    for (int k = 0; k < MAXB / 4; ++k) {
+        const int4 q = row4[k];
+        e[4 * k] = q.x;
+        e[4 * k + 1] = q.y;
+        e[4 * k + 2] = q.z;
+        e[4 * k + 3] = q.w;
+    }
+    int n = 0;
+    unsigned long long ow[MAXB / 8];
+#pragma unroll
+    for (int w = 0; w < MAXB / 8; ++w) ow[w] = 0ull;
+#pragma unroll
+    for (int k = 0; k < MAXB; ++k)
+        if (e[k] >= 0) {
+            ++n;
+            ow[k / 8] |= 1ull << (8 * (k % 8));
+        }
+    unsigned long long *orow = reinterpret_cast<unsigned long long *>(P.orders + (fbase + i) * MAXB);
+#pragma unroll
+    for (int w = 0; w < MAXB / 8; ++w) orow[w] = ow[w];
+    if (P.labels) {
+        // independent cycles of the batch = bonds - atoms + molecules = sum(deg - 2 + 2 [root]) / 2
+        const int r = n - 2 + 2 * (P.labels[fbase + i] == i);
+        const unsigned m = __activemask();
+        const int sum = __reduce_add_sync(m, r);
+        if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&P.stats->ring_molecules, (unsigned long long)(long long)sum);
+    }
+    // fast path: at most four bonds in the first slots (every C/H/O/N atom after the cleanup)
+    bool compact = n <= 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) compact = compact && ((k < n) == (e[k] >= 0));
+    if (!compact) {
+        po_hyb_slow<MAXB>(P, f, i);
+        return;
+    }
+    const int ti = P.types[i];
+    const int Zi = P.Z[ti];
+    const double *pos = P.pos + fbase * 3;
+    int nh = 0, no = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < n) {
+            const int Zj = P.Z[P.types[e[k]]];
+            nh += Zj == 1;
+            no += Zj == 8;
+        }
+    if (n == 0) {
+        P.perm[fbase + i] = 0u;
+        po_hyb_finish(P, fbase, i, 0, 0, 0, -1.0);
+        return;
+    }
+    double v[4][3];
+    if (n == 1) {
+        P.perm[fbase + i] = 1u << 28;
+        double shortest = -1.0;
+        if (po_can_act(1, 0, P.maxb[ti])) {
+            shortest = 1.0e5;
+            if (nh == 0) {
+                delta_exact(pos, G, P.periodic, i, e[0], v[0]);
+                shortest = sqrt(len2_rn(v[0]));
+            }
+        }
+        po_hyb_finish(P, fbase, i, 1, 0, no, shortest);
+        return;
+    }
+    // Open Babel's per-atom bond order: ascending z-rank of the partner (ties: index)
+    double z[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = k < n ? pos[(size_t)e[k] * 3 + 2] : 0.0;
+    uint32_t pm = (uint32_t)n << 28;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        if (a < n) {
+            int rank = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (b != a && b < n) rank += (z[b] < z[a]) || (z[b] == z[a] && e[b] < e[a]);
+            pm |= (uint32_t)a << (3 * rank);
+        }
+    P.perm[fbase + i] = pm;
+    // pass 1: average bond angle, in float first; the double evaluation decides near a threshold
+    float vf[4][3], rinv[4];
+    bool tiny = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < n) {
+            delta_exact(pos, G, P.periodic, e[k], i, v[k]);
+            vf[k][0] = (float)v[k][0];
+            vf[k][1] = (float)v[k][1];
+            vf[k][2] = (float)v[k][2];
+            const float l2 = vf[k][0] * vf[k][0] + vf[k][1] * vf[k][1] + vf[k][2] * vf[k][2];
+            tiny = tiny || l2 < 1e-4f;
+            rinv[k] = rsqrtf(l2);
+        }
+    float tot = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = x + 1; y < 4; ++y)
+            if (y < n) {
+                float dp = (vf[x][0] * vf[y][0] + vf[x][1] * vf[y][1] + vf[x][2] * vf[y][2]) * rinv[x] * rinv[y];
+                dp = fminf(fmaxf(dp, -0.9999999f), 0.9999999f);
+                tot += 57.29577951f * acosf(dp);
+                ++cnt;
+            }
+    double ang = (double)(tot / (float)cnt);
+    const float af = (float)ang;
+    if (tiny || fabsf(af - 115.f) < 0.1f || fabsf(af - 155.f) < 0.1f || (Zi == 7 && fabsf(af - 109.5f) < 0.1f)) {
+        double dt = 0.0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = x + 1; y < 4; ++y)
+                if (y < n) {
+                    const double l1 = sqrt(po_dot(v[x], v[x])), l2 = sqrt(po_dot(v[y], v[y]));
+                    if (!(fabs(l1) < 1e-3 || fabs(l2) < 1e-3)) dt += po_vector_angle(v[x], v[y]);
+                }
+        ang = dt / cnt;
+    }
+    int h = 0;
+    if (ang > 155.0)
+        h = 1;
+    else if (ang > 115.0)
+        h = 2;
+    if (Zi == 7 && n == 2 && nh == 1 && ang > 109.5) h = 2;
+    double shortest = -1.0;
+    if (po_can_act(n, h, P.maxb[ti])) {
+        shortest = 1.0e5;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < n && P.Z[P.types[e[k]]] != 1) shortest = fmin(shortest, sqrt(len2_rn(v[k])));
+    }
+    po_hyb_finish(P, fbase, i, n, h, no, shortest);
 }
 
 // pass 3 ("antialiasing") only acts on atoms all of whose neighbours already hold hyb 3, which no
@@ -309,15 +482,29 @@ __global__ void __launch_bounds__(256) k_po_pending(const __grid_constant__ PoPa
     const int ti = P.types[i];
     const int h = P.hyb[fbase + i];
     const int mx = P.maxb[ti];
-    bool act = false;
+    int bump = 0;
     if (deg > 0 && !ns) {
         if ((h == 1 || deg == 1) && val + 2 <= mx)
-            act = true;
+            bump = 2;
         else if ((h == 2 || deg == 1) && val + 1 <= mx)
-            act = true;
+            bump = 1;
+    }
+    // a turn only changes something if a partner can take the same raise; partners only ever get
+    // less able to (valences rise, bonds turn non-single), so whoever has none now never will
+    bool act = false;
+    if (bump) {
+        PoNb nb;
+        po_load_nb<MAXB>(P, fbase, i, nb);
+        for (int k = 0; k < nb.n && !act; ++k) {
+            const int b = nb.idx[k];
+            int db, vb;
+            bool nsb;
+            po_rowstat<MAXB>(P.orders, fbase + b, db, vb, nsb);
+            act = (P.hyb[fbase + b] == (bump == 2 ? 1 : 2) || db == 1) && vb + bump <= P.maxb[P.types[b]] && !nsb;
+        }
     }
     P.st[fbase + i] = act ? 1 : 0;
-    if (act) P.plist[atomicAdd(P.counters, 1)] = (int)(fbase + i);
+    if (act) P.plist[po_append(P.counters)] = (int)(fbase + i);
 }
 
 __device__ __forceinline__ double po_corrected_rad(double r, int h) { return h == 2 ? r * 0.95 : (h == 1 ? r * 0.90 : r); }
@@ -414,7 +601,12 @@ __device__ void po_turn(const PoParams &P, const FrameGeom &G, size_t fbase, int
         max_en = en;
         c = k;
     }
-    if (c >= 0) po_put<MAXB>(P, fbase, a, nb.slot[c], nb.idx[c], bump == 2 ? 3 : 2);
+    if (c >= 0) {
+        po_put<MAXB>(P, fbase, a, nb.slot[c], nb.idx[c], bump == 2 ? 3 : 2);
+        // the partner now holds a non-single bond: its own turn can only return early, so it stops waiting
+        __threadfence();
+        ((volatile uint8_t *)P.st)[fbase + nb.idx[c]] = 0;
+    }
 }
 
 // is any atom within two bonds of `a` still waiting with a smaller (key, index)?
@@ -441,20 +633,37 @@ __device__ bool po_blocked(const PoParams &P, size_t fbase, int a) {
 // one round of pass 6 over the list of waiting atom-frames: whoever is not blocked takes its turn,
 // the others go to the next round's list
 template <int MAXB>
-__global__ void __launch_bounds__(256) k_po_round(const __grid_constant__ PoParams P, const int *__restrict__ lin,
+__global__ void __launch_bounds__(256, 4) k_po_round(const __grid_constant__ PoParams P, const int *__restrict__ lin,
                                                   const int *__restrict__ nin, int *__restrict__ lout, int *nout) {
+    // per tile of 256 entries: sort out who may act, then the block takes the turns with full warps
+    __shared__ int s_go[256];
+    __shared__ int s_ngo;
     const int n = *nin;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const int af = lin[q];
-        const int f = af / P.N, a = af - f * P.N;
-        const size_t fbase = (size_t)f * P.N;
-        if (po_blocked<MAXB>(P, fbase, a)) {
-            lout[atomicAdd(nout, 1)] = af;
-            continue;
+    for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
+        if (threadIdx.x == 0) s_ngo = 0;
+        __syncthreads();
+        const int q = base + threadIdx.x;
+        if (q < n) {
+            const int af = lin[q];
+            const int f = af / P.N, a = af - f * P.N;
+            const size_t fbase = (size_t)f * P.N;
+            if (((const volatile uint8_t *)P.st)[fbase + a]) {  // else: released by a partner's turn
+                if (po_blocked<MAXB>(P, fbase, a))
+                    lout[po_append(nout)] = af;
+                else
+                    s_go[atomicAdd(&s_ngo, 1)] = af;
+            }
         }
-        po_turn<MAXB>(P, P.geom[f], fbase, a);
-        __threadfence();
-        ((volatile uint8_t *)P.st)[fbase + a] = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < s_ngo) {
+            const int af = s_go[threadIdx.x];
+            const int f = af / P.N, a = af - f * P.N;
+            const size_t fbase = (size_t)f * P.N;
+            po_turn<MAXB>(P, P.geom[f], fbase, a);
+            __threadfence();
+            ((volatile uint8_t *)P.st)[fbase + a] = 0;
+        }
+        __syncthreads();
     }
 }
 
@@ -471,6 +680,7 @@ __global__ void __launch_bounds__(1024) k_po_finish(const __grid_constant__ PoPa
             const int af = lin[q];
             const int f = af / P.N, a = af - f * P.N;
             const size_t fbase = (size_t)f * P.N;
+            if (!((const volatile uint8_t *)P.st)[fbase + a]) continue;  // released by a partner's turn
             if (po_blocked<MAXB>(P, fbase, a)) {
                 lout[atomicAdd(&s_next, 1)] = af;
                 continue;
