@@ -482,6 +482,8 @@ def main():
                 "config": {"workload": text, "atoms_per_frame": natoms, "frames_per_rank": frames,
                            "frames_total": frames * world, "density_per_A3": density,
                            "stages": "cell list + bonds + valence/angle cleanup + bond-type keys + molecule labels",
+                           "bond_orders": "keys with all-single levels in the step (what the CPU arm computes too); "
+                                          "the bond-order perception is timed as stages.bond_orders",
                            "parallelism": f"frames sharded over {world} rank(s), no data-path collective",
                            "l2": f"inputs are {frames * natoms * 24 / 1e6:.0f} MB per step per rank (> 126 MB L2)"
                                  if frames * natoms * 24 > 126e6 else "inputs fit L2 (not a headline configuration)",

@@ -10,8 +10,9 @@
 //                 average bond angle -> hybridisation (pass 1), pass-6 sort key and candidate lists, cycle count
 //   k_po_groups   per carbon: carboxylic / CO2 / allene patterns of bondtyp.txt (pass 4)
 //   k_po_carbonyl per carbon: the coded carbonyl rule of OBBondTyper::AssignFunctionalGroupBonds
-//   k_po_round    pass 6 in rounds over the list of atoms that can act: an atom takes its turn once
-//   k_po_finish   no atom within two bonds with a smaller (key, index) is still waiting -- the
+//   k_po_check    pass 6 in rounds over the list of atoms that can act: an atom takes its turn once
+//   k_po_act      no atom within two bonds with a smaller (key, index) is still waiting -- the
+//   k_po_finish
 //                 sequential semantics of the sorted loop, since a turn reads and writes nothing
 //                 beyond that radius; a few grid-wide rounds, then one block finishes long chains
 //   k_po_keys     64-bit key (element, degree, sorted orders) like k_keys_bo
@@ -21,6 +22,7 @@
 #define PO_ROUNDS 3
 #define PO_NC 8
 #define PO_NQ 9
+#define PO_NGO 16
 #define PO_MAXD 8  // degree after the valence cleanup is <= MaxBonds(Z) <= 6
 
 struct PoParams {
@@ -630,40 +632,37 @@ __device__ bool po_blocked(const PoParams &P, size_t fbase, int a) {
     return false;
 }
 
-// one round of pass 6 over the list of waiting atom-frames: whoever is not blocked takes its turn,
-// the others go to the next round's list
+// one round of pass 6 over the list of waiting atom-frames, in two launches: k_po_check sorts the list
+// into those who may act now and those who go to the next round (nobody acts meanwhile, so the view
+// is the state at the start of the round), k_po_act takes the turns with full warps
 template <int MAXB>
-__global__ void __launch_bounds__(256, 4) k_po_round(const __grid_constant__ PoParams P, const int *__restrict__ lin,
-                                                  const int *__restrict__ nin, int *__restrict__ lout, int *nout) {
-    // per tile of 256 entries: sort out who may act, then the block takes the turns with full warps
-    __shared__ int s_go[256];
-    __shared__ int s_ngo;
+__global__ void __launch_bounds__(256) k_po_check(const __grid_constant__ PoParams P, const int *__restrict__ lin,
+                                                  const int *__restrict__ nin, int *__restrict__ lout, int *nout,
+                                                  int *__restrict__ go, int *ngo) {
     const int n = *nin;
-    for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
-        if (threadIdx.x == 0) s_ngo = 0;
-        __syncthreads();
-        const int q = base + threadIdx.x;
-        if (q < n) {
-            const int af = lin[q];
-            const int f = af / P.N, a = af - f * P.N;
-            const size_t fbase = (size_t)f * P.N;
-            if (((const volatile uint8_t *)P.st)[fbase + a]) {  // else: released by a partner's turn
-                if (po_blocked<MAXB>(P, fbase, a))
-                    lout[po_append(nout)] = af;
-                else
-                    s_go[atomicAdd(&s_ngo, 1)] = af;
-            }
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < s_ngo) {
-            const int af = s_go[threadIdx.x];
-            const int f = af / P.N, a = af - f * P.N;
-            const size_t fbase = (size_t)f * P.N;
-            po_turn<MAXB>(P, P.geom[f], fbase, a);
-            __threadfence();
-            ((volatile uint8_t *)P.st)[fbase + a] = 0;
-        }
-        __syncthreads();
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int af = lin[q];
+        const int f = af / P.N, a = af - f * P.N;
+        const size_t fbase = (size_t)f * P.N;
+        if (!((const volatile uint8_t *)P.st)[fbase + a]) continue;  // released by a partner's turn
+        if (po_blocked<MAXB>(P, fbase, a))
+            lout[po_append(nout)] = af;
+        else
+            go[po_append(ngo)] = af;
+    }
+}
+
+template <int MAXB>
+__global__ void __launch_bounds__(256, 4) k_po_act(const __grid_constant__ PoParams P, const int *__restrict__ go,
+                                                   const int *__restrict__ ngo) {
+    const int n = *ngo;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int af = go[q];
+        const int f = af / P.N, a = af - f * P.N;
+        const size_t fbase = (size_t)f * P.N;
+        po_turn<MAXB>(P, P.geom[f], fbase, a);
+        __threadfence();
+        ((volatile uint8_t *)P.st)[fbase + a] = 0;
     }
 }
 
@@ -747,7 +746,9 @@ static void po_launch(mdb_ctx *ctx, const PoParams &P, int F, int N, cudaStream_
     // pass 6: a few grid-wide rounds (pairs like O=O or C=C need two), then a one-block tail
     int *la = P.plist, *lb = P.plist2;
     for (int r = 0; r < PO_ROUNDS; ++r) {
-        k_po_round<MAXB><<<148 * 8, 256, 0, stream>>>(P, la, P.counters + r, lb, P.counters + r + 1);
+        // the carbon list of pass 4 is free again: it holds the atoms cleared to act
+        k_po_check<MAXB><<<148 * 8, 256, 0, stream>>>(P, la, P.counters + r, lb, P.counters + r + 1, P.clist, P.counters + PO_NGO + r);
+        k_po_act<MAXB><<<148 * 8, 256, 0, stream>>>(P, P.clist, P.counters + PO_NGO + r);
         int *t = la;
         la = lb;
         lb = t;
@@ -802,7 +803,7 @@ int perceive_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, con
         po_launch<8>(ctx, P, nframes, natoms, stream);
     else
         po_launch<16>(ctx, P, nframes, natoms, stream);
-    ctx->launches += (d_keys ? 6 : 5) + PO_ROUNDS;
+    ctx->launches += (d_keys ? 6 : 5) + 2 * PO_ROUNDS;
     MDB_CUDA(cudaGetLastError());
     return 0;
 }
