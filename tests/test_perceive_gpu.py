@@ -154,3 +154,16 @@ def test_analyze_option_returns_perceived_keys(engine):
     assert np.array_equal(out["ell"].cpu().numpy(), plain["ell"].cpu().numpy())
     assert np.array_equal(out["labels"].cpu().numpy(), plain["labels"].cpu().numpy())
     assert not np.array_equal(out["keys"].cpu().numpy(), plain["keys"].cpu().numpy())
+    # the host-buffer pipeline (chunks of frames on internal streams) honours the option as well
+    engine.set_option("perceive_bond_orders", 1)
+    engine.set_option("frames_per_launch", 1)
+    try:
+        host = engine.analyze_host(frames, cell, types)
+        coded = engine.analyze_host(frames, cell, types, key_codes=True)
+        engine.check()
+    finally:
+        engine.set_option("perceive_bond_orders", 0)
+        engine.set_option("frames_per_launch", 0)
+    assert np.array_equal(np.asarray(host["keys"]).view(np.int64), want.cpu().numpy())
+    table = np.asarray(coded["keytable"]).view(np.uint64)
+    assert np.array_equal(table[np.asarray(coded["keycode"])].view(np.int64), want.cpu().numpy())
