@@ -29,6 +29,24 @@ if rank == 0:
     print("types equal", b.atombondtype == g["e2e_bonds"]["atombondtype"], "nstructure", b._nstructure, g["e2e_bonds"]["nstructure"])
     print("files", len(got), len(want), "identical", got == want)
 dist.barrier(device_ids=[local])
+# dump-only mode (perceived bond orders in the keys), fragments and atom_pref
+b3 = DatasetBuilder(atomname=g["atomname"], dumpfilename=os.path.join(GOLD, 'traj', 'dump.small'), dataset_name="golddump",
+                    cutoff=4.0, stepinterval=3, n_clusters=10000, nproc=1, fragment=True, atom_pref=True,
+                    qmkeywords=["%nproc=4\n#force mn15/6-31g**", "%nproc=4\n#force mn15/def2tzvp geom=chk"])
+b3.builddataset()
+dist.barrier(device_ids=[local])
+if rank == 0:
+    import numpy as np
+    got = {}
+    for base in (b3.dataset_dir, b3.gjfdir):
+        for dp, _, files in os.walk(base):
+            for fn in files:
+                p = os.path.join(dp, fn)
+                got[os.path.relpath(p, work)] = np.load(p).tolist() if fn.endswith(".npy") else hashlib.sha256(open(p, 'rb').read()).hexdigest()
+    want = g["e2e_dump"]["manifest"]
+    print("dump-only: types equal", b3.atombondtype == g["e2e_dump"]["atombondtype"], "nstructure", b3._nstructure, g["e2e_dump"]["nstructure"],
+          "files", len(got), len(want), "identical", got == want)
+dist.barrier(device_ids=[local])
 # clustering path with collectives (k-means partial-sum all-reduce, scaler bounds, selection gather)
 b2 = DatasetBuilder(atomname=g["atomname"], bondfilename=os.path.join(GOLD, 'traj', 'bonds.small'),
                     dumpfilename=os.path.join(GOLD, 'traj', 'dump.small'), dataset_name="clus", stepinterval=1, n_clusters=10, seed=3)
