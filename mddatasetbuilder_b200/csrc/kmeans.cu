@@ -563,7 +563,10 @@ template <int TMAX>
 __device__ __forceinline__ void kpp_dist_body(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
                                               long long n, int D, const int *cand, int T, int first_step, const KppState *st,
                                               double *dist, double *partial_blk, double *s_c, int chunk, bool stage,
-                                              double *xn, const double *crows = nullptr) {
+                                              double *xn, const double *xt, const double *crows = nullptr,
+                                              long long *tr = nullptr) {
+    const bool tron = tr && blockIdx.x == 1 && blockIdx.y == 0 && threadIdx.x == 0;
+    long long tq = tron ? clock64() : 0;
     double *s_cn = s_c + (size_t)D * TMAX;  // [TMAX] squared norms of the candidates
     double *s_w = s_cn + TMAX;              // [8][KPP_MAXT] warp partials
     if (stage) {
@@ -588,17 +591,24 @@ __device__ __forceinline__ void kpp_dist_body(const double *__restrict__ X, long
         }
     }
     __syncthreads();
+    if (tron) {
+        const long long now = clock64();
+        tr[3] += now - tq;  // staging the candidates
+        tq = now;
+    }
     const long long i = (long long)chunk * 256 + threadIdx.x;
     double acc[TMAX];
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) acc[t] = 0.0;
     if (i < n) {
         const double cl = first_step ? DBL_MAX : dist[(size_t)__ldcg(&st->best) * n + i];  // this thread's own write
-        const double *x = X + (rowidx ? (long long)rowidx[i] : i) * ldx;
+        // the rows come from the feature-major copy made once per seeding (k_kpp_transpose): consecutive
+        // threads read consecutive doubles, instead of one 32-byte sector per thread and feature
+        const double *x = xt + i;
         double x2 = 0.0;
 #pragma unroll 5
         for (int k = 0; k < D; ++k) {
-            const double xv = x[k];
+            const double xv = x[(size_t)k * n];
             if (first_step) x2 = fma(xv, xv, x2);
             const double2 *cr = reinterpret_cast<const double2 *>(s_c + k * TMAX);
 #pragma unroll
@@ -617,6 +627,11 @@ __device__ __forceinline__ void kpp_dist_body(const double *__restrict__ X, long
             if (t < T) dist[(size_t)t * n + i] = acc[t];
         }
     }
+    if (tron) {
+        const long long now = clock64();
+        tr[4] += now - tq;  // rows x candidates (thread 0's own)
+        tq = now;
+    }
     // block potentials in a fixed order: lanes by shuffle tree, warps serially
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -633,6 +648,17 @@ __device__ __forceinline__ void kpp_dist_body(const double *__restrict__ X, long
         partial_blk[threadIdx.x] = v;
     }
     __syncthreads();  // s_w is reused by the next chunk of a persistent block
+    if (tron) tr[5] += clock64() - tq;  // potentials
+}
+
+// feature-major copy of the seeding rows of every problem: xt[b][k][i] = X[row(b, i)][k]
+__global__ void __launch_bounds__(256) k_kpp_transpose(const double *__restrict__ X, long long ldx, const int *__restrict__ rowidx,
+                                                       long long n, int D, double *__restrict__ xt) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double *x = X + (rowidx ? (long long)rowidx[(size_t)blockIdx.y * n + i] : i) * ldx;
+    double *o = xt + (size_t)blockIdx.y * D * n + i;
+    for (int k = 0; k < D; ++k) o[(size_t)k * n] = x[k];
 }
 
 template <int TMAX>
@@ -640,15 +666,16 @@ __global__ void __launch_bounds__(256) k_kpp_dist(const double *__restrict__ X, 
                                                   long long n, int D, const int *__restrict__ cand, int T, int Tfull,
                                                   int first_step, const KppState *__restrict__ st,
                                                   double *__restrict__ dist, double *__restrict__ partial,
-                                                  double *__restrict__ xn) {
+                                                  double *__restrict__ xn, const double *__restrict__ xt) {
     xn += (size_t)blockIdx.y * n;
+    xt += (size_t)blockIdx.y * D * n;
     if (rowidx) rowidx += (size_t)blockIdx.y * n;
     cand += blockIdx.y * KPP_MAXT;
     st += blockIdx.y;
     dist += (size_t)blockIdx.y * Tfull * n;
     partial += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * KPP_MAXT;
     extern __shared__ double s_c[];
-    kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, first_step, st, dist, partial, s_c, blockIdx.x, true, xn);
+    kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, first_step, st, dist, partial, s_c, blockIdx.x, true, xn, xt);
 }
 
 // All K - 1 steps in ONE launch.  After its distance pass every block of a seeding problem takes a
@@ -661,8 +688,10 @@ __global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict
                                                         const int *__restrict__ rowidx, long long n, int D, int T, int K,
                                                         const double *__restrict__ rnd, int *cand, KppState *st, double *dist,
                                                         double *partial, int *indices, unsigned *sync, int nblk,
-                                                        double *crows, long long *trace, double *xn) {
+                                                        double *crows, long long *trace, double *xn,
+                                                        const double *__restrict__ xt) {
     xn += (size_t)blockIdx.y * n;
+    xt += (size_t)blockIdx.y * D * n;
     const int nb = gridDim.x;  // blocks per problem; each takes the 256-row chunks blockIdx.x, + nb, ...
     if (rowidx) rowidx += (size_t)blockIdx.y * n;
     rnd += (size_t)blockIdx.y * (size_t)max(K - 1, 1) * T;
@@ -680,7 +709,7 @@ __global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict
     __shared__ int s_last;
     for (int ch = blockIdx.x; ch < nblk; ch += nb)
         kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, 1, 1, st, dist, partial + (size_t)ch * KPP_MAXT, s_dyn, ch,
-                            ch == (int)blockIdx.x, xn);
+                            ch == (int)blockIdx.x, xn, xt);
     int Tprev = 1;
     long long tr0 = 0, tr1 = 0, tr2 = 0, trt = clock64();
     for (int step = 1; step <= K; ++step) {
@@ -728,7 +757,7 @@ __global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict
         }
         for (int ch = blockIdx.x; ch < nblk; ch += nb)
             kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, T, 0, st, dist, partial + (size_t)ch * KPP_MAXT, s_dyn, ch,
-                                ch == (int)blockIdx.x, xn, crows);
+                                ch == (int)blockIdx.x, xn, xt, crows, trace);
         Tprev = T;
     }
     if (trace && blockIdx.x == 1 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -751,7 +780,8 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
         }
     const int nblk = (int)cdiv(n, 256);
     const size_t nrand = (size_t)std::max(K - 1, 1) * T;
-    size_t need = align256((size_t)B * T * n * sizeof(double)) + align256((size_t)B * n * sizeof(double)) + align256((size_t)B * nblk * KPP_MAXT * sizeof(double)) +
+    size_t need = align256((size_t)B * T * n * sizeof(double)) + align256((size_t)B * n * sizeof(double)) +
+                  align256((size_t)B * D * n * sizeof(double)) + align256((size_t)B * nblk * KPP_MAXT * sizeof(double)) +
                   align256((size_t)B * nrand * sizeof(double)) + align256((size_t)B * KPP_MAXT * sizeof(int)) +
                   align256((size_t)B * sizeof(KppState)) + align256((size_t)B * 64 * sizeof(unsigned)) +
                   align256((size_t)B * KPP_MAXT * D * sizeof(double)) + 256 + 1024;
@@ -759,14 +789,17 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
     arena_reset(c);
     double *dist = (double *)arena_alloc(c, (size_t)B * T * n * sizeof(double));
     double *xn = (double *)arena_alloc(c, (size_t)B * n * sizeof(double));
+    double *xt = (double *)arena_alloc(c, (size_t)B * D * n * sizeof(double));
     double *partial = (double *)arena_alloc(c, (size_t)B * nblk * KPP_MAXT * sizeof(double));
     double *rnd = (double *)arena_alloc(c, (size_t)B * nrand * sizeof(double));
     int *cand = (int *)arena_alloc(c, (size_t)B * KPP_MAXT * sizeof(int));
     KppState *st = (KppState *)arena_alloc(c, (size_t)B * sizeof(KppState));
-    if (!dist || !xn || !partial || !rnd || !cand || !st) {
+    if (!dist || !xn || !xt || !partial || !rnd || !cand || !st) {
         mdb_set_error("kmeans_plusplus: arena too small (internal sizing error)");
         return -1;
     }
+    k_kpp_transpose<<<dim3((unsigned)nblk, (unsigned)B), 256, 0, stream>>>(d_X, ldx, d_rowidx, n, D, xt);
+    c->launches += 1;
     if (K > 1) MDB_CUDA(cudaMemcpyAsync(rnd, h_rand, (size_t)B * nrand * sizeof(double), cudaMemcpyHostToDevice, stream));
     std::vector<int> hc((size_t)B * KPP_MAXT, 0);
     for (int b = 0; b < B; ++b) hc[(size_t)b * KPP_MAXT] = h_first[b];
@@ -815,6 +848,7 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
             const int *arow = d_rowidx;
             int aD = D, aT = T, aK = K;
             const double *arnd = rnd;
+            const double *axt = xt;
             int anblk = nblk;
             long long *trace = nullptr;
             if (getenv("MDB_KPP_TRACE")) {  // developer switch: cycles of block 1 in the distance pass / waiting / selecting
@@ -822,7 +856,7 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
                 if (trace) MDB_CUDA(cudaMemsetAsync(trace, 0, 256, stream));
             }
             void *args[] = {&aX,   &aldx, &arow,    &an,        &aD,  &aT,    &aK,    &arnd,
-                            &cand, &st,   &dist,    &partial,   &d_indices, &bar, &anblk, &crows, &trace, &xn};
+                            &cand, &st,   &dist,    &partial,   &d_indices, &bar, &anblk, &crows, &trace, &xn, &axt};
             {
                 ProfScope ps(c, "k_kpp_persistent", stream);
                 MDB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)nb, (unsigned)B), dim3(256), args, smem_p, stream));
@@ -831,17 +865,18 @@ int kmeans_plusplus_run(mdb_ctx *c, int B, long long n, int D, const double *d_X
             MDB_CUDA(cudaGetLastError());
             MDB_CUDA(cudaStreamSynchronize(stream));
             if (trace) {
-                long long h[3];
+                long long h[6];
                 MDB_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
-                fprintf(stderr, "k_kpp_persistent block 1, cycles per step: distance pass %.0f, waiting %.0f, selecting %.0f\n",
-                        (double)h[0] / K, (double)h[1] / K, (double)h[2] / K);
+                fprintf(stderr, "k_kpp_persistent block 1 (nb %d, chunks %d), cycles per step: distance pass %.0f (staging %.0f, rows %.0f, "
+                        "potentials %.0f), waiting %.0f, selecting %.0f\n",
+                        nb, nblk, (double)h[0] / K, (double)h[3] / K, (double)h[4] / K, (double)h[5] / K, (double)h[1] / K, (double)h[2] / K);
             }
             return 0;
         }
     }
     auto launch_dist = [&](int Tn, int first_step) {
 #define MDB_KPP_LAUNCH(W) \
-    if (TW == W) k_kpp_dist<W><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial, xn);
+    if (TW == W) k_kpp_dist<W><<<gd, 256, smem, stream>>>(d_X, ldx, d_rowidx, n, D, cand, Tn, T, first_step, st, dist, partial, xn, xt);
         MDB_KPP_WIDTHS(MDB_KPP_LAUNCH)
 #undef MDB_KPP_LAUNCH
     };
