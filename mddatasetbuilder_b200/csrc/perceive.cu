@@ -6,8 +6,9 @@
 // most bondtyp.txt patterns left out; molecules with a cycle are counted).  PARITY UNPINNED
 // against Open Babel itself; bit-for-bit against the restatement (tests/test_perceive_gpu.py).
 //
-//   k_po_hyb      per atom: neighbours in Open Babel's bond order (ascending partner z-rank),
-//                 average bond angle -> hybridisation (pass 1), pass-6 sort key and candidate lists, cycle count
+//   k_po_hyb      per atom: order bytes, cycle count; atoms with >= 2 bonds go to a list for
+//   k_po_angle    neighbours in Open Babel's bond order (ascending partner z-rank), average bond
+//                 angle -> hybridisation (pass 1), pass-6 sort key and candidate lists
 //   k_po_groups   per carbon: carboxylic / CO2 / allene patterns of bondtyp.txt (pass 4)
 //   k_po_carbonyl per carbon: the coded carbonyl rule of OBBondTyper::AssignFunctionalGroupBonds
 //   k_po_check    pass 6 in rounds over the list of atoms that can act: an atom takes its turn once
@@ -22,6 +23,7 @@
 #define PO_ROUNDS 3
 #define PO_NC 8
 #define PO_NQ 9
+#define PO_NA 10
 #define PO_NGO 16
 #define PO_MAXD 8  // degree after the valence cleanup is <= MaxBonds(Z) <= 6
 
@@ -252,51 +254,10 @@ __device__ __forceinline__ bool po_can_act(int n, int h, int mx) {
     return n > 0 && (((h == 1 || n == 1) && n + 2 <= mx) || ((h == 2 || n == 1) && n + 1 <= mx));
 }
 
-template <int MAXB>
-__global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams P) {
-    const int f = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N) return;
+// the up-to-four-bond case of pass 1 with everything in registers: permutation, hybridisation, candidate lists
+__device__ __forceinline__ void po_hyb_fast(const PoParams &P, int f, int i, int n, const int (&e)[4]) {
     const size_t fbase = (size_t)f * P.N;
     const FrameGeom &G = P.geom[f];
-    int e[MAXB];
-    const int4 *row4 = reinterpret_cast<const int4 *>(P.ell + (fbase + i) * MAXB);
-#pragma unroll
-    for (int k = 0; k < MAXB / 4; ++k) {
-        const int4 q = row4[k];
-        e[4 * k] = q.x;
-        e[4 * k + 1] = q.y;
-        e[4 * k + 2] = q.z;
-        e[4 * k + 3] = q.w;
-    }
-    int n = 0;
-    unsigned long long ow[MAXB / 8];
-#pragma unroll
-    for (int w = 0; w < MAXB / 8; ++w) ow[w] = 0ull;
-#pragma unroll
-    for (int k = 0; k < MAXB; ++k)
-        if (e[k] >= 0) {
-            ++n;
-            ow[k / 8] |= 1ull << (8 * (k % 8));
-        }
-    unsigned long long *orow = reinterpret_cast<unsigned long long *>(P.orders + (fbase + i) * MAXB);
-#pragma unroll
-    for (int w = 0; w < MAXB / 8; ++w) orow[w] = ow[w];
-    if (P.labels) {
-        // independent cycles of the batch = bonds - atoms + molecules = sum(deg - 2 + 2 [root]) / 2
-        const int r = n - 2 + 2 * (P.labels[fbase + i] == i);
-        const unsigned m = __activemask();
-        const int sum = __reduce_add_sync(m, r);
-        if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&P.stats->ring_molecules, (unsigned long long)(long long)sum);
-    }
-    // fast path: at most four bonds in the first slots (every C/H/O/N atom after the cleanup)
-    bool compact = n <= 4;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) compact = compact && ((k < n) == (e[k] >= 0));
-    if (!compact) {
-        po_hyb_slow<MAXB>(P, f, i);
-        return;
-    }
     const int ti = P.types[i];
     const int Zi = P.Z[ti];
     const double *pos = P.pos + fbase * 3;
@@ -396,6 +357,72 @@ __global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams
             if (k < n && P.Z[P.types[e[k]]] != 1) shortest = fmin(shortest, sqrt(len2_rn(v[k])));
     }
     po_hyb_finish(P, fbase, i, n, h, no, shortest);
+}
+
+
+template <int MAXB>
+__global__ void __launch_bounds__(256) k_po_hyb(const __grid_constant__ PoParams P) {
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    const size_t fbase = (size_t)f * P.N;
+    int e[MAXB];
+    const int4 *row4 = reinterpret_cast<const int4 *>(P.ell + (fbase + i) * MAXB);
+#pragma unroll
+    for (int k = 0; k < MAXB / 4; ++k) {
+        const int4 q = row4[k];
+        e[4 * k] = q.x;
+        e[4 * k + 1] = q.y;
+        e[4 * k + 2] = q.z;
+        e[4 * k + 3] = q.w;
+    }
+    int n = 0;
+    unsigned long long ow[MAXB / 8];
+#pragma unroll
+    for (int w = 0; w < MAXB / 8; ++w) ow[w] = 0ull;
+#pragma unroll
+    for (int k = 0; k < MAXB; ++k)
+        if (e[k] >= 0) {
+            ++n;
+            ow[k / 8] |= 1ull << (8 * (k % 8));
+        }
+    unsigned long long *orow = reinterpret_cast<unsigned long long *>(P.orders + (fbase + i) * MAXB);
+#pragma unroll
+    for (int w = 0; w < MAXB / 8; ++w) orow[w] = ow[w];
+    if (P.labels) {
+        // independent cycles of the batch = bonds - atoms + molecules = sum(deg - 2 + 2 [root]) / 2
+        const int r = n - 2 + 2 * (P.labels[fbase + i] == i);
+        const unsigned m = __activemask();
+        const int sum = __reduce_add_sync(m, r);
+        if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&P.stats->ring_molecules, (unsigned long long)(long long)sum);
+    }
+    // fast path: at most four bonds in the first slots (every C/H/O/N atom after the cleanup)
+    bool compact = n <= 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) compact = compact && ((k < n) == (e[k] >= 0));
+    if (!compact) {
+        po_hyb_slow<MAXB>(P, f, i);
+        return;
+    }
+    // atoms with two or more bonds (angles to take) are compacted into a list and handled by full warps
+    // in k_po_angle; the rest finishes here
+    if (n >= 2) {
+        P.plist[po_append(P.counters + PO_NA)] = (int)(fbase + i);
+        return;
+    }
+    int e4[4] = {e[0], e[1], e[2], e[3]};
+    po_hyb_fast(P, f, i, n, e4);
+}
+
+template <int MAXB>
+__global__ void __launch_bounds__(256) k_po_angle(const __grid_constant__ PoParams P) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.counters[PO_NA]) return;
+    const int f = P.plist[q] / P.N, i = P.plist[q] - f * P.N;
+    const int4 r = *reinterpret_cast<const int4 *>(P.ell + ((size_t)f * P.N + i) * MAXB);
+    int e4[4] = {r.x, r.y, r.z, r.w};
+    const int n = (r.x >= 0) + (r.y >= 0) + (r.z >= 0) + (r.w >= 0);
+    po_hyb_fast(P, f, i, n, e4);
 }
 
 // pass 3 ("antialiasing") only acts on atoms all of whose neighbours already hold hyb 3, which no
@@ -734,6 +761,7 @@ static void po_launch(mdb_ctx *ctx, const PoParams &P, int F, int N, cudaStream_
     {
         ProfScope ps(ctx, "k_po_hyb", stream);
         k_po_hyb<MAXB><<<grid, 256, 0, stream>>>(P);
+        k_po_angle<MAXB><<<(int)cdiv((long long)F * N, 256), 256, 0, stream>>>(P);
     }
     {
         ProfScope ps(ctx, "k_po_groups+carbonyl+pending", stream);
@@ -803,7 +831,7 @@ int perceive_run(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos, con
         po_launch<8>(ctx, P, nframes, natoms, stream);
     else
         po_launch<16>(ctx, P, nframes, natoms, stream);
-    ctx->launches += (d_keys ? 6 : 5) + 2 * PO_ROUNDS;
+    ctx->launches += (d_keys ? 7 : 6) + 2 * PO_ROUNDS;
     MDB_CUDA(cudaGetLastError());
     return 0;
 }

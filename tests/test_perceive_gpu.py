@@ -90,6 +90,32 @@ def test_synthetic_frames_match_the_restatement(engine, natoms, density, sigma, 
     assert nmult > 0, "the sample must exercise multiple bonds"
 
 
+def test_wide_rows_and_triclinic_cell(engine):
+    """max_bonds = 16 rows (the remedy for crowded frames) and a tilted cell go through the same kernels."""
+    s = synth.make_system(1800, 0.07, seed=synth.BASE_SEED + 244, reactive_fraction=0.1)
+    rng = np.random.default_rng(3)
+    pos = s.pos0 + rng.normal(0, 0.08, s.pos0.shape)
+    L = s.box[0]
+    cell = np.array([[L, 0, 0], [0.3 * L, L, 0], [-0.2 * L, 0.25 * L, L]])
+    p = (pos / L) @ cell
+    types = s.types.astype(np.uint8)
+    Z = [ZNUM[s.atomname[t]] for t in types]
+    engine.set_option("max_bonds", 16)
+    try:
+        out = engine.analyze(p[None], cell, types)
+        engine.check()
+        got = engine.perceive(p[None], cell, types, out["ell"], labels=out["labels"])
+        rings = engine.perceive_stats()["rings"]
+        engine.check()
+    finally:
+        engine.set_option("max_bonds", 8)
+    ell = out["ell"].cpu().numpy()[0]
+    assert ell.shape[1] == 16
+    want, info = _oracle_orders(ell, p, Z, cell.reshape(-1), True)
+    assert np.array_equal(want, got["orders"].cpu().numpy()[0])
+    assert rings == info["rings"] and int((want > 1).sum()) > 0
+
+
 def _run_molecule(engine, spec):
     names = ["C", "H", "O"]
     P = np.array([s[1:] for s in spec], dtype=float) + 20.0
