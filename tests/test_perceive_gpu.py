@@ -131,6 +131,14 @@ def _run_molecule(engine, spec):
     return [sorted(int(o) for o in row if o) for row in orders]
 
 
+def test_atoms_without_bonds(engine):
+    """Isolated atoms (the reference's key "O", "H": element with no levels) and the O2 known answers."""
+    assert _run_molecule(engine, [("O", 0, 0, 0)]) == [[]]
+    assert _run_molecule(engine, [("H", 0, 0, 0), ("C", 5.0, 0, 0), ("O", 0, 7.0, 0)]) == [[], [], []]
+    assert _run_molecule(engine, [("O", 0, 0, 0), ("O", 1.0, 1.0, 1.0)]) == [[1], [1]]  # reference tests/test_bond.py:19-20
+    assert _run_molecule(engine, [("O", 0, 0, 0), ("O", 1.21, 0, 0)]) == [[2], [2]]
+
+
 def test_hand_built_molecules(engine):
     s, c = 1.087 * math.sin(math.radians(121.3)), 1.087 * math.cos(math.radians(121.3))
     lv = _run_molecule(engine, [("C", 0, 0, 0), ("C", 1.339, 0, 0), ("H", c, s, 0), ("H", c, -s, 0), ("H", 1.339 - c, s, 0),
