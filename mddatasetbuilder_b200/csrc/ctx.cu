@@ -208,7 +208,8 @@ int build_geometry(mdb_ctx *ctx, int nframes, int natoms, const double *h_cell, 
             memset(cell, 0, sizeof(cell));
             for (int a = 0; a < 3; ++a) {
                 double lo = h_bbox[f * 6 + a], hi = h_bbox[f * 6 + 3 + a];
-                double span = (hi - lo) * (1.0 + 1e-9) + 1e-6;
+                // at least 1 A thick, so that a single atom or a flat molecule still spans a proper box
+                double span = std::max((hi - lo) * (1.0 + 1e-9) + 1e-6, 1.0);
                 cell[a * 3 + a] = span;
                 g.origin[a] = lo;
             }
