@@ -145,7 +145,8 @@ int mdb_analyze_frames_host_coded(mdb_ctx *ctx, int nframes, int natoms, const d
  * [ntargets][ntypes] (the sphere includes the target itself), and updates the
  * running per-element maximum h_maxcount[ntypes] (in/out; the reference's
  * max_counter, datasetbuilder.py:271) -- synchronises.  d_targets: batch-local
- * atom-frame indices f*natoms + i (int32), or NULL for every atom of every frame.
+ * atom-frame indices f*natoms + i (int32), or NULL for every atom of every frame (NULL with
+ * ntargets == 0 is an empty list: nothing is computed).
  * Orthorhombic cells only. */
 int mdb_compositions(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
                      const double *h_cell, const uint8_t *d_types, int periodic, double cutoff,

@@ -23,7 +23,7 @@ static int check_ctx(mdb_ctx *c, const char *fn, bool need_elements = true) {
 static const char *err_text(int e) {
     switch (e) {
         case MDB_ERR_CELL_OVERFLOW:
-            return "more than 255 atoms fell into one cell (overlapping atoms?)";
+            return "more atoms fell into one cell than its rank field can index (at least 255; overlapping atoms?)";
         case MDB_ERR_BOND_OVERFLOW:
             return "an atom has more raw neighbours than max_bonds; set option max_bonds=16";
         case MDB_ERR_CSR_OVERFLOW:

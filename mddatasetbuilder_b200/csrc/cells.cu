@@ -47,11 +47,12 @@ __global__ void __launch_bounds__(256) k_bin(const double *__restrict__ pos, con
     grid_coords(G, periodic, pos[a * 3], pos[a * 3 + 1], pos[a * 3 + 2], u, c);
     int cid = (c[2] * G.n[1] + c[1]) * G.n[0] + c[0];
     int rank = atomicAdd(&cell_count[G.cell_base + cid], 1);
-    if (rank > 255) {
+    const int rmax = (1 << G.rank_bits) - 1;
+    if (rank > rmax) {
         atomicExch(err, MDB_ERR_CELL_OVERFLOW);
-        rank = 255;
+        rank = rmax;
     }
-    cr[a] = ((uint32_t)cid << 8) | (uint32_t)rank;
+    cr[a] = ((uint32_t)cid << G.rank_bits) | (uint32_t)rank;
 }
 
 __global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ pos, const uint8_t *__restrict__ types,
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ pos,
         atomicExch(err, MDB_ERR_TYPE_RANGE);
         t = 0;
     }
-    int slot = cell_start[G.cell_base + (v >> 8)] + (int)(v & 255u);
+    int slot = cell_start[G.cell_base + (v >> G.rank_bits)] + (int)(v & ((1u << G.rank_bits) - 1u));
     float4 r;
     if (rec_mode == 1) {
         // wrapped Angstrom coordinates (diagonal cell): u / n * L per axis

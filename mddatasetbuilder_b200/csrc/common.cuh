@@ -16,7 +16,7 @@
 #define MDB_MAXT 8             // max element types per trajectory
 #define MDB_MAXZ 18
 
-#define MDB_ERR_CELL_OVERFLOW 1  // > 255 atoms in one cell
+#define MDB_ERR_CELL_OVERFLOW 1  // more atoms in one cell than the rank field holds (>= 255)
 #define MDB_ERR_BOND_OVERFLOW 2  // more raw neighbours than max_bonds
 #define MDB_ERR_CSR_OVERFLOW 3
 #define MDB_ERR_TYPE_RANGE 4
@@ -33,6 +33,7 @@ struct FrameGeom {
     long long cell_base;  // first cell of this frame in the batch-wide cell arrays
     int ncell;
     int is_ortho;       // cell matrix is diagonal
+    int rank_bits;      // low bits of the per-atom (cell id, rank) word that hold the rank (>= 8)
 };
 
 struct ElemTables {

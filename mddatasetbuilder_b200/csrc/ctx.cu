@@ -266,6 +266,10 @@ int build_geometry(mdb_ctx *ctx, int nframes, int natoms, const double *h_cell, 
             for (int c = 0; c < 3; ++c) g.h[r * 3 + c] = (float)(g.ortho[r * 3 + c] / g.n[c]);
         g.cell_base = base;
         base += g.ncell;
+        // (cell id, rank within the cell) share 32 bits per atom: frames with few cells (small boxes
+        // under a large cutoff) get the spare bits as rank, i.e. room for more atoms per cell
+        g.rank_bits = 8;
+        while (g.rank_bits < 20 && ((long long)g.ncell << (g.rank_bits + 1)) <= (1LL << 31)) ++g.rank_bits;
     }
     *total_cells = base;
     (void)ctx;

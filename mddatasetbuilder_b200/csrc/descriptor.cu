@@ -25,7 +25,7 @@
 struct DescParams {
     const float4 *rec;
     const uint32_t *ccell;
-    const uint32_t *cr;  // per atom (cell id << 8 | rank within cell)
+    const uint32_t *cr;  // per atom (cell id << rank_bits | rank within cell)
     const int *cell_start;
     const FrameGeom *geom;
     const double *pos;
@@ -80,7 +80,7 @@ __device__ __forceinline__ void sphere_scan(const DescParams &P, int f, int a, V
     const size_t fbase = (size_t)f * P.N;
     const int cbase = (int)G.cell_base;
     const uint32_t v = P.cr[fbase + a];
-    const int slot = P.cell_start[cbase + (int)(v >> 8)] + (int)(v & 255u);
+    const int slot = P.cell_start[cbase + (int)(v >> G.rank_bits)] + (int)(v & ((1u << G.rank_bits) - 1u));
     const float4 me = P.rec[slot];
     const uint32_t cc = P.ccell[slot];
     const int c3[3] = {(int)(cc & 1023u), (int)((cc >> 10) & 1023u), (int)(cc >> 20)};
@@ -1027,7 +1027,16 @@ static int desc_setup(mdb_ctx *c, int F, int N, const double *d_pos, const doubl
             mdb_set_error("the descriptor path supports orthorhombic cells only (triclinic cell in this batch)");
             return -1;
         }
-        for (int v = 0; v < 3; ++v) lmax = std::max(lmax, fabs(g.ortho[v * 4]));
+        for (int v = 0; v < 3; ++v) {
+            lmax = std::max(lmax, fabs(g.ortho[v * 4]));
+            // beyond half an edge a sphere meets two images of one atom, which the reference
+            // (ASE get_distances, mic=True) counts once at its nearer image: not what the scan does
+            if (periodic && 2.0 * cutoff > fabs(g.ortho[v * 4])) {
+                mdb_set_error("cutoff " + std::to_string(cutoff) + " A exceeds half of a cell edge (" +
+                              std::to_string(fabs(g.ortho[v * 4])) + " A): not supported on the descriptor path");
+                return -1;
+            }
+        }
     }
     size_t need = align256(geom.size() * sizeof(FrameGeom)) + (need_cells ? cells_workspace_bytes(F, N, total_cells) : 0) +
                   extra_bytes + 4096;
@@ -1051,7 +1060,8 @@ static int desc_setup(mdb_ctx *c, int F, int N, const double *d_pos, const doubl
     P->pos = d_pos;
     P->types = d_types;
     P->targets = d_targets;
-    P->ntargets = d_targets ? ntargets : (long long)F * N;
+    // NULL = every atom of every frame; NULL with ntargets == 0 is an empty list (nothing to do)
+    P->ntargets = d_targets ? ntargets : (ntargets == 0 ? 0 : (long long)F * N);
     P->N = N;
     P->periodic = periodic;
     P->cutoff = cutoff;
@@ -1243,7 +1253,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
                     const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream,
                     const int *d_members, int memcap) {
     const int nt = c->el.nt;
-    const long long T = d_targets ? ntargets : (long long)F * N;
+    const long long T = d_targets ? ntargets : (ntargets == 0 ? 0 : (long long)F * N);
     if (T == 0) return 0;
     if (T >= (1LL << 31)) {
         mdb_set_error("too many targets in one call");

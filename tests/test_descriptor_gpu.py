@@ -88,6 +88,25 @@ def test_small_box_single_cell_axes(engine):
     _check(engine, s, s.pos0[None], np.arange(100, dtype=np.int32))
 
 
+def test_small_dense_box_more_than_255_atoms_in_the_single_cell(engine):
+    # 300 atoms in a 14.4 A box: one cell per axis under a 5 A cutoff holds the whole frame -- more than the
+    # 8 rank bits of a normal frame index; frames with few cells get wider rank fields
+    s = synth.make_system(300, 0.10, seed=synth.BASE_SEED + 43, dense=True)
+    assert 10.0 < s.box[0] < 15.0
+    _check(engine, s, s.pos0[None], np.arange(0, 300, 3, dtype=np.int32))
+
+
+def test_cutoff_above_half_the_cell_is_refused(engine):
+    s = synth.make_system(60, 0.05, seed=synth.BASE_SEED + 44)
+    engine.set_elements(s.atomname)
+    with pytest.raises(RuntimeError, match="half of a cell edge"):
+        engine.compositions(s.pos0[None], s.cell(), s.types, 0.51 * float(s.box[0]), targets=np.arange(4, dtype=np.int32))
+    # an empty target list is no work, not "every atom"
+    counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, 4.0, targets=np.zeros(0, dtype=np.int32))
+    engine.check()
+    assert tuple(counts.shape) == (0, len(s.atomname)) and not np.any(maxc)
+
+
 def test_large_clusters_every_size_class(engine):
     # dense phase with a 5.4 A cutoff: cluster sizes run past 96, so the register kernels (<= 64 atoms)
     # and both block-per-matrix classes (<= 96, <= 128) are all exercised
