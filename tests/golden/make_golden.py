@@ -39,6 +39,21 @@ def sha(path):
         return hashlib.sha256(f.read()).hexdigest()
 
 
+def split_inputs(dump, bonds, dump_lines, bond_lines, outdir, first=3):
+    """The 6-frame inputs as two files each (3 + 3 frames): ([dump parts], [bond parts])."""
+    out = []
+    for path, n, tag in ((dump, dump_lines, "dump"), (bonds, bond_lines, "bonds")):
+        with open(path) as f:
+            lines = f.readlines()
+        names = [os.path.join(outdir, f"{tag}.part{k}") for k in (1, 2)]
+        with open(names[0], "w") as f:
+            f.writelines(lines[: first * n])
+        with open(names[1], "w") as f:
+            f.writelines(lines[first * n:])
+        out.append(names)
+    return out
+
+
 def main():
     ref = refrun.load()
     from mddatasetbuilder.datasetbuilder import DatasetBuilder
@@ -144,6 +159,20 @@ def main():
                     else:
                         manifest[os.path.relpath(os.path.join(dirpath, fn), tmp)] = sha(os.path.join(dirpath, fn))
         g["e2e_dump"] = {"atombondtype": list(b.atombondtype), "nstructure": int(b._nstructure), "manifest": manifest}
+        # end-to-end, the trajectory given as two files each (the reference strides within every file,
+        # datasetbuilder.py:629-638), clustering switched off by n_clusters
+        shutil.rmtree(b.dataset_dir)
+        shutil.rmtree(b.gjfdir)
+        parts = split_inputs(dump, bonds, dd.steplinenum, db.steplinenum, tmp)
+        b = DatasetBuilder(atomname=list(s.atomname), bondfilename=parts[1], dumpfilename=parts[0], dataset_name="goldparts",
+                           cutoff=4.5, stepinterval=2, n_clusters=10000, nproc=1)
+        b.builddataset()
+        manifest = {}
+        for base in (b.dataset_dir, b.gjfdir):
+            for dirpath, _, files in os.walk(base):
+                for fn in files:
+                    manifest[os.path.relpath(os.path.join(dirpath, fn), tmp)] = sha(os.path.join(dirpath, fn))
+        g["e2e_parts"] = {"atombondtype": list(b.atombondtype), "nstructure": int(b._nstructure), "manifest": manifest}
     finally:
         os.chdir(cwd)
         shutil.rmtree(tmp, ignore_errors=True)
