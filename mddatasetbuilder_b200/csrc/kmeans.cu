@@ -446,10 +446,18 @@ struct KppState {
 __device__ __forceinline__ void kpp_select_pick_body(long long n, int T, int Tprev, int c, int K,
                                                      const double *__restrict__ rnd, const double *partial, int nblk,
                                                      const double *dist, int *cand, int *indices, KppState *st, double *s_dyn,
-                                                     double *s_pot, int *s_best) {
+                                                     double *s_pot, int *s_best, int *s_cand, double *s_rnd) {
     double *s_pre = s_dyn;               // [nblk + 1] prefix of the block sums of dist[best]
     double *s_par = s_dyn + (nblk + 1);  // [Tprev][nblk] partials, one row per candidate
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    // the previous step's candidates and this step's variates travel with the first round trip
+    // instead of costing one of their own later (s_cand: old candidates in, new candidates out)
+    if (tid < KPP_MAXT) {
+        const int oldc = tid < Tprev ? __ldcg(cand + tid) : 0;
+        const double u = (tid < T && c < K) ? rnd[(size_t)(c - 1) * T + tid] : 0.0;
+        s_cand[tid] = oldc;
+        s_rnd[tid] = u;
+    }
     for (int q = tid; q < nblk * Tprev; q += blockDim.x) {
         const int t = q / nblk, b = q - t * nblk;
         s_par[q] = __ldcg(partial + (size_t)b * KPP_MAXT + t);
@@ -470,7 +478,7 @@ __device__ __forceinline__ void kpp_select_pick_body(long long n, int T, int Tpr
             if (s_pot[t] < s_pot[best]) best = t;
         *s_best = best;
         st->best = best;
-        indices[c - 1] = __ldcg(cand + best);
+        indices[c - 1] = s_cand[best];
         s_pre[0] = 0.0;
     }
     __syncthreads();
@@ -493,7 +501,7 @@ __device__ __forceinline__ void kpp_select_pick_body(long long n, int T, int Tpr
     if (c >= K) return;  // the last call only selects
     const int best = *s_best;
     for (int t = warp; t < T; t += nwarps) {
-        const double r = rnd[(size_t)(c - 1) * T + t] * s_pot[best];
+        const double r = s_rnd[t] * s_pot[best];
         // block whose cumulative range holds r: first b with pre[b + 1] >= r
         int lo = 0, hi = nblk;
         while (lo < hi) {
@@ -531,7 +539,10 @@ __device__ __forceinline__ void kpp_select_pick_body(long long n, int T, int Tpr
                 pick = min(n - 1, (long long)lo * 256 + 256);  // rounding left r just past this block's rows
             }
         }
-        if (lane == 0) cand[t] = (int)pick;
+        if (lane == 0) {
+            cand[t] = (int)pick;
+            s_cand[t] = (int)pick;
+        }
     }
 }
 
@@ -548,9 +559,9 @@ __global__ void __launch_bounds__(1024) k_kpp_select_pick(long long n, int T, in
     indices += (size_t)blockIdx.y * K;
     st += blockIdx.y;
     extern __shared__ double s_dyn[];
-    __shared__ double s_pot[KPP_MAXT];
-    __shared__ int s_best;
-    kpp_select_pick_body(n, T, Tprev, c, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best);
+    __shared__ double s_pot[KPP_MAXT], s_rnd[KPP_MAXT];
+    __shared__ int s_best, s_cand[KPP_MAXT];
+    kpp_select_pick_body(n, T, Tprev, c, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best, s_cand, s_rnd);
 }
 
 // squared distances of the T candidate rows to every row as scikit-learn takes them in
@@ -704,8 +715,8 @@ __global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict
     unsigned *tickets = sync + blockIdx.y * 64;   // per problem: ticket counter and step flag, a cache line apart
     unsigned *flag = tickets + 32;
     extern __shared__ double s_dyn[];
-    __shared__ double s_pot[KPP_MAXT];
-    __shared__ int s_best;
+    __shared__ double s_pot[KPP_MAXT], s_rnd[KPP_MAXT];
+    __shared__ int s_best, s_cand[KPP_MAXT];
     __shared__ int s_last;
     for (int ch = blockIdx.x; ch < nblk; ch += nb)
         kpp_dist_body<TMAX>(X, ldx, rowidx, n, D, cand, 1, 1, st, dist, partial + (size_t)ch * KPP_MAXT, s_dyn, ch,
@@ -726,13 +737,13 @@ __global__ void __launch_bounds__(256) k_kpp_persistent(const double *__restrict
         __syncthreads();
         if (s_last) {
             __threadfence();
-            kpp_select_pick_body(n, T, Tprev, step, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best);
+            kpp_select_pick_body(n, T, Tprev, step, K, rnd, partial, nblk, dist, cand, indices, st, s_dyn, s_pot, &s_best,
+                                 s_cand, s_rnd);
             __syncthreads();
-            if (step < K)
+            if (step < K)  // the new candidates' rows, from the feature-major copy (no row-index hop)
                 for (int q = threadIdx.x; q < T * D; q += 256) {
                     const int t = q / D, k = q - t * D;
-                    const int ci = __ldcg(cand + t);
-                    crows[q] = X[(rowidx ? (long long)rowidx[ci] : (long long)ci) * ldx + k];
+                    crows[q] = xt[(size_t)k * n + s_cand[t]];
                 }
             __syncthreads();
             if (threadIdx.x == 0) {
