@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_members(const __grid_constant__ DescPar
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6a, clusters of 65..128 atoms: one thread block per matrix, matrix in shared memory.  Two threads
+// K6a, clusters of 65..160 atoms: one thread block per matrix, matrix in shared memory.  Two threads
 // share a row (even / odd columns), so the matrix-vector product and the rank-2 update are split
 // over 2 n threads; the row stride NMAX + 2 keeps the accesses of a half-warp on distinct banks.
 // Same step as the register kernels below (one fused reduction of (sigma, x.T x) per step); output is
@@ -977,10 +977,10 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     }
 }
 
-// bucket id by cluster size: classes of 4 up to 32 atoms, of 8 up to 64 (register-resident kernels), then 96 and 128
-#define DESC_NB 13
+// bucket id by cluster size: classes of 4 up to 32 atoms, of 8 up to 64 (register-resident kernels), then 96, 128 and 160
+#define DESC_NB 14
 __device__ __host__ __forceinline__ int desc_bucket(int n) {
-    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 + ((n - 33) >> 3) : n <= 96 ? 11 : n <= 128 ? 12 : DESC_NB;
+    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 + ((n - 33) >> 3) : n <= 96 ? 11 : n <= 128 ? 12 : n <= 160 ? 13 : DESC_NB;
 }
 
 __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ counts, int nt, long long ntargets,
@@ -1200,7 +1200,8 @@ static const char *bucket_name(int nmax, bool tql) {
         case 56: return tql ? "k_tql<56>" : "k_tridiag_reg2<56>";
         case 64: return tql ? "k_tql<64>" : "k_tridiag_reg2<64>";
         case 96: return tql ? "k_tql<96>" : "k_tridiag_blk<96>";
-        default: return tql ? "k_tql<128>" : "k_tridiag_blk<128>";
+        case 128: return tql ? "k_tql<128>" : "k_tridiag_blk<128>";
+        default: return tql ? "k_tql<160>" : "k_tridiag_blk<160>";
     }
 }
 
@@ -1261,7 +1262,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     }
     const int chunk = 1 << 16;
     // scratch: bucket bookkeeping + lists + d/e for one chunk at the largest NMAX in use
-    size_t extra = align256(T * sizeof(int)) * 2 + align256((size_t)chunk * 128 * sizeof(double)) * 2 +
+    size_t extra = align256(T * sizeof(int)) * 2 + align256((size_t)chunk * 160 * sizeof(double)) * 2 +
                    align256((size_t)chunk * sizeof(int)) + 16 * 256;
     DescParams P;
     if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, extra, d_members == nullptr))
@@ -1270,8 +1271,8 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     P.memcap = d_members ? memcap : 0;
     int *d_nsum = (int *)arena_alloc(c, T * sizeof(int));
     int *d_list = (int *)arena_alloc(c, T * sizeof(int));
-    double *dsc = (double *)arena_alloc(c, (size_t)chunk * 128 * sizeof(double));
-    double *esc = (double *)arena_alloc(c, (size_t)chunk * 128 * sizeof(double));
+    double *dsc = (double *)arena_alloc(c, (size_t)chunk * 160 * sizeof(double));
+    double *esc = (double *)arena_alloc(c, (size_t)chunk * 160 * sizeof(double));
     int *nsc = (int *)arena_alloc(c, (size_t)chunk * sizeof(int));
     int *d_book = (int *)arena_alloc(c, 256);            // bucket_n[16] | cursor[16] | ofs[16]
     int *d_maxcount = (int *)arena_alloc(c, 256);
@@ -1305,7 +1306,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     MDB_CUDA(cudaMemcpyAsync(hb, d_book, sizeof(hb), cudaMemcpyDeviceToHost, stream));
     MDB_CUDA(cudaStreamSynchronize(stream));
     if (hb[DESC_NB] > 0) {
-        mdb_set_error("a cutoff sphere holds more than 128 atoms; reduce the cutoff");
+        mdb_set_error("a cutoff sphere holds more than 160 atoms; reduce the cutoff");
         return -1;
     }
     int ofs[DESC_NB + 1];
@@ -1331,6 +1332,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     MDB_BUCKET(10, 64, 4, 32, 64, 2)
     MDB_BUCKET(11, 96, 1, 32, 64, 0)
     MDB_BUCKET(12, 128, 1, 32, 64, 0)
+    MDB_BUCKET(13, 160, 1, 32, 64, 0)
 #undef MDB_BUCKET
     return 0;
 }

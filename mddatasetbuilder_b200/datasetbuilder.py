@@ -400,9 +400,9 @@ class DatasetBuilder:
                         eng.check()
                         break
                     except RuntimeError as e:
-                        if "(2)" not in str(e) or cap >= 128:   # 2 = a list overflowed its capacity
+                        if "(2)" not in str(e) or cap >= 160:   # 2 = a list overflowed its capacity
                             raise
-                        cap = min(128, cap * 2)
+                        cap = min(160, cap * 2)
                 maxc = maxc_new
                 nmax = max(int(counts.sum(dim=1).max().item()), 1)
                 out = eng.descriptors(pos, cell, d_types, self.cutoff, counts, maxc, targets=targets, periodic=self.pbc,

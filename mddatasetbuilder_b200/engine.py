@@ -274,7 +274,7 @@ class Engine:
         return [m[k, : min(n[k], cap)] for k in range(T)]
 
     def descriptors(self, pos, cell, types, cutoff, counts, maxcount, targets=None, periodic=True, want_X=True,
-                    want_eig=False, eigcap=128, members=None):
+                    want_eig=False, eigcap=160, members=None):
         """Coulomb-matrix spectrum + padded sorted feature rows (datasetbuilder.py:236-349).
         members = the lists from `compositions(members_cap=...)` for the same targets: the cluster is
         then gathered from them (no cell list, `cutoff` unused)."""

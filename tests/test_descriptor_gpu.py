@@ -120,6 +120,21 @@ def test_large_clusters_every_size_class(engine):
     assert worst < 1.0
 
 
+def test_clusters_up_to_160_atoms_and_the_limit(engine):
+    # 5.9 A in the dense phase: the largest class (<= 160 atoms); 7.5 A goes past it and is refused
+    s = synth.make_system(1500, 0.11, seed=synth.BASE_SEED + 47, dense=True)
+    targets = np.arange(0, 1500, 5, dtype=np.int32)
+    engine.set_elements(s.atomname)
+    counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, 5.9, targets=targets)
+    n = counts.sum(dim=1).cpu().numpy()
+    assert n.max() > 128 and n.max() <= 160, (n.min(), n.max())
+    worst = _check(engine, s, s.pos0[None], targets, cutoff=5.9)
+    assert worst < 1.0
+    counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, 7.5, targets=targets[:8])
+    with pytest.raises(RuntimeError, match="more than 160 atoms"):
+        engine.descriptors(s.pos0[None], s.cell(), s.types, 7.5, counts, maxc, targets=targets[:8])
+
+
 def test_descriptors_are_reproducible_bit_for_bit(engine):
     # the matrix is built in ascending atom index whatever order the cell scan delivered the members in,
     # so two runs (whose cell lists are filled in different atomic orders) give identical rows
