@@ -1,6 +1,14 @@
-"""Module entry point (reference __main__.py:1-6)."""
+"""``python -m mddatasetbuilder_b200``: runs the ``datasetbuilder`` command line on the B200 path."""
 
-from .datasetbuilder import _commandline
+import sys
+
+from . import datasetbuilder
+
+
+def main() -> int:
+    datasetbuilder._commandline()
+    return 0
+
 
 if __name__ == "__main__":
-    _commandline()
+    sys.exit(main())
