@@ -139,6 +139,18 @@ int mdb_analyze_frames_host_coded(mdb_ctx *ctx, int nframes, int natoms, const d
                                   int32_t *h_ell, int ell_width, uint8_t *h_keycode,
                                   uint64_t *h_keytable, int32_t *h_labels);
 
+/* Same pipeline with the bonds returned as a list instead of rows: h_edges [edge_cap][2] receives every
+ * bond once as (i, j), i < j (frame-local 0-based indices, ascending i then j), the bonds of frame f at
+ * h_edge_ptr[f] .. h_edge_ptr[f+1] (h_edge_ptr [nframes + 1]) -- the shape in which the reference walks
+ * them, `for b in OBMolBondIter(mol)` (detect.py:282-291) or the id / partner columns of a bond file.
+ * About 8 bytes per bond instead of 16 per atom take the device-to-host copy off the PCIe critical path
+ * (a chunk's copy is sized after its kernels finished; the next chunk is already queued by then).
+ * h_keycode / h_keytable / h_labels as above, each may be NULL.  A too small edge_cap is an error. */
+int mdb_analyze_frames_host_edges(mdb_ctx *ctx, int nframes, int natoms, const double *h_pos,
+                                  const double *h_cell, const uint8_t *h_types, int periodic,
+                                  int32_t *h_edges, long long edge_cap, long long *h_edge_ptr,
+                                  uint8_t *h_keycode, uint64_t *h_keytable, int32_t *h_labels);
+
 /* ---- K5: element composition of the cutoff sphere -----------------------------
  * Replaces, per target atom, `distances = get_distances(a, all, mic=True);
  * Counter(symbols[distances < cutoff])` (datasetbuilder.py:312-322): d_counts

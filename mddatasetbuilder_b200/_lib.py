@@ -34,6 +34,8 @@ SIGNATURES = {
     "mdb_components": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
     "mdb_dps": (C.c_int, [c_ctx, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp]),
     "mdb_analyze_frames": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "mdb_analyze_frames_host_edges": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp,
+                                                _vp]),
     "mdb_analyze_frames_host": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "mdb_analyze_frames_host_coded": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp,
                                                 _vp]),

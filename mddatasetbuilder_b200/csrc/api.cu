@@ -459,6 +459,37 @@ __global__ void __launch_bounds__(256) k_ell_narrow(const int32_t *__restrict__ 
     *reinterpret_cast<int4 *>(out + a * 4) = q;
 }
 
+// Bond list of a chunk as (i, j) pairs with i < j, by ascending i then j (frame-local indices): what
+// iterating the bonds of the reference's OBMol yields (detect.py:282-291), each bond once.
+__global__ void __launch_bounds__(256) k_edge_count(const int32_t *__restrict__ ell, int maxb, int N, long long fn,
+                                                    int *__restrict__ cnt) {
+    long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a > fn) return;
+    int c = 0;
+    if (a < fn) {
+        const int i = (int)(a % N);
+        for (int k = 0; k < maxb; ++k) c += ell[a * maxb + k] > i;
+    }
+    cnt[a] = c;
+}
+
+__global__ void __launch_bounds__(256) k_edge_fill(const int32_t *__restrict__ ell, int maxb, int N, long long fn,
+                                                   const int *__restrict__ ofs, int2 *__restrict__ edges) {
+    long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= fn) return;
+    const int i = (int)(a % N);
+    int o = ofs[a];
+    for (int k = 0; k < maxb; ++k) {
+        const int e = ell[a * maxb + k];
+        if (e > i) edges[o++] = make_int2(i, e);
+    }
+}
+
+__global__ void k_frame_offsets(const int *__restrict__ ofs, int N, int F, int *__restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f <= F) out[f] = ofs[(size_t)f * N];
+}
+
 struct PipeBuf {
     double *pos = nullptr;
     int32_t *ell = nullptr;
@@ -466,6 +497,10 @@ struct PipeBuf {
     uint64_t *keys = nullptr;
     int32_t *labels = nullptr;
     uint8_t *code = nullptr;
+    int *ecnt = nullptr;    // edge-list output: per atom-frame offsets (after the scan), [cn + 1]
+    int2 *edges = nullptr;  // [cn * max_bonds / 2]
+    void *escan = nullptr;  // scan scratch
+    int *fofs = nullptr;    // per-frame offsets [per + 1]
 };
 
 // keys -> one-byte codes through a 256-slot open-addressing dictionary shared by the whole call
@@ -490,7 +525,9 @@ __global__ void __launch_bounds__(256) k_key_encode(const uint64_t *__restrict__
 
 static int analyze_host_impl(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
                              const uint8_t *h_types, int periodic, int32_t *h_ell, int ell_width, uint64_t *h_keys,
-                             uint8_t *h_keycode, uint64_t *h_keytable, int32_t *h_labels) {
+                             uint8_t *h_keycode, uint64_t *h_keytable, int32_t *h_labels, int32_t *h_edges = nullptr,
+                             long long edge_cap = 0, long long *h_edge_ptr = nullptr) {
+    if (h_edge_ptr) h_edge_ptr[0] = 0;
     if (nframes <= 0 || natoms <= 0) return 0;
     const int maxb = c->opt_max_bonds;
     // the host path pipelines copies against compute, so it wants more, smaller chunks than the device
@@ -509,7 +546,12 @@ static int analyze_host_impl(mdb_ctx *c, int nframes, int natoms, const double *
     }
     const bool narrow = ell_width == 4 && maxb != 4;
     const size_t sz_ell4 = narrow ? align256(cn * 4 * sizeof(int32_t)) : 0;
-    const size_t need = sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4 + sz_code;
+    // edge-list output: counts / offsets, the pairs, scan scratch and per-frame offsets ride in the same buffers
+    const size_t sz_ecnt = h_edges ? align256((cn + 16) * sizeof(int)) : 0,
+                 sz_edges = h_edges ? align256(cn * (size_t)(maxb / 2) * sizeof(int2)) : 0,
+                 sz_escan = h_edges ? align256(scan_scratch_bytes((long long)cn + 1)) : 0,
+                 sz_fofs = h_edges ? align256(((size_t)per + 1) * sizeof(int)) : 0;
+    const size_t need = sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4 + sz_code + sz_ecnt + sz_edges + sz_escan + sz_fofs;
     PipeBuf b[2];
     for (int k = 0; k < 2; ++k) {
         if (c->pipe_cap[k] < need) {
@@ -527,6 +569,18 @@ static int analyze_host_impl(mdb_ctx *c, int nframes, int natoms, const double *
         b[k].labels = (int32_t *)(m + sz_pos + sz_ell + sz_keys);
         b[k].ell4 = (int32_t *)(m + sz_pos + sz_ell + sz_keys + sz_lab);
         b[k].code = (uint8_t *)(m + sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4);
+        char *e = m + sz_pos + sz_ell + sz_keys + sz_lab + sz_ell4 + sz_code;
+        b[k].ecnt = (int *)e;
+        b[k].edges = (int2 *)(e + sz_ecnt);
+        b[k].escan = e + sz_ecnt + sz_edges;
+        b[k].fofs = (int *)(e + sz_ecnt + sz_edges + sz_escan);
+        if (h_edges && c->pipe_hofs_cap[k] < (size_t)per + 1) {
+            if (c->pipe_hofs[k]) MDB_CUDA(cudaFreeHost(c->pipe_hofs[k]));
+            c->pipe_hofs[k] = nullptr;
+            c->pipe_hofs_cap[k] = 0;
+            MDB_CUDA(cudaMallocHost(&c->pipe_hofs[k], ((size_t)per + 1) * sizeof(int)));
+            c->pipe_hofs_cap[k] = (size_t)per + 1;
+        }
     }
     // the dictionary lives behind the code bytes of buffer 0
     unsigned long long *d_table = h_keycode ? (unsigned long long *)(b[0].code + align256(cn)) : nullptr;
@@ -541,7 +595,40 @@ static int analyze_host_impl(mdb_ctx *c, int nframes, int natoms, const double *
     MDB_CUDA(cudaMemcpyAsync(c->pipe_types, h_types, natoms, cudaMemcpyHostToDevice, s_c));
     MDB_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(BondStats), s_c));
     if (d_table) MDB_CUDA(cudaMemsetAsync(d_table, 0xFF, 256 * sizeof(uint64_t), s_c));
-    int chunk = 0;
+    long long edges_total = 0;
+    int emit_err = 0;
+    // device -> host copies of one finished chunk.  With the edge list the size of the copy is only known
+    // once the chunk has been computed, so that chunk's copies are issued one iteration later (the next
+    // chunk's input copy and kernels are already queued by then: nothing idles while the host waits).
+    auto emit = [&](int f0, int F, int k) -> int {
+        PipeBuf &B = b[k];
+        const size_t o = (size_t)f0 * natoms, n = (size_t)F * natoms;
+        MDB_CUDA(cudaStreamWaitEvent(s_out, c->pipe_comp[k], 0));
+        if (h_edges) {
+            MDB_CUDA(cudaEventSynchronize(c->pipe_comp[k]));
+            const int *hf = c->pipe_hofs[k];
+            const long long E = hf[F];
+            if (edges_total + E > edge_cap) {
+                mdb_set_error("mdb_analyze_frames_host_edges: edge capacity " + std::to_string(edge_cap) + " is too small");
+                emit_err = 1;
+                return -1;
+            }
+            for (int f = 0; f < F; ++f) h_edge_ptr[f0 + f + 1] = edges_total + hf[f + 1];
+            if (E) MDB_CUDA(cudaMemcpyAsync(h_edges + 2 * edges_total, B.edges, (size_t)E * sizeof(int2), cudaMemcpyDeviceToHost, s_out));
+            edges_total += E;
+        } else if (h_ell && narrow) {
+            MDB_CUDA(cudaMemcpyAsync(h_ell + o * 4, B.ell4, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        } else if (h_ell) {
+            MDB_CUDA(cudaMemcpyAsync(h_ell + o * maxb, B.ell, n * maxb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        }
+        if (h_keys) MDB_CUDA(cudaMemcpyAsync(h_keys + o, B.keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_out));
+        if (h_keycode) MDB_CUDA(cudaMemcpyAsync(h_keycode + o, B.code, n, cudaMemcpyDeviceToHost, s_out));
+        if (h_labels)
+            MDB_CUDA(cudaMemcpyAsync(h_labels + o, B.labels, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        MDB_CUDA(cudaEventRecord(c->pipe_out[k], s_out));
+        return 0;
+    };
+    int chunk = 0, prev_f0 = -1, prev_F = 0;
     for (int f0 = 0; f0 < nframes; f0 += per, ++chunk) {
         const int F = std::min(per, nframes - f0);
         const size_t o = (size_t)f0 * natoms, n = (size_t)F * natoms;
@@ -561,28 +648,38 @@ static int analyze_host_impl(mdb_ctx *c, int nframes, int natoms, const double *
             k_key_encode<<<cdiv((long long)n, 256), 256, 0, s_c>>>(B.keys, (long long)n, d_table, B.code, c->d_stats);
             c->launches++;
         }
-        if (h_ell && narrow) {
+        if (h_ell && narrow && !h_edges) {
             k_ell_narrow<<<cdiv((long long)n, 256), 256, 0, s_c>>>(B.ell, maxb, 4, (long long)n, B.ell4, c->d_stats);
             c->launches++;
         }
+        if (h_edges) {
+            k_edge_count<<<cdiv((long long)n + 1, 256), 256, 0, s_c>>>(B.ell, maxb, natoms, (long long)n, B.ecnt);
+            if (device_exclusive_scan(c, B.ecnt, (long long)n + 1, B.escan, s_c)) {
+                cudaDeviceSynchronize();
+                return -1;
+            }
+            k_edge_fill<<<cdiv((long long)n, 256), 256, 0, s_c>>>(B.ell, maxb, natoms, (long long)n, B.ecnt, B.edges);
+            k_frame_offsets<<<cdiv(F + 1, 256), 256, 0, s_c>>>(B.ecnt, natoms, F, B.fofs);
+            c->launches += 3;
+            MDB_CUDA(cudaMemcpyAsync(c->pipe_hofs[k], B.fofs, ((size_t)F + 1) * sizeof(int), cudaMemcpyDeviceToHost, s_c));
+        }
         MDB_CUDA(cudaEventRecord(c->pipe_comp[k], s_c));
-        MDB_CUDA(cudaStreamWaitEvent(s_out, c->pipe_comp[k], 0));
-        if (h_ell && narrow)
-            MDB_CUDA(cudaMemcpyAsync(h_ell + o * 4, B.ell4, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
-        else if (h_ell)
-            MDB_CUDA(cudaMemcpyAsync(h_ell + o * maxb, B.ell, n * maxb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
-        if (h_keys) MDB_CUDA(cudaMemcpyAsync(h_keys + o, B.keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_out));
-        if (h_keycode) MDB_CUDA(cudaMemcpyAsync(h_keycode + o, B.code, n, cudaMemcpyDeviceToHost, s_out));
-        if (h_labels)
-            MDB_CUDA(cudaMemcpyAsync(h_labels + o, B.labels, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
-        MDB_CUDA(cudaEventRecord(c->pipe_out[k], s_out));
+        if (h_edges) {
+            if (prev_f0 >= 0 && emit(prev_f0, prev_F, k ^ 1)) break;
+            prev_f0 = f0;
+            prev_F = F;
+        } else if (emit(f0, F, k)) {
+            break;
+        }
     }
+    if (h_edges && !emit_err && prev_f0 >= 0) emit(prev_f0, prev_F, (chunk - 1) & 1);
     MDB_CUDA(cudaStreamSynchronize(s_in));
     MDB_CUDA(cudaStreamSynchronize(s_c));
     MDB_CUDA(cudaStreamSynchronize(s_out));
     if (h_keycode && h_keytable) MDB_CUDA(cudaMemcpy(h_keytable, d_table, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     BondStats hs;
     MDB_CUDA(cudaMemcpy(&hs, c->d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    if (emit_err) return -1;
     if (hs.err) {
         mdb_set_error(std::string("mdb_analyze_frames_host: ") + err_text(hs.err));
         return hs.err;
@@ -596,6 +693,19 @@ extern "C" int mdb_analyze_frames_host(mdb_ctx *c, int nframes, int natoms, cons
     if (check_ctx(c, "mdb_analyze_frames_host")) return -1;
     return analyze_host_impl(c, nframes, natoms, h_pos, h_cell, h_types, periodic, h_ell, ell_width, h_keys, nullptr, nullptr,
                              h_labels);
+}
+
+extern "C" int mdb_analyze_frames_host_edges(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,
+                                             const uint8_t *h_types, int periodic, int32_t *h_edges, long long edge_cap,
+                                             long long *h_edge_ptr, uint8_t *h_keycode, uint64_t *h_keytable,
+                                             int32_t *h_labels) {
+    if (check_ctx(c, "mdb_analyze_frames_host_edges")) return -1;
+    if (!h_edges || !h_edge_ptr || edge_cap < 0 || (h_keycode && !h_keytable)) {
+        mdb_set_error("mdb_analyze_frames_host_edges: h_edges and h_edge_ptr are required (and h_keytable with h_keycode)");
+        return -1;
+    }
+    return analyze_host_impl(c, nframes, natoms, h_pos, h_cell, h_types, periodic, nullptr, 0, nullptr, h_keycode, h_keytable,
+                             h_labels, h_edges, edge_cap, h_edge_ptr);
 }
 
 extern "C" int mdb_analyze_frames_host_coded(mdb_ctx *c, int nframes, int natoms, const double *h_pos, const double *h_cell,

@@ -83,6 +83,8 @@ struct mdb_ctx {
     cudaEvent_t pipe_in[2] = {}, pipe_comp[2] = {}, pipe_out[2] = {};
     uint8_t *pipe_types = nullptr;
     size_t pipe_types_cap = 0;
+    int *pipe_hofs[2] = {};  // page-locked per-frame edge offsets of the chunk in flight (edge-list host output)
+    size_t pipe_hofs_cap[2] = {};
     // operands / results of the tensor-core assignment (grow-only)
     char *tc_mem = nullptr;
     size_t tc_bytes = 0;

@@ -74,6 +74,7 @@ extern "C" void mdb_destroy(mdb_ctx *c) {
     }
     for (int i = 0; i < 2; ++i) {
         if (c->pipe_mem[i]) cudaFree(c->pipe_mem[i]);
+        if (c->pipe_hofs[i]) cudaFreeHost(c->pipe_hofs[i]);
         if (c->pipe_in[i]) cudaEventDestroy(c->pipe_in[i]);
         if (c->pipe_comp[i]) cudaEventDestroy(c->pipe_comp[i]);
         if (c->pipe_out[i]) cudaEventDestroy(c->pipe_out[i]);

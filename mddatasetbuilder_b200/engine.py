@@ -429,11 +429,12 @@ class Engine:
         _lib.check(rc, "mdb_kmeans_apply_update")
 
     def analyze_host(self, pos, cell, types, periodic=True, want_keys=True, want_labels=True, out=None,
-                     ell_width=0, key_codes=False):
+                     ell_width=0, key_codes=False, edges=False):
         """Host-buffer path (e2e): numpy / pinned tensors in, numpy out; H2D and D2H copies
         are pipelined inside the library.  key_codes=True returns the bond-type keys as one byte per
         atom ("keycode") plus the dictionary "keytable" (256 x uint64, unused = all ones) instead of
-        "keys"."""
+        "keys".  edges=True (implies key codes) returns the bonds as a list, each once: "edges" [E, 2] with
+        i < j and "edge_ptr" [F + 1] (frame f owns edges[edge_ptr[f]:edge_ptr[f + 1]]) instead of "ell"."""
         torch = _torch()
         if isinstance(pos, torch.Tensor):
             pos_np = pos.numpy()
@@ -446,7 +447,7 @@ class Engine:
         cells = self._cells(cell, F) if periodic else None
         out = out or {}
         ell = out.get("ell")
-        if ell is None:
+        if ell is None and not edges:
             ell = np.empty((F, N, ell_width or self.max_bonds), dtype=np.int32)
         labels = out.get("labels") if want_labels else None
         if want_labels and labels is None:
@@ -457,6 +458,25 @@ class Engine:
                 return C.c_void_p(0)
             return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else C.c_void_p(a.ctypes.data)
 
+        if edges:
+            ebuf = out.get("edges")
+            if ebuf is None:
+                ebuf = np.empty((F * N * 2, 2), dtype=np.int32)   # room for an average degree of 4
+            eptr = out.get("edge_ptr")
+            if eptr is None:
+                eptr = np.empty(F + 1, dtype=np.int64)
+            code = out.get("keycode") if want_keys else None
+            if want_keys and code is None:
+                code = np.empty((F, N), dtype=np.uint8)
+            table = out.get("keytable") if want_keys else None
+            if want_keys and table is None:
+                table = np.empty(256, dtype=np.uint64)
+            ecap = int(ebuf.shape[0]) if not isinstance(ebuf, torch.Tensor) else int(ebuf.shape[0])
+            rc = self.L.mdb_analyze_frames_host_edges(self.ctx, int(F), int(N), p(pos_np), _np_ptr(cells), p(types_np),
+                                                      int(bool(periodic)), p(ebuf), ecap, p(eptr), p(code), p(table),
+                                                      p(labels))
+            _lib.check(rc, "mdb_analyze_frames_host_edges")
+            return {"edges": ebuf, "edge_ptr": eptr, "keycode": code, "keytable": table, "labels": labels}
         if key_codes:
             code = out.get("keycode")
             if code is None:

@@ -158,6 +158,23 @@ def test_host_path_matches_device_path(engine):
     used = table != np.uint64(0xFFFFFFFFFFFFFFFF)
     assert set(table[used].tolist()) == set(np.unique(host["keys"]).tolist())
     assert np.array_equal(coded["labels"], host["labels"]) and np.array_equal(coded["ell"], narrow["ell"])
+    # the bond list (every bond once, i < j, by ascending i then j) holds exactly the bonds of the rows
+    for per in (1, 3, 100):
+        engine.set_option("frames_per_launch", per)
+        try:
+            el = engine.analyze_host(frames, s.cell(), s.types, edges=True)
+        finally:
+            engine.set_option("frames_per_launch", 0)
+        ptr = el["edge_ptr"]
+        assert ptr[0] == 0 and np.all(np.diff(ptr) >= 0)
+        for f in range(frames.shape[0]):
+            i, k = np.nonzero(full[f] >= 0)
+            j = full[f][i, k]
+            want = np.stack([i[j > i], j[j > i]], axis=1)
+            assert np.array_equal(el["edges"][ptr[f]:ptr[f + 1]], want)
+        assert np.array_equal(el["labels"], host["labels"]) and np.array_equal(el["keytable"][el["keycode"]], host["keys"])
+    with pytest.raises(RuntimeError, match="edge capacity"):
+        engine.analyze_host(frames, s.cell(), s.types, edges=True, out={"edges": np.empty((10, 2), dtype=np.int32)})
 
 
 def test_bondfile_keys(engine):
