@@ -659,9 +659,9 @@ static int analyze_host_impl(mdb_ctx *c, int nframes, int natoms, const double *
                 return -1;
             }
             k_edge_fill<<<cdiv((long long)n, 256), 256, 0, s_c>>>(B.ell, maxb, natoms, (long long)n, B.ecnt, B.edges);
-            k_frame_offsets<<<cdiv(F + 1, 256), 256, 0, s_c>>>(B.ecnt, natoms, F, B.fofs);
+            // written straight into page-locked host memory (unified addressing): no copy-engine queueing
+            k_frame_offsets<<<cdiv(F + 1, 256), 256, 0, s_c>>>(B.ecnt, natoms, F, c->pipe_hofs[k]);
             c->launches += 3;
-            MDB_CUDA(cudaMemcpyAsync(c->pipe_hofs[k], B.fofs, ((size_t)F + 1) * sizeof(int), cudaMemcpyDeviceToHost, s_c));
         }
         MDB_CUDA(cudaEventRecord(c->pipe_comp[k], s_c));
         if (h_edges) {

@@ -277,6 +277,10 @@ int build_geometry(mdb_ctx *ctx, int nframes, int natoms, const double *h_cell, 
     return 0;
 }
 
+__global__ void k_copy_words(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t nwords) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 int upload_geometry(mdb_ctx *c, const std::vector<FrameGeom> &g, FrameGeom *d_geom, cudaStream_t stream) {
     int slot = c->ring_pos;
     c->ring_pos = (c->ring_pos + 1) % mdb_ctx::kRing;
@@ -289,7 +293,12 @@ int upload_geometry(mdb_ctx *c, const std::vector<FrameGeom> &g, FrameGeom *d_ge
         c->h_geom_cap[slot] = bytes + 4096;
     }
     memcpy(c->h_geom[slot], g.data(), bytes);
-    MDB_CUDA(cudaMemcpyAsync(d_geom, c->h_geom[slot], bytes, cudaMemcpyHostToDevice, stream));
+    // a kernel reads the page-locked staging copy (unified addressing) instead of a DMA copy: in the
+    // host-buffer pipeline a small copy on the compute stream would queue behind the next chunk's 100 MB
+    // input copy in the copy engine and hold this chunk's kernels back by that long
+    k_copy_words<<<(unsigned)std::min<size_t>(cdiv((long long)(bytes / 4), 256), 128), 256, 0, stream>>>(
+        reinterpret_cast<const uint32_t *>(c->h_geom[slot]), reinterpret_cast<uint32_t *>(d_geom), bytes / 4);
+    MDB_CUDA(cudaGetLastError());
     MDB_CUDA(cudaEventRecord(c->h_geom_ev[slot], stream));
     return 0;
 }
