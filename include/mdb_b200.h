@@ -360,6 +360,17 @@ int mdb_reader_parse_buffer(const mdb_reader *r, const char *buf, size_t len, do
 int mdb_write_xyz_batch(int nfiles, const char *const *paths, const long long *offsets,
                         const char *symbols4, const double *h_pos, int nthreads);
 
+/* Gaussian input files of many structures at once: the reference's _convertgjf (datasetbuilder.py:468-521)
+ * with detect_multiplicity (:446-466), byte for byte.  File k holds atoms [offsets[k], offsets[k+1]) of the
+ * flat arrays (symbols4: 4-byte NUL-padded symbols, znum: atomic numbers, pos: [n][3]); its molecules are the
+ * consecutive runs of sizes mol_sizes[mol_offsets[k] .. mol_offsets[k+1]).  keywords: the qmkeywords sections
+ * (several -> %chk lines and --link1-- sections); fragment != 0 -> "guess=fragment=K" input for structures of
+ * more than one molecule.  Written by nthreads threads (<= 0: hardware concurrency). */
+int mdb_write_gjf_batch(int nfiles, const char *const *paths, const long long *offsets,
+                        const char *symbols4, const int32_t *znum, const double *pos,
+                        const long long *mol_offsets, const int32_t *mol_sizes, int nkeywords,
+                        const char *const *keywords, int fragment, int nthreads);
+
 /* Per-launch CUDA-event timing on the launching stream (bench.py's live roofline
  * measurement).  mdb_profile_read synchronises and writes "name count total_ms" lines
  * accumulated since the previous read into buf. */

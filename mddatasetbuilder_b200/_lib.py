@@ -77,6 +77,8 @@ SIGNATURES = {
                                        _vp]),
     "mdb_reader_parse_buffer": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _vp, _vp, _vp, _vp, C.c_int]),
     "mdb_write_xyz_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), _vp, _vp, _vp, C.c_int]),
+    "mdb_write_gjf_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), _vp, _vp, _vp, _vp, _vp, _vp, C.c_int,
+                                      C.POINTER(C.c_char_p), C.c_int, C.c_int]),
     "mdb_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "mdb_profile_read": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),
     "mdb_perceive_bond_orders": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),

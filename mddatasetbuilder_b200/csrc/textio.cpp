@@ -830,3 +830,114 @@ extern "C" int mdb_write_xyz_batch(int nfiles, const char *const *paths, const l
     if (bad.load() >= 0) return fail(std::string("cannot write ") + paths[bad.load()]);
     return 0;
 }
+
+// ---- output: Gaussian input files, many at once ------------------------------------------------
+// The reference's _convertgjf (datasetbuilder.py:468-521), byte for byte: lines joined by "\n" --
+// [%chk=<name>.chk when there are several keyword sections,] keywords (+ " guess=fragment=K"), the title
+// block, charge / multiplicity line ("0 M" or "0 M 0 m1 0 m2 ..." in fragment mode), one line per atom
+// ("S x y z" or "S(Fragment=k) x y z", %.5f), then for every further keyword section "\n--link1--\n",
+// [%chk,] keywords, title, "0 M", "\n", and a final "\n".  Multiplicities follow detect_multiplicity
+// (:446-466): an O2 molecule is a triplet, otherwise (sum of Z) % 2 + 1; M = sum(m) - K + 1.
+// File k holds atoms [offsets[k], offsets[k+1]); its molecules are mol_sizes[mol_offsets[k] ..
+// mol_offsets[k+1]) (consecutive runs of the file's atoms); znum are the atomic numbers per atom.
+extern "C" int mdb_write_gjf_batch(int nfiles, const char *const *paths, const long long *offsets, const char *symbols4,
+                                   const int32_t *znum, const double *pos, const long long *mol_offsets,
+                                   const int32_t *mol_sizes, int nkeywords, const char *const *keywords, int fragment,
+                                   int nthreads) {
+    if (nfiles < 0 || nkeywords < 1 || !keywords ||
+        (nfiles > 0 && (!paths || !offsets || !symbols4 || !znum || !pos || !mol_offsets || !mol_sizes)))
+        return fail("mdb_write_gjf_batch: bad arguments");
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    static const char *kTitle = "\nGenerated by MDDatasetMaker (Author: Jinzhe Zeng)\n";
+    std::atomic<int> next(0), bad(-1);
+    auto work = [&]() {
+        std::string buf, chk;
+        std::vector<int> mult;
+        char line[160];
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= nfiles) break;
+            const long long a = offsets[k];
+            const long long m0 = mol_offsets[k], m1 = mol_offsets[k + 1];
+            const int K = (int)(m1 - m0);
+            mult.assign((size_t)K, 1);
+            long long at = a;
+            long long msum = 0;
+            for (int q = 0; q < K; ++q) {
+                const int sz = mol_sizes[m0 + q];
+                long long zsum = 0;
+                for (int i = 0; i < sz; ++i) zsum += znum[at + i];
+                const bool o2 = sz == 2 && znum[at] == 8 && znum[at + 1] == 8;
+                mult[(size_t)q] = o2 ? 3 : (int)(zsum % 2 + 1);
+                msum += mult[(size_t)q];
+                at += sz;
+            }
+            const long long whole = msum - K + 1;
+            chk.clear();
+            if (nkeywords > 1) {
+                // %chk=<basename without its extension>.chk
+                std::string path(paths[k]);
+                const size_t slash = path.find_last_of('/');
+                std::string base = slash == std::string::npos ? path : path.substr(slash + 1);
+                const size_t dot = base.find_last_of('.');
+                if (dot != std::string::npos && dot > 0) base = base.substr(0, dot);
+                chk = "%chk=" + base + ".chk";
+            }
+            buf.clear();
+            auto item = [&](const std::string &sitem) {  // an item of the "\n".join that is not the last one
+                buf += sitem;
+                buf += '\n';
+            };
+            const bool frag = fragment && K != 1;
+            if (!chk.empty()) item(chk);
+            if (frag)
+                item(std::string(keywords[0]) + " guess=fragment=" + std::to_string(K));
+            else
+                item(keywords[0]);
+            item(kTitle);
+            {
+                std::string ml = "0 " + std::to_string(whole);
+                if (frag)
+                    for (int q = 0; q < K; ++q) ml += " 0 " + std::to_string(mult[(size_t)q]);
+                item(ml);
+            }
+            at = a;
+            for (int q = 0; q < K; ++q) {
+                const int sz = mol_sizes[m0 + q];
+                for (int i = 0; i < sz; ++i, ++at) {
+                    char sym[5] = {0, 0, 0, 0, 0};
+                    memcpy(sym, symbols4 + 4 * at, 4);
+                    int m;
+                    if (frag)
+                        m = snprintf(line, sizeof(line), "%s(Fragment=%d) %.5f %.5f %.5f\n", sym, q + 1, pos[3 * at], pos[3 * at + 1],
+                                     pos[3 * at + 2]);
+                    else
+                        m = snprintf(line, sizeof(line), "%s %.5f %.5f %.5f\n", sym, pos[3 * at], pos[3 * at + 1], pos[3 * at + 2]);
+                    buf.append(line, (size_t)m);
+                }
+            }
+            for (int w = 1; w < nkeywords; ++w) {
+                item("\n--link1--\n");
+                if (!chk.empty()) item(chk);
+                item(keywords[w]);
+                item(kTitle);
+                item("0 " + std::to_string(whole));
+                item("\n");
+            }
+            buf += '\n';  // the last item of the join: "\n" itself, without a separator after it
+            FILE *f = fopen(paths[k], "wb");
+            if (!f || fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+                int expect = -1;
+                bad.compare_exchange_strong(expect, k);
+            }
+            if (f) fclose(f);
+        }
+    };
+    std::vector<std::thread> th;
+    const int nt = std::min(nthreads, std::max(nfiles, 1));
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (bad.load() >= 0) return fail(std::string("cannot write ") + paths[bad.load()]);
+    return 0;
+}

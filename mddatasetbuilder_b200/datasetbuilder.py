@@ -40,7 +40,7 @@ from .atoms import atomic_numbers
 from .detect import Detect, DetectDump, unpack_key
 from .utils import must_be_list
 from .writer import detect_multiplicity as _detect_multiplicity
-from .writer import wrap_positions, write_gjf, write_xyz, write_xyz_batch  # noqa: F401
+from .writer import wrap_positions, write_gjf, write_gjf_batch, write_xyz, write_xyz_batch  # noqa: F401
 
 
 def _dist():
@@ -577,6 +577,7 @@ class DatasetBuilder:
         lengths = np.linalg.norm(cell3, axis=1)
         results = 0
         xyz_paths, xyz_symbols, xyz_positions = [], [], []
+        gjf_paths, gjf_molsizes = [], []
         for (atoma, trajatomfilename, itype, itotal), cutoffatomid in zip(sel, members):
             folder = str(itotal // 1000).zfill(self.foldermaxlength)
             atomtypenum = str(itype).zfill(self.maxlength)
@@ -597,13 +598,15 @@ class DatasetBuilder:
             xyz_symbols.append(symbols)
             xyz_positions.append(positions)
             if self.writegjf:
-                write_gjf(os.path.join(self.gjfdir, folder, name + ".gjf"), takenatomidindex, symbols, positions,
-                          self.qmkeywords, self.fragment)
+                gjf_paths.append(os.path.join(self.gjfdir, folder, name + ".gjf"))
+                gjf_molsizes.append([len(t) for t in takenatomids])
             if self.atom_pref:
                 np.save(os.path.join(self.gjfdir, folder, name + ".atom_pref.npy"), np.array([tags]))
             results += 1
         # the xyz files of the frame in one native call (formatting + I/O on several threads)
         write_xyz_batch(xyz_paths, xyz_symbols, xyz_positions)
+        if self.writegjf:  # and the Gaussian inputs of the same structures (_convertgjf, datasetbuilder.py:468-521)
+            write_gjf_batch(gjf_paths, gjf_molsizes, xyz_symbols, xyz_positions, self.qmkeywords, self.fragment)
         return results
 
     def lineiter(self, detector):

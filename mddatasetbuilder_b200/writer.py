@@ -62,6 +62,38 @@ def write_xyz_batch(paths, symbols_list, positions_list, nthreads=0):
         raise RuntimeError(_lib.last_error())
 
 
+def write_gjf_batch(paths, molsizes_list, symbols_list, positions_list, qmkeywords, fragment, nthreads=0):
+    """The same files as ``write_gjf`` for many structures at once, formatted and written by the native
+    library on several threads (csrc/textio.cpp: mdb_write_gjf_batch) -- byte-identical output.
+    molsizes_list[k]: sizes of the molecules of structure k (consecutive runs of its atoms)."""
+    import ctypes as C
+
+    from . import _lib
+
+    n = len(paths)
+    if n == 0:
+        return
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in symbols_list], out=off[1:])
+    moff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(m) for m in molsizes_list], out=moff[1:])
+    msz = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.int32) for m in molsizes_list]), dtype=np.int32)
+    flat = np.concatenate([np.asarray(s) for s in symbols_list])
+    sym = np.ascontiguousarray(flat.astype("S4"))
+    names, inverse = np.unique(flat, return_inverse=True)
+    znum = np.ascontiguousarray(np.array([atomic_numbers[str(x)] for x in names], dtype=np.int32)[inverse])
+    pos = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in positions_list]))
+    arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    kws = [k.encode() for k in qmkeywords]
+    karr = (C.c_char_p * len(kws))(*kws)
+    rc = _lib.lib().mdb_write_gjf_batch(n, arr, C.c_void_p(off.ctypes.data), C.c_void_p(sym.ctypes.data),
+                                        C.c_void_p(znum.ctypes.data), C.c_void_p(pos.ctypes.data),
+                                        C.c_void_p(moff.ctypes.data), C.c_void_p(msz.ctypes.data), len(kws), karr,
+                                        int(bool(fragment)), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(_lib.last_error())
+
+
 def detect_multiplicity(symbols):
     """Reference datasetbuilder.py:446-466 (charge 0; O2 is a triplet)."""
     if list(symbols) == ["O", "O"]:

@@ -346,3 +346,48 @@ def test_native_xyz_batch_writer_is_byte_identical(tmp_path):
         assert open(a, "rb").read() == open(b, "rb").read()
     with pytest.raises(RuntimeError):
         write_xyz_batch([str(tmp_path / "no_such_dir" / "x.xyz")], syms[:1], poss[:1])
+
+
+@pytest.mark.parametrize("fragment", [False, True])
+@pytest.mark.parametrize("keywords", [["%nproc=4\n#force mn15/6-31g**"],
+                                      ["%nproc=4\n#force mn15/6-31g**", "%nproc=4\n#force mn15/def2tzvp geom=chk", "%mem=2GB\n#sp"]])
+def test_native_gjf_batch_writer_is_byte_identical(tmp_path, fragment, keywords):
+    """mdb_write_gjf_batch writes the bytes of the reference's _convertgjf (datasetbuilder.py:468-521; the Python
+    restatement in writer.write_gjf is pinned by the golden files): multiplicities incl. the O2 triplet, fragments,
+    %chk / --link1-- sections, %.5f coordinates."""
+    from mddatasetbuilder_b200.writer import write_gjf, write_gjf_batch
+
+    rng = np.random.default_rng(1)
+    pa, pb, syms, poss, sizes = [], [], [], [], []
+    for k in range(150):
+        nm = int(rng.integers(1, 6))
+        ms = [int(rng.integers(1, 9)) for _ in range(nm)]
+        s = []
+        for q, m in enumerate(ms):
+            if k % 7 == 0 and q == 0:
+                ms[0] = 2
+                s += ["O", "O"]                  # an O2 molecule: triplet
+            else:
+                s += list(rng.choice(np.array(["H", "C", "O", "N", "Cl"]), m))
+        s = np.array(s)
+        p = rng.normal(0, 10.0 ** rng.integers(-3, 3), (len(s), 3))
+        if k == 1:
+            p[0] = [0.0, -0.0, -4e-6]
+        if k == 2:
+            p[0] = [0.000005, 1.000015, -2.5e-6]  # halves at the fifth decimal
+        idx, at = [], 0
+        for m in ms:
+            idx.append(range(at, at + m))
+            at += m
+        pa.append(str(tmp_path / f"a_{k}.x.gjf"))
+        pb.append(str(tmp_path / f"b_{k}.x.gjf"))
+        syms.append(s)
+        poss.append(p)
+        sizes.append(ms)
+        write_gjf(pa[-1], idx, s, p, keywords, fragment)
+    write_gjf_batch(pb, sizes, syms, poss, keywords, fragment, nthreads=3)
+    for a, b in zip(pa, pb):
+        # the %chk line carries the file's own name: compare with the names aligned
+        assert open(a, "rb").read().replace(b"a_", b"b_") == open(b, "rb").read(), a
+    with pytest.raises(RuntimeError):
+        write_gjf_batch([str(tmp_path / "no_such_dir" / "x.gjf")], sizes[:1], syms[:1], poss[:1], keywords, fragment)

@@ -18,7 +18,7 @@ import cProfile, pstats, io
 pr_ = cProfile.Profile() if os.environ.get('MDB_CPROFILE') else None
 t0 = time.time()
 if pr_: pr_.enable()
-b.builddataset(writegjf=False); torch.cuda.synchronize()
+b.builddataset(writegjf=bool(os.environ.get('MDB_WRITEGJF'))); torch.cuda.synchronize()
 if pr_: pr_.disable()
 dt = time.time() - t0
 if pr_:
