@@ -40,7 +40,7 @@ from .atoms import atomic_numbers
 from .detect import Detect, DetectDump, unpack_key
 from .utils import must_be_list
 from .writer import detect_multiplicity as _detect_multiplicity
-from .writer import wrap_positions, write_gjf, write_gjf_batch, write_xyz, write_xyz_batch  # noqa: F401
+from .writer import FrameWrapper, wrap_positions, write_gjf, write_gjf_batch, write_xyz, write_xyz_batch  # noqa: F401
 
 
 def _dist():
@@ -575,6 +575,7 @@ class DatasetBuilder:
                                      np.array([a - 1 for a, *_ in sel], dtype=np.int32), periodic=self.pbc)
         symbols_all = np.asarray(self.crddetector.atomnames)
         lengths = np.linalg.norm(cell3, axis=1)
+        wrap = FrameWrapper(cell3, self.pbc)
         results = 0
         xyz_paths, xyz_symbols, xyz_positions = [], [], []
         gjf_paths, gjf_molsizes = [], []
@@ -582,7 +583,7 @@ class DatasetBuilder:
             folder = str(itotal // 1000).zfill(self.foldermaxlength)
             atomtypenum = str(itype).zfill(self.maxlength)
             # make cutoff atoms in molecules: every molecule with ANY atom inside the sphere (:562-567)
-            mols = np.unique(molrank[cutoffatomid])
+            mols = sorted(set(molrank[cutoffatomid].tolist()))  # = np.unique for these few values
             takenatomids = [mol_atoms[mol_ptr[m]:mol_ptr[m + 1]] for m in mols]
             takenatomidindex, idsum = [], 0
             for t in takenatomids:
@@ -592,7 +593,7 @@ class DatasetBuilder:
             symbols = symbols_all[idx]
             tags = np.zeros(len(idx), dtype=int)
             tags[np.nonzero(idx == atoma - 1)[0][0]] = 1
-            positions = wrap_positions(pos_h[idx], cell3, pos_h[atoma - 1] / lengths, self.pbc)
+            positions = wrap(pos_h[idx], pos_h[atoma - 1] / lengths)
             name = f"{self.xyzfilename}_{trajatomfilename}_{atomtypenum}"
             xyz_paths.append(os.path.join(self.dataset_dir, folder, name + ".xyz"))
             xyz_symbols.append(symbols)

@@ -32,6 +32,34 @@ def wrap_positions(positions, cell, center, pbc, eps=1e-7):
     return np.dot(fractional, cell)
 
 
+class FrameWrapper:
+    """``wrap_positions`` for many clusters of one frame: the cell, its transpose and the periodic axes are
+    prepared once; every call then runs the same NumPy operations on arrays of the same layout as
+    ``wrap_positions`` does, so the coordinates are bit-identical."""
+
+    def __init__(self, cell, pbc, eps=1e-7):
+        self.cell = np.asarray(cell, dtype=float).reshape(3, 3)
+        self.cell_t = self.cell.T
+        self.pbc = np.array([pbc] * 3 if isinstance(pbc, (bool, np.bool_)) else pbc, dtype=bool)
+        self.free = np.logical_not(self.pbc)
+        self.all_periodic = bool(self.pbc.all())
+        self.eps = eps
+
+    def __call__(self, positions, center):
+        shift = np.asarray(center, dtype=float) - 0.5 - self.eps
+        shift[self.free] = 0.0
+        fractional = np.linalg.solve(self.cell_t, positions.T).T - shift
+        if self.all_periodic:
+            fractional %= 1.0
+            fractional += shift
+        else:
+            for i in range(3):
+                if self.pbc[i]:
+                    fractional[:, i] %= 1.0
+                    fractional[:, i] += shift[i]
+        return np.dot(fractional, self.cell)
+
+
 def write_xyz(path, symbols, positions):
     """ASE simple xyz: count line, empty comment line, ``%-2s %22.15f %22.15f %22.15f``."""
     with open(path, "w") as f:
