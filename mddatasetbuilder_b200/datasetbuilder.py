@@ -585,14 +585,8 @@ class DatasetBuilder:
             # make cutoff atoms in molecules: every molecule with ANY atom inside the sphere (:562-567)
             mols = sorted(set(molrank[cutoffatomid].tolist()))  # = np.unique for these few values
             takenatomids = [mol_atoms[mol_ptr[m]:mol_ptr[m + 1]] for m in mols]
-            takenatomidindex, idsum = [], 0
-            for t in takenatomids:
-                takenatomidindex.append(range(idsum, idsum + len(t)))
-                idsum += len(t)
             idx = np.concatenate(takenatomids)
             symbols = symbols_all[idx]
-            tags = np.zeros(len(idx), dtype=int)
-            tags[np.nonzero(idx == atoma - 1)[0][0]] = 1
             positions = wrap(pos_h[idx], pos_h[atoma - 1] / lengths)
             name = f"{self.xyzfilename}_{trajatomfilename}_{atomtypenum}"
             xyz_paths.append(os.path.join(self.dataset_dir, folder, name + ".xyz"))
@@ -602,6 +596,8 @@ class DatasetBuilder:
                 gjf_paths.append(os.path.join(self.gjfdir, folder, name + ".gjf"))
                 gjf_molsizes.append([len(t) for t in takenatomids])
             if self.atom_pref:
+                tags = np.zeros(len(idx), dtype=int)
+                tags[np.nonzero(idx == atoma - 1)[0][0]] = 1
                 np.save(os.path.join(self.gjfdir, folder, name + ".atom_pref.npy"), np.array([tags]))
             results += 1
         # the xyz files of the frame in one native call (formatting + I/O on several threads)
