@@ -247,19 +247,16 @@ def choose_per_cluster(labels_local, n_clusters, n_each, seed, rank=0, world=1, 
     totals = all_counts.sum(axis=0)
     offsets = np.cumsum(all_counts, axis=0) - all_counts  # first global member index of each rank
     rng = np.random.default_rng(seed)
-    picks, tags = [], []
-    for k in range(n_clusters):
-        if totals[k] == 0:
-            continue
-        draws = rng.integers(0, totals[k], size=n_each)
-        for j, g in enumerate(draws):
-            loc = g - offsets[rank, k]
-            if 0 <= loc < all_counts[rank, k]:
-                picks.append(order[starts[k] + loc])
-                tags.append((k, j))
-    picks = np.asarray(picks, dtype=np.int64)
+    # all clusters in one call (every rank draws the same numbers): n_each global member positions per
+    # non-empty cluster; a rank keeps the draws that fall into its own run of the cluster's members
+    nz = np.nonzero(totals[:n_clusters])[0]
+    draws = rng.integers(0, totals[nz][:, None], size=(len(nz), n_each))
+    loc = draws - offsets[rank, nz][:, None]
+    mine = (loc >= 0) & (loc < all_counts[rank, nz][:, None])
+    kk, jj = np.nonzero(mine)  # row-major: ascending cluster, then draw number
+    picks = np.asarray(order[starts[nz[kk]] + loc[kk, jj]], dtype=np.int64)
     if with_tags:
-        return picks, np.asarray(tags, dtype=np.int64).reshape(-1, 2)
+        return picks, np.stack([nz[kk], jj], axis=1).astype(np.int64).reshape(-1, 2)
     return picks
 
 
