@@ -391,3 +391,21 @@ def test_native_gjf_batch_writer_is_byte_identical(tmp_path, fragment, keywords)
         assert open(a, "rb").read().replace(b"a_", b"b_") == open(b, "rb").read(), a
     with pytest.raises(RuntimeError):
         write_gjf_batch([str(tmp_path / "no_such_dir" / "x.gjf")], sizes[:1], syms[:1], poss[:1], keywords, fragment)
+
+
+def test_frame_wrapper_equals_wrap_positions_bit_for_bit():
+    """The per-frame wrapper used by the output cut runs the same NumPy operations as wrap_positions (ASE's
+    Atoms.wrap as called at datasetbuilder.py:572-576, pinned by the golden xyz files): identical bytes for
+    orthorhombic and tilted cells, full and partial periodicity."""
+    from mddatasetbuilder_b200.writer import FrameWrapper, wrap_positions
+
+    rng = np.random.default_rng(0)
+    for t in range(600):
+        cell = np.diag(rng.uniform(5, 60, 3)) if t % 3 else rng.uniform(-5, 40, (3, 3)) + np.diag([30, 30, 30])
+        pbc = True if t % 4 else [bool(x) for x in rng.integers(0, 2, 3)]
+        pos = rng.normal(0, 40, (200, 3))
+        idx = rng.integers(0, 200, int(rng.integers(1, 60)))
+        center = pos[idx[0]] / np.linalg.norm(cell, axis=1)
+        a = wrap_positions(pos[idx], cell, center, pbc)
+        b = FrameWrapper(cell, pbc)(pos[idx], center)
+        assert a.tobytes() == b.tobytes()
