@@ -298,6 +298,7 @@ int upload_geometry(mdb_ctx *c, const std::vector<FrameGeom> &g, FrameGeom *d_ge
     // input copy in the copy engine and hold this chunk's kernels back by that long
     k_copy_words<<<(unsigned)std::min<size_t>(cdiv((long long)(bytes / 4), 256), 128), 256, 0, stream>>>(
         reinterpret_cast<const uint32_t *>(c->h_geom[slot]), reinterpret_cast<uint32_t *>(d_geom), bytes / 4);
+    c->launches++;
     MDB_CUDA(cudaGetLastError());
     MDB_CUDA(cudaEventRecord(c->h_geom_ev[slot], stream));
     return 0;
