@@ -4,14 +4,22 @@
     python bench.py --gpus N --steps K --warmup W            # this framework
     python bench.py --impl reference --gpus N --steps K ...  # CPU baseline arm
 
-Workload (BASELINE.json configs[1], "C2"): synthetic 100k-atom C/H/O ReaxFF-style dump,
-1,000 frames, dump-only distance-based bond detection.  One step = one pass of the hot
-path (cell list -> bonds -> valence/angle cleanup -> bond-type keys -> molecule labels)
-over the rank's 1,000 frames = 1e8 atom-frames.  Multi-GPU: frames shard across ranks with
-no data-path collective (weak scaling: every rank owns 1,000 frames).
+Workload (BASELINE.json configs[2], "C3"): synthetic 1M-atom periodic C/H/O box at 0.05 atoms/A^3,
+1,000 frames per rank, bond table (CSR with bond orders, the content of a `fix reaxff/bonds` file) +
+per-atom Coulomb-matrix descriptor + MiniBatchKMeans(K = 10,000) per bond type + per-cluster selection:
+the whole of `DatasetBuilder._readtimestepsbond` + `_writecoulumbmatrix` for every type
+(reference datasetbuilder.py:185-281, 351-384), run as the streaming job of
+`mddatasetbuilder_b200/streaming.py` (pass A keys / group-by / compositions / molecule labels, pass B
+descriptors -> scaler bounds + training pool, training, pass C descriptors -> scale -> assignment,
+selection).  The job's frames are split into K equal steps (a step = frames/K frames taken through all
+three passes; training and selection happen once per job and are inside the timed region), so
+`value` = atom-frames of the job / wall time of the WHOLE job.  Warm-up = a smaller job of W steps.
+With N > 1 (torchrun) every rank owns 1,000 frames (configs[3] shape, weak scaling): the trajectory is
+the union, batches interleave over the ranks, the collectives of the job are inside the timed region.
 
-`value` is measured with the frames resident in HBM; `e2e` goes through the host-buffer C-ABI
-call (pinned host positions in; bond list, key codes and molecule labels back out) with the copies timed.
+`value` has the inputs resident in HBM; `e2e` runs the same job from page-locked host arrays (every
+batch of every pass is copied host -> device inside the timed region, the selection comes back to the
+host).  `stages.c2_bonds` keeps the dump-only bond path of configs[1] (round 1's headline).
 """
 
 from __future__ import annotations
@@ -29,15 +37,13 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOADS = {
-    # name: (atoms per frame, frames per rank, number density, dense?, BASELINE.json config text)
-    "c2": (100_000, 1000, 0.02, False,
-           "configs[1]: synthetic 100k-atom C/H/O ReaxFF dump, 1,000 frames, dump-only distance-based bond detection"),
-    "c2-small": (100_000, 100, 0.02, False, "reduced C2 (100 frames) for quick checks -- not a headline number"),
-    "c3": (1_000_000, 100, 0.05, False, "C3-shaped frames (1M atoms, 100 frames) through the dump-only bond path"),
-}
+C3_TEXT = ("configs[2]: synthetic 1M-atom periodic C/H/O box, 1,000 frames, bonds file + per-atom descriptor + "
+           "MiniBatchKMeans, 1 B200")
+C4_TEXT = ("configs[3] shape: synthetic 1M-atom trajectory, 1,000 frames per rank sharded across the B200s "
+           "(weak scaling of configs[2]), NCCL collectives of the clustering inside the timed region")
 METRIC = "atom-frames/sec (bond+descriptor+kmeans) at 1/2/4/8 B200; HBM GB/s vs peak"
 UNIT = "atom-frames/s"
+NATOMS, FRAMES, DENSITY, KCLUST = 1_000_000, 1000, 0.05, 10_000
 
 
 def measured_peaks():
@@ -63,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "250", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -76,11 +82,11 @@ class ClockSampler:
     def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.3)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for ts, line in self.lines:
-            if ts < t0 - 0.05 or ts > t1 + 0.15:
+            if ts < t0 - 0.05 or ts > t1 + 0.3:
                 continue
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
@@ -100,60 +106,100 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference's path; Open Babel itself cannot be built here)
+# CPU baseline: the oracle port of the reference's per-frame stages on the host cores
 # --------------------------------------------------------------------------------------
-def cpu_baseline(natoms, density, dense, seed, target_seconds=15.0, cores=None):
-    """Times the O(N^2) periodic ConnectTheDots pair loop (the reference's cost model,
-    detect.py:275 -> OBMol::ConnectTheDots) on every host core, on a bounded sample of
-    the same 100k-atom frames: each thread runs 1/stride of one frame's z-sorted rows."""
+def cpu_baseline(natoms=NATOMS, density=DENSITY, seed=20261019 + 3, target_seconds=15.0, cores=None, sysm=None):
+    """The reference's CPU path for this workload, stage by stage, on ONE 1M-atom frame with every
+    host thread busy, each stage on a bounded sample (kind "port": oracle/ restates ASE's minimum-image
+    sphere cut and the Coulomb matrix in C, numpy.linalg.eigh and scikit-learn are the real ones):
+      keys        oracle bond_keys_bondfile on the whole frame (detect.py:105-119), one thread;
+      descriptor  `_writestepmatrix` + `_calcoulumbmatrix` (datasetbuilder.py:283-349): O(N) sphere cut
+                  against all 1M atoms + Coulomb matrix + eigh, S sampled targets per thread;
+      assignment  sklearn `_labels_inertia` of those rows against K = 10,000 centres.
+    value = cores / (seconds per atom-frame summed over the stages)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from mddatasetbuilder_b200 import synth
     from oracle import oracle as O
 
     cores = cores or len(os.sched_getaffinity(0))
-    s = synth.make_system(natoms, density, seed=seed, dense=dense)
+    s = sysm or synth.make_system(natoms, density, seed=seed)
     Z = np.array([O.ATOMIC_NUMBERS[s.atomname[t]] for t in s.types], dtype=np.int32)
-    cell = s.cell()
-    # calibrate: one thread, a thin slice
-    t = time.perf_counter()
-    O.ctd_sample(Z, s.pos0, cell, True, 512, 0)
-    one = (time.perf_counter() - t) * 512  # seconds per full frame per thread
-    stride = max(1, int(round(one / target_seconds)))
+    diag = np.array([O.ATOMIC_NUMBERS[s.atomname[t]] ** 2.4 / 2 for t in s.types])
+    t0 = time.perf_counter()
+    O.bond_keys_bondfile(s.types, s.rowptr, s.bo)
+    t_keys = (time.perf_counter() - t0) / natoms               # seconds per atom-frame, one thread
+    # calibrate the descriptor sample: a handful of targets on one thread
+    rng = np.random.default_rng(seed)
+    probe = rng.integers(0, natoms, 4).astype(np.int32)
+    t0 = time.perf_counter()
+    O.descriptor_gather(Z, diag, s.pos0, s.box, True, 5.0, probe)
+    per_target = (time.perf_counter() - t0) / len(probe)
+    S = max(2, int(target_seconds / max(per_target, 1e-6)))
+
+    def work(k):
+        tg = np.random.default_rng(seed + 1 + k).integers(0, natoms, S).astype(np.int32)
+        counts, mem, mats = O.descriptor_gather(Z, diag, s.pos0, s.box, True, 5.0, tg)
+        eigs = O.coulomb_eigs(mats)
+        return counts, eigs, mem
+
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
-        list(ex.map(lambda k: O.ctd_sample(Z, s.pos0, cell, True, stride, k % stride), range(cores)))
-    wall = time.perf_counter() - t0
-    value = cores * natoms / stride / wall
+        outs = list(ex.map(work, range(cores)))
+    wall_desc = time.perf_counter() - t0
+    t_desc = wall_desc / S                                      # seconds per atom-frame per thread
+    # assignment of the sampled rows against K centres with the real scikit-learn (its own thread pool)
+    eigs = [e for _, es, _ in outs for e in es]
+    ec = np.array([[int((s.types[m] == el).sum()) for el in range(len(s.atomname))] for _, _, ms in outs for m in ms])
+    pads = np.array([O.ATOMIC_NUMBERS[a] ** 2.4 / 2 for a in s.atomname])
+    X, _ = O.feature_rows(eigs, ec, pads)
+    Xs = O.minmax_scale(X)[0]
+    reps = max(1, 20000 // len(Xs))
+    Xa = np.tile(Xs, (reps, 1))
+    C = Xa[np.random.default_rng(seed).integers(0, len(Xa), KCLUST)] + 1e-3
+    from sklearn.cluster._kmeans import _labels_inertia
+
+    t0 = time.perf_counter()
+    _labels_inertia(np.ascontiguousarray(Xa), np.ones(len(Xa)), np.ascontiguousarray(C), n_threads=cores)
+    t_assign = (time.perf_counter() - t0) / len(Xa) * cores     # core-seconds per row
+    per_atom_frame = t_keys + t_desc + t_assign
+    value = cores / per_atom_frame
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"O(N^2) periodic ConnectTheDots pair loop (oracle/oracle.c) over 1/{stride} of the z-sorted "
-                      f"rows of one {natoms}-atom frame per thread, {cores} threads, {wall:.1f} s wall; cleanup, keys "
-                      f"and dps excluded (negligible next to the pair loop)",
-            "seconds": wall, "stride": stride}
+            "sample": f"one {natoms}-atom frame at {density} atoms/A^3: bond-type keys of the whole frame (1 thread, "
+                      f"{t_keys * 1e9:.0f} ns/atom); sphere cut against all atoms + Coulomb matrix (oracle/oracle.c) + "
+                      f"numpy eigh for {S} sampled targets on each of {cores} threads ({t_desc * 1e3:.2f} ms/target/thread, "
+                      f"{wall_desc:.1f} s wall); sklearn _labels_inertia of {len(Xa)} rows vs K={KCLUST} "
+                      f"({t_assign * 1e6:.1f} core-us/row). Training and selection excluded (negligible next to the "
+                      f"O(N) sphere cut per target)",
+            "seconds": wall_desc, "targets_per_thread": S,
+            "seconds_per_atom_frame_per_core": {"keys": t_keys, "descriptor": t_desc, "assignment": t_assign}}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    natoms, frames, density, dense, text = WORKLOADS[args.workload]
-    per_step = max(3.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    from mddatasetbuilder_b200 import synth
+
+    sysm = synth.make_system(NATOMS, DENSITY, seed=synth.BASE_SEED + 3)
+    per_step = max(2.0, min(12.0, 150.0 / max(args.steps + args.warmup, 1)))
     for _ in range(args.warmup):
-        cpu_baseline(natoms, density, dense, 20261019 + 2, target_seconds=per_step / 4)
-    vals, secs = [], []
-    base = None
+        cpu_baseline(target_seconds=per_step / 4, sysm=sysm)
+    vals, secs, base = [], [], None
     for _ in range(args.steps):
-        base = cpu_baseline(natoms, density, dense, 20261019 + 2, target_seconds=per_step)
+        t0 = time.perf_counter()
+        base = cpu_baseline(target_seconds=per_step, sysm=sysm)
+        secs.append(time.perf_counter() - t0)
         vals.append(base["value"])
-        secs.append(base["seconds"])
     value = float(np.mean(vals))
     base["value"] = value
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": text, "atoms_per_frame": natoms, "frames_per_step": "bounded sample",
-                       "note": "reference CPU path = oracle port (Open Babel is not installable offline); each step is "
-                               "a bounded sample of one frame's pair loop on all host threads"},
+            "config": {"workload": C3_TEXT, "atoms_per_frame": NATOMS, "frames_per_step": "bounded sample",
+                       "note": "reference CPU path = oracle port of its stages (ase / openbabel are not installable "
+                               "offline) + the real numpy eigh and scikit-learn; each step is a bounded sample of one "
+                               "1M-atom frame on all host threads"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -161,158 +207,112 @@ def run_reference(args):
     return 0
 
 
-def measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_ranks, world, peaks):
-    """Descriptor and k-means stages of the metric, device-resident, CUDA-event timed, on a slice
-    of the same frames (every atom a target, like a bond type that covers the whole frame;
-    K = 10,000 centroids as the reference's default n_clusters)."""
-    nf = max(1, min(frames, (1 << 20) // natoms))       # ~1M targets per pass
-    sub = pos[:nf]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    res = {}
-    maxc = None
-    _, mc0 = eng.compositions(sub[:1], cell, types, 5.0, periodic=True)
-    memcap = int(mc0.sum()) + 8                           # list capacity: a bound on the largest sphere
-    eng.check()
-    for it in range(2):                                   # pass 0 warms up
-        # the one-pass flow of DatasetBuilder: the composition scan leaves the membership lists behind and
-        # the descriptor pass gathers from them (no second cell scan)
-        ev[0].record()
-        counts, maxc, members = eng.compositions(sub, cell, types, 5.0, periodic=True, members_cap=memcap)
-        ev[1].record()
-        out = eng.descriptors(sub, cell, types, 5.0, counts, maxc, periodic=True, members=members)
-        ev[2].record()
-        torch.cuda.synchronize()
-        del members
-    X = out["X"]
-    rows, D = int(X.shape[0]), int(X.shape[1])
-    n_mean = float(out["n"].double().mean().item())
-    t_comp = max_over_ranks(ev[0].elapsed_time(ev[1]))
-    t_desc = max_over_ranks(ev[1].elapsed_time(ev[2]))
-    res["composition"] = {"atom_frames_per_s": world * rows / (t_comp / 1e3), "ms": t_comp, "targets": rows}
-    res["descriptor"] = {"atom_frames_per_s": world * rows / (t_desc / 1e3), "ms": t_desc, "targets": rows,
-                         "mean_cluster_size": n_mean, "D": D,
-                         "hbm_frac_algorithmic": (16 + 8 * D) * rows / (t_desc / 1e3) / 1e9 / peaks["hbm_gbs"],
-                         "note": "FP64-pipe bound (Householder + QL), not HBM bound; see DESIGN.md"}
-    # bond-order perception of the dump-only key (detect.py:279-280) on the same frames
-    an = eng.analyze(sub, cell, types)
-    for it in range(2):
-        ev[3].record()
-        pb = eng.perceive(sub, cell, types, an["ell"], labels=an["labels"])
-        ev[4].record()
-        torch.cuda.synchronize()
-    t_po = max_over_ranks(ev[3].elapsed_time(ev[4]))
-    res["bond_orders"] = {"atom_frames_per_s": world * rows / (t_po / 1e3), "ms": t_po, "atom_frames": rows,
-                          "multiple_bonds": int((pb["orders"] > 1).sum().item()) // 2,
-                          "rings": eng.perceive_stats()["rings"]}
-    del an, pb
-    mn, mx = eng.minmax_fit(X)
-    eng.minmax_transform(X, mn.cpu().numpy(), mx.cpu().numpy())
-    K = 10000
-    centers = X[torch.randperm(rows, device=X.device)[:K]].contiguous()
-    for it in range(2):
-        ev[3].record()
-        labels, _, _ = eng.kmeans_assign(X, centers)
-        ev[4].record()
-        torch.cuda.synchronize()
-    t_as = max_over_ranks(ev[3].elapsed_time(ev[4]))
-    res["kmeans_assign"] = {"atom_frames_per_s": world * rows / (t_as / 1e3), "ms": t_as, "rows": rows, "K": K, "D": D,
-                            "fp64_tflops": 2.0 * rows * K * D / (t_as / 1e3) / 1e12}
-    # tensor-core screening pass + float64 re-check of near-ties (same labels)
-    for it in range(2):
-        ev[3].record()
-        labels_tc, nre = eng.kmeans_assign_tc(X, centers)
-        ev[4].record()
-        torch.cuda.synchronize()
-    t_tc = max_over_ranks(ev[3].elapsed_time(ev[4]))
-    res["kmeans_assign_tc"] = {"atom_frames_per_s": world * rows / (t_tc / 1e3), "ms": t_tc, "rows": rows, "K": K, "D": D,
-                               "rechecked_in_float64": nre, "labels_equal_float64_path": bool(torch.equal(labels, labels_tc)),
-                               "effective_tflops": 2.0 * rows * K * D / (t_tc / 1e3) / 1e12,
-                               "tensor_tflops_issued": 2.0 * rows * K * (3 * ((D + 15) // 16 * 16) + 16) / (t_tc / 1e3) / 1e12}
-    return res
+# --------------------------------------------------------------------------------------
+class HostSource:
+    """The same frames as page-locked host arrays: every batch of every pass is copied to the device inside
+    the timed region.  `slots` distinct frames are kept on the host and reused cyclically (frame f reads
+    slot f % slots), so the page-locked footprint stays bounded; the bytes copied are the full job's."""
+
+    def __init__(self, torch, dev, pos, rowptr, col, bo, cell, frames, frames_per_batch, rank, world, slots):
+        self.torch, self.dev = torch, dev
+        self.slots = min(slots, int(pos.shape[0]))
+        self.h_pos = torch.empty((self.slots,) + tuple(pos.shape[1:]), dtype=pos.dtype, pin_memory=True)
+        self.h_rowptr = torch.empty((self.slots,) + tuple(rowptr.shape[1:]), dtype=rowptr.dtype, pin_memory=True)
+        self.h_col = torch.empty((self.slots,) + tuple(col.shape[1:]), dtype=col.dtype, pin_memory=True)
+        self.h_bo = torch.empty((self.slots,) + tuple(bo.shape[1:]), dtype=bo.dtype, pin_memory=True)
+        self.h_pos.copy_(pos[: self.slots])
+        self.h_rowptr.copy_(rowptr[: self.slots])
+        self.h_col.copy_(col[: self.slots])
+        self.h_bo.copy_(bo[: self.slots])
+        self.cell = np.ascontiguousarray(np.broadcast_to(np.asarray(cell, dtype=np.float64).reshape(-1, 9), (frames, 9)))
+        self.F, self.B, self.rank, self.world = frames, frames_per_batch, rank, world
+        self.h2d_bytes = 0
+        B = frames_per_batch
+        self.d = [tuple(torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                        for t in (self.h_pos, self.h_rowptr, self.h_col, self.h_bo)) for _ in range(2)]
+
+    def batches(self):
+        from mddatasetbuilder_b200.streaming import FrameBatch
+
+        nb = -(-self.F // self.B)
+        for i in range(nb):
+            f0, f1 = i * self.B, min(self.F, (i + 1) * self.B)
+            nf = f1 - f0
+            buf = self.d[i & 1]
+            for f in range(nf):                                   # slot-wise copies (cyclic reuse of the host frames)
+                sl = (f0 + f) % self.slots
+                for dst, src in zip(buf, (self.h_pos, self.h_rowptr, self.h_col, self.h_bo)):
+                    dst[f].copy_(src[sl], non_blocking=True)
+                    self.h2d_bytes += src[sl].numel() * src.element_size()
+            g = i * self.world + self.rank
+            yield FrameBatch(g, g * self.B, buf[0][:nf], self.cell[f0:f1], rowptr=buf[1][:nf], col=buf[2][:nf], bo=buf[3][:nf])
 
 
-def measure_text_reader(sysm, natoms, args, eng=None):
-    """LAMMPS dump text -> float64 positions through the library's reader (csrc/textio.cpp, host threads):
-    what feeds the GPU when the input is a trajectory file rather than arrays (measured
-    separately, on a 1e5-atom slice)."""
-    import shutil
-    import tempfile
-
+def measure_c2_bonds(torch, dev, local, max_over_ranks, world, peaks):
+    """Round 1's headline, kept as a stage: configs[1], 100k atoms x 1,000 frames, dump-only bond path
+    (cell list -> bonds -> cleanup -> keys -> molecule labels), device resident, 3 warm-up + 5 timed passes."""
     from mddatasetbuilder_b200 import synth
-    from mddatasetbuilder_b200.reader import KIND_DUMP, TextReader
+    from mddatasetbuilder_b200.engine import Engine
 
-    nf = 8
-    d = tempfile.mkdtemp(prefix="mdb_bench_")
-    try:
-        fn = os.path.join(d, "dump.bench")
-        synth.write_lammps_dump(fn, sysm, synth.frame_positions(sysm, nf))
-        reps = 4                                   # the 8-frame file four times over: 32 frames per pass
-        size = os.path.getsize(fn) * reps
-        best = None
-        buf = np.empty((nf, natoms, 3), dtype=np.float64)
-        for _ in range(3):
-            r = TextReader(KIND_DUMP, [fn] * reps, nthreads=0)
-            t0 = time.perf_counter()
-            got = 0
-            while True:
-                pos, _cell = r.read(nf, pinned=buf)
-                if len(pos) == 0:
-                    break
-                got += len(pos)
-            dt = time.perf_counter() - t0
-            r.close()
-            best = dt if best is None else min(best, dt)
-        res = {"atom_frames_per_s": got * natoms / best, "mb_per_s": size / 1e6 / best, "frames": got,
-               "file_mb": size / 1e6, "host_threads": len(os.sched_getaffinity(0)),
-               "note": "host-side parse (mmap + from_chars), page-cached file; not part of `value` or `e2e`"}
-        if eng is not None:
-            # the same file through the device parser: host slices frames into page-locked memory, H2D, k_parse_dump
-            import torch
-
-            bestd, fb = None, 0
-            r = TextReader(KIND_DUMP, [fn] * reps, nthreads=0)   # one reader: its page-locked staging is reused
-            for _ in range(4):
-                r.rewind()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                got = 0
-                while True:
-                    pos, _cell = r.read_device(nf, eng, prefetch=True)
-                    if pos.shape[0] == 0:
-                        break
-                    got += int(pos.shape[0])
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                fb = getattr(r, "device_fallback_frames", 0)
-                bestd = dt if bestd is None else min(bestd, dt)
-            r.close()
-            # the device route is the one DatasetBuilder reads through: it is the stage's figure, the host route rides along
-            host = {k: res[k] for k in ("atom_frames_per_s", "mb_per_s", "host_threads", "note")}
-            res = {"atom_frames_per_s": got * natoms / bestd, "mb_per_s": size / 1e6 / bestd, "frames": got,
-                   "file_mb": size / 1e6, "route": "device parser (TextReader.read_device)", "host_parser": host}
-            res["device_parser"] = {"atom_frames_per_s": got * natoms / bestd, "mb_per_s": size / 1e6 / bestd,
-                                    "frames_handed_back_to_host": fb,
-                                    "note": "text -> float64 positions in HBM (csrc/textparse.cu), bit-identical to the host parser; "
-                                            "batches of 8 frames, the next one staged while this one is parsed"}
-        return res
-    finally:
-        shutil.rmtree(d, ignore_errors=True)
+    natoms, frames = 100_000, 1000
+    sysm = synth.make_system(natoms, 0.02, seed=synth.BASE_SEED + 2)
+    eng = Engine(local, sysm.atomname)
+    pos = synth.frame_positions_device(sysm, frames, dev)
+    types = eng.to_device_types(sysm.types)
+    cell = sysm.cell()
+    out = {"ell": torch.empty((frames, natoms, eng.max_bonds), dtype=torch.int32, device=dev),
+           "keys": torch.empty((frames, natoms), dtype=torch.int64, device=dev),
+           "labels": torch.empty((frames, natoms), dtype=torch.int32, device=dev)}
+    for _ in range(3):
+        eng.analyze(pos, cell, types, True, out=out)
+    eng.check()
+    eng.profile_read()
+    eng.profile(True)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    ev0.record()
+    for _ in range(steps):
+        eng.analyze(pos, cell, types, True, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+    eng.profile(False)
+    prof = eng.profile_read()
+    nnz = int((out["ell"][:8] >= 0).sum().item())
+    dbar = nnz / float(8 * natoms)
+    alg = 24.0 + 4.0 + 4.0 * dbar
+    kern = {k: {"launches": c, "ms_per_step": m / steps} for k, (c, m) in prof.items()}
+    kb = kern.get("k_bonds") or kern.get("k_bonds_tile") or {}
+    res = {"workload": "configs[1]: synthetic 100k-atom C/H/O ReaxFF dump, 1,000 frames, dump-only distance-based bond detection",
+           "atom_frames_per_s": world * frames * natoms / (ms / 1e3), "ms_per_pass": ms, "mean_degree": dbar,
+           "algorithmic_bytes_per_atom_frame": alg, "kernels": kern,
+           "path_hbm_frac": alg * frames * natoms / (sum(v["ms_per_step"] for v in kern.values()) / 1e3) / 1e9 / peaks["hbm_gbs"]}
+    if kb:
+        res["k_bonds_hbm_frac"] = alg * frames * natoms / (kb["ms_per_step"] / 1e3) / 1e9 / peaks["hbm_gbs"]
+    del pos, out
+    eng.close()
+    torch.cuda.empty_cache()
+    return res
 
 
 # --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=0, help="override frames per rank (testing)")
+    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per rank (testing; the workload is 1000)")
+    ap.add_argument("--atoms", type=int, default=NATOMS, help="atoms per frame (testing; the workload is 1e6)")
+    ap.add_argument("--clusters", type=int, default=KCLUST)
+    ap.add_argument("--batch-frames", type=int, default=0, help="frames per device batch (0: ~8M atom-frames)")
+    ap.add_argument("--pool-rows", type=int, default=1 << 21)
+    ap.add_argument("--host-slots", type=int, default=64)
+    ap.add_argument("--exchange", default="replicated", choices=["replicated", "allreduce"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
-    ap.add_argument("--cell-edge", type=float, default=0.0)
-    ap.add_argument("--frames-per-launch", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -322,6 +322,7 @@ def main():
 
     from mddatasetbuilder_b200 import synth
     from mddatasetbuilder_b200.engine import Engine
+    from mddatasetbuilder_b200.streaming import ResidentSource, StreamingSelector
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -347,30 +348,38 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    natoms, frames, density, dense, text = WORKLOADS[args.workload]
-    if args.frames:
-        frames = args.frames
-    sysm = synth.make_system(natoms, density, seed=synth.BASE_SEED + 2 + 1000 * rank, dense=dense)
+    peaks, peak_kind = measured_peaks()
+    natoms = args.atoms
+    steps = max(1, args.steps)
+    fps = max(1, args.frames // steps)             # frames per step
+    frames = fps * steps                           # frames of the timed job (per rank)
+    wframes = fps * max(args.warmup, 0)            # frames of the warm-up job
+    bf = args.batch_frames or max(1, min(fps, (8 << 20) // natoms))
+    sysm = synth.make_system(natoms, DENSITY, seed=synth.BASE_SEED + 3 + 1000 * rank)
     eng = Engine(local, sysm.atomname)
-    if args.cell_edge:
-        eng.set_option("cell_edge", args.cell_edge)
-    if args.frames_per_launch:
-        eng.set_option("frames_per_launch", args.frames_per_launch)
-    pos = synth.frame_positions_device(sysm, frames, dev)
-    types = eng.to_device_types(sysm.types)
+    nres = max(frames, wframes)
+    pos = synth.frame_positions_device(sysm, nres, dev)
+    rowptr, col, bo = synth.bond_table_device(sysm, nres, dev)
     cell = sysm.cell()
-    out = {"ell": torch.empty((frames, natoms, eng.max_bonds), dtype=torch.int32, device=dev),
-           "keys": torch.empty((frames, natoms), dtype=torch.int64, device=dev),
-           "labels": torch.empty((frames, natoms), dtype=torch.int32, device=dev)}
+    kw = {"exchange": args.exchange} if world > 1 else {}
 
-    def step():
-        eng.analyze(pos, cell, types, True, out=out)
+    def job(source, nfr):
+        sel = StreamingSelector(eng, sysm.types, cutoff=5.0, n_clusters=args.clusters, n_each=1, seed=synth.BASE_SEED,
+                                periodic=True, pool_rows=args.pool_rows, want_molecules=True, kmeans_kwargs=kw)
+        res = sel.run(source)
+        return sel, res
 
-    for _ in range(max(args.warmup, 0)):
-        step()
-    stats = eng.check()
+    def resident(nfr):
+        return ResidentSource(pos[:nfr], cell, bf, rowptr=rowptr[:nfr], col=col[:nfr], bo=bo[:nfr], rank=rank, world=world,
+                              local=True)
+
+    # ---- warm-up: a job of W steps -------------------------------------------------------------
+    if wframes:
+        job(resident(wframes), wframes)
+    eng.check()
     eng.profile_read()
 
+    # ---- timed: the job of K steps, inputs resident in HBM ---------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -381,8 +390,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
-        step()
+    sel, res = job(resident(frames), frames)
     ev1.record()
     torch.cuda.synchronize()
     w1 = time.time()
@@ -392,136 +400,106 @@ def main():
     eng.profile(False)
     prof = eng.profile_read()
     clocks = sampler.stop(w0, w1)
-    stats = eng.check()
-    ms_per_step = ms_total / args.steps
-    units_per_step = world * frames * natoms
-    value = units_per_step / (ms_per_step / 1e3)
+    ms_per_step = ms_total / steps
+    units = world * frames * natoms
+    value = units / (ms_total / 1e3)
+    nchosen = sum(len(v) for v in res.chosen.values())
+    phases = {k: max_over_ranks(v) for k, v in res.timings.items()}
 
-    # measured mean degree -> algorithmic bytes per atom-frame (SURVEY.md §8d, FP64 input):
-    # 24 B xyz + 4 B row pointer + 4 B per directed CSR entry
-    nnz = int((out["ell"][: min(frames, 8)] >= 0).sum().item())
-    dbar = nnz / float(min(frames, 8) * natoms)
-    alg_bytes = 24.0 + 4.0 + 4.0 * dbar
-    peaks, peak_kind = measured_peaks()
-    kern = {k: {"launches": c, "ms_per_step": ms / args.steps} for k, (c, ms) in prof.items()}
-    gpu_ms = sum(v["ms_per_step"] for v in kern.values()) or float("nan")
+    # ---- kernels: time share of every kernel of the job; roofline of the dominant one --------------
+    kern = {k: {"launches": c, "ms": m} for k, (c, m) in prof.items()}
+    gpu_ms = sum(v["ms"] for v in kern.values()) or float("nan")
     for v in kern.values():
-        v["share"] = v["ms_per_step"] / gpu_ms
-    mine = {k: v for k, v in kern.items() if k != "memset"}
-    dom = max(mine, key=lambda k: mine[k]["ms_per_step"])
-    launches_dom = mine[dom]["launches"] / args.steps
-    units_per_launch = frames * natoms / launches_dom
-    dur_s = mine[dom]["ms_per_step"] / launches_dom / 1e3
-    achieved = alg_bytes * units_per_launch / dur_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            with open(tpath) as f:
-                per = json.load(f).get(dom, {}).get("dram_bytes_per_atom_frame")
-            if per is not None:
-                traffic = per * units_per_launch  # ncu --set full capture, scaled to this launch size
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                "algorithmic_bytes_per_atom_frame": alg_bytes, "mean_degree": dbar,
-                "units_per_launch": units_per_launch, "launch_ms": dur_s * 1e3,
-                # whole path: algorithmic bytes / summed GPU time of every launch of the step (one rank)
-                "path_achieved": alg_bytes * frames * natoms / (gpu_ms / 1e3) / 1e9,
-                "path_frac": alg_bytes * frames * natoms / (gpu_ms / 1e3) / 1e9 / peaks["hbm_gbs"]}
+        v["share"] = v["ms"] / gpu_ms
+    # descriptor kernels by family
+    desc_ms = sum(v["ms"] for k, v in kern.items() if k.startswith("k_tridiag") or k.startswith("k_tql") or k.startswith("k_eig"))
+    # mean n and n^3 of the cutoff spheres (one batch of frames): useful flops of the tridiagonalisation
+    cnt, _ = eng.compositions(pos[:1], cell, eng.to_device_types(sysm.types), 5.0, periodic=True)
+    nn = cnt.sum(dim=1).double()
+    n_mean, n3_mean = float(nn.mean().item()), float((nn ** 3).mean().item())
+    del cnt, nn
+    ntarget_passes = 2 * frames * natoms          # pass B + pass C
+    useful_flops = (8.0 / 3.0) * n3_mean * ntarget_passes
+    fp64_peak = eng.fp64_peak_tflops()
+    Dmean = float(np.mean([st["D"] for st in res.stats["fit"].values()])) if res.stats.get("fit") else 0.0
+    dom = max((k for k in kern if k != "memset"), key=lambda k: kern[k]["ms"])
+    desc_alg_bytes = (16.0 + 8.0 * Dmean) * ntarget_passes
+    roofline = {"bound": "fp64", "kernel": "k_tridiag_* + k_tql (descriptor: Householder tridiagonalisation + QL)",
+                "dominant_single_kernel": dom,
+                "achieved": useful_flops / (desc_ms / 1e3) / 1e12 if desc_ms else None, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (useful_flops / (desc_ms / 1e3) / 1e12 / fp64_peak) if desc_ms and fp64_peak else None,
+                "traffic": None, "peak_source": "DFMA peak measured in this run (k_fp64_peak)",
+                "useful_flops_per_target": (8.0 / 3.0) * n3_mean, "mean_sphere_atoms": n_mean,
+                "descriptor_ms": desc_ms, "descriptor_ns_per_target": desc_ms * 1e6 / ntarget_passes if desc_ms else None,
+                "hbm": {"algorithmic_bytes_per_target": 16.0 + 8.0 * Dmean,
+                        "achieved_gbs": desc_alg_bytes / (desc_ms / 1e3) / 1e9 if desc_ms else None,
+                        "peak_gbs": peaks["hbm_gbs"], "peak_source": peak_kind,
+                        "frac": (desc_alg_bytes / (desc_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if desc_ms else None},
+                "job_hbm": {"algorithmic_bytes_per_atom_frame": 727.0,
+                            "achieved_gbs": 727.0 * frames * natoms / (ms_total / 1e3) / 1e9,
+                            "frac": 727.0 * frames * natoms / (ms_total / 1e3) / 1e9 / peaks["hbm_gbs"],
+                            "note": "SURVEY.md 8(d): keys 29 + connectivity 16 + composition 22 + descriptor 336 + assign 324 B"}}
+    comm = None
+    if world > 1:
+        comm = {"exchange": args.exchange, "training_allreduce": res.stats.get("fit_comm"), "other": res.stats.get("comm"),
+                "train_phase_s": phases.get("train"), "job_s": ms_total / 1e3}
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    # ---- e2e: the same job from page-locked host arrays ------------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_pos = torch.empty((frames, natoms, 3), dtype=torch.float64, pin_memory=True)
-        h_pos.copy_(pos)
-        # results: the bonds as a list (every bond once, (i, j) pairs per frame -- what walking the reference's
-        # OBMol bonds yields), bond-type key codes + dictionary, molecule labels
-        h_out = {"edges": torch.empty((frames * natoms, 2), dtype=torch.int32, pin_memory=True),
-                 "edge_ptr": torch.empty(frames + 1, dtype=torch.int64, pin_memory=True),
-                 "keycode": torch.empty((frames, natoms), dtype=torch.uint8, pin_memory=True),
-                 "keytable": torch.empty(256, dtype=torch.int64, pin_memory=True),
-                 "labels": torch.empty((frames, natoms), dtype=torch.int32, pin_memory=True)}
-        # the same with 4-slot bond rows per atom instead of the list (C/H/O: max valence 4, checked on device)
-        h_rows = {"ell": torch.empty((frames, natoms, 4), dtype=torch.int32, pin_memory=True),
-                  "keycode": h_out["keycode"], "keytable": h_out["keytable"], "labels": h_out["labels"]}
+        hs = HostSource(torch, dev, pos, rowptr, col, bo, cell, frames, bf, rank, world, args.host_slots)
+        del pos, rowptr, col, bo
+        torch.cuda.empty_cache()
+        barrier()
         torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, eres = job(hs, frames)
+        nsel = sum(len(v) for v in eres.chosen.values())   # the selection is host data on return
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        e_ms = max_over_ranks((t1 - t0) * 1e3)
+        same = eres.chosen == res.chosen if hs.slots >= frames else None
+        e2e = {"value": units / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(hs.h2d_bytes // steps),
+               "d2h_bytes_per_step": int(nsel * 16 // steps + 1), "ms_per_step": e_ms / steps,
+               "selected_structures": nsel, "same_selection_as_resident_run": same,
+               "host_frames_kept": hs.slots,
+               "api": "StreamingSelector.run(source) with page-locked host arrays (positions, CSR bond table): every "
+                      "batch of each of the three passes is copied host -> device inside the timed region; the chosen "
+                      "(step, atom) lists come back to the host",
+               "phases_s": {k: max_over_ranks(v) for k, v in eres.timings.items()}}
+        del hs
 
-        def e2e_step():
-            eng.analyze_host(h_pos, cell, sysm.types, True, out=h_out, edges=True)
-
-        def e2e_rows_step():
-            eng.analyze_host(h_pos, cell, sysm.types, True, out=h_rows, ell_width=4, key_codes=True)
-
-        def timed(fn):
-            for _ in range(min(args.warmup, 2) or 1):
-                fn()
-            barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                fn()  # synchronises internally: results are in host memory on return
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            barrier()
-            return max_over_ranks((t1 - t0) * 1e3) / args.steps
-
-        r_ms = timed(e2e_rows_step)
-        e_ms = timed(e2e_step)
-        # spot-check: the host path returned the same results as the device path
-        nedges = int(h_out["edge_ptr"][frames].item())
-        same = bool(torch.equal(h_out["labels"][:2], out["labels"][:2].cpu()) and
-                    torch.equal(h_out["keytable"][h_out["keycode"][:2].long()], out["keys"][:2].cpu()) and
-                    torch.equal(h_rows["ell"][:2], out["ell"][:2, :, :4].cpu()) and
-                    bool((out["ell"][:2, :, 4:] < 0).all().item()))
-        for f in range(2):
-            rows = out["ell"][f].cpu()
-            ii, kk = torch.nonzero(rows >= 0, as_tuple=True)
-            jj = rows[ii, kk].long()
-            want = torch.stack([ii[jj > ii], jj[jj > ii]], dim=1).int()
-            same = same and bool(torch.equal(h_out["edges"][int(h_out["edge_ptr"][f]):int(h_out["edge_ptr"][f + 1])], want))
-        e2e = {"value": units_per_step / (e_ms / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_pos.numel() * 8 + natoms),
-               "d2h_bytes_per_step": int(nedges * 8 + (frames + 1) * 8 + frames * natoms * 5 + 256 * 8),
-               "ms_per_step": e_ms, "matches_device_path": same, "bonds_per_step": nedges,
-               "api": "Engine.analyze_host(edges=True) -> mdb_analyze_frames_host_edges (pinned host buffers, pipelined "
-                      "H2D/compute/D2H); results returned: bond list [E,2] int32 + per-frame offsets, bond-type key codes "
-                      "[F,N] uint8 + dictionary [256] uint64, molecule labels [F,N] int32",
-               "rows_variant": {"value": units_per_step / (r_ms / 1e3), "ms_per_step": r_ms,
-                                "d2h_bytes_per_step": int(frames * natoms * 21 + 256 * 8),
-                                "api": "mdb_analyze_frames_host_coded: 4-slot bond rows [F,N,4] int32 instead of the list"}}
-        del h_rows
-        del h_pos, h_out
-
-    # ---- the other two stages of the metric, on the same frames (reported beside the headline) ----
     stages = None
     if not args.no_stages:
-        stages = measure_stages(eng, pos, cell, types, natoms, frames, args, torch, max_over_ranks, world, peaks)
-        if rank == 0:
-            stages["text_reader"] = measure_text_reader(sysm, natoms, args, eng)
+        torch.cuda.empty_cache()
+        stages = {"c2_bonds": measure_c2_bonds(torch, dev, local, max_over_ranks, world, peaks)}
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        base = cpu_baseline(natoms, density, dense, synth.BASE_SEED + 2)
+        base = cpu_baseline(natoms=natoms, sysm=sysm if natoms == NATOMS else None)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": text, "atoms_per_frame": natoms, "frames_per_rank": frames,
-                           "frames_total": frames * world, "density_per_A3": density,
-                           "stages": "cell list + bonds + valence/angle cleanup + bond-type keys + molecule labels",
-                           "bond_orders": "keys with all-single levels in the step (what the CPU arm computes too); "
-                                          "the bond-order perception is timed as stages.bond_orders",
-                           "parallelism": f"frames sharded over {world} rank(s), no data-path collective",
-                           "l2": f"inputs are {frames * natoms * 24 / 1e6:.0f} MB per step per rank (> 126 MB L2)"
-                                 if frames * natoms * 24 > 126e6 else "inputs fit L2 (not a headline configuration)",
-                           "seed": synth.BASE_SEED + 2},
-                "roofline": roofline, "kernels": kern, "stages": stages, "cpu_baseline": base, "e2e": e2e,
-                "gpu_launches": int(launches),
-                "clocks": clocks,
-                "bond_stats_per_step": stats}
+                "config": {"workload": C3_TEXT if world == 1 else C4_TEXT, "atoms_per_frame": natoms,
+                           "frames_per_rank": frames, "frames_total": frames * world, "frames_per_step": fps,
+                           "frames_per_device_batch": bf, "density_per_A3": DENSITY, "n_clusters": args.clusters,
+                           "pool_rows": args.pool_rows, "cutoff_A": 5.0,
+                           "stages": "bond-type keys from the bond table + device group-by + sphere compositions + molecule "
+                                     "labels (pass A); descriptors -> scaler bounds + training pool (pass B); MiniBatchKMeans "
+                                     "per bond type; descriptors -> scale -> tcgen05 assignment (pass C); selection",
+                           "step": "1/steps of the job's frames through all three passes; training + selection once per "
+                                   "job, inside the timed region; warm-up = a job of `warmup` steps",
+                           "bond_types": len(res.keys), "clustered_types": len(res.maxcount),
+                           "selected_structures": nchosen,
+                           "parallelism": f"frame batches interleaved over {world} rank(s); training {args.exchange}",
+                           "l2": f"inputs are {frames * natoms * 45 / 1e9:.1f} GB per rank (> 126 MB L2)",
+                           "seed": synth.BASE_SEED + 3},
+                "phases_s": phases, "roofline": roofline, "kernels": kern, "fit": {str(k): v for k, v in res.stats["fit"].items()},
+                "stages": stages, "cpu_baseline": base, "e2e": e2e, "comm": comm,
+                "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

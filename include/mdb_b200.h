@@ -95,6 +95,37 @@ int mdb_bond_keys(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell,
 int mdb_bond_keys_bo(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell,
                      const double *d_bo, const uint8_t *d_types, uint64_t *d_keys, void *stream);
 
+/* Bond-file mode keys from a CSR bond table (one row per atom and frame): d_rowptr [F][N+1]
+ * frame-local offsets, d_bo [F][colcap] the bond orders in file order -- the columns
+ * s[4+nb : 4+2nb] of a `fix reaxff/bonds` line (detect.py:112-115).  Same key as mdb_bond_keys_bo. */
+int mdb_bond_keys_csr(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_rowptr, const double *d_bo,
+                      long long colcap, const uint8_t *d_types, uint64_t *d_keys, void *stream);
+
+/* ---- group-by of DatasetBuilder._readtimestepsbond (datasetbuilder.py:185-214) on the device ----
+ * The reference turns every frame into {key -> [atom ids]} and appends (step, ids) to one list per
+ * bond type.  Here a key dictionary lives on the device for the whole run -- d_tab_keys [cap]
+ * (initialise to all ones = empty), d_tab_count [cap] (0; atoms seen per key, all frames),
+ * d_tab_first [cap] (all ones; smallest (step << 32 | atom index) per key = first-seen order,
+ * datasetbuilder.py:205-206) -- and every call adds one batch of frames:
+ *   d_codes [F][N]   out: table slot of each atom-frame (0xffff = dropped by d_keep);
+ *   d_order [F*N]    out (optional): batch-local atom-frame indices f*N + i sorted by slot, ascending
+ *                    inside a slot (frames, then atom ids: the row order of a bond type);
+ *   d_seg  [cap+1]   out (optional): d_order[d_seg[s] .. d_seg[s+1]) belongs to slot s;
+ *                    d_seg[cap] = number of kept atom-frames.
+ * d_keep [F][N] (optional, 0 = drop) is the model-deviation filter of detect.py:215-223.  Slot numbers
+ * depend on insertion order, translate them through d_tab_keys.  cap: power of two, 32..4096; more
+ * than cap distinct keys raises the device error flag (mdb_bond_stats). */
+int mdb_group_keys(mdb_ctx *ctx, int nframes, int natoms, const uint64_t *d_keys, const uint8_t *d_keep,
+                   long long step0, int cap, uint64_t *d_tab_keys, long long *d_tab_count,
+                   long long *d_tab_first, uint16_t *d_codes, int32_t *d_order, long long *d_seg,
+                   void *stream);
+
+/* Per-type max_counter (datasetbuilder.py:262-272): d_maxc [cap][8] (in/out) takes, for the slot of every
+ * target, the element-wise maximum of its composition d_counts [ntargets][ntypes].  d_targets: atom-frame
+ * indices into d_codes, or NULL = 0 .. ntargets-1. */
+int mdb_type_maxcount(mdb_ctx *ctx, const int32_t *d_targets, long long ntargets, const uint16_t *d_codes,
+                      const int32_t *d_counts, int32_t *d_maxc, void *stream);
+
 /* ---- K4: connectivity --------------------------------------------------------
  * Replaces the partition computed by dps(bonds) (dps.pyx:17-46): d_labels[f][i] =
  * smallest atom index of the molecule containing i (the DFS root the reference
@@ -102,6 +133,11 @@ int mdb_bond_keys_bo(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell
  * written by mdb_bond_keys. */
 int mdb_components(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_ell,
                    int32_t *d_labels, int seeded, void *stream);
+
+/* The same partition from a CSR bond table (bond-file mode, DetectBond.readmolecule, detect.py:137-144):
+ * d_rowptr [F][N+1], d_col [F][colcap] 0-based partners, every bond listed from both ends. */
+int mdb_components_csr(mdb_ctx *ctx, int nframes, int natoms, const int32_t *d_rowptr, const int32_t *d_col,
+                       long long colcap, int32_t *d_labels, void *stream);
 
 /* Exact dps output (molecule order by smallest index, members in the reference's
  * LIFO-DFS visiting order, dps.pyx:27-43) for one frame, from a CSR whose row
@@ -219,6 +255,15 @@ int mdb_minmax_fit(mdb_ctx *ctx, long long rows, int D, const double *d_X, long 
                    double *d_min, double *d_max, void *stream);
 int mdb_minmax_transform(mdb_ctx *ctx, long long rows, int D, double *d_X, long long ldx,
                          const double *h_min, const double *h_max, void *stream);
+/* Streaming fit (MinMaxScaler.partial_fit): folds the column bounds of these rows into the running
+ * d_min / d_max [D], which the caller starts at (+DBL_MAX, -DBL_MAX). */
+int mdb_minmax_accumulate(mdb_ctx *ctx, long long rows, int D, const double *d_X, long long ldx,
+                          double *d_min, double *d_max, void *stream);
+/* d_out[d_dst[r]] = d_X[d_src[r]] for r < n (rows of D doubles): collects the rows of a batch that
+ * belong to the seeded training pool of the streaming clustering. */
+int mdb_gather_rows(mdb_ctx *ctx, long long n, int D, const double *d_X, long long ldx,
+                    const long long *d_src, const long long *d_dst, double *d_out, long long ldo,
+                    void *stream);
 
 /* ---- K7: k-means assignment ---------------------------------------------------------
  * Replaces sklearn _labels_inertia / lloyd_iter_chunked_dense(update_centers=False)
@@ -280,6 +325,17 @@ int mdb_kpp_step(mdb_ctx *ctx, long long n, int D, const double *d_X, long long 
 int mdb_kmeans_plusplus(mdb_ctx *ctx, int nbatch, long long n, int D, const double *d_X, long long ldx,
                         const int32_t *d_rowidx, int K, int n_local_trials, const double *h_rand,
                         const int32_t *h_first_center, int32_t *d_indices, void *stream);
+
+/* ---- per-cluster selection on stored labels (datasetbuilder.py:378-383) ------------------------
+ * `idx = np.where(labels == k)[0]; choice(idx, n_each)` needs, per cluster, its member count and then
+ * the row of member number p.  mdb_label_hist adds the member counts of d_labels [rows] to d_hist [K];
+ * mdb_pick_rows resolves npicks queries d_picks [npicks][4] = (first row, end row, cluster, p): the row
+ * (index into d_labels) of the p-th member of that cluster inside [first row, end row), ascending row
+ * order, or -1 when the range holds fewer members. */
+int mdb_label_hist(mdb_ctx *ctx, long long rows, int K, const int32_t *d_labels, int32_t *d_hist,
+                   void *stream);
+int mdb_pick_rows(mdb_ctx *ctx, const int32_t *d_labels, int npicks, const long long *d_picks,
+                  long long *d_rows, void *stream);
 
 /* ---- bond orders for the dump-only key ---------------------------------------------
  * Replaces `mol.PerceiveBondOrders()` (reference detect.py:279-280; Open Babel 3.1.x
@@ -370,6 +426,10 @@ int mdb_write_gjf_batch(int nfiles, const char *const *paths, const long long *o
                         const char *symbols4, const int32_t *znum, const double *pos,
                         const long long *mol_offsets, const int32_t *mol_sizes, int nkeywords,
                         const char *const *keywords, int fragment, int nthreads);
+
+/* DFMA throughput of the device in TFLOP/s, measured by a register-resident fused multiply-add kernel
+ * (bench.py's denominator for the FP64-bound descriptor kernels).  Synchronises. */
+int mdb_fp64_peak(mdb_ctx *ctx, double *h_tflops, void *stream);
 
 /* Per-launch CUDA-event timing on the launching stream (bench.py's live roofline
  * measurement).  mdb_profile_read synchronises and writes "name count total_ms" lines

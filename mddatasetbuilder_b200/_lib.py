@@ -31,6 +31,15 @@ SIGNATURES = {
     "mdb_ell_to_csr": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "mdb_bond_keys": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdb_bond_keys_bo": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mdb_bond_keys_csr": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, C.c_longlong, _vp, _vp, _vp]),
+    "mdb_components_csr": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, C.c_longlong, _vp, _vp]),
+    "mdb_group_keys": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp]),
+    "mdb_type_maxcount": (C.c_int, [c_ctx, _vp, C.c_longlong, _vp, _vp, _vp, _vp]),
+    "mdb_minmax_accumulate": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp]),
+    "mdb_gather_rows": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, C.c_longlong, _vp]),
+    "mdb_label_hist": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, _vp, _vp]),
+    "mdb_pick_rows": (C.c_int, [c_ctx, _vp, C.c_int, _vp, _vp, _vp]),
     "mdb_components": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
     "mdb_dps": (C.c_int, [c_ctx, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp]),
     "mdb_analyze_frames": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
@@ -79,6 +88,7 @@ SIGNATURES = {
     "mdb_write_xyz_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), _vp, _vp, _vp, C.c_int]),
     "mdb_write_gjf_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), _vp, _vp, _vp, _vp, _vp, _vp, C.c_int,
                                       C.POINTER(C.c_char_p), C.c_int, C.c_int]),
+    "mdb_fp64_peak": (C.c_int, [c_ctx, C.POINTER(C.c_double), _vp]),
     "mdb_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "mdb_profile_read": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),
     "mdb_perceive_bond_orders": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),

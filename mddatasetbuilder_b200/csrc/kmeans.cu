@@ -341,11 +341,17 @@ __global__ void __launch_bounds__(256) k_minmax_init(unsigned long long *omin, u
 }
 
 __global__ void __launch_bounds__(256) k_minmax_decode(const unsigned long long *omin, const unsigned long long *omax,
-                                                       double *mn, double *mx, int D) {
+                                                       double *mn, double *mx, int D, int accumulate) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < D) {
-        mn[c] = dbl_unorder(omin[c]);
-        mx[c] = dbl_unorder(omax[c]);
+        const double a = dbl_unorder(omin[c]), b = dbl_unorder(omax[c]);
+        if (!accumulate) {
+            mn[c] = a;
+            mx[c] = b;
+        } else if (a <= b) {  // running bounds over several calls (streaming scaler fit)
+            mn[c] = fmin(mn[c], a);
+            mx[c] = fmax(mx[c], b);
+        }
     }
 }
 
@@ -1047,8 +1053,7 @@ int minmax_fit_run(mdb_ctx *c, long long rows, int D, const double *d_X, long lo
         k_colminmax<<<grid, 256, 0, stream>>>(d_X, ldx, rows, D, omin, omax);
     }
     c->launches += 2;
-    (void)accumulate;
-    k_minmax_decode<<<cdiv(D, 256), 256, 0, stream>>>(omin, omax, d_min, d_max, D);
+    k_minmax_decode<<<cdiv(D, 256), 256, 0, stream>>>(omin, omax, d_min, d_max, D, accumulate);
     c->launches++;
     MDB_CUDA(cudaGetLastError());
     return 0;

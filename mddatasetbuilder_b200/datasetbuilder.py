@@ -157,6 +157,8 @@ class DatasetBuilder:
         self.seed = seed
         self.frames_per_batch = int(os.environ.get("MDB_FRAMES_PER_BATCH", "0"))
         self._cache_bytes = int(float(os.environ.get("MDB_CACHE_GB", "8")) * (1 << 30))
+        # rows of a bond type the clustering trains on at most (all of them when the type has fewer)
+        self.pool_rows = int(os.environ.get("MDB_POOL_ROWS", str(1 << 21)))
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -176,7 +178,7 @@ class DatasetBuilder:
         return int(max(1, min(256, (4 << 20) // n)))
 
     def _dump_batches(self):
-        """Yield (first step, positions [F,N,3] on the GPU, cells [F,9]) for the batches this rank
+        """Yield (first step, positions [F,N,3] on the GPU, cells [F,9], batch number) for the batches this rank
         owns.  Parsed frames are kept on the GPU for the later passes while they fit the cache
         budget; otherwise the text is parsed again (like the reference does for every bond type,
         datasetbuilder.py:243)."""
@@ -196,7 +198,7 @@ class DatasetBuilder:
                 pos, cell = rd.read_device(B, self.engine, self.stepinterval, prefetch=(world == 1))
                 if len(pos) == 0:
                     break
-                item = (step0, pos, cell.copy())
+                item = (step0, pos, cell.copy(), b)
                 if cache is not None:
                     used += pos.numel() * 8
                     if used <= self._cache_bytes:
@@ -227,7 +229,7 @@ class DatasetBuilder:
                 nf = len(nbr)
                 if nf == 0:
                     break
-                yield step0, nbr, bo
+                yield step0, nbr, bo, b
             else:
                 nf = rd.skip(B, self.stepinterval)
                 if nf == 0:
@@ -251,9 +253,7 @@ class DatasetBuilder:
                 self._readtimestepsbond()
             elif runstep == 1:
                 self._chosen = {}
-                for bondtype in self.atombondtype:
-                    self._writecoulumbmatrix(bondtype, None)
-                    gc.collect()
+                self._cluster_types()
             elif runstep == 2:
                 os.makedirs(self.dataset_dir, exist_ok=True)
                 if self.writegjf:
@@ -273,171 +273,107 @@ class DatasetBuilder:
         self.bondtyperestore[key] = typestr
         return typestr
 
-    def _readtimestepsbond(self):
-        """Read and store the bond of each atom in each frame (datasetbuilder.py:185-214)."""
+    def _frame_source(self):
+        """The frames this rank owns as `streaming.FrameBatch`es: dump batches, zipped by frame index with the
+        bond-file batches when there is a bond file (datasetbuilder.py:428-433), plus the model-deviation
+        filter when an error file is given."""
         import torch
 
-        eng = self.engine
-        N = self.crddetector._N
-        types0 = (self.bonddetector.atomtype - 1).astype(np.uint8)
-        d_types = eng.to_device_types(types0)
-        typerows = defaultdict(list)   # type string -> [(step, atom ids 1-based ascending)]
-        first_seen = {}
-        nstep = 0
+        from .streaming import FrameBatch
+
+        builder = self
         errors = self._error_rows() if self.errorfilename is not None else None
+        N = self.crddetector._N
 
-        def collect(step0, keys):
-            nonlocal nstep
-            for f in range(keys.shape[0]):
-                kf = keys[f]
-                order = np.argsort(kf, kind="stable")
-                ks = kf[order]
-                cut = np.nonzero(np.diff(ks))[0] + 1
-                starts = np.concatenate([[0], cut])
-                ends = np.concatenate([cut, [len(ks)]])
-                step = step0 + f
-                keep = None
-                if errors is not None:
-                    keep = errors[step] > self.errorlimit
-                for a, b in zip(starts, ends):
-                    ids = order[a:b]
-                    if keep is not None:
-                        ids = ids[keep[ids]]
-                        if ids.size == 0:
-                            continue
-                    t = self._bondtype(ks[a])
-                    typerows[t].append((step, (ids + 1).astype(np.int64)))
-                    fs = (step, int(ids[0]))
-                    if t not in first_seen or fs < first_seen[t]:
-                        first_seen[t] = fs
-                nstep += 1
+        class Source:
+            def batches(self_inner):
+                def keep_of(step0, nf):
+                    if errors is None:
+                        return None
+                    if step0 + nf > len(errors):
+                        raise RuntimeError(f"the model deviation file holds {len(errors)} rows after striding, "
+                                           f"the trajectory needs at least {step0 + nf}")
+                    rows = []
+                    for r in errors[step0:step0 + nf]:
+                        if len(r) < N:
+                            raise RuntimeError(f"a model deviation row holds {len(r)} per-atom values, the frames have {N} atoms")
+                        rows.append(r[:N] > builder.errorlimit)
+                    return torch.as_tensor(np.stack(rows).astype(np.uint8), device=builder.engine.device)
 
-        if self.bonddetector is self.crddetector:
-            eng.set_option("perceive_bond_orders", 1 if self.perceive_bond_orders else 0)
-            try:
-                for step0, pos, cell in self._dump_batches():
-                    out = eng.analyze(pos, cell, d_types, self.pbc, want_ell=False, want_keys=True, want_labels=False)
-                    eng.check()
-                    collect(step0, out["keys"].cpu().numpy().view(np.uint64))
-                self._rings = eng.perceive_stats()["rings"] if self.perceive_bond_orders else 0
-                if self._rings:
-                    logger.warning(f"{self._rings} molecule-frames contain a ring: their bond orders come "
-                                   "without Open Babel's ring passes (planar-ring sp2, aromatic Kekule)")
-            finally:
-                eng.set_option("perceive_bond_orders", 0)
-        else:
-            for step0, nbr, bo in self._bond_batches():
-                keys = eng.bond_keys_bo(nbr, bo, d_types)
-                collect(step0, keys.cpu().numpy().view(np.uint64))
-        counts = {t: sum(len(ids) for _, ids in rows) for t, rows in typerows.items()}
-        d = _dist()
-        if d is not None:
-            gathered = [None] * d.get_world_size()
-            d.all_gather_object(gathered, (first_seen, counts, nstep))
-            first_seen, counts, nstep = {}, Counter(), 0
-            for fs, cn, ns in gathered:
-                for t, v in fs.items():
-                    if t not in first_seen or v < first_seen[t]:
-                        first_seen[t] = v
-                counts.update(cn)
-                nstep += ns
+                if builder.bonddetector is builder.crddetector:
+                    for step0, pos, cell, g in builder._dump_batches():
+                        yield FrameBatch(g, step0, pos, cell, keep=keep_of(step0, int(pos.shape[0])))
+                else:
+                    for (step0, pos, cell, g), (_, nbr, bo, _g) in zip(builder._dump_batches(), builder._bond_batches()):
+                        nf = min(int(pos.shape[0]), int(nbr.shape[0]))
+                        # the reference ignores the error file in bond-file mode (DetectBond.readatombondtype)
+                        yield FrameBatch(g, step0, pos[:nf], cell[:nf], nbr=nbr[:nf], bo=bo[:nf])
+
+        return Source()
+
+    def _selector(self, only_keys=None):
+        from .streaming import StreamingSelector
+
+        types0 = (self.bonddetector.atomtype - 1).astype(np.uint8)
+        return StreamingSelector(self.engine, types0, cutoff=self.cutoff, n_clusters=self.n_clusters, n_each=self.n_each,
+                                 seed=self.seed, periodic=self.pbc, perceive_bond_orders=self.perceive_bond_orders,
+                                 pool_rows=self.pool_rows, only_keys=only_keys, log=logger.info)
+
+    def _readtimestepsbond(self):
+        """Read and store the bond of each atom in each frame (datasetbuilder.py:185-214): pass A of the
+        streaming selector -- keys, the device-side group-by, max_counter per type."""
+        sel = self._selector()
+        sel.pass_a(self._frame_source())
+        self._sel = sel
+        if getattr(sel, "rings", 0):
+            logger.warning(f"{sel.rings} molecule-frames contain a ring: their bond orders come "
+                           "without Open Babel's ring passes (planar-ring sp2, aromatic Kekule)")
+        self._rings = getattr(sel, "rings", 0)
         # first-seen order (the reference's order depends on imap_unordered arrival; this is the
         # order it produces with one worker)
-        self.atombondtype = sorted(first_seen, key=lambda t: first_seen[t])
-        self._typerows = typerows
-        self._typecounts = dict(counts)
-        self._nstep = nstep
+        self._typekey = {self._bondtype(k): k for k in sel.keys}
+        self.atombondtype = [self._bondtype(k) for k in sel.keys]
+        self._typecounts = {self._bondtype(k): n for k, n in sel.counts.items()}
+        self._nstep = sel.nstep
 
     def _error_rows(self):
-        """Model-deviation rows by step (datasetbuilder.py:640-653: one header line per file,
-        one line per frame, per-atom values from column 7 on, assumed in atom-id order)."""
+        """Model-deviation rows by step (datasetbuilder.py:640-653: one header line per file, one line per
+        frame, per-atom values from column 7 on, in atom-id order); strided per file in lockstep with the
+        frame reader, which restarts its stride at every file."""
         rows = []
         for fn in must_be_list(self.errorfilename):
             with open(fn) as f:
-                for k, line in enumerate(f):
-                    if k == 0:
-                        continue
-                    rows.append(np.array(line.split(), dtype=float)[7:])
-        return rows[:: self.stepinterval] if self.stepinterval > 1 else rows
+                per_file = [np.array(line.split(), dtype=float)[7:] for k, line in enumerate(f) if k > 0 and line.strip()]
+            rows.extend(per_file[:: self.stepinterval] if self.stepinterval > 1 else per_file)
+        return rows
+
+    def _cluster_types(self, only=None):
+        """Descriptors + clustering + selection (datasetbuilder.py:216-281, 351-384) of every bond type in
+        three passes over the frames (streaming.py)."""
+        sel = self._sel
+        sel.only_keys = None if only is None else {self._typekey[t] for t in only}
+        sel.big = [k for k in sel.keys if sel.counts[k] > sel.K and (sel.only_keys is None or k in sel.only_keys)]
+        src = self._frame_source()
+        if sel.big:
+            sel.pass_b(src)
+            for k in sel.big:
+                logger.info(f"Max counter of {self._bondtype(k)} is "
+                            f"{Counter({str(a): int(c) for a, c in zip(self.atomname, sel.maxcount[k]) if c})}")
+            sel.train()
+            sel.pass_c(src)
+        res = sel.select()
+        for k, rows in res.chosen.items():
+            t = self._bondtype(k)
+            self._chosen[t] = rows
+            self._nstructure += len(rows)
 
     def _writecoulumbmatrix(self, trajatomfilename, fc):
         """Descriptors + clustering of one bond type (datasetbuilder.py:216-281); stores the
-        chosen [(step, atom)] rows in ``self._chosen[type]``."""
-        import torch
-
-        from .kmeans import clusterdatas
-
-        eng = self.engine
-        rows = self._typerows.get(trajatomfilename, [])
-        self.dstep = {step: ids for step, ids in rows}
-        n_atoms = self._typecounts.get(trajatomfilename, 0)
-        d = _dist()
-        if n_atoms > self.n_clusters:
-            N = self.crddetector._N
-            d_types = eng.to_device_types((self.crddetector.atomtype - 1).astype(np.uint8))
-            nt = len(self.atomname)
-            # ONE pass over the frames: sphere compositions (-> max_counter over every row of this type) and,
-            # from the membership lists the same scan leaves behind, the Coulomb-matrix spectra.  The padded
-            # sorted rows need the final max_counter, so they are assembled from the stored spectra afterwards
-            # (the reference makes the same two steps inside its parent loop, datasetbuilder.py:253-272).
-            maxc = np.zeros(nt, dtype=np.int32)
-            per_batch = []
-            cap = getattr(self, "_memcap", 32)
-            for step0, pos, cell in self._dump_batches():
-                tg, sa = [], []
-                for f in range(pos.shape[0]):
-                    ids = self.dstep.get(step0 + f)
-                    if ids is not None and len(ids):
-                        tg.append(f * N + (ids - 1))
-                        sa.append(np.stack([np.full(len(ids), step0 + f), ids], axis=1))
-                if not tg:
-                    continue
-                targets = np.concatenate(tg).astype(np.int32)
-                while True:
-                    counts, maxc_new, members = eng.compositions(pos, cell, d_types, self.cutoff, targets=targets,
-                                                                 periodic=self.pbc, maxcount=maxc, members_cap=cap)
-                    try:
-                        eng.check()
-                        break
-                    except RuntimeError as e:
-                        if "(2)" not in str(e) or cap >= 160:   # 2 = a list overflowed its capacity
-                            raise
-                        cap = min(160, cap * 2)
-                maxc = maxc_new
-                nmax = max(int(counts.sum(dim=1).max().item()), 1)
-                out = eng.descriptors(pos, cell, d_types, self.cutoff, counts, maxc, targets=targets, periodic=self.pbc,
-                                      want_X=False, want_eig=True, eigcap=nmax, members=members)
-                per_batch.append((out["eig"], out["n"], counts, np.concatenate(sa)))
-                del members
-            self._memcap = cap
-            eng.check()
-            if d is not None:
-                t = torch.as_tensor(maxc, device=eng.device)
-                d.all_reduce(t, op=d.ReduceOp.MAX)
-                maxc = t.cpu().numpy().astype(np.int32)
-            logger.info(f"Max counter of {trajatomfilename} is "
-                        f"{Counter({str(a): int(c) for a, c in zip(self.atomname, maxc) if c})}")
-            Xs, stepatoms = [], []
-            for eig, nn, counts, sa in per_batch:
-                Xs.append(eng.feature_rows(eig, nn, counts, maxc))
-                stepatoms.append(sa)
-            todo = None
-            D = int(maxc.sum())
-            X = torch.cat(Xs) if Xs else torch.zeros((0, D), dtype=torch.float64, device=eng.device)
-            stepatom = np.concatenate(stepatoms) if stepatoms else np.zeros((0, 2), dtype=np.int64)
-            del Xs, todo, per_batch
-            picks, tags = clusterdatas(eng, X, self.n_clusters, self.n_each, seed=self.seed, with_tags=True)
-            chosen = [(int(stepatom[i, 0]), int(stepatom[i, 1]), (int(t[0]), int(t[1]))) for i, t in zip(picks, tags)]
-            del X
-        else:
-            chosen = [(int(step), int(a), (step, int(a))) for step, ids in rows for a in ids]
-        if d is not None:
-            gathered = [None] * d.get_world_size()
-            d.all_gather_object(gathered, chosen)
-            chosen = [c for part in gathered for c in part]
-        chosen.sort(key=lambda c: c[2])
-        self._chosen[trajatomfilename] = [(c[0], c[1]) for c in chosen]
-        self._nstructure += len(chosen)
+        chosen [(step, atom)] rows in ``self._chosen[type]``.  `builddataset` handles every type in one
+        go (`_cluster_types`); this per-type entry is kept for callers of the reference's method."""
+        if not hasattr(self, "_chosen"):
+            self._chosen = {}
+        self._cluster_types(only=[trajatomfilename])
 
     @classmethod
     def _clusterdatas(cls, X, n_clusters, n_each=1, seed=0):
@@ -526,13 +462,13 @@ class DatasetBuilder:
                 os.makedirs(os.path.join(self.gjfdir, folder), exist_ok=True)
         written = 0
         if self.crddetector is self.bonddetector:
-            for step0, pos, cell in self._dump_batches():
+            for step0, pos, cell, _g in self._dump_batches():
                 for f in range(pos.shape[0]):
                     if (step0 + f) in self.dstep:
                         written += self._writestepxyzfile((step0 + f, (pos[f], cell[f], None)))
         else:
             bonds = self._bond_batches()
-            for (step0, pos, cell), (bstep0, nbr, _) in zip(self._dump_batches(), bonds):
+            for (step0, pos, cell, _g), (bstep0, nbr, _, _gb) in zip(self._dump_batches(), bonds):
                 # bond file and dump are matched by frame index (datasetbuilder.py:428-433)
                 for f in range(min(pos.shape[0], nbr.shape[0])):
                     if (step0 + f) in self.dstep:

@@ -93,6 +93,12 @@ class Engine:
             out[name] = (int(cnt), float(ms))
         return out
 
+    def fp64_peak_tflops(self) -> float:
+        """Measured DFMA peak of this GPU (TFLOP/s)."""
+        v = C.c_double(0.0)
+        _lib.check(self.L.mdb_fp64_peak(self.ctx, C.byref(v), self.stream()), "mdb_fp64_peak")
+        return float(v.value)
+
     def stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
@@ -199,6 +205,84 @@ class Engine:
                                      self.stream())
         _lib.check(rc, "mdb_bond_keys_bo")
         return keys
+
+    def bond_keys_csr(self, rowptr, bo, types, colcap=None):
+        """Bond-file mode keys from a CSR bond table: rowptr [F,N+1] int32 (frame-local), bo [F,colcap] float64."""
+        torch = _torch()
+        F, N = int(rowptr.shape[0]), int(rowptr.shape[1]) - 1
+        colcap = int(colcap if colcap is not None else bo.shape[1])
+        keys = torch.empty((F, N), dtype=torch.int64, device=self.device)
+        rc = self.L.mdb_bond_keys_csr(self.ctx, F, N, _ptr(rowptr), _ptr(bo), colcap, _ptr(types), _ptr(keys), self.stream())
+        _lib.check(rc, "mdb_bond_keys_csr")
+        return keys
+
+    def components_csr(self, rowptr, col, colcap=None, out=None):
+        """Molecule labels (smallest atom index of the molecule) from a CSR bond table."""
+        torch = _torch()
+        F, N = int(rowptr.shape[0]), int(rowptr.shape[1]) - 1
+        colcap = int(colcap if colcap is not None else col.shape[1])
+        labels = out if out is not None else torch.empty((F, N), dtype=torch.int32, device=self.device)
+        rc = self.L.mdb_components_csr(self.ctx, F, N, _ptr(rowptr), _ptr(col), colcap, _ptr(labels), self.stream())
+        _lib.check(rc, "mdb_components_csr")
+        return labels
+
+    # ------------------------------------------------------------------ group-by (streaming pass A)
+    def key_table(self, cap=1024):
+        """Empty device key dictionary for `group_keys`: (keys, counts, first) int64 [cap]."""
+        torch = _torch()
+        return (torch.full((cap,), -1, dtype=torch.int64, device=self.device),
+                torch.zeros(cap, dtype=torch.int64, device=self.device),
+                torch.full((cap,), -1, dtype=torch.int64, device=self.device))
+
+    def group_keys(self, keys, table, step0=0, keep=None, want_order=True):
+        """Adds a batch of keys [F,N] to the dictionary `table`; returns (codes [F,N] int16 bit pattern of the
+        uint16 slot, order [F*N] int32 or None, seg [cap+1] int64 or None) -- see mdb_group_keys."""
+        torch = _torch()
+        F, N = int(keys.shape[0]), int(keys.shape[1])
+        cap = int(table[0].numel())
+        codes = torch.empty((F, N), dtype=torch.int16, device=self.device)
+        order = torch.empty(F * N, dtype=torch.int32, device=self.device) if want_order else None
+        seg = torch.empty(cap + 1, dtype=torch.int64, device=self.device) if want_order else None
+        if keep is not None:
+            keep = keep.to(self.device, dtype=torch.uint8).contiguous()
+        rc = self.L.mdb_group_keys(self.ctx, F, N, _ptr(keys), _ptr(keep), int(step0), cap, _ptr(table[0]), _ptr(table[1]),
+                                   _ptr(table[2]), _ptr(codes), _ptr(order), _ptr(seg), self.stream())
+        _lib.check(rc, "mdb_group_keys")
+        return codes, order, seg
+
+    def type_maxcount(self, codes, counts, maxc, targets=None):
+        """maxc [cap, 8] int32 (in/out): element-wise maximum of the compositions per key slot."""
+        T = int(counts.shape[0])
+        rc = self.L.mdb_type_maxcount(self.ctx, _ptr(targets), T, _ptr(codes), _ptr(counts), _ptr(maxc), self.stream())
+        _lib.check(rc, "mdb_type_maxcount")
+
+    def minmax_accumulate(self, X, mn, mx):
+        rows, D = X.shape
+        rc = self.L.mdb_minmax_accumulate(self.ctx, int(rows), int(D), _ptr(X), int(X.stride(0)), _ptr(mn), _ptr(mx),
+                                          self.stream())
+        _lib.check(rc, "mdb_minmax_accumulate")
+
+    def gather_rows(self, X, src, dst, out):
+        """out[dst[r]] = X[src[r]] (src / dst int64 device tensors)."""
+        n = int(src.numel())
+        rc = self.L.mdb_gather_rows(self.ctx, n, int(X.shape[1]), _ptr(X), int(X.stride(0)), _ptr(src), _ptr(dst), _ptr(out),
+                                    int(out.stride(0)), self.stream())
+        _lib.check(rc, "mdb_gather_rows")
+
+    def label_hist(self, labels, hist):
+        """hist [K] int32 += member counts of labels [rows] int32."""
+        rc = self.L.mdb_label_hist(self.ctx, int(labels.numel()), int(hist.numel()), _ptr(labels), _ptr(hist), self.stream())
+        _lib.check(rc, "mdb_label_hist")
+
+    def pick_rows(self, labels, picks):
+        """picks [n,4] int64 = (first row, end row, cluster, p) -> row of the p-th member of the cluster in the
+        range (ascending), -1 if there is none."""
+        torch = _torch()
+        picks = torch.as_tensor(picks, dtype=torch.int64, device=self.device).contiguous()
+        out = torch.empty(int(picks.shape[0]), dtype=torch.int64, device=self.device)
+        rc = self.L.mdb_pick_rows(self.ctx, _ptr(labels), int(picks.shape[0]), _ptr(picks), _ptr(out), self.stream())
+        _lib.check(rc, "mdb_pick_rows")
+        return out
 
     def components(self, ell):
         torch = _torch()

@@ -10,10 +10,11 @@ flow below follows scikit-learn 1.9 step by step (``cluster/_kmeans.py``: ``_kme
 same order scikit-learn draws them.  The reference seeds nothing (its results differ from run
 to run); this implementation is reproducible for a given ``seed``.
 
-Multi-GPU: when ``torch.distributed`` is initialised every rank holds a shard of the rows;
-the mini-batch is drawn ``batch_size / world`` rows per rank, the centroid partial sums and
-weights are all-reduced (NCCL) before the update, scaler bounds are all-reduced MIN/MAX, and the
-seeding subset is all-gathered so every rank computes identical initial centres.
+Multi-GPU: the training rows (the streaming selector's seeded pool) are replicated on every rank and so
+is the RandomState, hence every rank draws the same mini-batches.  ``exchange="replicated"`` runs the
+whole step on every rank (no collective, bit-identical for any number of ranks); ``exchange="allreduce"``
+gives rank r the r-th slice of each mini-batch and combines centroid sums, weights and the batch inertia
+with ONE packed all-reduce per step (NCCL), which changes the summation order only.
 """
 
 from __future__ import annotations
@@ -37,13 +38,6 @@ class MinMaxScalerB200:
         import torch
 
         mn, mx = self.eng.minmax_fit(X)
-        d = _dist()
-        if d is not None:
-            if X.shape[0] == 0:
-                mn.fill_(float("inf"))
-                mx.fill_(float("-inf"))
-            d.all_reduce(mn, op=d.ReduceOp.MIN)
-            d.all_reduce(mx, op=d.ReduceOp.MAX)
         self.data_min_ = mn.cpu().numpy()
         self.data_max_ = mx.cpu().numpy()
         self.eng.minmax_transform(X, self.data_min_, self.data_max_)
@@ -53,7 +47,7 @@ class MinMaxScalerB200:
 
 class MiniBatchKMeansB200:
     def __init__(self, engine, n_clusters=8, init_size=None, n_init=3, batch_size=1024, max_iter=100,
-                 max_no_improvement=10, reassignment_ratio=0.01, seed=0, verbose=False):
+                 max_no_improvement=10, reassignment_ratio=0.01, seed=0, verbose=False, exchange="replicated"):
         self.eng = engine
         self.n_clusters = int(n_clusters)
         self.init_size = init_size
@@ -64,6 +58,7 @@ class MiniBatchKMeansB200:
         self.reassignment_ratio = reassignment_ratio
         self.seed = seed
         self.verbose = verbose
+        self.exchange = exchange    # "replicated": every rank runs the whole step; "allreduce": batch slices + one all-reduce
 
     # ------------------------------------------------------------------ seeding
     def _init_centroids_all(self, X, rs, init_size):
@@ -94,24 +89,42 @@ class MiniBatchKMeansB200:
 
     # ------------------------------------------------------------------ one mini-batch step
     def _mini_batch_step(self, X, batch_idx, centers, weight_sums, rs, random_reassign):
-        """sklearn _mini_batch_step; updates centers / weight_sums in place, returns inertia."""
+        """sklearn _mini_batch_step; updates centers / weight_sums in place, returns inertia.
+
+        With ``exchange == "allreduce"`` and torch.distributed initialised, every rank holds the same rows
+        X and the same batch; rank r assigns and sums only its slice of the batch, and ONE packed
+        all-reduce (sums | weights | inertia) makes the update identical everywhere."""
         import torch
 
         eng = self.eng
         K = self.n_clusters
-        labels, inertia, _ = eng.kmeans_assign(X, centers, rowidx=batch_idx, want_inertia=True)
-        sums, wsum = eng.kmeans_partial_sums(X, labels, K, rowidx=batch_idx, out=self._sums_buf)
-        d = _dist()
-        if d is not None:
-            d.all_reduce(sums)
-            d.all_reduce(wsum)
-            t = torch.tensor([inertia], dtype=torch.float64, device=eng.device)
-            d.all_reduce(t)
-            inertia = float(t.item())
+        d = _dist() if self.exchange == "allreduce" else None
+        B = int(batch_idx.numel())
+        if d is not None and d.get_world_size() > 1:
+            w, r = d.get_world_size(), d.get_rank()
+            lo, hi = (B * r) // w, (B * (r + 1)) // w
+            part = batch_idx[lo:hi]
+            sums, wsum = self._sums_buf
+            if hi > lo:
+                labels, inertia, _ = eng.kmeans_assign(X, centers, rowidx=part, want_inertia=True)
+                eng.kmeans_partial_sums(X, labels, K, rowidx=part, out=self._sums_buf)
+            else:
+                inertia = 0.0
+                self._packed.zero_()
+            self._packed[-1] = inertia
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            d.all_reduce(self._packed)
+            t1.record()
+            self._comm_events.append((t0, t1))
+            inertia = float(self._packed[-1].item())
+        else:
+            labels, inertia, _ = eng.kmeans_assign(X, centers, rowidx=batch_idx, want_inertia=True)
+            sums, wsum = eng.kmeans_partial_sums(X, labels, K, rowidx=batch_idx, out=self._sums_buf)
         eng.kmeans_apply_update(centers, weight_sums, sums, wsum)
         if random_reassign and self.reassignment_ratio > 0:
             ws = weight_sums.cpu().numpy()
-            B = int(batch_idx.numel())
             to_reassign = ws < self.reassignment_ratio * ws.max()
             if to_reassign.sum() > 0.5 * B:
                 indices_dont_reassign = np.argsort(ws)[int(0.5 * B):]
@@ -127,19 +140,13 @@ class MiniBatchKMeansB200:
         return inertia
 
     # ------------------------------------------------------------------ fit
-    def fit(self, X):
+    def fit(self, X, compute_labels=True):
+        """``MiniBatchKMeans.fit`` on the device rows X [n, D] (every rank holds the same X when
+        torch.distributed is initialised: the streaming selector replicates its training pool)."""
         import torch
 
         eng = self.eng
-        d = _dist()
-        world = d.get_world_size() if d is not None else 1
-        rank = d.get_rank() if d is not None else 0
-        n_local = int(X.shape[0])
-        n_samples = n_local
-        if d is not None:
-            t = torch.tensor([n_local], dtype=torch.int64, device=eng.device)
-            d.all_reduce(t)
-            n_samples = int(t.item())
+        n_samples = int(X.shape[0])
         K = self.n_clusters
         D = int(X.shape[1])
         batch_size = min(self.batch_size, n_samples)
@@ -150,28 +157,15 @@ class MiniBatchKMeansB200:
             init_size = 3 * K
         init_size = min(init_size, n_samples)
         rs = np.random.RandomState(self.seed)
-        self._sums_buf = (torch.empty((K, D), dtype=torch.float64, device=eng.device),
-                          torch.empty(K, dtype=torch.float64, device=eng.device))
+        self._packed = torch.zeros(K * D + K + 1, dtype=torch.float64, device=eng.device)
+        self._sums_buf = (self._packed[: K * D].view(K, D), self._packed[K * D: K * D + K])
+        self._comm_events = []
 
-        # seeding pool: in the distributed case every rank contributes init_size / world rows
-        if d is not None:
-            share = -(-init_size // world)
-            take = np.random.RandomState(self.seed + 7919 * (rank + 1)).randint(0, max(n_local, 1), share)
-            part = X[torch.as_tensor(take, device=eng.device)] if n_local else torch.zeros((share, D), dtype=X.dtype,
-                                                                                            device=eng.device)
-            gathered = [torch.empty_like(part) for _ in range(world)]
-            d.all_gather(gathered, part.contiguous())
-            pool = torch.cat(gathered)[:init_size].contiguous()
-            pool_is_all = False
-        else:
-            pool = X
-            pool_is_all = True
-        n_pool = int(pool.shape[0])
-        validation_indices = rs.randint(0, n_pool, init_size)
+        validation_indices = rs.randint(0, n_samples, init_size)
         valid_idx = torch.as_tensor(validation_indices, dtype=torch.int32, device=eng.device)
         best_inertia, centers = None, None
-        for c in self._init_centroids_all(pool, rs, init_size if pool_is_all else None):
-            _, inertia, _ = eng.kmeans_assign(pool, c, rowidx=valid_idx, want_inertia=True)
+        for c in self._init_centroids_all(X, rs, init_size):
+            _, inertia, _ = eng.kmeans_assign(X, c, rowidx=valid_idx, want_inertia=True)
             if best_inertia is None or inertia < best_inertia:
                 centers, best_inertia = c, inertia
         centers = centers.contiguous()
@@ -180,11 +174,9 @@ class MiniBatchKMeansB200:
         n_since_last_reassign = 0
         counts_zero = True
         n_steps = (self.max_iter * n_samples) // batch_size
-        local_batch = batch_size if d is None else max(1, batch_size // world)
-        rs_local = rs if d is None else np.random.RandomState(self.seed + 104729 * (rank + 1))
         i = -1
         for i in range(n_steps):
-            idx = rs_local.randint(0, max(n_local, 1), local_batch)
+            idx = rs.randint(0, n_samples, batch_size)
             batch_idx = torch.as_tensor(idx, dtype=torch.int32, device=eng.device)
             n_since_last_reassign += batch_size
             # weights only grow, so once no centre has a zero count the test never fires again (one sync less per step)
@@ -214,17 +206,27 @@ class MiniBatchKMeansB200:
         self.cluster_centers_ = centers
         self.counts_ = weight_sums
         self.n_steps_ = i + 1
-        # final full-data assignment: tensor-core screening + float64 re-check (same labels as float64)
-        if D <= 112 and n_local >= 4096:
-            self.labels_, self.n_rechecked_ = eng.kmeans_assign_tc(X, centers)
-            self.inertia_ = eng.kmeans_inertia(X, centers, self.labels_)
-        else:
-            self.labels_, self.inertia_, _ = eng.kmeans_assign(X, centers, want_inertia=True)
-        if d is not None:
-            t = torch.tensor([self.inertia_], dtype=torch.float64, device=eng.device)
-            d.all_reduce(t)
-            self.inertia_ = float(t.item())
+        self.comm_ms_ = None
+        if self._comm_events:
+            torch.cuda.synchronize()
+            self.comm_ms_ = float(sum(a.elapsed_time(b) for a, b in self._comm_events))
+            self.comm_bytes_per_step_ = int(self._packed.numel() * 8)
+        self._comm_events = []
+        if compute_labels:
+            self.labels_, self.inertia_ = self.predict(X, with_inertia=True)
         return self
+
+    def predict(self, X, with_inertia=False):
+        """Labels of rows X against the fitted centres: tensor-core screening + float64 re-check (same labels
+        as float64) for large inputs, the float64 kernel otherwise."""
+        eng = self.eng
+        centers = self.cluster_centers_
+        if int(X.shape[1]) <= 112 and int(X.shape[0]) >= 4096:
+            labels, self.n_rechecked_ = eng.kmeans_assign_tc(X, centers)
+            inertia = eng.kmeans_inertia(X, centers, labels) if with_inertia else None
+        else:
+            labels, inertia, _ = eng.kmeans_assign(X, centers, want_inertia=with_inertia)
+        return (labels, inertia) if with_inertia else labels
 
     def fit_predict(self, X):
         return self.fit(X).labels_
@@ -261,25 +263,13 @@ def choose_per_cluster(labels_local, n_clusters, n_each, seed, rank=0, world=1, 
 
 
 def clusterdatas(engine, X, n_clusters, n_each=1, seed=0, with_tags=False):
-    """``DatasetBuilder._clusterdatas`` (datasetbuilder.py:351-384) on device rows X [rows, D];
-    X is scaled in place.  Returns the selected LOCAL row indices (numpy) -- with_tags adds the
-    (cluster, draw) pair of every pick, which orders the picks globally across ranks."""
-    import torch
-
+    """``DatasetBuilder._clusterdatas`` (datasetbuilder.py:351-384) on device rows X [rows, D] held by this
+    process; X is scaled in place.  Returns the selected row indices (numpy) -- with_tags adds the
+    (cluster, draw) pair of every pick.  (Row sets spread over ranks or larger than HBM go through
+    ``streaming.StreamingSelector``.)"""
     MinMaxScalerB200(engine).fit_transform(X)
-    d = _dist()
     n_total = int(X.shape[0])
-    if d is not None:
-        t = torch.tensor([n_total], dtype=torch.int64, device=engine.device)
-        d.all_reduce(t)
-        n_total = int(t.item())
     clus = MiniBatchKMeansB200(engine, n_clusters=n_clusters, init_size=min(3 * n_clusters, n_total), n_init=3,
                                seed=seed)
     labels = clus.fit_predict(X).cpu().numpy()
-    if d is None:
-        return choose_per_cluster(labels, n_clusters, n_each, seed, with_tags=with_tags)
-    counts = torch.as_tensor(np.bincount(labels, minlength=n_clusters)[:n_clusters], device=engine.device)
-    allc = [torch.empty_like(counts) for _ in range(d.get_world_size())]
-    d.all_gather(allc, counts)
-    return choose_per_cluster(labels, n_clusters, n_each, seed, d.get_rank(), d.get_world_size(),
-                              torch.stack(allc).cpu().numpy(), with_tags=with_tags)
+    return choose_per_cluster(labels, n_clusters, n_each, seed, with_tags=with_tags)

@@ -93,6 +93,8 @@ class SynthSystem:
     col: np.ndarray
     bo: np.ndarray               # float64 per CSR entry: order + U(-0.3, 0.3)
     seed: int
+    eid: np.ndarray = None       # bond number of every CSR entry (both directions of a bond share it)
+    order: np.ndarray = None     # nominal order of every bond
     meta: dict = field(default_factory=dict)
 
     @property
@@ -200,18 +202,22 @@ def make_system(natoms: int, density: float, seed: int = BASE_SEED, atomname=("C
     rowptr = np.cumsum(deg).astype(np.int32)
     col = np.zeros(int(rowptr[-1]), dtype=np.int32)
     bo = np.zeros(int(rowptr[-1]))
+    eid = np.zeros(int(rowptr[-1]), dtype=np.int32)
     fill = rowptr[:-1].astype(np.int64).copy()
     noise = rng.uniform(-0.3, 0.3, size=len(edges))
-    for (i, j, o), e in zip(edges, noise):
+    for b, ((i, j, o), e) in enumerate(zip(edges, noise)):
         v = round(o + e, 3)
         col[fill[i]] = j
         bo[fill[i]] = v
+        eid[fill[i]] = b
         fill[i] += 1
         col[fill[j]] = i
         bo[fill[j]] = v
+        eid[fill[j]] = b
         fill[j] += 1
     return SynthSystem(atomname, types, pos, box, rowptr, col, bo, seed,
-                       {"density": density, "molecules": counts, "spacing": spacing, "dense": dense})
+                       meta={"density": density, "molecules": counts, "spacing": spacing, "dense": dense},
+                       eid=eid, order=np.array([o for _, _, o in edges], dtype=np.float64))
 
 
 def frame_positions(sys: SynthSystem, nframes: int, sigma: float = 0.05, seed: int | None = None) -> np.ndarray:
@@ -248,6 +254,31 @@ def frame_positions_device(sys: SynthSystem, nframes: int, device, sigma: float 
         out[f0:f1] = p
     out[0] = base
     return out
+
+
+def bond_table_device(sys: SynthSystem, nframes: int, device, seed: int | None = None, amplitude: float = 0.3):
+    """Bond-file mode input for `nframes` frames on the device, as CSR: rowptr [F, N+1] int32 (frame-local),
+    col [F, nnz] int32 and bo [F, nnz] float64.  The topology is the generator's; every frame draws its own
+    bond orders `nominal + U(-amplitude, amplitude)` per bond (both directions of a bond carry the same value,
+    like a `fix reaxff/bonds` table), rounded to the 3 decimals the text format keeps.  Frame 0 = `sys.bo`."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed((sys.seed if seed is None else seed) + 15485863)
+    nnz = int(sys.rowptr[-1])
+    rowptr = torch.as_tensor(sys.rowptr, dtype=torch.int32, device=device)[None].repeat(nframes, 1)
+    col = torch.as_tensor(sys.col, dtype=torch.int32, device=device)[None].repeat(nframes, 1)
+    eid = torch.as_tensor(sys.eid, dtype=torch.int64, device=device)
+    nominal = torch.as_tensor(sys.order, dtype=torch.float64, device=device)
+    bo = torch.empty((nframes, nnz), dtype=torch.float64, device=device)
+    chunk = max(1, int(2 ** 26 // max(len(sys.order), 1)))
+    for f0 in range(0, nframes, chunk):
+        f1 = min(nframes, f0 + chunk)
+        u = torch.rand((f1 - f0, len(sys.order)), dtype=torch.float32, device=device, generator=gen).double()
+        v = torch.round((nominal[None] + amplitude * (2.0 * u - 1.0)) * 1e3) / 1e3
+        bo[f0:f1] = v[:, eid]
+    bo[0] = torch.as_tensor(sys.bo, dtype=torch.float64, device=device)
+    return rowptr.contiguous(), col.contiguous(), bo
 
 
 # ----------------------------------------------------------------------------
