@@ -60,7 +60,8 @@ struct mdb_ctx {
     double opt_cell_edge = 0.0;
     int opt_max_bonds = 8;
     int opt_frames_per_launch = 0;
-    int opt_perceive = 0;  // dump-only keys carry perceived bond orders (perceive.cu)
+    int opt_perceive = 0;
+    int opt_desc_legacy = 0;  // 1: round-1 descriptor kernels (one column per lane / warp pairs) for A/B runs  // dump-only keys carry perceived bond orders (perceive.cu)
     uint64_t launches = 0;
     // arena
     char *arena = nullptr;

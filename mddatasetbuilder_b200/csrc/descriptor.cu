@@ -650,6 +650,274 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6a-mc, clusters of up to 48 atoms (round 2): the register-resident Householder scheme with SEVERAL
+// columns per lane.  A group of LPM lanes owns one matrix, lane g holds columns g, g + LPM, ... (CPL
+// "slots" of NMAX doubles each), so a warp works on 32 / LPM matrices and
+//   * every shared-memory broadcast (x_i in the T x pass, (v_i, w_i) in the rank-2 update) feeds CPL
+//     fused multiply-adds instead of one,
+//   * the per-step scalar work (one butterfly, rsqrt / rcp, the (v, w) publication) is paid once per
+//     32 / LPM matrices instead of once per matrix,
+//   * a slot whose columns are all finished (slot c is done once k >= (c + 1) LPM - 1) drops out of the
+//     unrolled code at compile time.
+// ncu of the one-column kernel had the FP64 pipe 32 % active with ~8,900 warp instructions per 32-atom
+// matrix, half of them per-step overhead; this layout needs ~2,600.  The Coulomb matrix is built straight
+// into the registers (lane g evaluates its own columns, no staging copy), which also takes the shared
+// memory per matrix from 9 KB to 2 KB.  The 33..48 classes use LPM = 32, CPL = 2 on ONE warp (the
+// warp-pair kernel below needed three named barriers per step and ran 3.3 x slower per matrix than the
+// 32-atom class for 1.7 x the arithmetic).
+// ---------------------------------------------------------------------------------------------
+template <int NMAX, int LPM, int CPL>
+struct McSmem {
+    double vec[NMAX][3];
+    double xs[LPM * CPL];
+    double2 vw[LPM * CPL];
+    int z[NMAX];
+    int t[NMAX];
+    int idx[NMAX];
+    double L[3];
+    int n;
+    int pad;
+};
+
+template <int NMAX, int LPM, int CPL>
+struct McCtx {
+    McSmem<NMAX, LPM, CPL> *S;
+    double *dsc, *esc;  // scratch of this matrix: element k at [k * nslots]
+    size_t nslots;
+    int gl, n;
+    bool valid, hi;
+};
+
+template <int K, int NMAX, int LPM, int CPL>
+__device__ __forceinline__ void mc_step(double (&a)[CPL][NMAX], const McCtx<NMAX, LPM, CPL> &cx) {
+    constexpr int C0 = (K + 1) / LPM;  // slots below C0 hold finished columns only
+    McSmem<NMAX, LPM, CPL> *S = cx.S;
+    const int gl = cx.gl, n = cx.n;
+    double x[CPL];
+#pragma unroll
+    for (int c = C0; c < CPL; ++c) {
+        const int col = c * LPM + gl;
+        x[c] = (col > K && col < n) ? a[c][K] : 0.0;
+        S->xs[col] = x[c];
+    }
+    __syncwarp();
+    double acc0[CPL], acc1[CPL];
+#pragma unroll
+    for (int c = C0; c < CPL; ++c) acc0[c] = acc1[c] = 0.0;
+#pragma unroll
+    for (int i = K + 1; i < NMAX; ++i) {
+        const double xi = S->xs[i];
+#pragma unroll
+        for (int c = C0; c < CPL; ++c) {
+            if (((i - K - 1) & 1) == 0) acc0[c] = fma(a[c][i], xi, acc0[c]);
+            else acc1[c] = fma(a[c][i], xi, acc1[c]);
+        }
+    }
+    double pt[CPL];
+    double sg0 = 0.0, ta0 = 0.0;
+#pragma unroll
+    for (int c = C0; c < CPL; ++c) {
+        pt[c] = acc0[c] + acc1[c];
+        sg0 = fma(x[c], x[c], sg0);
+        ta0 = fma(x[c], pt[c], ta0);
+    }
+    // fused reduction of (sigma, tau) over the LPM lanes of the group (see k_tridiag_reg)
+    const bool hi = cx.hi;
+    double keep = hi ? ta0 : sg0;
+    keep += __shfl_xor_sync(0xffffffffu, hi ? sg0 : ta0, LPM >> 1);
+#pragma unroll
+    for (int o = LPM >> 2; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    const double other = __shfl_xor_sync(0xffffffffu, keep, LPM >> 1);
+    const double sig = hi ? other : keep, tau = hi ? keep : other;
+    constexpr int C1 = (K + 1) / LPM, L1 = (K + 1) % LPM;  // owner of column K + 1
+    const double x1 = S->xs[K + 1];
+    const double pt1 = __shfl_sync(0xffffffffu, pt[C1], L1, LPM);
+    const double t00 = __shfl_sync(0xffffffffu, a[C1][K + 1], L1, LPM);
+    const bool doit = sig > 0.0;
+    const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
+    const double alpha = x1 >= 0.0 ? -rs : rs;
+    const double H = sig - alpha * x1;
+    const double iH = doit ? fast_rcp(H) : 0.0;
+    const double Kc = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
+    constexpr int CK = K / LPM, LK = K % LPM;  // owner of column K
+    if (gl == LK && cx.valid && K < n) {
+        cx.dsc[(size_t)K * cx.nslots] = a[CK][K];
+        if (K + 1 < n) cx.esc[(size_t)K * cx.nslots] = alpha;
+    }
+    double v[CPL], w[CPL];
+#pragma unroll
+    for (int c = C0; c < CPL; ++c) {
+        const int col = c * LPM + gl;
+        v[c] = (col == K + 1) ? x[c] - alpha : x[c];
+        const double pg = (pt[c] - alpha * a[c][K + 1]) * iH;
+        w[c] = (col > K) ? pg - Kc * v[c] : 0.0;
+        S->vw[col] = make_double2(v[c], w[c]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = K + 1; i < NMAX; ++i) {
+        const double2 q = S->vw[i];
+#pragma unroll
+        for (int c = C0; c < CPL; ++c) a[c][i] = fma(-q.x, w[c], fma(-q.y, v[c], a[c][i]));
+    }
+}
+
+template <int K, int NMAX, int LPM, int CPL>
+struct McSteps {
+    static __device__ __forceinline__ void run(double (&a)[CPL][NMAX], const McCtx<NMAX, LPM, CPL> &cx) {
+        mc_step<K, NMAX, LPM, CPL>(a, cx);
+        McSteps<K + 1, NMAX, LPM, CPL>::run(a, cx);
+    }
+};
+template <int NMAX, int LPM, int CPL>
+struct McSteps<NMAX - 1, NMAX, LPM, CPL> {
+    static __device__ __forceinline__ void run(double (&)[CPL][NMAX], const McCtx<NMAX, LPM, CPL> &) {}
+};
+
+template <int NMAX, int LPM, int CPL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_tridiag_mc(const __grid_constant__ DescParams P, const int *__restrict__ list,
+                                                                 int nlist, int slot0, int nslots, double *__restrict__ dsc,
+                                                                 double *__restrict__ esc, int *__restrict__ nsc) {
+    static_assert(NMAX <= LPM * CPL, "every column needs a lane slot");
+    static_assert(LPM >= 4 && LPM <= 32 && (LPM & (LPM - 1)) == 0, "lane groups are powers of two");
+    constexpr int G = 32 / LPM;
+    typedef McSmem<NMAX, LPM, CPL> Sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Sm *Sw = reinterpret_cast<Sm *>(smem_raw) + (threadIdx.x >> 5) * G;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / LPM, gl = lane % LPM;
+    const int sw0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * G;  // first slot of this warp
+    for (int g = 0; g < G; ++g) {
+        const int sg = sw0 + g;
+        Sm *Sg = Sw + g;
+        if (lane == 0) Sg->n = 0;
+        if (sg >= nslots) continue;  // warp-uniform
+        const int ord = list[slot0 + sg];
+        const int gt = P.targets ? P.targets[ord] : ord;
+        const int f = gt / P.N, at = gt - f * P.N;
+        const FrameGeom &G0 = P.geom[f];
+        const double *pos = P.pos + (size_t)f * P.N * 3;
+        __syncwarp();
+        const double pa[3] = {pos[(size_t)at * 3], pos[(size_t)at * 3 + 1], pos[(size_t)at * 3 + 2]};
+        const double Lg[3] = {G0.ortho[0], G0.ortho[4], G0.ortho[8]};
+        gather_scan(P, f, at, ord, [&](int j, int tj) {
+            const int k = atomicAdd(&Sg->n, 1);
+            if (k < NMAX) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double D = pos[(size_t)j * 3 + c] - pa[c];
+                    if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
+                    Sg->vec[k][c] = D;
+                }
+                Sg->z[k] = P.Z[tj];
+                Sg->t[k] = tj;
+                Sg->idx[k] = j;
+            }
+        });
+        if (lane == 0) {
+            Sg->L[0] = Lg[0];
+            Sg->L[1] = Lg[1];
+            Sg->L[2] = Lg[2];
+        }
+    }
+    __syncwarp();
+    Sm *S = Sw + grp;
+    const int s = sw0 + grp;
+    const bool valid = s < nslots;
+    int n = S->n;
+    if (n > NMAX) {
+        if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        n = NMAX;
+    }
+    // canonical member order (ascending atom index, the order of np.where at datasetbuilder.py:315):
+    // every lane moves the entries of its own columns to their ranks
+    {
+        double v0[CPL], v1[CPL], v2[CPL];
+        int zz[CPL], tt[CPL], rank[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int e = c * LPM + gl;
+            rank[c] = -1;
+            if (e < n) {
+                v0[c] = S->vec[e][0];
+                v1[c] = S->vec[e][1];
+                v2[c] = S->vec[e][2];
+                zz[c] = S->z[e];
+                tt[c] = S->t[e];
+                const int ii = S->idx[e];
+                int r = 0;
+                for (int q = 0; q < n; ++q) r += S->idx[q] < ii;
+                rank[c] = r;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+            if (rank[c] >= 0) {
+                S->vec[rank[c]][0] = v0[c];
+                S->vec[rank[c]][1] = v1[c];
+                S->vec[rank[c]][2] = v2[c];
+                S->z[rank[c]] = zz[c];
+                S->t[rank[c]] = tt[c];
+            }
+        __syncwarp();
+    }
+    // Coulomb matrix (datasetbuilder.py:341-348) straight into the registers: lane g evaluates rows
+    // 0 .. NMAX-1 of its columns.  Both vectors lie within +-L/2 of the target, so one conditional shift per
+    // axis gives the minimum image; rows / columns >= n are zero.
+    double a[CPL][NMAX];
+    {
+        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
+        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
+        double c0[CPL], c1[CPL], c2[CPL], zc[CPL], dg[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int col = c * LPM + gl;
+            const bool ok = col < n;
+            const int cc = ok ? col : 0;
+            c0[c] = S->vec[cc][0];
+            c1[c] = S->vec[cc][1];
+            c2[c] = S->vec[cc][2];
+            zc[c] = ok && n > 0 ? (double)S->z[cc] : 0.0;
+            dg[c] = ok && n > 0 ? P.diag[S->t[cc]] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) {
+            const double r0 = S->vec[i][0], r1 = S->vec[i][1], r2c = S->vec[i][2];
+            const double zi = i < n ? (double)S->z[i] : 0.0;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int col = c * LPM + gl;
+                double dx = c0[c] - r0, dy = c1[c] - r1, dz = c2[c] - r2c;
+                if (P.periodic) {
+                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+                }
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? zi * zc[c] * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                a[c][i] = (i == col) ? dg[c] : mv;
+            }
+        }
+    }
+    McCtx<NMAX, LPM, CPL> cx;
+    cx.S = S;
+    cx.dsc = dsc + s;
+    cx.esc = esc + s;
+    cx.nslots = (size_t)nslots;
+    cx.gl = gl;
+    cx.n = n;
+    cx.valid = valid;
+    cx.hi = (lane & (LPM >> 1)) != 0;
+    McSteps<0, NMAX, LPM, CPL>::run(a, cx);
+    if (valid) {
+        constexpr int CL = (NMAX - 1) / LPM, LL = (NMAX - 1) % LPM;
+        if (gl == LL && n == NMAX) dsc[s + (size_t)(NMAX - 1) * nslots] = a[CL][NMAX - 1];
+        if (gl == 0) nsc[s] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6a'', clusters of 33..64 atoms: the same register-resident scheme on a pair of warps (lane g of
 // the pair, 0 <= g < 64, holds column g).  The pair meets at a named barrier three times per step:
 // after publishing x, after publishing the per-warp partial sums, and after publishing (v, w).
@@ -1249,6 +1517,50 @@ static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int of
     return 0;
 }
 
+static const char *mc_name(int nmax) {
+    switch (nmax) {
+        case 8: return "k_tridiag_mc<8>";
+        case 12: return "k_tridiag_mc<12>";
+        case 16: return "k_tridiag_mc<16>";
+        case 20: return "k_tridiag_mc<20>";
+        case 24: return "k_tridiag_mc<24>";
+        case 28: return "k_tridiag_mc<28>";
+        case 32: return "k_tridiag_mc<32>";
+        case 40: return "k_tridiag_mc<40>";
+        default: return "k_tridiag_mc<48>";
+    }
+}
+
+// multi-column register kernel + QL for one size class
+template <int NMAX, int LPM, int CPL, int WARPS, int MINB, int QTHREADS>
+static int run_bucket_mc(mdb_ctx *c, const DescParams &P, const int *d_list, int ofs, int cnt, double *dsc, double *esc,
+                         int *nsc, int chunk, const int *d_counts, const int *d_padorder, const double *d_padval,
+                         const int *d_maxcount, int D, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream) {
+    constexpr int G = 32 / LPM;
+    const size_t smem_tri = sizeof(McSmem<NMAX, LPM, CPL>) * WARPS * G;
+    const size_t smem_ql = (size_t)2 * NMAX * QTHREADS * sizeof(double);
+    MDB_CUDA(cudaFuncSetAttribute(k_tridiag_mc<NMAX, LPM, CPL, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_tri));
+    MDB_CUDA(cudaFuncSetAttribute(k_tql<NMAX, QTHREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ql));
+    for (int s0 = 0; s0 < cnt; s0 += chunk) {
+        const int ns = std::min(chunk, cnt - s0);
+        {
+            ProfScope ps(c, mc_name(NMAX), stream);
+            k_tridiag_mc<NMAX, LPM, CPL, WARPS, MINB><<<cdiv(ns, WARPS * G), WARPS * 32, smem_tri, stream>>>(
+                P, d_list, cnt, ofs + s0, ns, dsc, esc, nsc);
+        }
+        {
+            ProfScope ps(c, bucket_name(NMAX, true), stream);
+            k_tql<NMAX, QTHREADS><<<cdiv(ns, QTHREADS), QTHREADS, smem_ql, stream>>>(
+                d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap,
+                d_n, c->d_stats);
+        }
+        c->launches += 2;
+    }
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                     int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
                     const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream,
@@ -1319,15 +1631,33 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     if (hb[B] && run_bucket<NMAX, WARPS, LPM, QT, REG>(c, P, d_list, ofs[B], hb[B], dsc, esc, nsc, chunk, d_counts, d_padorder, \
                                                        d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))               \
         return -1;
-    MDB_BUCKET(0, 8, 8, 8, 128, 1)
-    MDB_BUCKET(1, 12, 8, 16, 128, 1)
-    MDB_BUCKET(2, 16, 8, 16, 128, 1)
-    MDB_BUCKET(3, 20, 8, 32, 128, 1)
-    MDB_BUCKET(4, 24, 8, 32, 128, 1)
-    MDB_BUCKET(5, 28, 8, 32, 128, 1)
-    MDB_BUCKET(6, 32, 8, 32, 128, 1)
-    MDB_BUCKET(7, 40, 4, 32, 64, 2)
-    MDB_BUCKET(8, 48, 4, 32, 64, 2)
+#define MDB_BUCKET_MC(B, NMAX, LPM, CPL, WARPS, MINB, QT)                                                                  \
+    if (hb[B] && run_bucket_mc<NMAX, LPM, CPL, WARPS, MINB, QT>(c, P, d_list, ofs[B], hb[B], dsc, esc, nsc, chunk, d_counts,  \
+                                                                d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, \
+                                                                stream))                                                      \
+        return -1;
+    if (c->opt_desc_legacy) {
+        MDB_BUCKET(0, 8, 8, 8, 128, 1)
+        MDB_BUCKET(1, 12, 8, 16, 128, 1)
+        MDB_BUCKET(2, 16, 8, 16, 128, 1)
+        MDB_BUCKET(3, 20, 8, 32, 128, 1)
+        MDB_BUCKET(4, 24, 8, 32, 128, 1)
+        MDB_BUCKET(5, 28, 8, 32, 128, 1)
+        MDB_BUCKET(6, 32, 8, 32, 128, 1)
+        MDB_BUCKET(7, 40, 4, 32, 64, 2)
+        MDB_BUCKET(8, 48, 4, 32, 64, 2)
+    } else {
+        MDB_BUCKET_MC(0, 8, 4, 2, 4, 4, 128)
+        MDB_BUCKET_MC(1, 12, 4, 3, 4, 4, 128)
+        MDB_BUCKET_MC(2, 16, 8, 2, 4, 4, 128)
+        MDB_BUCKET_MC(3, 20, 8, 3, 4, 2, 128)
+        MDB_BUCKET_MC(4, 24, 8, 3, 4, 2, 128)
+        MDB_BUCKET_MC(5, 28, 16, 2, 4, 2, 128)
+        MDB_BUCKET_MC(6, 32, 16, 2, 4, 2, 128)
+        MDB_BUCKET_MC(7, 40, 32, 2, 4, 2, 64)
+        MDB_BUCKET_MC(8, 48, 32, 2, 4, 2, 64)
+    }
+#undef MDB_BUCKET_MC
     MDB_BUCKET(9, 56, 4, 32, 64, 2)
     MDB_BUCKET(10, 64, 4, 32, 64, 2)
     MDB_BUCKET(11, 96, 1, 32, 64, 0)
