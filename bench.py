@@ -231,7 +231,7 @@ class HostSource:
         self.d = [tuple(torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
                         for t in (self.h_pos, self.h_rowptr, self.h_col, self.h_bo)) for _ in range(2)]
 
-    def batches(self):
+    def batches(self, needed=None):
         from mddatasetbuilder_b200.streaming import FrameBatch
 
         nb = -(-self.F // self.B)
@@ -239,12 +239,15 @@ class HostSource:
             f0, f1 = i * self.B, min(self.F, (i + 1) * self.B)
             nf = f1 - f0
             buf = self.d[i & 1]
+            g = i * self.world + self.rank
+            if needed is not None and not needed(g):              # pass C reuses the spectra it kept: no copy
+                yield FrameBatch(g, g * self.B, buf[0][:nf], self.cell[f0:f1], rowptr=buf[1][:nf], col=buf[2][:nf], bo=buf[3][:nf])
+                continue
             for f in range(nf):                                   # slot-wise copies (cyclic reuse of the host frames)
                 sl = (f0 + f) % self.slots
                 for dst, src in zip(buf, (self.h_pos, self.h_rowptr, self.h_col, self.h_bo)):
                     dst[f].copy_(src[sl], non_blocking=True)
                     self.h2d_bytes += src[sl].numel() * src.element_size()
-            g = i * self.world + self.rank
             yield FrameBatch(g, g * self.B, buf[0][:nf], self.cell[f0:f1], rowptr=buf[1][:nf], col=buf[2][:nf], bo=buf[3][:nf])
 
 
@@ -493,7 +496,7 @@ def main():
                            "step": "1/steps of the job's frames through all three passes; training + selection once per "
                                    "job, inside the timed region; warm-up = a job of `warmup` steps",
                            "bond_types": len(res.keys), "clustered_types": len(res.maxcount),
-                           "selected_structures": nchosen,
+                           "selected_structures": nchosen, "spectra_cache": res.stats.get("spectra_cache"),
                            "parallelism": f"frame batches interleaved over {world} rank(s); training {args.exchange}",
                            "l2": f"inputs are {frames * natoms * 45 / 1e9:.1f} GB per rank (> 126 MB L2)",
                            "seed": synth.BASE_SEED + 3},

@@ -247,6 +247,22 @@ int mdb_feature_rows(mdb_ctx *ctx, long long ntargets, const double *d_eig, int 
                      const int32_t *d_n, const int32_t *d_counts, const int32_t *h_maxcount,
                      double *d_X, void *stream);
 
+/* Compact spectra for callers that keep them across passes (the streaming job computes every row twice --
+ * scaler bounds first, assignment later -- and keeps the spectra of as many frames as HBM allows):
+ * mdb_descriptors_members_compact = mdb_descriptors_members with the eigenvalues of target t written to
+ * d_eig_flat[d_eig_off[t] .. d_eig_off[t+1]) (ascending; d_eig_off int32 [ntargets + 1] is an output, the
+ * caller sizes d_eig_flat with the sum of d_counts); mdb_feature_rows_compact = mdb_feature_rows from that
+ * layout: the same padded sorted rows, bit for bit. */
+int mdb_descriptors_members_compact(mdb_ctx *ctx, int nframes, int natoms, const double *d_pos,
+                                    const double *h_cell, const uint8_t *d_types, int periodic,
+                                    const int32_t *d_targets, long long ntargets, const int32_t *d_counts,
+                                    const int32_t *h_maxcount, const int32_t *d_members, int cap,
+                                    double *d_X, double *d_eig_flat, int32_t *d_eig_off, int32_t *d_n,
+                                    void *stream);
+int mdb_feature_rows_compact(mdb_ctx *ctx, long long ntargets, const double *d_eig_flat,
+                             const int32_t *d_eig_off, const int32_t *d_counts, const int32_t *h_maxcount,
+                             double *d_X, void *stream);
+
 /* ---- MinMaxScaler (datasetbuilder.py:369-370; sklearn preprocessing/_data.py) ------
  * fit: column minima / maxima of d_X [rows][D] (row stride ldx doubles) into d_min /
  * d_max [D] (device).  transform: X = X * scale + min_ in place with scale = 1/range

@@ -58,6 +58,9 @@ SIGNATURES = {
                                            _vp, _vp, C.c_int, _vp, _vp]),
     "mdb_descriptors_members": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_longlong, _vp, _vp,
                                           _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
+    "mdb_descriptors_members_compact": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_longlong, _vp, _vp,
+                                                  _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mdb_feature_rows_compact": (C.c_int, [c_ctx, C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mdb_feature_rows": (C.c_int, [c_ctx, C.c_longlong, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdb_minmax_fit": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp]),
     "mdb_minmax_transform": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp]),

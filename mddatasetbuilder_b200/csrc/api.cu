@@ -321,6 +321,34 @@ extern "C" int mdb_descriptors_members(mdb_ctx *c, int nframes, int natoms, cons
                            h_maxcount, d_X, d_eig, eigcap, d_n, (cudaStream_t)stream, d_members, cap);
 }
 
+extern "C" int mdb_descriptors_members_compact(mdb_ctx *c, int nframes, int natoms, const double *d_pos, const double *h_cell,
+                                               const uint8_t *d_types, int periodic, const int32_t *d_targets,
+                                               long long ntargets, const int32_t *d_counts, const int32_t *h_maxcount,
+                                               const int32_t *d_members, int cap, double *d_X, double *d_eig_flat,
+                                               int32_t *d_eig_off, int32_t *d_n, void *stream) {
+    if (check_ctx(c, "mdb_descriptors_members_compact")) return -1;
+    if ((long long)nframes * natoms >= (1LL << 31) - 64) {
+        mdb_set_error("mdb_descriptors_members_compact: batch too large, split the frames");
+        return -1;
+    }
+    if (!d_members || cap < 1 || !d_eig_flat || !d_eig_off) {
+        mdb_set_error("mdb_descriptors_members_compact: d_members / cap / d_eig_flat / d_eig_off are required");
+        return -1;
+    }
+    return descriptors_run(c, nframes, natoms, d_pos, h_cell, d_types, periodic, 5.0, d_targets, ntargets, d_counts,
+                           h_maxcount, d_X, d_eig_flat, 0, d_n, (cudaStream_t)stream, d_members, cap, d_eig_off);
+}
+
+extern "C" int mdb_feature_rows_compact(mdb_ctx *c, long long ntargets, const double *d_eig_flat, const int32_t *d_eig_off,
+                                        const int32_t *d_counts, const int32_t *h_maxcount, double *d_X, void *stream) {
+    if (check_ctx(c, "mdb_feature_rows_compact")) return -1;
+    if (!d_eig_off) {
+        mdb_set_error("mdb_feature_rows_compact: d_eig_off is required");
+        return -1;
+    }
+    return feature_rows_run(c, ntargets, d_eig_flat, 0, nullptr, d_counts, h_maxcount, d_X, (cudaStream_t)stream, d_eig_off);
+}
+
 extern "C" int mdb_feature_rows(mdb_ctx *c, long long ntargets, const double *d_eig, int eigcap, const int32_t *d_n,
                                 const int32_t *d_counts, const int32_t *h_maxcount, double *d_X, void *stream) {
     if (check_ctx(c, "mdb_feature_rows")) return -1;

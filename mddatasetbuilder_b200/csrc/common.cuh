@@ -61,6 +61,7 @@ struct mdb_ctx {
     int opt_max_bonds = 8;
     int opt_frames_per_launch = 0;
     int opt_perceive = 0;
+    const int *cur_eig_off = nullptr;  // compact-spectra offsets of the descriptor call in flight
     int opt_desc_legacy = 0;  // 1: round-1 descriptor kernels (one column per lane / warp pairs) for A/B runs  // dump-only keys carry perceived bond orders (perceive.cu)
     uint64_t launches = 0;
     // arena
@@ -179,9 +180,9 @@ int compositions_run(mdb_ctx *c, int F, int N, const double *d_pos, const double
 int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                     int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
                     const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream,
-                    const int *d_members = nullptr, int memcap = 0);
+                    const int *d_members = nullptr, int memcap = 0, int *d_eig_off = nullptr);
 int feature_rows_run(mdb_ctx *c, long long T, const double *d_eig, int eigcap, const int *d_n, const int *d_counts,
-                     const int *h_maxcount, double *d_X, cudaStream_t stream);
+                     const int *h_maxcount, double *d_X, cudaStream_t stream, const int *d_eig_off = nullptr);
 
 // kmeans.cu
 int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_X, long long ldx, const int *d_rowidx,

@@ -464,6 +464,35 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
 // Reciprocal and reciprocal square root are MUFU seeds + Newton steps (a few ulp; the spectrum
 // tolerance is 1e-5): the IEEE sequences would triple the size of the unrolled code.
 // ---------------------------------------------------------------------------------------------
+// the same with NS Newton steps: the MUFU seeds are good to ~2^-20, one step gives ~2^-40 (1e-12), which a
+// Householder reflector tolerates (a relative error d in H perturbs the similarity transform by d ||A||; the
+// spectrum tolerance is 1e-5 with a floor of 1e-8 ||M||)
+#ifndef MDB_NEWTON
+#define MDB_NEWTON 1
+#endif
+template <int NS>
+__device__ __forceinline__ double fast_rcp_n(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < NS; ++it) {
+        const double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+template <int NS>
+__device__ __forceinline__ double fast_rsqrt_n(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+#pragma unroll
+    for (int it = 0; it < NS; ++it) {
+        const double e = fma(-h * y, y, 0.5);
+        y = fma(y, e, y);
+    }
+    return y;
+}
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -660,14 +689,13 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
 //   * a slot whose columns are all finished (slot c is done once k >= (c + 1) LPM - 1) drops out of the
 //     unrolled code at compile time.
 // ncu of the one-column kernel had the FP64 pipe 32 % active with ~8,900 warp instructions per 32-atom
-// matrix, half of them per-step overhead; this layout needs ~2,600.  The Coulomb matrix is built straight
-// into the registers (lane g evaluates its own columns, no staging copy), which also takes the shared
-// memory per matrix from 9 KB to 2 KB.  The 33..48 classes use LPM = 32, CPL = 2 on ONE warp (the
+// matrix, half of them per-step overhead.  The 33..48 classes use LPM = 32, CPL = 2 on ONE warp (the
 // warp-pair kernel below needed three named barriers per step and ran 3.3 x slower per matrix than the
 // 32-atom class for 1.7 x the arithmetic).
 // ---------------------------------------------------------------------------------------------
 template <int NMAX, int LPM, int CPL>
 struct McSmem {
+    double A[NMAX][NMAX + 1];  // staging copy of the Coulomb matrix (each pair evaluated once)
     double vec[NMAX][3];
     double xs[LPM * CPL];
     double2 vw[LPM * CPL];
@@ -693,6 +721,12 @@ __device__ __forceinline__ void mc_step(double (&a)[CPL][NMAX], const McCtx<NMAX
     constexpr int C0 = (K + 1) / LPM;  // slots below C0 hold finished columns only
     McSmem<NMAX, LPM, CPL> *S = cx.S;
     const int gl = cx.gl, n = cx.n;
+    // the unrolled code is far larger than the instruction caches (ncu: `no_instruction` was the top stall
+    // with free-running warps): the warps of the block stay within two steps of each other and share the lines
+#ifndef MDB_MC_SYNC
+#define MDB_MC_SYNC 1
+#endif
+    if ((K & MDB_MC_SYNC) == 0) __syncthreads();
     double x[CPL];
 #pragma unroll
     for (int c = C0; c < CPL; ++c) {
@@ -734,10 +768,10 @@ __device__ __forceinline__ void mc_step(double (&a)[CPL][NMAX], const McCtx<NMAX
     const double pt1 = __shfl_sync(0xffffffffu, pt[C1], L1, LPM);
     const double t00 = __shfl_sync(0xffffffffu, a[C1][K + 1], L1, LPM);
     const bool doit = sig > 0.0;
-    const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
+    const double rs = doit ? sig * fast_rsqrt_n<MDB_NEWTON>(sig) : 0.0;
     const double alpha = x1 >= 0.0 ? -rs : rs;
     const double H = sig - alpha * x1;
-    const double iH = doit ? fast_rcp(H) : 0.0;
+    const double iH = doit ? fast_rcp_n<MDB_NEWTON>(H) : 0.0;
     const double Kc = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
     constexpr int CK = K / LPM, LK = K % LPM;  // owner of column K
     if (gl == LK && cx.valid && K < n) {
@@ -862,43 +896,41 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_tridiag_mc(const __grid_co
             }
         __syncwarp();
     }
-    // Coulomb matrix (datasetbuilder.py:341-348) straight into the registers: lane g evaluates rows
-    // 0 .. NMAX-1 of its columns.  Both vectors lie within +-L/2 of the target, so one conditional shift per
-    // axis gives the minimum image; rows / columns >= n are zero.
-    double a[CPL][NMAX];
-    {
+    // Coulomb matrix (datasetbuilder.py:341-348) into the staging copy: the n(n-1)/2 pairs are dealt evenly to
+    // the lanes of the group, pair p -> (i, j), j < i.  Both vectors lie within +-L/2 of the target, so one
+    // conditional shift per axis gives the minimum image.  Rows / columns >= n are zero.
+    for (int q = gl; q < NMAX * NMAX; q += LPM) S->A[q / NMAX][q % NMAX] = 0.0;
+    __syncwarp();
+    for (int i = gl; i < n; i += LPM) S->A[i][i] = P.diag[S->t[i]];
+    if (n > 1) {
         const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
         const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
-        double c0[CPL], c1[CPL], c2[CPL], zc[CPL], dg[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const int col = c * LPM + gl;
-            const bool ok = col < n;
-            const int cc = ok ? col : 0;
-            c0[c] = S->vec[cc][0];
-            c1[c] = S->vec[cc][1];
-            c2[c] = S->vec[cc][2];
-            zc[c] = ok && n > 0 ? (double)S->z[cc] : 0.0;
-            dg[c] = ok && n > 0 ? P.diag[S->t[cc]] : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < NMAX; ++i) {
-            const double r0 = S->vec[i][0], r1 = S->vec[i][1], r2c = S->vec[i][2];
-            const double zi = i < n ? (double)S->z[i] : 0.0;
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int col = c * LPM + gl;
-                double dx = c0[c] - r0, dy = c1[c] - r1, dz = c2[c] - r2c;
-                if (P.periodic) {
-                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-                }
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? zi * zc[c] * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                a[c][i] = (i == col) ? dg[c] : mv;
+        const int npair = n * (n - 1) / 2;
+        for (int p = gl; p < npair; p += LPM) {
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (i * (i - 1) / 2 > p) --i;
+            while ((i + 1) * i / 2 <= p) ++i;
+            const int j = p - i * (i - 1) / 2;
+            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
+            if (P.periodic) {
+                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
             }
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+            S->A[i][j] = mv;
+            S->A[j][i] = mv;
         }
+    }
+    __syncwarp();
+    double a[CPL][NMAX];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        const int col = c * LPM + gl;
+        const int cc = col < NMAX ? col : 0;
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) a[c][i] = col < NMAX ? S->A[i][cc] : 0.0;
     }
     McCtx<NMAX, LPM, CPL> cx;
     cx.S = S;
@@ -1132,7 +1164,7 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
                                                  const double *__restrict__ padval,  // pad value per element
                                                  const int *__restrict__ maxcount, int D, double *__restrict__ X,
                                                  double *__restrict__ eig, int eigcap, int *__restrict__ nout,
-                                                 BondStats *stats) {
+                                                 BondStats *stats, const int *__restrict__ eig_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double(*d)[THREADS] = reinterpret_cast<double(*)[THREADS]>(smem_raw);
     double(*e)[THREADS] = d + NMAX;
@@ -1223,7 +1255,10 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     }
     const int ord = list[slot0 + s];
     if (nout) nout[ord] = n;
-    if (eig) {
+    if (eig && eig_off) {  // compact spectra: target t owns eig[eig_off[t] .. eig_off[t + 1])
+        double *o = eig + eig_off[ord];
+        for (int k = 0; k < n; ++k) o[k] = d[k][tid];
+    } else if (eig) {
         double *o = eig + (size_t)ord * eigcap;
         for (int k = 0; k < eigcap; ++k) o[k] = k < n ? d[k][tid] : __longlong_as_double(0x7ff8000000000000LL);
     }
@@ -1371,8 +1406,31 @@ __global__ void __launch_bounds__(128) k_feature_rows(long long T, const double 
     while (w < D) o[w++] = 0.0;
 }
 
+__global__ void __launch_bounds__(128) k_feature_rows_compact(long long T, const double *__restrict__ eig,
+                                                              const int *__restrict__ off, const int *__restrict__ counts, int nt,
+                                                              const int *__restrict__ padorder, const double *__restrict__ padval,
+                                                              const int *__restrict__ maxcount, int D, double *__restrict__ X) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int n = off[t + 1] - off[t];
+    const double *d = eig + off[t];
+    double *o = X + (size_t)t * D;
+    int w = 0, k = 0;
+    for (int q = 0; q < nt; ++q) {
+        const int el = padorder[q];
+        const int reps = maxcount[el] - counts[(size_t)t * nt + el];
+        const double pv = padval[el];
+        for (int r = 0; r < reps; ++r) {
+            while (k < n && d[k] <= pv && w < D) o[w++] = d[k++];
+            if (w < D) o[w++] = pv;
+        }
+    }
+    while (k < n && w < D) o[w++] = d[k++];
+    while (w < D) o[w++] = 0.0;
+}
+
 int feature_rows_run(mdb_ctx *c, long long T, const double *d_eig, int eigcap, const int *d_n, const int *d_counts,
-                     const int *h_maxcount, double *d_X, cudaStream_t stream) {
+                     const int *h_maxcount, double *d_X, cudaStream_t stream, const int *d_eig_off) {
     if (T <= 0) return 0;
     const int nt = c->el.nt;
     int D = 0;
@@ -1400,8 +1458,12 @@ int feature_rows_run(mdb_ctx *c, long long T, const double *d_eig, int eigcap, c
     MDB_CUDA(cudaMemcpyAsync(d_padval, c->el.diag, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
     {
         ProfScope ps(c, "k_feature_rows", stream);
-        k_feature_rows<<<cdiv(T, 128), 128, 0, stream>>>(T, d_eig, eigcap, d_n, d_counts, nt, d_padorder, d_padval, d_maxcount,
-                                                        D, d_X);
+        if (d_eig_off)
+            k_feature_rows_compact<<<cdiv(T, 128), 128, 0, stream>>>(T, d_eig, d_eig_off, d_counts, nt, d_padorder, d_padval,
+                                                                    d_maxcount, D, d_X);
+        else
+            k_feature_rows<<<cdiv(T, 128), 128, 0, stream>>>(T, d_eig, eigcap, d_n, d_counts, nt, d_padorder, d_padval,
+                                                            d_maxcount, D, d_X);
     }
     c->launches++;
     MDB_CUDA(cudaGetLastError());
@@ -1509,7 +1571,7 @@ static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int of
             ProfScope ps(c, bucket_name(NMAX, true), stream);
             k_tql<NMAX, QTHREADS><<<cdiv(ns, QTHREADS), QTHREADS, smem_ql, stream>>>(
                 d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap,
-                d_n, c->d_stats);
+                d_n, c->d_stats, c->cur_eig_off);
         }
         c->launches += 2;
     }
@@ -1553,7 +1615,7 @@ static int run_bucket_mc(mdb_ctx *c, const DescParams &P, const int *d_list, int
             ProfScope ps(c, bucket_name(NMAX, true), stream);
             k_tql<NMAX, QTHREADS><<<cdiv(ns, QTHREADS), QTHREADS, smem_ql, stream>>>(
                 d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap,
-                d_n, c->d_stats);
+                d_n, c->d_stats, c->cur_eig_off);
         }
         c->launches += 2;
     }
@@ -1564,8 +1626,9 @@ static int run_bucket_mc(mdb_ctx *c, const DescParams &P, const int *d_list, int
 int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                     int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
                     const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream,
-                    const int *d_members, int memcap) {
+                    const int *d_members, int memcap, int *d_eig_off) {
     const int nt = c->el.nt;
+    c->cur_eig_off = nullptr;
     const long long T = d_targets ? ntargets : (ntargets == 0 ? 0 : (long long)F * N);
     if (T == 0) return 0;
     if (T >= (1LL << 31)) {
@@ -1575,7 +1638,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     const int chunk = 1 << 16;
     // scratch: bucket bookkeeping + lists + d/e for one chunk at the largest NMAX in use
     size_t extra = align256(T * sizeof(int)) * 2 + align256((size_t)chunk * 160 * sizeof(double)) * 2 +
-                   align256((size_t)chunk * sizeof(int)) + 16 * 256;
+                   align256((size_t)chunk * sizeof(int)) + 16 * 256 + (d_eig_off ? align256(scan_scratch_bytes(T + 1)) : 0);
     DescParams P;
     if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, extra, d_members == nullptr))
         return -1;
@@ -1614,6 +1677,18 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     MDB_CUDA(cudaMemcpyAsync(d_padval, c->el.diag, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
     k_bucket_count<<<cdiv(T, 256), 256, 0, stream>>>(d_counts, nt, T, d_book, d_nsum);
     c->launches++;
+    if (d_eig_off) {
+        // compact spectra: offsets = exclusive scan of the sphere sizes (caller sized d_eig with sum(counts))
+        void *tmp = arena_alloc(c, scan_scratch_bytes(T + 1));
+        if (!tmp) {
+            mdb_set_error("descriptors_run: arena too small (internal sizing error)");
+            return -1;
+        }
+        MDB_CUDA(cudaMemcpyAsync(d_eig_off, d_nsum, T * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        MDB_CUDA(cudaMemsetAsync(d_eig_off + T, 0, sizeof(int), stream));
+        if (device_exclusive_scan(c, d_eig_off, T + 1, tmp, stream)) return -1;
+        c->cur_eig_off = d_eig_off;
+    }
     int hb[DESC_NB + 1];
     MDB_CUDA(cudaMemcpyAsync(hb, d_book, sizeof(hb), cudaMemcpyDeviceToHost, stream));
     MDB_CUDA(cudaStreamSynchronize(stream));
@@ -1647,15 +1722,15 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
         MDB_BUCKET(7, 40, 4, 32, 64, 2)
         MDB_BUCKET(8, 48, 4, 32, 64, 2)
     } else {
-        MDB_BUCKET_MC(0, 8, 4, 2, 4, 4, 128)
-        MDB_BUCKET_MC(1, 12, 4, 3, 4, 4, 128)
-        MDB_BUCKET_MC(2, 16, 8, 2, 4, 4, 128)
-        MDB_BUCKET_MC(3, 20, 8, 3, 4, 2, 128)
-        MDB_BUCKET_MC(4, 24, 8, 3, 4, 2, 128)
-        MDB_BUCKET_MC(5, 28, 16, 2, 4, 2, 128)
-        MDB_BUCKET_MC(6, 32, 16, 2, 4, 2, 128)
-        MDB_BUCKET_MC(7, 40, 32, 2, 4, 2, 64)
-        MDB_BUCKET_MC(8, 48, 32, 2, 4, 2, 64)
+        MDB_BUCKET_MC(0, 8, 4, 2, 8, 2, 128)
+        MDB_BUCKET_MC(1, 12, 4, 3, 8, 2, 128)
+        MDB_BUCKET_MC(2, 16, 8, 2, 8, 2, 128)
+        MDB_BUCKET_MC(3, 20, 8, 3, 8, 1, 128)
+        MDB_BUCKET_MC(4, 24, 8, 3, 8, 1, 128)
+        MDB_BUCKET_MC(5, 28, 16, 2, 8, 1, 128)
+        MDB_BUCKET_MC(6, 32, 16, 2, 8, 1, 128)
+        MDB_BUCKET_MC(7, 40, 32, 2, 8, 1, 64)
+        MDB_BUCKET_MC(8, 48, 32, 2, 8, 1, 64)
     }
 #undef MDB_BUCKET_MC
     MDB_BUCKET(9, 56, 4, 32, 64, 2)

@@ -390,6 +390,38 @@ class Engine:
         _lib.check(rc, "mdb_descriptors")
         return {"X": X, "eig": eig, "n": n}
 
+    def descriptors_compact(self, pos, cell, types, counts, maxcount, targets, members, total_n, periodic=True, want_X=True):
+        """`descriptors(members=...)` that also keeps the spectra compactly: returns (X or None, eig_flat
+        [total_n] float64, eig_off [T + 1] int32); total_n = counts.sum().  `feature_rows_compact` rebuilds the
+        same rows from them later."""
+        torch = _torch()
+        pos = self.to_device_pos(pos)
+        types = self.to_device_types(types)
+        F, N = int(pos.shape[0]), int(pos.shape[1])
+        cells = self._cells(cell, F) if periodic else None
+        targets = torch.as_tensor(targets, dtype=torch.int32, device=self.device).contiguous()
+        T = int(targets.numel())
+        mc = np.ascontiguousarray(maxcount, dtype=np.int32)
+        X = torch.empty((T, int(mc.sum())), dtype=torch.float64, device=self.device) if want_X else None
+        eig = torch.empty(max(int(total_n), 1), dtype=torch.float64, device=self.device)
+        off = torch.empty(T + 1, dtype=torch.int32, device=self.device)
+        n = torch.empty(T, dtype=torch.int32, device=self.device)
+        rc = self.L.mdb_descriptors_members_compact(self.ctx, F, N, _ptr(pos), _np_ptr(cells), _ptr(types), int(bool(periodic)),
+                                                    _ptr(targets), T, _ptr(counts), _np_ptr(mc), _ptr(members),
+                                                    int(members.shape[1]), _ptr(X), _ptr(eig), _ptr(off), _ptr(n), self.stream())
+        _lib.check(rc, "mdb_descriptors_members_compact")
+        return X, eig, off
+
+    def feature_rows_compact(self, eig, off, counts, maxcount):
+        """Padded sorted rows [T, D] from compact spectra (see descriptors_compact)."""
+        torch = _torch()
+        mc = np.ascontiguousarray(maxcount, dtype=np.int32)
+        T = int(off.numel()) - 1
+        X = torch.empty((T, int(mc.sum())), dtype=torch.float64, device=self.device)
+        rc = self.L.mdb_feature_rows_compact(self.ctx, T, _ptr(eig), _ptr(off), _ptr(counts), _np_ptr(mc), _ptr(X), self.stream())
+        _lib.check(rc, "mdb_feature_rows_compact")
+        return X
+
     def feature_rows(self, eig, n, counts, maxcount):
         """Padded sorted feature rows [T, D] from stored spectra (eig [T, eigcap], n [T]) and compositions once
         the final per-element maxima are known (closed form of datasetbuilder.py:236-276)."""

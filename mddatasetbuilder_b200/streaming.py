@@ -78,7 +78,7 @@ class StreamingSelector:
     def __init__(self, engine, types, cutoff=5.0, n_clusters=10000, n_each=1, seed=0, periodic=True,
                  perceive_bond_orders=False, pool_rows=1 << 21, table_cap=1024, want_molecules=False,
                  only_keys: Optional[Iterable[int]] = None, log: Optional[Callable[[str], None]] = None,
-                 kmeans_kwargs: Optional[dict] = None):
+                 kmeans_kwargs: Optional[dict] = None, cache_gb: Optional[float] = None, cache_reserve_gb: float = 24.0):
         import torch
 
         self.eng = engine
@@ -99,6 +99,9 @@ class StreamingSelector:
         self.torch = torch
         self.nt = len(engine.atomname)
         self.comm = {}
+        self.cache_gb = cache_gb                  # HBM for spectra kept from pass B to pass C (None: what is free)
+        self.cache_reserve_gb = cache_reserve_gb
+        self.cache, self.cache_bytes, self.cache_budget = {}, 0, 0
 
     # ------------------------------------------------------------------ helpers
     def _sync(self):
@@ -203,10 +206,7 @@ class StreamingSelector:
         return self
 
     # ------------------------------------------------------------------ rows of one batch, type by type
-    def _batch_rows(self, b: FrameBatch, st: _Store):
-        eng = self.eng
-        if not st.kept or not self.big:
-            return
+    def _ranges(self, st: _Store):
         ranges = []
         for k in self.big:
             s = self.slot_of.get(k)
@@ -215,7 +215,24 @@ class StreamingSelector:
             a, e = int(st.seg[s]), int(st.seg[s + 1])
             if e > a:
                 ranges.append((k, a, e))
+        return ranges
+
+    def _batch_rows(self, b: FrameBatch, st: _Store, fill_cache=False):
+        """Yields (key, X [rows, D], a, e) for every clustered type present in the batch: rows a .. e of the
+        batch's order array.  Spectra kept by pass B (`fill_cache`, while the HBM budget lasts) are reused by
+        pass C instead of a second sphere scan + eigen-solve: `mdb_feature_rows_compact` rebuilds the rows
+        bit for bit."""
+        eng, torch = self.eng, self.torch
+        if not st.kept or not self.big:
+            return
+        ranges = self._ranges(st)
         if not ranges:
+            return
+        cached = self.cache.get(st.gidx)
+        if cached is not None and not fill_cache:
+            for k, a, e in ranges:
+                eig, off, cnt = cached[k]
+                yield k, eng.feature_rows_compact(eig, off, cnt, self.maxcount[k]), a, e
             return
         lo, hi = min(a for _, a, _ in ranges), max(e for _, _, e in ranges)
         tg = st.order[lo:hi]
@@ -229,11 +246,30 @@ class StreamingSelector:
                 if "(2)" not in str(e) or self.memcap >= 160:
                     raise
                 self.memcap = min(160, self.memcap * 2)
+        keep = None
+        if fill_cache and self.cache_budget > 0:
+            # sphere sizes summed per type: one read-back per batch
+            csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=eng.device), counts.sum(dim=1).cumsum(0)])
+            ends = csum[torch.as_tensor([x - lo for _, a, e in ranges for x in (a, e)], device=eng.device)].cpu().numpy()
+            totals = {k: int(ends[2 * i + 1] - ends[2 * i]) for i, (k, _, _) in enumerate(ranges)}
+            need = sum(8 * totals[k] + (e - a) * (4 + 4 * self.nt) + 1024 for k, a, e in ranges)
+            if need <= self.cache_budget:
+                self.cache_budget -= need
+                self.cache_bytes += need
+                keep = {}
         for k, a, e in ranges:
-            out = eng.descriptors(b.pos, b.cell, self.types, self.cutoff, counts[a - lo:e - lo], self.maxcount[k],
-                                  targets=st.order[a:e], periodic=self.periodic, want_X=True,
-                                  members=members[a - lo:e - lo])
-            yield k, out["X"], a, e
+            cn = counts[a - lo:e - lo]
+            mem = members[a - lo:e - lo]
+            if keep is not None:
+                X, eig, off = eng.descriptors_compact(b.pos, b.cell, self.types, cn, self.maxcount[k], st.order[a:e], mem,
+                                                      totals[k], periodic=self.periodic)
+                keep[k] = (eig, off, cn.clone())
+            else:
+                X = eng.descriptors(b.pos, b.cell, self.types, self.cutoff, cn, self.maxcount[k], targets=st.order[a:e],
+                                    periodic=self.periodic, want_X=True, members=mem)["X"]
+            yield k, X, a, e
+        if keep is not None:
+            self.cache[st.gidx] = keep
 
     # ------------------------------------------------------------------ pass B
     def _pool_indices(self):
@@ -256,10 +292,19 @@ class StreamingSelector:
         self.pool = {k: torch.zeros((min(self.counts[k], self.pool_rows), self.D[k]), dtype=torch.float64,
                                     device=eng.device) for k in self.big}
         stores = {s.gidx: s for s in self.stores}
+        # spectra cache for pass C: what is free now minus the labels pass C stores and its working set
+        self.cache, self.cache_bytes = {}, 0
+        if self.cache_gb is None:
+            free, _ = torch.cuda.mem_get_info(eng.device)
+            free += torch.cuda.memory_reserved(eng.device) - torch.cuda.memory_allocated(eng.device)
+            rows_local = sum(int(st.kept) for st in self.stores)
+            self.cache_budget = int(free - 4 * rows_local - self.cache_reserve_gb * (1 << 30))
+        else:
+            self.cache_budget = int(self.cache_gb * (1 << 30))
         for b in source.batches():
             st = stores[b.gidx]
             gi = self.gpos[b.gidx]
-            for k, X, a, e in self._batch_rows(b, st):
+            for k, X, a, e in self._batch_rows(b, st, fill_cache=True):
                 eng.minmax_accumulate(X, self.mn[k], self.mx[k])
                 g0 = int(self.row0[k][gi])
                 g1 = g0 + (e - a)
@@ -323,7 +368,13 @@ class StreamingSelector:
         self.hist = {k: torch.zeros((nb, self.K), dtype=torch.int32, device=eng.device) for k in self.big}
         stores = {s.gidx: s for s in self.stores}
         rechecked = 0
-        for b in source.batches():
+        # batches whose spectra were kept need no input tensors: sources that stage data (host -> device copies,
+        # text parsing) may skip them
+        try:
+            it = source.batches(needed=lambda g: g not in self.cache)
+        except TypeError:
+            it = source.batches()
+        for b in it:
             st = stores[b.gidx]
             gi = self.gpos[b.gidx]
             for k, X, a, e in self._batch_rows(b, st):
@@ -337,6 +388,8 @@ class StreamingSelector:
                 self.labels[k].append((b.gidx, a, e, lab))
                 del X
         eng.check()
+        self.cached_batches = len(self.cache)
+        self.cache = {}
         self.rechecked = rechecked
         d = _dist()
         if d is not None:
@@ -443,6 +496,8 @@ class StreamingSelector:
         res.timings = tm
         res.stats = {"fit": getattr(self, "fit_stats", {}), "rechecked_in_float64": getattr(self, "rechecked", 0),
                      "memcap": self.memcap, "rings": getattr(self, "rings", 0), "comm": self.comm,
+                     "spectra_cache": {"batches": getattr(self, "cached_batches", 0), "of": len(self.stores),
+                                       "gb": self.cache_bytes / 1e9},
                      "fit_comm": getattr(self, "fit_comm", None)}
         return res
 
@@ -464,7 +519,7 @@ class ResidentSource:
         self.B = int(frames_per_batch)
         self.rank, self.world, self.local = rank, world, local
 
-    def batches(self):
+    def batches(self, needed=None):
         F = int(self.pos.shape[0])
         nb = -(-F // self.B)
         for i in range(nb):

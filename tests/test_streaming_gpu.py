@@ -169,8 +169,8 @@ def _in_memory_selection(engine, s, pos, bo_frames, K, n_each, seed, pool_rows):
     return out
 
 
-@pytest.mark.parametrize("pool_rows,batch", [(1 << 21, 2), (90, 3)])
-def test_streamed_selection_equals_in_memory(engine, pool_rows, batch):
+@pytest.mark.parametrize("pool_rows,batch,cache_gb", [(1 << 21, 2, None), (90, 3, 0.0), (90, 2, 0.0002)])
+def test_streamed_selection_equals_in_memory(engine, pool_rows, batch, cache_gb):
     """SURVEY.md hard part 3 / VERDICT item 2: the three-pass job picks exactly the rows the in-memory
     path picks -- all rows in the pool (first case) and with a seeded sub-sample as pool (second)."""
     from mddatasetbuilder_b200.streaming import ResidentSource, StreamingSelector
@@ -180,8 +180,11 @@ def test_streamed_selection_equals_in_memory(engine, pool_rows, batch):
     pos = _t(engine, synth.frame_positions(s, F))
     rowptr, col, bo = synth.bond_table_device(s, F, engine.device)
     sel = StreamingSelector(engine, s.types, cutoff=5.0, n_clusters=K, n_each=n_each, seed=seed, periodic=True,
-                            pool_rows=pool_rows, want_molecules=True)
+                            pool_rows=pool_rows, want_molecules=True, cache_gb=cache_gb)
     res = sel.run(ResidentSource(pos, s.cell(), batch, rowptr=rowptr, col=col, bo=bo))
+    nb = -(-F // batch)
+    nc = res.stats["spectra_cache"]["batches"]       # pass C: kept spectra / recomputed / a mix of both
+    assert (nc == nb) if cache_gb is None else (nc == 0) if cache_gb == 0.0 else (0 < nc < nb)
     want = _in_memory_selection(engine, s, pos, bo.cpu().numpy(), K, n_each, seed, sel.pool_rows)
     assert [int(k) for k in res.keys] == list(want.keys()), "bond types / first-seen order differ"
     assert len(sel.big) >= 3
