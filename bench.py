@@ -421,7 +421,9 @@ def main():
     nn = cnt.sum(dim=1).double()
     n_mean, n3_mean = float(nn.mean().item()), float((nn ** 3).mean().item())
     del cnt, nn
-    ntarget_passes = 2 * frames * natoms          # pass B + pass C
+    sc = res.stats.get("spectra_cache") or {"batches": 0, "of": 1}
+    # pass B computes every descriptor, pass C only those of the batches whose spectra were not kept
+    ntarget_passes = frames * natoms * (2.0 - sc["batches"] / max(sc["of"], 1))
     useful_flops = (8.0 / 3.0) * n3_mean * ntarget_passes
     fp64_peak = eng.fp64_peak_tflops()
     Dmean = float(np.mean([st["D"] for st in res.stats["fit"].values()])) if res.stats.get("fit") else 0.0

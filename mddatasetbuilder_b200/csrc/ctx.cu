@@ -137,7 +137,7 @@ extern "C" int mdb_set_option(mdb_ctx *c, const char *key, double v) {
     else if (k == "perceive_bond_orders")
         c->opt_perceive = v != 0.0;
     else if (k == "desc_legacy")
-        c->opt_desc_legacy = v != 0.0;
+        c->opt_desc_legacy = (int)v;  // 0 default mix, 1 round-1 kernels, 2 multi-column kernels everywhere
     else {
         mdb_set_error("unknown option " + k);
         return -1;

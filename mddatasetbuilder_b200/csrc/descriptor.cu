@@ -724,7 +724,7 @@ __device__ __forceinline__ void mc_step(double (&a)[CPL][NMAX], const McCtx<NMAX
     // the unrolled code is far larger than the instruction caches (ncu: `no_instruction` was the top stall
     // with free-running warps): the warps of the block stay within two steps of each other and share the lines
 #ifndef MDB_MC_SYNC
-#define MDB_MC_SYNC 1
+#define MDB_MC_SYNC 7
 #endif
     if ((K & MDB_MC_SYNC) == 0) __syncthreads();
     double x[CPL];
@@ -1711,7 +1711,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
                                                                 d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, \
                                                                 stream))                                                      \
         return -1;
-    if (c->opt_desc_legacy) {
+    if (c->opt_desc_legacy == 1) {
         MDB_BUCKET(0, 8, 8, 8, 128, 1)
         MDB_BUCKET(1, 12, 8, 16, 128, 1)
         MDB_BUCKET(2, 16, 8, 16, 128, 1)
@@ -1722,13 +1722,21 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
         MDB_BUCKET(7, 40, 4, 32, 64, 2)
         MDB_BUCKET(8, 48, 4, 32, 64, 2)
     } else {
+        // measured per class on B200 (tools/desc_ab.py, 0.05 atoms/A^3): several columns per lane win up to 24
+        // atoms (4 matrices per warp) and tie with the warp-pair kernel at 33..48 (no named barriers); at 25..32
+        // the one-column kernel keeps 16 warps per SM against 8 and stays ahead (2.88 vs 3.05 ms)
         MDB_BUCKET_MC(0, 8, 4, 2, 8, 2, 128)
         MDB_BUCKET_MC(1, 12, 4, 3, 8, 2, 128)
         MDB_BUCKET_MC(2, 16, 8, 2, 8, 2, 128)
         MDB_BUCKET_MC(3, 20, 8, 3, 8, 1, 128)
         MDB_BUCKET_MC(4, 24, 8, 3, 8, 1, 128)
-        MDB_BUCKET_MC(5, 28, 16, 2, 8, 1, 128)
-        MDB_BUCKET_MC(6, 32, 16, 2, 8, 1, 128)
+        if (c->opt_desc_legacy == 2) {
+            MDB_BUCKET_MC(5, 28, 16, 2, 8, 1, 128)
+            MDB_BUCKET_MC(6, 32, 16, 2, 8, 1, 128)
+        } else {
+            MDB_BUCKET(5, 28, 8, 32, 128, 1)
+            MDB_BUCKET(6, 32, 8, 32, 128, 1)
+        }
         MDB_BUCKET_MC(7, 40, 32, 2, 8, 1, 64)
         MDB_BUCKET_MC(8, 48, 32, 2, 8, 1, 64)
     }

@@ -169,7 +169,7 @@ def _in_memory_selection(engine, s, pos, bo_frames, K, n_each, seed, pool_rows):
     return out
 
 
-@pytest.mark.parametrize("pool_rows,batch,cache_gb", [(1 << 21, 2, None), (90, 3, 0.0), (90, 2, 0.0002)])
+@pytest.mark.parametrize("pool_rows,batch,cache_gb", [(1 << 21, 2, None), (90, 3, 0.0), (90, 2, 0.002)])
 def test_streamed_selection_equals_in_memory(engine, pool_rows, batch, cache_gb):
     """SURVEY.md hard part 3 / VERDICT item 2: the three-pass job picks exactly the rows the in-memory
     path picks -- all rows in the pool (first case) and with a seeded sub-sample as pool (second)."""
