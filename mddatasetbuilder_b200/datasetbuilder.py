@@ -132,6 +132,13 @@ class DatasetBuilder:
         self.clusteratom = clusteratom if clusteratom else atomname
         self.atombondtype = []
         self.perceive_bond_orders = bool(perceive_bond_orders)
+        if bondfilename is None and self.perceive_bond_orders:
+            outside = [str(a) for a in atomname if str(a) not in ("C", "H", "O", "N")]
+            if outside:
+                raise RuntimeError(
+                    f"dump-only bond orders are a restatement of Open Babel's PerceiveBondOrders for C/H/O(/N) only; "
+                    f"elements {outside} would be typed differently from the reference. Give a bond file, or pass "
+                    f"perceive_bond_orders=False for all-single keys (DESIGN.md section 4)")
         self.stepinterval = stepinterval
         if nproc:
             self.nproc = nproc
@@ -337,14 +344,38 @@ class DatasetBuilder:
         self._nstep = sel.nstep
 
     def _error_rows(self):
-        """Model-deviation rows by step (datasetbuilder.py:640-653: one header line per file, one line per
-        frame, per-atom values from column 7 on, in atom-id order); strided per file in lockstep with the
-        frame reader, which restarts its stride at every file."""
+        """Model-deviation rows by step, in atom-id order (datasetbuilder.py:640-653 + detect.py:215-219: one
+        header line per file, one line per frame, per-atom values from column 7 on in the dump's LINE order,
+        re-ordered by the id column like `sorted(zip(ids, lerror))`).  Rows are strided per file in lockstep
+        with the frame reader, which restarts its stride at every file (the reference zips unstrided rows with
+        strided frames -- the evident intent is the aligned pairing)."""
+        import itertools
+
         rows = []
-        for fn in must_be_list(self.errorfilename):
+        det = self.crddetector
+        N = det._N
+        fns = must_be_list(self.errorfilename)
+        dumps = must_be_list(det.filename)
+        if len(fns) != len(dumps):
+            raise RuntimeError(f"{len(dumps)} dump file(s) but {len(fns)} model deviation file(s)")
+        head = det.steplinenum - N
+        for fn, dfn in zip(fns, dumps):
             with open(fn) as f:
-                per_file = [np.array(line.split(), dtype=float)[7:] for k, line in enumerate(f) if k > 0 and line.strip()]
-            rows.extend(per_file[:: self.stepinterval] if self.stepinterval > 1 else per_file)
+                per_file = [line for k, line in enumerate(f) if k > 0 and line.strip()]
+            per_file = per_file[:: self.stepinterval] if self.stepinterval > 1 else per_file
+            with open(dfn) as f:
+                frames = itertools.islice(itertools.zip_longest(*[f] * det.steplinenum), 0, None, self.stepinterval)
+                for line, lines in zip(per_file, frames):
+                    if lines[-1] is None:
+                        break                                     # truncated last frame
+                    vals = np.array(line.split(), dtype=float)[7:]
+                    if len(vals) < N:
+                        raise RuntimeError(f"{fn}: a model deviation row holds {len(vals)} per-atom values, the frames "
+                                           f"have {N} atoms")
+                    ids = np.array([int(l.split()[det.id_idx]) for l in lines[head:head + N]])
+                    by_id = np.empty(N)
+                    by_id[ids - 1] = vals[:N]
+                    rows.append(by_id)
         return rows
 
     def _cluster_types(self, only=None):

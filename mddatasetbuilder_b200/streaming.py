@@ -102,6 +102,7 @@ class StreamingSelector:
         self.cache_gb = cache_gb                  # HBM for spectra kept from pass B to pass C (None: what is free)
         self.cache_reserve_gb = cache_reserve_gb
         self.cache, self.cache_bytes, self.cache_budget = {}, 0, 0
+        self.capture_rows = None
 
     # ------------------------------------------------------------------ helpers
     def _sync(self):
@@ -305,6 +306,8 @@ class StreamingSelector:
             st = stores[b.gidx]
             gi = self.gpos[b.gidx]
             for k, X, a, e in self._batch_rows(b, st, fill_cache=True):
+                if self.capture_rows is not None:      # tests: the unscaled rows of every type, in row order
+                    self.capture_rows.setdefault(k, []).append((b.gidx, X.clone()))
                 eng.minmax_accumulate(X, self.mn[k], self.mx[k])
                 g0 = int(self.row0[k][gi])
                 g1 = g0 + (e - a)

@@ -144,3 +144,24 @@ def test_device_kmeans_plusplus_matches_sklearn(engine, n, D, K, seed):
         rands.append(rs.uniform(size=(max(K - 1, 0), T)) if K > 1 else np.zeros((1, T)))
     got3 = engine.kmeans_plusplus(_t(engine, X), K, np.stack(rands), np.array(firsts)).cpu().numpy()
     assert np.array_equal(got3, np.stack(wants))
+
+
+@pytest.mark.parametrize("n,D,K,seed", [(6000, 12, 40, 0), (3000, 30, 25, 7), (900, 8, 300, 3)])
+def test_seeded_fit_matches_sklearn(engine, n, D, K, seed):
+    """`MiniBatchKMeansB200(seed=s)` draws from one RandomState in the order
+    scikit-learn's MiniBatchKMeans(random_state=s) does (validation rows, n_init seedings, mini-batches,
+    reassignments), so the whole fit -- number of steps, centres, labels -- reproduces sklearn's.  Centres to
+    1e-9 relative (the update sums members in a different order), labels identical."""
+    from sklearn.cluster import MiniBatchKMeans
+
+    from mddatasetbuilder_b200.kmeans import MiniBatchKMeansB200
+
+    rng = np.random.default_rng(100 + seed)
+    blobs = rng.random((K, D))
+    X = blobs[rng.integers(0, K, n)] + rng.normal(0, 0.03, (n, D))
+    ref = MiniBatchKMeans(n_clusters=K, init_size=min(3 * K, n), n_init=3, random_state=seed).fit(X)
+    km = MiniBatchKMeansB200(engine, n_clusters=K, init_size=min(3 * K, n), n_init=3, seed=seed).fit(_t(engine, X))
+    assert km.n_steps_ == ref.n_steps_, "the fits stopped at different steps"
+    C = km.cluster_centers_.cpu().numpy()
+    assert np.allclose(C, ref.cluster_centers_, rtol=1e-9, atol=1e-12), "centres differ from scikit-learn's"
+    assert np.array_equal(km.labels_.cpu().numpy(), ref.labels_)
