@@ -174,9 +174,14 @@ class MiniBatchKMeansB200:
         n_since_last_reassign = 0
         counts_zero = True
         n_steps = (self.max_iter * n_samples) // batch_size
+        # scikit-learn >= 1.4 draws the mini-batch with `random_state.choice(n, batch, p=sample_weight / sum, replace=True)`
+        # = searchsorted(cumsum(p) / cumsum(p)[-1], random_sample(batch), side="right") (numpy RandomState.choice);
+        # the cdf is built once, with the same arithmetic
+        cdf = np.cumsum(np.ones(n_samples) / float(n_samples))
+        cdf /= cdf[-1]
         i = -1
         for i in range(n_steps):
-            idx = rs.randint(0, n_samples, batch_size)
+            idx = cdf.searchsorted(rs.random_sample(batch_size), side="right")
             batch_idx = torch.as_tensor(idx, dtype=torch.int32, device=eng.device)
             n_since_last_reassign += batch_size
             # weights only grow, so once no centre has a zero count the test never fires again (one sync less per step)
