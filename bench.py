@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--pool-rows", type=int, default=1 << 21)
     ap.add_argument("--host-slots", type=int, default=64)
     ap.add_argument("--exchange", default="replicated", choices=["replicated", "allreduce"])
+    ap.add_argument("--train-threads", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
@@ -368,7 +369,8 @@ def main():
 
     def job(source, nfr):
         sel = StreamingSelector(eng, sysm.types, cutoff=5.0, n_clusters=args.clusters, n_each=1, seed=synth.BASE_SEED,
-                                periodic=True, pool_rows=args.pool_rows, want_molecules=True, kmeans_kwargs=kw)
+                                periodic=True, pool_rows=args.pool_rows, want_molecules=True, kmeans_kwargs=kw,
+                                train_threads=args.train_threads)
         res = sel.run(source)
         return sel, res
 
@@ -398,10 +400,15 @@ def main():
     torch.cuda.synchronize()
     w1 = time.time()
     barrier()
-    launches = eng.launches - l0
+    launches = eng.launches - l0 + sum(w.launches for w in sel.worker_engines())
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     eng.profile(False)
     prof = eng.profile_read()
+    for w in sel.worker_engines():                 # the training threads' own contexts
+        w.profile(False)
+        for name, (cnt, ms) in w.profile_read().items():
+            c0, m0 = prof.get(name, (0, 0.0))
+            prof[name] = (c0 + cnt, m0 + ms)
     clocks = sampler.stop(w0, w1)
     ms_per_step = ms_total / steps
     units = world * frames * natoms
@@ -499,7 +506,8 @@ def main():
                                    "job, inside the timed region; warm-up = a job of `warmup` steps",
                            "bond_types": len(res.keys), "clustered_types": len(res.maxcount),
                            "selected_structures": nchosen, "spectra_cache": res.stats.get("spectra_cache"),
-                           "parallelism": f"frame batches interleaved over {world} rank(s); training {args.exchange}",
+                           "parallelism": f"frame batches interleaved over {world} rank(s); training {args.exchange}, "
+                                          f"bond types dealt over the ranks, {args.train_threads} concurrent fits per rank",
                            "l2": f"inputs are {frames * natoms * 45 / 1e9:.1f} GB per rank (> 126 MB L2)",
                            "seed": synth.BASE_SEED + 3},
                 "phases_s": phases, "roofline": roofline, "kernels": kern, "fit": {str(k): v for k, v in res.stats["fit"].items()},

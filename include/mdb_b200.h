@@ -322,6 +322,14 @@ int mdb_kmeans_partial_sums(mdb_ctx *ctx, long long nbatch, int D, int K, const 
 int mdb_kmeans_apply_update(mdb_ctx *ctx, int K, int D, double *d_centers, double *d_weight_sums,
                             const double *d_sums, const double *d_wsum, void *stream);
 
+/* Both halves in one call for a mini-batch of at most 4096 rows held by ONE process, in scikit-learn's own
+ * operation order (update_center_dense, cluster/_k_means_minibatch.pyx:59-108: centre * weight_sum, members
+ * added in ascending sample order, times 1 / new weight_sum): with equal labels the centres equal sklearn's
+ * bit for bit. */
+int mdb_kmeans_update_exact(mdb_ctx *ctx, long long nbatch, int D, const double *d_X, long long ldx,
+                            const int32_t *d_rowidx, const double *d_weights, const int32_t *d_labels,
+                            double *d_centers, double *d_weight_sums, void *stream);
+
 /* k-means++ seeding step (sklearn cluster/_kmeans.py:180-279, run by MiniBatchKMeans on
  * its init subset): for ncand (<= 32) candidate rows, d_dist[t][i] = min(d_closest[i],
  * ||x_i - x_cand[t]||^2) and d_pot[t] = sum_i weight_i * d_dist[t][i].  d_closest may be

@@ -392,6 +392,16 @@ extern "C" int mdb_kmeans_partial_sums(mdb_ctx *c, long long nbatch, int D, int 
     return kmeans_sums_run(c, nbatch, D, K, d_X, ldx, d_rowidx, d_weights, d_labels, d_sums, d_wsum, (cudaStream_t)stream);
 }
 
+int kmeans_update_exact_run(mdb_ctx *c, long long B, int D, const double *d_X, long long ldx, const int *d_rowidx,
+                            const double *d_w, const int *d_labels, double *d_C, double *d_weight_sums, cudaStream_t stream);
+extern "C" int mdb_kmeans_update_exact(mdb_ctx *c, long long nbatch, int D, const double *d_X, long long ldx,
+                                       const int32_t *d_rowidx, const double *d_weights, const int32_t *d_labels,
+                                       double *d_centers, double *d_weight_sums, void *stream) {
+    if (check_ctx(c, "mdb_kmeans_update_exact", false)) return -1;
+    return kmeans_update_exact_run(c, nbatch, D, d_X, ldx, d_rowidx, d_weights, d_labels, d_centers, d_weight_sums,
+                                   (cudaStream_t)stream);
+}
+
 extern "C" int mdb_kmeans_apply_update(mdb_ctx *c, int K, int D, double *d_centers, double *d_weight_sums,
                                        const double *d_sums, const double *d_wsum, void *stream) {
     if (check_ctx(c, "mdb_kmeans_apply_update", false)) return -1;

@@ -82,6 +82,7 @@ class Engine:
 
     def profile(self, on: bool):
         _lib.check(self.L.mdb_profile_enable(self.ctx, int(on)), "mdb_profile_enable")
+        self._profiling = bool(on)
 
     def profile_read(self):
         """{kernel name: (launch count, total ms)} since the last read (synchronises)."""
@@ -505,6 +506,13 @@ class Engine:
                                             _ptr(weights), _ptr(labels), _ptr(sums), _ptr(wsum), self.stream())
         _lib.check(rc, "mdb_kmeans_partial_sums")
         return sums, wsum
+
+    def kmeans_update_exact(self, X, labels, centers, weight_sums, rowidx=None, weights=None):
+        """Mini-batch M-step (<= 4096 rows) in scikit-learn's operation order, in place."""
+        rc = self.L.mdb_kmeans_update_exact(self.ctx, int(labels.numel()), int(X.shape[1]), _ptr(X), int(X.stride(0)),
+                                            _ptr(rowidx), _ptr(weights), _ptr(labels), _ptr(centers), _ptr(weight_sums),
+                                            self.stream())
+        _lib.check(rc, "mdb_kmeans_update_exact")
 
     def kpp_step(self, X, cand, closest, dist_out, pot_out, rowidx=None, weights=None):
         """One k-means++ seeding step: distances of the candidate rows to every row (clipped

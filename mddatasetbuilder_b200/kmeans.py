@@ -119,10 +119,14 @@ class MiniBatchKMeansB200:
             t1.record()
             self._comm_events.append((t0, t1))
             inertia = float(self._packed[-1].item())
+            eng.kmeans_apply_update(centers, weight_sums, sums, wsum)
         else:
             labels, inertia, _ = eng.kmeans_assign(X, centers, rowidx=batch_idx, want_inertia=True)
-            sums, wsum = eng.kmeans_partial_sums(X, labels, K, rowidx=batch_idx, out=self._sums_buf)
-        eng.kmeans_apply_update(centers, weight_sums, sums, wsum)
+            if B <= 4096:      # sklearn's own operation order: bit-identical centres
+                eng.kmeans_update_exact(X, labels, centers, weight_sums, rowidx=batch_idx)
+            else:
+                sums, wsum = eng.kmeans_partial_sums(X, labels, K, rowidx=batch_idx, out=self._sums_buf)
+                eng.kmeans_apply_update(centers, weight_sums, sums, wsum)
         if random_reassign and self.reassignment_ratio > 0:
             ws = weight_sums.cpu().numpy()
             to_reassign = ws < self.reassignment_ratio * ws.max()

@@ -78,7 +78,8 @@ class StreamingSelector:
     def __init__(self, engine, types, cutoff=5.0, n_clusters=10000, n_each=1, seed=0, periodic=True,
                  perceive_bond_orders=False, pool_rows=1 << 21, table_cap=1024, want_molecules=False,
                  only_keys: Optional[Iterable[int]] = None, log: Optional[Callable[[str], None]] = None,
-                 kmeans_kwargs: Optional[dict] = None, cache_gb: Optional[float] = None, cache_reserve_gb: float = 24.0):
+                 kmeans_kwargs: Optional[dict] = None, cache_gb: Optional[float] = None, cache_reserve_gb: float = 24.0,
+                 train_threads: int = 4):
         import torch
 
         self.eng = engine
@@ -103,6 +104,9 @@ class StreamingSelector:
         self.cache_reserve_gb = cache_reserve_gb
         self.cache, self.cache_bytes, self.cache_budget = {}, 0, 0
         self.capture_rows = None
+        self.train_threads = int(train_threads)
+        self._workers = []
+        self.eng_profile = False
 
     # ------------------------------------------------------------------ helpers
     def _sync(self):
@@ -341,27 +345,104 @@ class StreamingSelector:
         return self
 
     # ------------------------------------------------------------------ training
+    def _fit_one(self, eng, k):
+        pool = self.pool[k]
+        eng.minmax_transform(pool, self.mn_h[k], self.mx_h[k])
+        n = int(pool.shape[0])
+        km = MiniBatchKMeansB200(eng, n_clusters=self.K, init_size=min(3 * self.K, n), n_init=3, seed=self.seed,
+                                 **self.kmeans_kwargs)
+        km.fit(pool, compute_labels=False)
+        stats = {"steps": km.n_steps_, "pool_rows": n, "rows": self.counts[k], "D": self.D[k]}
+        return km.cluster_centers_, stats, km
+
     def train(self):
-        eng = self.eng
+        """MiniBatchKMeans per clustered type on its scaled pool.  The fits are independent, latency-bound
+        loops (one 1024-row mini-batch per step, a host decision after every step), so they run concurrently:
+        `train_threads` host threads, each with its own context (scratch arena) and CUDA stream, take the
+        types largest first; with several ranks the types are dealt over the ranks first and the centres
+        broadcast by their owner (every fit is seeded by itself, so neither changes any result).  The
+        "allreduce" exchange keeps every rank in every fit instead (mini-batch slices + one packed all-reduce)."""
+        import threading
+
+        torch, eng = self.torch, self.eng
         self.centers = {}
         self.fit_stats = {}
         self.fit_comm = {"allreduce_ms": 0.0, "steps": 0, "bytes_per_step": 0}
-        for k in self.big:
-            pool = self.pool[k]
-            eng.minmax_transform(pool, self.mn_h[k], self.mx_h[k])
-            n = int(pool.shape[0])
-            km = MiniBatchKMeansB200(eng, n_clusters=self.K, init_size=min(3 * self.K, n), n_init=3, seed=self.seed,
-                                     **self.kmeans_kwargs)
-            km.fit(pool, compute_labels=False)
-            self.centers[k] = km.cluster_centers_
-            self.fit_stats[k] = {"steps": km.n_steps_, "pool_rows": n, "rows": self.counts[k], "D": self.D[k]}
-            if km.comm_ms_ is not None:
+        d = _dist()
+        world = d.get_world_size() if d is not None else 1
+        rank = d.get_rank() if d is not None else 0
+        todo = sorted(self.big, key=lambda k: (-int(self.pool[k].shape[0]) * self.D[k], k))
+        if self.kmeans_kwargs.get("exchange") == "allreduce" and world > 1:
+            for k in self.big:
+                self.centers[k], self.fit_stats[k], km = self._fit_one(eng, k)
                 fc = self.fit_comm
-                fc["allreduce_ms"] += km.comm_ms_
+                fc["allreduce_ms"] += km.comm_ms_ or 0.0
                 fc["steps"] += km.n_steps_
-                fc["bytes_per_step"] = max(fc["bytes_per_step"], km.comm_bytes_per_step_)
+                fc["bytes_per_step"] = max(fc["bytes_per_step"], getattr(km, "comm_bytes_per_step_", 0))
+            self.pool = None
+            return self
+        owner = {k: i % world for i, k in enumerate(todo)}
+        mine = [k for k in todo if owner[k] == rank]
+        nthreads = max(1, min(self.train_threads, len(mine)))
+        self._sync()
+        if nthreads <= 1:
+            for k in mine:
+                self.centers[k], self.fit_stats[k], _ = self._fit_one(eng, k)
+        else:
+            from .engine import Engine
+
+            while len(self._workers) < nthreads:
+                w = Engine(eng.device.index, eng.atomname)
+                self._workers.append((w, torch.cuda.Stream(device=eng.device)))
+            for w, _ in self._workers:
+                w.profile(getattr(eng, "_profiling", False))
+            lock = threading.Lock()
+            queue = list(mine)
+            errors = []
+
+            def run(w, stream):
+                try:
+                    torch.cuda.set_device(eng.device)
+                    with torch.cuda.stream(stream):
+                        while True:
+                            with lock:
+                                if not queue or errors:
+                                    return
+                                k = queue.pop(0)
+                            c, st, _ = self._fit_one(w, k)
+                            stream.synchronize()
+                            with lock:
+                                self.centers[k], self.fit_stats[k] = c, st
+                except Exception as e:          # surfaced on the main thread
+                    with lock:
+                        errors.append(e)
+
+            threads = [threading.Thread(target=run, args=wk) for wk in self._workers[:nthreads]]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+        if world > 1:
+            self._sync()
+            t0 = time.perf_counter()
+            for k in todo:
+                if owner[k] != rank:
+                    self.centers[k] = torch.empty((self.K, self.D[k]), dtype=torch.float64, device=eng.device)
+                d.broadcast(self.centers[k], src=owner[k])
+            gathered = [None] * world
+            d.all_gather_object(gathered, self.fit_stats)
+            for part in gathered:
+                self.fit_stats.update(part)
+            self._sync()
+            self.comm["centres_broadcast"] = {"ms": (time.perf_counter() - t0) * 1e3,
+                                              "bytes": int(sum(self.K * self.D[k] * 8 for k in todo))}
         self.pool = None
         return self
+
+    def worker_engines(self):
+        return [w for w, _ in self._workers]
 
     # ------------------------------------------------------------------ pass C
     def pass_c(self, source):
