@@ -313,7 +313,7 @@ def main():
     ap.add_argument("--pool-rows", type=int, default=1 << 21)
     ap.add_argument("--host-slots", type=int, default=64)
     ap.add_argument("--exchange", default="replicated", choices=["replicated", "allreduce"])
-    ap.add_argument("--train-threads", type=int, default=4)
+    ap.add_argument("--train-threads", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")

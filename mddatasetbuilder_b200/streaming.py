@@ -79,7 +79,7 @@ class StreamingSelector:
                  perceive_bond_orders=False, pool_rows=1 << 21, table_cap=1024, want_molecules=False,
                  only_keys: Optional[Iterable[int]] = None, log: Optional[Callable[[str], None]] = None,
                  kmeans_kwargs: Optional[dict] = None, cache_gb: Optional[float] = None, cache_reserve_gb: float = 24.0,
-                 train_threads: int = 4):
+                 train_threads: int = 1):
         import torch
 
         self.eng = engine

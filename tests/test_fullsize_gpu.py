@@ -105,3 +105,117 @@ def test_descriptor_and_assignment_properties_100k(engine):
     # row = spectrum + pads: the row sum equals the padded trace
     assert np.allclose(X.sum(axis=1), (maxc * pads).sum(), rtol=1e-9)
     engine.set_elements(["C", "H", "O"])
+
+
+# ---------------------------------------------------------------------------------------------
+# Oracle comparisons AT the BASELINE config sizes: the cell-list oracle
+# (oracle.c orc_connect_the_dots mode 1, O(N)) bit-compares whole frames, the O(N)-per-target descriptor
+# oracle checks sampled targets, the perception restatement runs on full 100k-atom frames.
+# ---------------------------------------------------------------------------------------------
+def _Z(s):
+    from oracle import oracle as O
+
+    return np.array([O.ATOMIC_NUMBERS[s.atomname[t]] for t in s.types], dtype=np.int32)
+
+
+@pytest.mark.parametrize("natoms,density,frames", [(100_000, 0.02, (0, 3)), (1_000_000, 0.05, (1,))])
+def test_bonds_labels_keys_bit_exact_at_config_size(engine, natoms, density, frames):
+    from oracle import oracle as O
+    from tests.util import ell_to_canonical
+
+    s = synth.make_system(natoms, density, seed=synth.BASE_SEED + 2)
+    engine.set_elements(s.atomname)
+    try:
+        pos = synth.frame_positions_device(s, max(frames) + 1, engine.device)
+        out = engine.analyze(pos, s.cell(), s.types)
+        engine.check()
+        Z = _Z(s)
+        for f in frames:
+            P = pos[f].cpu().numpy()
+            bonds, _ = O.connect_the_dots(Z, P, s.cell(), True, mode=1)
+            rp, col = O.bonds_to_csr(natoms, bonds)
+            crp, ccol = O.canonical_csr(rp, col)
+            grp, gcol = ell_to_canonical(out["ell"][f].cpu().numpy())
+            assert np.array_equal(grp, crp) and np.array_equal(gcol, ccol), f"bond list of frame {f} differs from the oracle"
+            assert np.array_equal(out["labels"][f].cpu().numpy(), O.dps(rp, col)[2]), "molecule labels differ"
+            assert np.array_equal(out["keys"][f].cpu().numpy().view(np.uint64), O.bond_keys_degree(s.types, rp))
+        # the bond-file route on the same system: keys and labels from the CSR table
+        rowptr, colt, bo = synth.bond_table_device(s, 2, engine.device)
+        keys = engine.bond_keys_csr(rowptr, bo, engine.to_device_types(s.types)).cpu().numpy().view(np.uint64)
+        labels = engine.components_csr(rowptr, colt).cpu().numpy()
+        boh = bo[1].cpu().numpy()
+        assert np.array_equal(keys[1], O.bond_keys_bondfile(s.types, s.rowptr, boh))
+        assert np.array_equal(labels[1], O.dps(s.rowptr, s.col)[2])
+    finally:
+        engine.set_elements(["C", "H", "O"])
+
+
+@pytest.mark.parametrize("natoms,density", [(100_000, 0.02), (1_000_000, 0.05)])
+def test_descriptor_rows_vs_oracle_at_config_size(engine, natoms, density):
+    """2,000 sampled targets of one full-size frame: sphere membership bit-exact, padded sorted rows within
+    |delta| <= 1e-5 * max(|ref|, 1e-3 * ||M||) of sphere cut + Coulomb matrix (oracle.c) + numpy eigh."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+
+    s = synth.make_system(natoms, density, seed=synth.BASE_SEED + 3)
+    engine.set_elements(s.atomname)
+    try:
+        pos = synth.frame_positions_device(s, 2, engine.device)
+        P = pos[1].cpu().numpy()
+        types = engine.to_device_types(s.types)
+        rng = np.random.default_rng(natoms)
+        tg = np.sort(rng.choice(natoms, 2000, replace=False)).astype(np.int32)
+        counts, maxc, members = engine.compositions(pos[1:2], s.cell(), types, 5.0, targets=tg, members_cap=96)
+        out = engine.descriptors(pos[1:2], s.cell(), types, 5.0, counts, maxc, targets=tg, members=members)
+        engine.check()
+        X = out["X"].cpu().numpy()
+        Z = _Z(s)
+        diag = np.array([O.ATOMIC_NUMBERS[s.atomname[t]] ** 2.4 / 2 for t in s.types])
+        chunks = np.array_split(tg, 32)
+        with ThreadPoolExecutor(16) as ex:
+            res = list(ex.map(lambda c: O.descriptor_gather(Z, diag, P, s.box, True, 5.0, c), chunks))
+        mem = [m for _, ms, _ in res for m in ms]
+        mats = [m for _, _, ms in res for m in ms]
+        got_mem = members.cpu().numpy()
+        for k in range(len(tg)):
+            assert np.array_equal(np.sort(got_mem[k][got_mem[k] >= 0]), mem[k]), "sphere membership differs"
+        ec = np.array([[int((s.types[m] == el).sum()) for el in range(len(s.atomname))] for m in mem])
+        assert np.array_equal(ec, counts.cpu().numpy())
+        pads = np.array([O.ATOMIC_NUMBERS[a] ** 2.4 / 2 for a in s.atomname])
+        R, _ = O.feature_rows(O.coulomb_eigs(mats), ec, pads)
+        mc = ec.max(axis=0)
+        assert np.array_equal(mc, maxc)
+        norms = np.array([np.abs(np.linalg.eigvalsh(M)).max() for M in mats])[:, None]
+        tol = 1e-5 * np.maximum(np.abs(R), 1e-3 * norms)
+        assert np.all(np.abs(X - R) <= tol), "descriptor rows outside the stated tolerance"
+    finally:
+        engine.set_elements(["C", "H", "O"])
+
+
+def test_perception_full_frames_vs_restatement(engine):
+    """Bond orders of two 100k-atom frames per density (tools/perceive_big_check.py as a test): every ELL slot
+    equals the restated PerceiveBondOrders (oracle/perceive.py)."""
+    from tests.test_perceive_gpu import ZNUM, _oracle_orders
+
+    for density, dense in ((0.02, False), (0.10, True)):
+        s = synth.make_system(100_000, density, seed=synth.BASE_SEED + 2, dense=dense)
+        engine.set_elements(s.atomname)
+        try:
+            frames = synth.frame_positions(s, 2, sigma=0.08)
+            cell = np.diag(s.box).reshape(9)
+            out = engine.analyze(frames, cell, s.types)
+            engine.check()
+            got = engine.perceive(frames, cell, s.types, out["ell"], labels=out["labels"])
+            engine.check()
+            Z = [ZNUM[s.atomname[t]] for t in s.types]
+            orders = got["orders"].cpu().numpy()
+            ell = out["ell"].cpu().numpy()
+            nmult = 0
+            for f in range(2):
+                want, _ = _oracle_orders(ell[f], frames[f], Z, cell, True)
+                assert np.array_equal(want, orders[f]), f"density {density} frame {f}: bond orders differ"
+                nmult += int((want > 1).sum()) // 2
+            assert nmult > 1000
+        finally:
+            engine.set_elements(["C", "H", "O"])
