@@ -66,7 +66,9 @@ __device__ __forceinline__ double ase_axis_general(double D, double L) {
 // what ASE's general_find_mic returns (Minkowski reduction + image search) up to the last
 // bits of the length; only a distance within ~1e-13 A of the cutoff could be decided differently.
 // ortho = lattice vectors as columns (frac -> cart), frac = its inverse (FrameGeom).
-__device__ __noinline__ void mic_general(const double *__restrict__ ortho, const double *__restrict__ frac, double &x, double &y,
+// (Kept inline on purpose: as a __noinline__ call from the unrolled register kernels it returned garbage on
+// sm_100a / CUDA 12.9 -- tools/tric_debug.py, the stand-alone tools/micro/mic_test.cu is fine.)
+__device__ __forceinline__ void mic_general(const double *__restrict__ ortho, const double *__restrict__ frac, double &x, double &y,
                                          double &z) {
     double f0 = frac[0] * x + frac[1] * y + frac[2] * z;
     double f1 = frac[3] * x + frac[4] * y + frac[5] * z;
@@ -514,27 +516,36 @@ double dv[3];
         const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
         const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
         const int npair = n * (n - 1) / 2;
-        for (int p = tid; p < npair; p += T) {
-            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-            while (i * (i - 1) / 2 > p) --i;
-            while ((i + 1) * i / 2 <= p) ++i;
-            const int j = p - i * (i - 1) / 2;
-            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic && S->gp->is_ortho) {
-
-                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-
-                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-
-                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-
-            } else if (P.periodic)
-
+        if (!P.periodic || S->gp->is_ortho) {
+            for (int p = tid; p < npair; p += T) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
+                if (P.periodic) {
+                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+                }
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
+        } else {  // general cell: minimum image through the cell matrix
+            for (int p = tid; p < npair; p += T) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
                 mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-            S->A[i][j] = mv;
-            S->A[j][i] = mv;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
         }
     }
     __syncthreads();
@@ -749,27 +760,36 @@ double dv[3];
         const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
         const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
         const int npair = n * (n - 1) / 2;
-        for (int p = gl; p < npair; p += LPM) {
-            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-            while (i * (i - 1) / 2 > p) --i;
-            while ((i + 1) * i / 2 <= p) ++i;
-            const int j = p - i * (i - 1) / 2;
-            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic && S->gp->is_ortho) {
-
-                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-
-                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-
-                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-
-            } else if (P.periodic)
-
+        if (!P.periodic || S->gp->is_ortho) {
+            for (int p = gl; p < npair; p += LPM) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
+                if (P.periodic) {
+                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+                }
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
+        } else {  // general cell: minimum image through the cell matrix
+            for (int p = gl; p < npair; p += LPM) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
                 mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-            S->A[i][j] = mv;
-            S->A[j][i] = mv;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
         }
     }
     __syncwarp();
@@ -1069,27 +1089,36 @@ double dv[3];
         const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
         const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
         const int npair = n * (n - 1) / 2;
-        for (int p = gl; p < npair; p += LPM) {
-            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-            while (i * (i - 1) / 2 > p) --i;
-            while ((i + 1) * i / 2 <= p) ++i;
-            const int j = p - i * (i - 1) / 2;
-            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic && S->gp->is_ortho) {
-
-                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-
-                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-
-                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-
-            } else if (P.periodic)
-
+        if (!P.periodic || S->gp->is_ortho) {
+            for (int p = gl; p < npair; p += LPM) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
+                if (P.periodic) {
+                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+                }
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
+        } else {  // general cell: minimum image through the cell matrix
+            for (int p = gl; p < npair; p += LPM) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
                 mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-            S->A[i][j] = mv;
-            S->A[j][i] = mv;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
         }
     }
     __syncwarp();
@@ -1279,27 +1308,36 @@ double dv[3];
         const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
         const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
         const int npair = n * (n - 1) / 2;
-        for (int p = gl; p < npair; p += 64) {
-            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-            while (i * (i - 1) / 2 > p) --i;
-            while ((i + 1) * i / 2 <= p) ++i;
-            const int j = p - i * (i - 1) / 2;
-            double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-            if (P.periodic && S->gp->is_ortho) {
-
-                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-
-                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-
-                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-
-            } else if (P.periodic)
-
+        if (!P.periodic || S->gp->is_ortho) {
+            for (int p = gl; p < npair; p += 64) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
+                if (P.periodic) {
+                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+                }
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
+        } else {  // general cell: minimum image through the cell matrix
+            for (int p = gl; p < npair; p += 64) {
+                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                while (i * (i - 1) / 2 > p) --i;
+                while ((i + 1) * i / 2 <= p) ++i;
+                const int j = p - i * (i - 1) / 2;
+                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
                 mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-            S->A[i][j] = mv;
-            S->A[j][i] = mv;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+                S->A[i][j] = mv;
+                S->A[j][i] = mv;
+            }
         }
     }
     PAIR_SYNC();

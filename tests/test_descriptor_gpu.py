@@ -99,7 +99,7 @@ def test_small_dense_box_more_than_255_atoms_in_the_single_cell(engine):
 def test_cutoff_above_half_the_cell_is_refused(engine):
     s = synth.make_system(60, 0.05, seed=synth.BASE_SEED + 44)
     engine.set_elements(s.atomname)
-    with pytest.raises(RuntimeError, match="half of a cell edge"):
+    with pytest.raises(RuntimeError, match="half of a cell height"):
         engine.compositions(s.pos0[None], s.cell(), s.types, 0.51 * float(s.box[0]), targets=np.arange(4, dtype=np.int32))
     # an empty target list is no work, not "every atom"
     counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, 4.0, targets=np.zeros(0, dtype=np.int32))
