@@ -120,7 +120,7 @@ int mdb_group_keys(mdb_ctx *ctx, int nframes, int natoms, const uint64_t *d_keys
                    long long *d_tab_first, uint16_t *d_codes, int32_t *d_order, long long *d_seg,
                    void *stream);
 
-/* Per-type max_counter (datasetbuilder.py:262-272): d_maxc [cap][8] (in/out) takes, for the slot of every
+/* Per-type max_counter (datasetbuilder.py:262-272): d_maxc [cap][16] (in/out; 16 = the element-type capacity of the library) takes, for the slot of every
  * target, the element-wise maximum of its composition d_counts [ntargets][ntypes].  d_targets: atom-frame
  * indices into d_codes, or NULL = 0 .. ntargets-1. */
 int mdb_type_maxcount(mdb_ctx *ctx, const int32_t *d_targets, long long ntargets, const uint16_t *d_codes,

@@ -13,7 +13,7 @@
 #define MDB_TOMB 0x80000000u   // this neighbour entry was deleted
 #define MDB_PEND 0x40000000u   // (slot 0) row owner is a pending valence/angle violator
 #define MDB_DIRTY 0x20000000u  // (slot 0) row needs compaction
-#define MDB_MAXT 8             // max element types per trajectory
+#define MDB_MAXT 16            // max element types per trajectory
 #define MDB_MAXZ 18
 
 #define MDB_ERR_CELL_OVERFLOW 1  // more atoms in one cell than the rank field holds (>= 255)

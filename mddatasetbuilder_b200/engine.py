@@ -34,6 +34,8 @@ class Engine:
     """Owns one ``mdb_ctx`` (one per process and GPU, like one Pool worker of the
     reference, utils.py:198-231, but driving a whole device)."""
 
+    MAXT = 16   # element types per trajectory (MDB_MAXT in csrc/common.cuh)
+
     def __init__(self, device: int = 0, atomname=("C", "H", "O"), max_bonds: int = 8):
         torch = _torch()
         if not torch.cuda.is_available():
@@ -252,7 +254,7 @@ class Engine:
         return codes, order, seg
 
     def type_maxcount(self, codes, counts, maxc, targets=None):
-        """maxc [cap, 8] int32 (in/out): element-wise maximum of the compositions per key slot."""
+        """maxc [cap, Engine.MAXT] int32 (in/out): element-wise maximum of the compositions per key slot."""
         T = int(counts.shape[0])
         rc = self.L.mdb_type_maxcount(self.ctx, _ptr(targets), T, _ptr(codes), _ptr(counts), _ptr(maxc), self.stream())
         _lib.check(rc, "mdb_type_maxcount")

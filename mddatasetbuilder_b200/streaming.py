@@ -136,7 +136,7 @@ class StreamingSelector:
     def pass_a(self, source):
         torch, eng = self.torch, self.eng
         table = eng.key_table(self.cap)
-        maxc = torch.zeros((self.cap, 8), dtype=torch.int32, device=eng.device)
+        maxc = torch.zeros((self.cap, eng.MAXT), dtype=torch.int32, device=eng.device)
         stores: List[_Store] = []
         nstep = 0
         rings = 0

@@ -290,3 +290,47 @@ def test_triclinic_cell(engine, tilt):
         assert sum(len(v) for v in res.chosen.values()) > 0 and len(sel_job.big) > 0
     finally:
         engine.set_elements(["C", "H", "O"])
+
+
+def test_ten_element_types(engine):
+    """More than 8 element types on the whole path (the library holds 16): bonds, keys, compositions and
+    descriptor rows of a 10-element soup against the oracle."""
+    from mddatasetbuilder_b200.engine import Engine
+
+    names = ["H", "C", "N", "O", "F", "Si", "P", "S", "Cl", "B"]
+    rng = np.random.default_rng(12)
+    n, L = 1500, 30.0
+    # jittered lattice: no overlapping atoms, plenty of bonded pairs
+    g = 12
+    sites = rng.permutation(g ** 3)[:n]
+    pos = (np.stack([sites % g, (sites // g) % g, sites // (g * g)], axis=1) + 0.5) * (L / g) + rng.normal(0, 0.35, (n, 3))
+    pos = np.round(np.mod(pos, L), 6)
+    types = rng.integers(0, len(names), n).astype(np.uint8)
+    eng = Engine(0, names)
+    try:
+        cell = np.diag([L, L, L])
+        out = eng.analyze(pos[None], cell.reshape(9), types, True)
+        eng.check()
+        Z = np.array([O.ATOMIC_NUMBERS[a] for a in names], dtype=np.int32)[types]
+        bonds, _ = O.connect_the_dots(Z, pos, cell, True, mode=1)
+        rp, col = O.bonds_to_csr(n, bonds)
+        from tests.util import ell_to_canonical
+
+        grp, gcol = ell_to_canonical(out["ell"][0].cpu().numpy())
+        crp, ccol = O.canonical_csr(rp, col)
+        assert np.array_equal(grp, crp) and np.array_equal(gcol, ccol)
+        assert np.array_equal(out["keys"][0].cpu().numpy().view(np.uint64), O.bond_keys_degree(types, rp))
+        targets = np.arange(0, n, 5, dtype=np.int32)
+        counts, maxc = eng.compositions(pos[None], cell.reshape(9), types, 5.0, targets=targets)
+        diag = np.array([O.ATOMIC_NUMBERS[a] ** 2.4 / 2 for a in names])
+        cn, mem, mats = O.descriptor_gather(Z, diag[types], pos, np.array([L, L, L]), True, 5.0, targets)
+        comp = np.array([np.bincount(types[m], minlength=len(names)) for m in mem])
+        assert np.array_equal(counts.cpu().numpy(), comp)
+        X = eng.descriptors(pos[None], cell.reshape(9), types, 5.0, counts, maxc, targets=targets)["X"].cpu().numpy()
+        eng.check()
+        eigs = O.coulomb_eigs(mats)
+        R, _ = O.feature_rows(eigs, comp, diag)
+        norms = np.array([np.abs(e).max() for e in eigs])[:, None]
+        assert np.all(np.abs(X - R) <= RTOL * np.maximum(np.abs(R), 1e-3 * norms))
+    finally:
+        eng.close()

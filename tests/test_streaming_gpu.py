@@ -93,7 +93,7 @@ def test_type_maxcount(engine):
     counts = rng.integers(0, 30, size=(T, nt)).astype(np.int32)
     import torch
 
-    maxc = torch.zeros((cap, 8), dtype=torch.int32, device=engine.device)
+    maxc = torch.zeros((cap, engine.MAXT), dtype=torch.int32, device=engine.device)
     engine.type_maxcount(_t(engine, codes.view(np.int16)), _t(engine, counts), maxc)
     m = maxc.cpu().numpy()
     for s in range(9):
