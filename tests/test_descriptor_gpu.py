@@ -299,14 +299,14 @@ def test_ten_element_types(engine):
 
     names = ["H", "C", "N", "O", "F", "Si", "P", "S", "Cl", "B"]
     rng = np.random.default_rng(12)
-    n, L = 1500, 30.0
-    # jittered lattice: no overlapping atoms, plenty of bonded pairs
-    g = 12
+    n, L = 900, 30.0
+    # jittered lattice: no overlapping atoms, plenty of bonded pairs (and over-coordinated atoms for the cleanup)
+    g = 10
     sites = rng.permutation(g ** 3)[:n]
     pos = (np.stack([sites % g, (sites // g) % g, sites // (g * g)], axis=1) + 0.5) * (L / g) + rng.normal(0, 0.35, (n, 3))
     pos = np.round(np.mod(pos, L), 6)
     types = rng.integers(0, len(names), n).astype(np.uint8)
-    eng = Engine(0, names)
+    eng = Engine(0, names, max_bonds=16)
     try:
         cell = np.diag([L, L, L])
         out = eng.analyze(pos[None], cell.reshape(9), types, True)
