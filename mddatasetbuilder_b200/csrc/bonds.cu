@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(BOND_THREADS) k_bonds(const __grid_constant__ 
     __shared__ int s_pend[PEND][BOND_THREADS];
     __shared__ float s_cut2f[MDB_MAXT * MDB_MAXT];
     const int tid = threadIdx.x;
-    if (tid < MDB_MAXT * MDB_MAXT) s_cut2f[tid] = P.el.cut2f[tid];
+    for (int q = tid; q < MDB_MAXT * MDB_MAXT; q += BOND_THREADS) s_cut2f[q] = P.el.cut2f[q];
     __syncthreads();
     const int N = P.N;
     const int f = blockIdx.y;
