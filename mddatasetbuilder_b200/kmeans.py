@@ -122,7 +122,7 @@ class MiniBatchKMeansB200:
             eng.kmeans_apply_update(centers, weight_sums, sums, wsum)
         else:
             labels, inertia, _ = eng.kmeans_assign(X, centers, rowidx=batch_idx, want_inertia=True)
-            if B <= 4096:      # sklearn's own operation order: bit-identical centres
+            if B <= 4096 and int(X.shape[1]) <= 256:      # sklearn's own operation order: bit-identical centres
                 eng.kmeans_update_exact(X, labels, centers, weight_sums, rowidx=batch_idx)
             else:
                 sums, wsum = eng.kmeans_partial_sums(X, labels, K, rowidx=batch_idx, out=self._sums_buf)
@@ -144,15 +144,16 @@ class MiniBatchKMeansB200:
         return inertia
 
     # ------------------------------------------------------------------ fit
-    def fit(self, X, compute_labels=True):
-        """``MiniBatchKMeans.fit`` on the device rows X [n, D] (every rank holds the same X when
-        torch.distributed is initialised: the streaming selector replicates its training pool)."""
+    def seed(self, X):
+        """First half of ``MiniBatchKMeans.fit``: the validation draw and the n_init k-means++ seedings, best one
+        kept.  Returns the state ``run_loop`` continues from (the RandomState goes along, so the split changes
+        no draw).  The streaming selector runs this half for the next bond type on a second stream while the
+        mini-batch loop of the current one is running."""
         import torch
 
         eng = self.eng
         n_samples = int(X.shape[0])
         K = self.n_clusters
-        D = int(X.shape[1])
         batch_size = min(self.batch_size, n_samples)
         init_size = self.init_size
         if init_size is None:
@@ -161,10 +162,6 @@ class MiniBatchKMeansB200:
             init_size = 3 * K
         init_size = min(init_size, n_samples)
         rs = np.random.RandomState(self.seed)
-        self._packed = torch.zeros(K * D + K + 1, dtype=torch.float64, device=eng.device)
-        self._sums_buf = (self._packed[: K * D].view(K, D), self._packed[K * D: K * D + K])
-        self._comm_events = []
-
         validation_indices = rs.randint(0, n_samples, init_size)
         valid_idx = torch.as_tensor(validation_indices, dtype=torch.int32, device=eng.device)
         best_inertia, centers = None, None
@@ -172,7 +169,20 @@ class MiniBatchKMeansB200:
             _, inertia, _ = eng.kmeans_assign(X, c, rowidx=valid_idx, want_inertia=True)
             if best_inertia is None or inertia < best_inertia:
                 centers, best_inertia = c, inertia
-        centers = centers.contiguous()
+        return {"rs": rs, "centers": centers.contiguous(), "batch_size": batch_size}
+
+    def run_loop(self, X, state):
+        """Second half of ``MiniBatchKMeans.fit``: the mini-batch steps until the smoothed inertia stops improving."""
+        import torch
+
+        eng = self.eng
+        n_samples = int(X.shape[0])
+        K = self.n_clusters
+        D = int(X.shape[1])
+        rs, centers, batch_size = state["rs"], state["centers"], state["batch_size"]
+        self._packed = torch.zeros(K * D + K + 1, dtype=torch.float64, device=eng.device)
+        self._sums_buf = (self._packed[: K * D].view(K, D), self._packed[K * D: K * D + K])
+        self._comm_events = []
         weight_sums = torch.zeros(K, dtype=torch.float64, device=eng.device)
         ewa, ewa_min, no_improvement = None, None, 0
         n_since_last_reassign = 0
@@ -221,6 +231,12 @@ class MiniBatchKMeansB200:
             self.comm_ms_ = float(sum(a.elapsed_time(b) for a, b in self._comm_events))
             self.comm_bytes_per_step_ = int(self._packed.numel() * 8)
         self._comm_events = []
+        return self
+
+    def fit(self, X, compute_labels=True):
+        """``MiniBatchKMeans.fit`` on the device rows X [n, D] (every rank holds the same X when
+        torch.distributed is initialised: the streaming selector replicates its training pool)."""
+        self.run_loop(X, self.seed(X))
         if compute_labels:
             self.labels_, self.inertia_ = self.predict(X, with_inertia=True)
         return self

@@ -79,7 +79,7 @@ class StreamingSelector:
                  perceive_bond_orders=False, pool_rows=1 << 21, table_cap=1024, want_molecules=False,
                  only_keys: Optional[Iterable[int]] = None, log: Optional[Callable[[str], None]] = None,
                  kmeans_kwargs: Optional[dict] = None, cache_gb: Optional[float] = None, cache_reserve_gb: float = 24.0,
-                 train_threads: int = 1):
+                 train_threads: int = 1, overlap_seeding: bool = True):
         import torch
 
         self.eng = engine
@@ -105,6 +105,7 @@ class StreamingSelector:
         self.cache, self.cache_bytes, self.cache_budget = {}, 0, 0
         self.capture_rows = None
         self.train_threads = int(train_threads)
+        self.overlap_seeding = bool(overlap_seeding)
         self._workers = []
         self.eng_profile = False
 
@@ -356,14 +357,14 @@ class StreamingSelector:
         return km.cluster_centers_, stats, km
 
     def train(self):
-        """MiniBatchKMeans per clustered type on its scaled pool.  The fits are independent, latency-bound
-        loops (one 1024-row mini-batch per step, a host decision after every step), so they run concurrently:
-        `train_threads` host threads, each with its own context (scratch arena) and CUDA stream, take the
-        types largest first; with several ranks the types are dealt over the ranks first and the centres
-        broadcast by their owner (every fit is seeded by itself, so neither changes any result).  The
-        "allreduce" exchange keeps every rank in every fit instead (mini-batch slices + one packed all-reduce)."""
-        import threading
-
+        """MiniBatchKMeans per clustered type on its scaled pool.  A fit is a seeding (3 x k-means++, one long
+        handshake-bound kernel) followed by a loop of small mini-batch steps with a host decision after each;
+        the seeding of the next type runs on a second context / stream while the loop of the current one runs
+        (`overlap_seeding`).  With several ranks the types are dealt over the ranks and the centres broadcast by
+        their owner.  Every fit carries its own RandomState, so neither changes any result.  The "allreduce"
+        exchange keeps every rank in every fit instead (mini-batch slices + one packed all-reduce per step).
+        (Tried and dropped: several fits on host threads -- the co-operative seeding kernels serialise and the
+        interpreter lock makes the step loops slower, 8.2 -> 9.5 s for 15 types.)"""
         torch, eng = self.torch, self.eng
         self.centers = {}
         self.fit_stats = {}
@@ -383,47 +384,58 @@ class StreamingSelector:
             return self
         owner = {k: i % world for i, k in enumerate(todo)}
         mine = [k for k in todo if owner[k] == rank]
-        nthreads = max(1, min(self.train_threads, len(mine)))
         self._sync()
-        if nthreads <= 1:
+        if not self.overlap_seeding or len(mine) < 2:
             for k in mine:
                 self.centers[k], self.fit_stats[k], _ = self._fit_one(eng, k)
         else:
+            # seeding (scaling of the pool, validation draw, 3 x k-means++: one long co-operative kernel that is
+            # bound by its own handshakes) of type t + 1 on a second context / stream while the mini-batch loop of
+            # type t runs on the main one: the seeds arrive through a queue, each fit keeps its own RandomState
+            import queue
+            import threading
+
             from .engine import Engine
 
-            while len(self._workers) < nthreads:
-                w = Engine(eng.device.index, eng.atomname)
-                self._workers.append((w, torch.cuda.Stream(device=eng.device)))
-            for w, _ in self._workers:
-                w.profile(getattr(eng, "_profiling", False))
-            lock = threading.Lock()
-            queue = list(mine)
-            errors = []
+            if not self._workers:
+                self._workers.append((Engine(eng.device.index, eng.atomname), torch.cuda.Stream(device=eng.device)))
+            w, stream = self._workers[0]
+            w.profile(getattr(eng, "_profiling", False))
+            q: "queue.Queue" = queue.Queue(maxsize=2)
 
-            def run(w, stream):
+            def seeder():
                 try:
                     torch.cuda.set_device(eng.device)
                     with torch.cuda.stream(stream):
-                        while True:
-                            with lock:
-                                if not queue or errors:
-                                    return
-                                k = queue.pop(0)
-                            c, st, _ = self._fit_one(w, k)
+                        for k in mine:
+                            pool = self.pool[k]
+                            w.minmax_transform(pool, self.mn_h[k], self.mx_h[k])
+                            n = int(pool.shape[0])
+                            km = MiniBatchKMeansB200(w, n_clusters=self.K, init_size=min(3 * self.K, n), n_init=3,
+                                                     seed=self.seed, **self.kmeans_kwargs)
+                            state = km.seed(pool)
                             stream.synchronize()
-                            with lock:
-                                self.centers[k], self.fit_stats[k] = c, st
+                            q.put((k, state))
                 except Exception as e:          # surfaced on the main thread
-                    with lock:
-                        errors.append(e)
+                    q.put((None, e))
 
-            threads = [threading.Thread(target=run, args=wk) for wk in self._workers[:nthreads]]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
-            if errors:
-                raise errors[0]
+            th = threading.Thread(target=seeder)
+            th.start()
+            try:
+                for _ in mine:
+                    k, state = q.get()
+                    if k is None:
+                        raise state
+                    pool = self.pool[k]
+                    n = int(pool.shape[0])
+                    km = MiniBatchKMeansB200(eng, n_clusters=self.K, init_size=min(3 * self.K, n), n_init=3, seed=self.seed,
+                                             **self.kmeans_kwargs)
+                    km.run_loop(pool, state)
+                    self.centers[k] = km.cluster_centers_
+                    self.fit_stats[k] = {"steps": km.n_steps_, "pool_rows": n, "rows": self.counts[k], "D": self.D[k]}
+                    self.pool[k] = None
+            finally:
+                th.join()
         if world > 1:
             self._sync()
             t0 = time.perf_counter()
