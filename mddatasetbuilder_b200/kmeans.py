@@ -144,7 +144,7 @@ class MiniBatchKMeansB200:
         return inertia
 
     # ------------------------------------------------------------------ fit
-    def seed(self, X):
+    def seed_centers(self, X):
         """First half of ``MiniBatchKMeans.fit``: the validation draw and the n_init k-means++ seedings, best one
         kept.  Returns the state ``run_loop`` continues from (the RandomState goes along, so the split changes
         no draw).  The streaming selector runs this half for the next bond type on a second stream while the
@@ -236,7 +236,7 @@ class MiniBatchKMeansB200:
     def fit(self, X, compute_labels=True):
         """``MiniBatchKMeans.fit`` on the device rows X [n, D] (every rank holds the same X when
         torch.distributed is initialised: the streaming selector replicates its training pool)."""
-        self.run_loop(X, self.seed(X))
+        self.run_loop(X, self.seed_centers(X))
         if compute_labels:
             self.labels_, self.inertia_ = self.predict(X, with_inertia=True)
         return self

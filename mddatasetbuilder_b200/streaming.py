@@ -413,7 +413,7 @@ class StreamingSelector:
                             n = int(pool.shape[0])
                             km = MiniBatchKMeansB200(w, n_clusters=self.K, init_size=min(3 * self.K, n), n_init=3,
                                                      seed=self.seed, **self.kmeans_kwargs)
-                            state = km.seed(pool)
+                            state = km.seed_centers(pool)
                             stream.synchronize()
                             q.put((k, state))
                 except Exception as e:          # surfaced on the main thread
