@@ -79,7 +79,7 @@ class StreamingSelector:
                  perceive_bond_orders=False, pool_rows=1 << 21, table_cap=1024, want_molecules=False,
                  only_keys: Optional[Iterable[int]] = None, log: Optional[Callable[[str], None]] = None,
                  kmeans_kwargs: Optional[dict] = None, cache_gb: Optional[float] = None, cache_reserve_gb: float = 24.0,
-                 train_threads: int = 1, overlap_seeding: bool = True):
+                 train_threads: int = 1, overlap_seeding: bool = False):
         import torch
 
         self.eng = engine
@@ -363,7 +363,9 @@ class StreamingSelector:
         (`overlap_seeding`).  With several ranks the types are dealt over the ranks and the centres broadcast by
         their owner.  Every fit carries its own RandomState, so neither changes any result.  The "allreduce"
         exchange keeps every rank in every fit instead (mini-batch slices + one packed all-reduce per step).
-        (Tried and dropped: several fits on host threads -- the co-operative seeding kernels serialise and the
+        Measured on B200 (15 types, K = 10,000): the overlap is a loss -- the persistent seeding kernel spins on its
+        flags and the step kernels of the other stream starve each other (train 8.2 -> 17.4 s) -- so it is off by
+        default.  (Also tried and dropped: several fits on host threads -- the co-operative seeding kernels serialise and the
         interpreter lock makes the step loops slower, 8.2 -> 9.5 s for 15 types.)"""
         torch, eng = self.torch, self.eng
         self.centers = {}
