@@ -193,9 +193,22 @@ class MiniBatchKMeansB200:
         # the cdf is built once, with the same arithmetic
         cdf = np.cumsum(np.ones(n_samples) / float(n_samples))
         cdf /= cdf[-1]
+        last = n_samples - 1
+
+        def draw():
+            # = cdf.searchsorted(u, side="right"), without the 21-level binary search through a 16 MB table
+            # (220 us per step at 2M rows): the cdf is the grid (i + 1) / n up to rounding, so floor(u * n) is
+            # within one of the answer and two compare-and-step rounds against the table make it exact
+            u = rs.random_sample(batch_size)
+            c = np.minimum((u * n_samples).astype(np.int64), last)
+            for _ in range(3):
+                c = c - ((c > 0) & (cdf[np.maximum(c - 1, 0)] > u))
+                c = c + ((c <= last) & (cdf[np.minimum(c, last)] <= u))
+            return c
+
         i = -1
         for i in range(n_steps):
-            idx = cdf.searchsorted(rs.random_sample(batch_size), side="right")
+            idx = draw()
             batch_idx = torch.as_tensor(idx, dtype=torch.int32, device=eng.device)
             n_since_last_reassign += batch_size
             # weights only grow, so once no centre has a zero count the test never fires again (one sync less per step)

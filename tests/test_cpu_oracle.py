@@ -409,3 +409,21 @@ def test_frame_wrapper_equals_wrap_positions_bit_for_bit():
         a = wrap_positions(pos[idx], cell, center, pbc)
         b = FrameWrapper(cell, pbc)(pos[idx], center)
         assert a.tobytes() == b.tobytes()
+
+
+def test_minibatch_draw_equals_numpy_choice():
+    """kmeans.py draws its mini-batches like scikit-learn 1.9 (`RandomState.choice(n, B, p=uniform)` =
+    searchsorted on the cdf); the fast form used there is the same function of the same variates."""
+    for n in (5, 900, 12345, 1 << 18):
+        p = np.ones(n) / n
+        rs1, rs2 = np.random.RandomState(3), np.random.RandomState(3)
+        cdf = np.cumsum(np.ones(n) / float(n))
+        cdf /= cdf[-1]
+        for _ in range(20):
+            want = rs1.choice(n, 1024, p=p, replace=True)
+            u = rs2.random_sample(1024)
+            c = np.minimum((u * n).astype(np.int64), n - 1)
+            for _ in range(3):
+                c = c - ((c > 0) & (cdf[np.maximum(c - 1, 0)] > u))
+                c = c + ((c <= n - 1) & (cdf[np.minimum(c, n - 1)] <= u))
+            assert np.array_equal(want, c)
