@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--host-slots", type=int, default=64)
     ap.add_argument("--exchange", default="replicated", choices=["replicated", "allreduce"])
     ap.add_argument("--train-threads", type=int, default=1)
+    ap.add_argument("--overlap-seeding", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
@@ -370,7 +371,7 @@ def main():
     def job(source, nfr):
         sel = StreamingSelector(eng, sysm.types, cutoff=5.0, n_clusters=args.clusters, n_each=1, seed=synth.BASE_SEED,
                                 periodic=True, pool_rows=args.pool_rows, want_molecules=True, kmeans_kwargs=kw,
-                                train_threads=args.train_threads)
+                                train_threads=args.train_threads, overlap_seeding=args.overlap_seeding)
         res = sel.run(source)
         return sel, res
 

@@ -136,6 +136,8 @@ extern "C" int mdb_set_option(mdb_ctx *c, const char *key, double v) {
         c->opt_frames_per_launch = (int)v;
     else if (k == "perceive_bond_orders")
         c->opt_perceive = v != 0.0;
+    else if (k == "ql_pwk")
+        c->opt_ql_pwk = v != 0.0;
     else if (k == "desc_legacy")
         c->opt_desc_legacy = (int)v;  // 0 default mix, 1 round-1 kernels, 2 multi-column kernels everywhere
     else {

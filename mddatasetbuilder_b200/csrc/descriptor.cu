@@ -445,6 +445,50 @@ __device__ __forceinline__ void canonical_member_order(Sm *S, int n, int e, Sync
     sync();
 }
 
+// Coulomb matrix (datasetbuilder.py:341-348) of the n members held in S->vec / S->z / S->t into the staging copy
+// S->A, every pair once, by `nl` lanes (this one is lane `gl`).  Rows are folded -- row i together with row
+// n - i gives n pairs -- so that the lanes stay busy without any index arithmetic per pair.  Both vectors lie
+// within +-L/2 of the target, so one conditional shift per axis gives the minimum image of a pair in a diagonal
+// cell, and none is needed when the sphere is small against the box (4 r_max < L, decided once per matrix);
+// general cells go through mic_general.  The reciprocal distance is a MUFU seed + two Newton steps.
+template <class Sm>
+__device__ __forceinline__ void coulomb_pairs(const DescParams &P, Sm *S, int n, int gl, int nl) {
+    if (n < 2) return;
+    const bool general = P.periodic && !S->gp->is_ortho;
+    const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
+    const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
+    // largest member distance from the target (every lane scans the list: n broadcasts, no reduction needed)
+    bool wrap = false;
+    if (P.periodic && !general) {
+        double r2max = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double a = S->vec[k][0], b = S->vec[k][1], c = S->vec[k][2];
+            r2max = fmax(r2max, a * a + b * b + c * c);
+        }
+        const double lmin = fmin(L0, fmin(L1, L2));
+        wrap = !(16.0 * r2max < lmin * lmin);
+    }
+    for (int i = 1; i <= n / 2; ++i) {
+        const int rb = n - i;
+        const int cnt = (rb == i) ? i : n;
+        for (int t = gl; t < cnt; t += nl) {
+            const int a = t < i ? i : rb;
+            const int b = t < i ? t : t - i;
+            double dx = S->vec[b][0] - S->vec[a][0], dy = S->vec[b][1] - S->vec[a][1], dz = S->vec[b][2] - S->vec[a][2];
+            if (wrap) {
+                dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
+                dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
+                dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
+            } else if (general)
+                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const double mv = r2 > 0.0 ? (double)(S->z[a] * S->z[b]) * fast_rsqrt(r2) : 0.0;  // inf -> 0 (:347)
+            S->A[a][b] = mv;
+            S->A[b][a] = mv;
+        }
+    }
+}
+
 template <int NMAX>
 struct BlkSmem {
     double A[NMAX][NMAX + 2];
@@ -512,42 +556,7 @@ double dv[3];
     canonical_member_order(S, n, tid, [] { __syncthreads(); });
     // Coulomb matrix (datasetbuilder.py:341-348), each pair once; see k_tridiag_reg for the minimum image
     for (int i = tid; i < n; i += T) S->A[i][i] = P.diag[S->t[i]];
-    if (n > 1) {
-        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
-        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
-        const int npair = n * (n - 1) / 2;
-        if (!P.periodic || S->gp->is_ortho) {
-            for (int p = tid; p < npair; p += T) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                if (P.periodic) {
-                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-                }
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        } else {  // general cell: minimum image through the cell matrix
-            for (int p = tid; p < npair; p += T) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        }
-    }
+    coulomb_pairs(P, S, n, tid, T);
     __syncthreads();
     const int row = tid >> 1, hf = tid & 1;
     double *arow = &S->A[row][0];
@@ -756,42 +765,7 @@ double dv[3];
     for (int q = gl; q < NMAX * NMAX; q += LPM) S->A[q / NMAX][q % NMAX] = 0.0;
     __syncwarp();
     for (int i = gl; i < n; i += LPM) S->A[i][i] = P.diag[S->t[i]];
-    if (n > 1) {
-        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
-        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
-        const int npair = n * (n - 1) / 2;
-        if (!P.periodic || S->gp->is_ortho) {
-            for (int p = gl; p < npair; p += LPM) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                if (P.periodic) {
-                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-                }
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        } else {  // general cell: minimum image through the cell matrix
-            for (int p = gl; p < npair; p += LPM) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        }
-    }
+    coulomb_pairs(P, S, n, gl, LPM);
     __syncwarp();
     double a[NMAX];
     {
@@ -1085,42 +1059,7 @@ double dv[3];
     for (int q = gl; q < NMAX * NMAX; q += LPM) S->A[q / NMAX][q % NMAX] = 0.0;
     __syncwarp();
     for (int i = gl; i < n; i += LPM) S->A[i][i] = P.diag[S->t[i]];
-    if (n > 1) {
-        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
-        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
-        const int npair = n * (n - 1) / 2;
-        if (!P.periodic || S->gp->is_ortho) {
-            for (int p = gl; p < npair; p += LPM) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                if (P.periodic) {
-                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-                }
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        } else {  // general cell: minimum image through the cell matrix
-            for (int p = gl; p < npair; p += LPM) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        }
-    }
+    coulomb_pairs(P, S, n, gl, LPM);
     __syncwarp();
     double a[CPL][NMAX];
 #pragma unroll
@@ -1304,42 +1243,7 @@ double dv[3];
     }
     canonical_member_order(S, n, gl, [barid] { asm volatile("bar.sync %0, 64;" ::"r"(barid) : "memory"); });
     for (int i = gl; i < n; i += 64) S->A[i][i] = P.diag[S->t[i]];
-    if (n > 1) {
-        const double L0 = S->L[0], L1 = S->L[1], L2 = S->L[2];
-        const double hL0 = 0.5 * L0, hL1 = 0.5 * L1, hL2 = 0.5 * L2;
-        const int npair = n * (n - 1) / 2;
-        if (!P.periodic || S->gp->is_ortho) {
-            for (int p = gl; p < npair; p += 64) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                if (P.periodic) {
-                    dx += dx > hL0 ? -L0 : (dx < -hL0 ? L0 : 0.0);
-                    dy += dy > hL1 ? -L1 : (dy < -hL1 ? L1 : 0.0);
-                    dz += dz > hL2 ? -L2 : (dz < -hL2 ? L2 : 0.0);
-                }
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        } else {  // general cell: minimum image through the cell matrix
-            for (int p = gl; p < npair; p += 64) {
-                int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                while (i * (i - 1) / 2 > p) --i;
-                while ((i + 1) * i / 2 <= p) ++i;
-                const int j = p - i * (i - 1) / 2;
-                double dx = S->vec[j][0] - S->vec[i][0], dy = S->vec[j][1] - S->vec[i][1], dz = S->vec[j][2] - S->vec[i][2];
-                mic_general(S->gp->ortho, S->gp->frac, dx, dy, dz);
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                const double mv = r2 > 0.0 ? (double)(S->z[i] * S->z[j]) * rsqrt(r2) : 0.0;  // inf -> 0 (:347)
-                S->A[i][j] = mv;
-                S->A[j][i] = mv;
-            }
-        }
-    }
+    coulomb_pairs(P, S, n, gl, 64);
     PAIR_SYNC();
     double a[NMAX];
     {
@@ -1378,7 +1282,7 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
                                                  const double *__restrict__ padval,  // pad value per element
                                                  const int *__restrict__ maxcount, int D, double *__restrict__ X,
                                                  double *__restrict__ eig, int eigcap, int *__restrict__ nout,
-                                                 BondStats *stats, const int *__restrict__ eig_off) {
+                                                 BondStats *stats, const int *__restrict__ eig_off, int pwk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double(*d)[THREADS] = reinterpret_cast<double(*)[THREADS]>(smem_raw);
     double(*e)[THREADS] = d + NMAX;
@@ -1393,6 +1297,89 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     // 1e-12 ||M||, four orders below the floor of the stated tolerance; reciprocals and square roots
     // are MUFU seeds + Newton steps (fast_rcp / fast_rsqrt), a few ulp
     const double EPS = 1e-12;
+    if (pwk) {
+        // Square-root-free QL (Pal-Walker-Kahan, the recurrence of LAPACK dsterf): the off-diagonals are kept
+        // squared, a rotation costs two reciprocals and no square root (~26 instructions against ~45 of the
+        // tqli form below).  Same deflation threshold, applied to e^2.
+        for (int k = 0; k + 1 < n; ++k) {
+            const double v = e[k][tid];
+            e[k][tid] = v * v;
+        }
+        const double EPS2 = EPS * EPS;
+        int l = 0;
+        int jtot = 0;
+        // m = lowest index >= l with a negligible e2[m] (n - 1 when there is none).  The O(n) search for it runs
+        // only when l has passed the previous m; otherwise e2[l] is tested at the top of every iteration and every
+        // other off-diagonal right when a sweep rewrites it, which is the only time it changes (ncu: searching
+        // from l in every iteration cost as many instructions as the rotations themselves).
+        int m = -1;
+        while (l < n) {
+            if (m < l) {
+                for (m = l; m < n - 1; ++m) {
+                    const double dd = fabs(d[m][tid]) + fabs(d[m + 1][tid]);
+                    if (e[m][tid] <= EPS2 * dd * dd) break;
+                }
+                if (m < n - 1) e[m][tid] = 0.0;
+            }
+            if (m == l) {
+                ++l;
+                continue;
+            }
+            {
+                const double dd = fabs(d[l][tid]) + fabs(d[l + 1][tid]);
+                if (e[l][tid] <= EPS2 * dd * dd) {  // l has converged; m stays valid for l + 1
+                    e[l][tid] = 0.0;
+                    ++l;
+                    continue;
+                }
+            }
+            if (jtot++ > 80 * NMAX) {
+                atomicExch(&stats->err, MDB_ERR_EIG_NOCONV);
+                break;
+            }
+            const double p0 = d[l][tid];
+            const double e2l = e[l][tid];
+            const double rte = e2l * fast_rsqrt(e2l);  // sqrt(e2[l]) > 0 here
+            double sigma = (d[l + 1][tid] - p0) * (0.5 * fast_rcp(rte));
+            const double t1 = fma(sigma, sigma, 1.0);
+            const double r1 = t1 * fast_rsqrt(t1);
+            sigma = p0 - rte * fast_rcp(sigma + (sigma >= 0.0 ? r1 : -r1));
+            double c = 1.0, sn = 0.0;
+            double gamma = d[m][tid] - sigma;
+            double p = gamma * gamma;
+            double dup = fabs(d[m][tid]);  // |d[i + 2]| as the sweep left it
+            int msplit = -1;
+            for (int i = m - 1; i >= l; --i) {
+                const double bb = e[i][tid];
+                const double r = p + bb;
+                const double enew = sn * r;  // new e2[i + 1]
+                if (i != m - 1) e[i + 1][tid] = enew;
+                const double oldc = c;
+                // 1 / c = r / p: both reciprocals depend on p only and run side by side (the chain of one
+                // rotation holds one MUFU + Newton sequence instead of two)
+                const double ir = fast_rcp(r);
+                const double ip = fast_rcp(p);
+                const bool pz = p == 0.0;
+                c = p * ir;
+                sn = bb * ir;
+                const double oldgam = gamma;
+                const double alpha = d[i][tid];
+                gamma = c * (alpha - sigma) - sn * oldgam;
+                const double dn = oldgam + (alpha - gamma);
+                d[i + 1][tid] = dn;
+                const double dd = fabs(dn) + dup;
+                if (i != m - 1 && enew <= EPS2 * dd * dd) msplit = i + 1;
+                dup = fabs(dn);
+                p = pz ? oldc * bb : gamma * gamma * (r * ip);
+            }
+            e[l][tid] = sn * p;
+            d[l][tid] = sigma + gamma;
+            if (msplit >= 0) {
+                e[msplit][tid] = 0.0;
+                m = msplit;
+            }
+        }
+    } else {
     // m = lowest index >= l of a negligible off-diagonal.  The O(n) search for it runs only at the
     // start (and after an exact-zero stop); afterwards e[l] is tested at the top of every iteration
     // and every other off-diagonal right when a sweep rewrites it, which is the only time it changes.
@@ -1457,6 +1444,7 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
             if (msplit >= 0) m = msplit;
         }
     }
+    }
     // ascending insertion sort
     for (int a = 1; a < n; ++a) {
         const double v = d[a][tid];
@@ -1494,10 +1482,10 @@ __global__ void __launch_bounds__(THREADS) k_tql(const int *__restrict__ list, i
     }
 }
 
-// bucket id by cluster size: classes of 4 up to 32 atoms, of 8 up to 64 (register-resident kernels), then 96, 128 and 160
-#define DESC_NB 14
+// bucket id by cluster size: classes of 4 up to 48 atoms, of 8 up to 64 (register-resident kernels), then 96, 128 and 160
+#define DESC_NB 16
 __device__ __host__ __forceinline__ int desc_bucket(int n) {
-    return n <= 8 ? 0 : n <= 32 ? (n - 5) >> 2 : n <= 64 ? 7 + ((n - 33) >> 3) : n <= 96 ? 11 : n <= 128 ? 12 : n <= 160 ? 13 : DESC_NB;
+    return n <= 8 ? 0 : n <= 48 ? (n - 5) >> 2 : n <= 64 ? 11 + ((n - 49) >> 3) : n <= 96 ? 13 : n <= 128 ? 14 : n <= 160 ? 15 : DESC_NB;
 }
 
 __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ counts, int nt, long long ntargets,
@@ -1743,7 +1731,9 @@ static const char *bucket_name(int nmax, bool tql) {
         case 24: return tql ? "k_tql<24>" : "k_tridiag_reg<24>";
         case 28: return tql ? "k_tql<28>" : "k_tridiag_reg<28>";
         case 32: return tql ? "k_tql<32>" : "k_tridiag_reg<32>";
+        case 36: return tql ? "k_tql<36>" : "k_tridiag_reg2<36>";
         case 40: return tql ? "k_tql<40>" : "k_tridiag_reg2<40>";
+        case 44: return tql ? "k_tql<44>" : "k_tridiag_reg2<44>";
         case 48: return tql ? "k_tql<48>" : "k_tridiag_reg2<48>";
         case 56: return tql ? "k_tql<56>" : "k_tridiag_reg2<56>";
         case 64: return tql ? "k_tql<64>" : "k_tridiag_reg2<64>";
@@ -1789,7 +1779,7 @@ static int run_bucket(mdb_ctx *c, const DescParams &P, const int *d_list, int of
             ProfScope ps(c, bucket_name(NMAX, true), stream);
             k_tql<NMAX, QTHREADS><<<cdiv(ns, QTHREADS), QTHREADS, smem_ql, stream>>>(
                 d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap,
-                d_n, c->d_stats, c->cur_eig_off);
+                d_n, c->d_stats, c->cur_eig_off, c->opt_ql_pwk);
         }
         c->launches += 2;
     }
@@ -1806,7 +1796,9 @@ static const char *mc_name(int nmax) {
         case 24: return "k_tridiag_mc<24>";
         case 28: return "k_tridiag_mc<28>";
         case 32: return "k_tridiag_mc<32>";
+        case 36: return "k_tridiag_mc<36>";
         case 40: return "k_tridiag_mc<40>";
+        case 44: return "k_tridiag_mc<44>";
         default: return "k_tridiag_mc<48>";
     }
 }
@@ -1833,7 +1825,7 @@ static int run_bucket_mc(mdb_ctx *c, const DescParams &P, const int *d_list, int
             ProfScope ps(c, bucket_name(NMAX, true), stream);
             k_tql<NMAX, QTHREADS><<<cdiv(ns, QTHREADS), QTHREADS, smem_ql, stream>>>(
                 d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap,
-                d_n, c->d_stats, c->cur_eig_off);
+                d_n, c->d_stats, c->cur_eig_off, c->opt_ql_pwk);
         }
         c->launches += 2;
     }
@@ -1867,7 +1859,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     double *dsc = (double *)arena_alloc(c, (size_t)chunk * 160 * sizeof(double));
     double *esc = (double *)arena_alloc(c, (size_t)chunk * 160 * sizeof(double));
     int *nsc = (int *)arena_alloc(c, (size_t)chunk * sizeof(int));
-    int *d_book = (int *)arena_alloc(c, 256);            // bucket_n[16] | cursor[16] | ofs[16]
+    int *d_book = (int *)arena_alloc(c, 512);            // bucket_n[32] | cursor[32] | ofs[32]
     int *d_maxcount = (int *)arena_alloc(c, 256);
     int *d_padorder = (int *)arena_alloc(c, 256);
     double *d_padval = (double *)arena_alloc(c, 256);
@@ -1889,7 +1881,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
         }
         order[y + 1] = v;
     }
-    MDB_CUDA(cudaMemsetAsync(d_book, 0, 256, stream));
+    MDB_CUDA(cudaMemsetAsync(d_book, 0, 512, stream));
     MDB_CUDA(cudaMemcpyAsync(d_maxcount, h_maxcount, nt * sizeof(int), cudaMemcpyHostToDevice, stream));
     MDB_CUDA(cudaMemcpyAsync(d_padorder, order, nt * sizeof(int), cudaMemcpyHostToDevice, stream));
     MDB_CUDA(cudaMemcpyAsync(d_padval, c->el.diag, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -1917,8 +1909,8 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     int ofs[DESC_NB + 1];
     ofs[0] = 0;
     for (int b = 0; b < DESC_NB; ++b) ofs[b + 1] = ofs[b] + hb[b];
-    MDB_CUDA(cudaMemcpyAsync(d_book + 32, ofs, sizeof(ofs), cudaMemcpyHostToDevice, stream));
-    k_bucket_fill<<<cdiv(T, 256), 256, 0, stream>>>(d_nsum, T, d_book + 32, d_book + 16, d_list);
+    MDB_CUDA(cudaMemcpyAsync(d_book + 64, ofs, sizeof(ofs), cudaMemcpyHostToDevice, stream));
+    k_bucket_fill<<<cdiv(T, 256), 256, 0, stream>>>(d_nsum, T, d_book + 64, d_book + 32, d_list);
     c->launches++;
 #define MDB_BUCKET(B, NMAX, WARPS, LPM, QT, REG)                                                                              \
     if (hb[B] && run_bucket<NMAX, WARPS, LPM, QT, REG>(c, P, d_list, ofs[B], hb[B], dsc, esc, nsc, chunk, d_counts, d_padorder, \
@@ -1938,7 +1930,9 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
         MDB_BUCKET(5, 28, 8, 32, 128, 1)
         MDB_BUCKET(6, 32, 8, 32, 128, 1)
         MDB_BUCKET(7, 40, 4, 32, 64, 2)
-        MDB_BUCKET(8, 48, 4, 32, 64, 2)
+        MDB_BUCKET(8, 40, 4, 32, 64, 2)
+        MDB_BUCKET(9, 48, 4, 32, 64, 2)
+        MDB_BUCKET(10, 48, 4, 32, 64, 2)
     } else {
         // measured per class on B200 (tools/desc_ab.py, 0.05 atoms/A^3): several columns per lane win up to 24
         // atoms (4 matrices per warp) and tie with the warp-pair kernel at 33..48 (no named barriers); at 25..32
@@ -1955,15 +1949,17 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
             MDB_BUCKET(5, 28, 8, 32, 128, 1)
             MDB_BUCKET(6, 32, 8, 32, 128, 1)
         }
-        MDB_BUCKET_MC(7, 40, 32, 2, 8, 1, 64)
-        MDB_BUCKET_MC(8, 48, 32, 2, 8, 1, 64)
+        MDB_BUCKET_MC(7, 36, 32, 2, 8, 1, 64)
+        MDB_BUCKET_MC(8, 40, 32, 2, 8, 1, 64)
+        MDB_BUCKET_MC(9, 44, 32, 2, 8, 1, 64)
+        MDB_BUCKET_MC(10, 48, 32, 2, 8, 1, 64)
     }
 #undef MDB_BUCKET_MC
-    MDB_BUCKET(9, 56, 4, 32, 64, 2)
-    MDB_BUCKET(10, 64, 4, 32, 64, 2)
-    MDB_BUCKET(11, 96, 1, 32, 64, 0)
-    MDB_BUCKET(12, 128, 1, 32, 64, 0)
-    MDB_BUCKET(13, 160, 1, 32, 64, 0)
+    MDB_BUCKET(11, 56, 4, 32, 64, 2)
+    MDB_BUCKET(12, 64, 4, 32, 64, 2)
+    MDB_BUCKET(13, 96, 1, 32, 64, 0)
+    MDB_BUCKET(14, 128, 1, 32, 64, 0)
+    MDB_BUCKET(15, 160, 1, 32, 64, 0)
 #undef MDB_BUCKET
     return 0;
 }
