@@ -117,14 +117,10 @@ __device__ __forceinline__ void member_delta(int periodic, const FrameGeom &G, c
         mic_general(G.ortho, G.frac, out[0], out[1], out[2]);
 }
 
+// exact (double) membership decision of a borderline pair: the diagonal-cell form follows ASE per axis, the
+// general form takes the minimum image through the cell matrix; each scan carries only its own
 __device__ __forceinline__ bool sphere_exact(const DescParams &P, const FrameGeom &G, const double *pos, int a, int j) {
     double v[3];
-    if (P.periodic && !G.is_ortho) {
-        const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
-        member_delta(1, G, pos, j, pa, v);
-        const double d2g = __dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2]));
-        return __dsqrt_rn(d2g) < P.cutoff;
-    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         double D = __dsub_rn(pos[(size_t)j * 3 + c], pos[(size_t)a * 3 + c]);
@@ -132,6 +128,14 @@ __device__ __forceinline__ bool sphere_exact(const DescParams &P, const FrameGeo
     }
     double d2 = __dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2]));
     return __dsqrt_rn(d2) < P.cutoff;
+}
+__device__ __forceinline__ bool sphere_exact_general(const DescParams &P, const FrameGeom &G, const double *pos, int a, int j) {
+    if (!P.periodic || G.is_ortho) return sphere_exact(P, G, pos, a, j);
+    double v[3];
+    const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
+    member_delta(1, G, pos, j, pa, v);
+    const double d2g = __dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2]));
+    return __dsqrt_rn(d2g) < P.cutoff;
 }
 
 // The same scan for general (triclinic) cells: the records hold grid units (fractional coordinate x cells per
@@ -205,7 +209,7 @@ __device__ __forceinline__ void sphere_scan_general(const DescParams &P, int f, 
                             const int j = (int)(ow & MDB_IDX_MASK);
                             bool in = true;
                             if (!(d2 < P.cut2f - P.margin)) {
-                                in = sphere_exact(P, G, pos, a, j);
+                                in = sphere_exact_general(P, G, pos, a, j);
                                 atomicAdd(&P.stats->exact_tests, 1ull);
                             }
                             if (in) visit(j, (int)(ow >> MDB_IDX_BITS));
@@ -221,10 +225,6 @@ __device__ __forceinline__ void sphere_scan_general(const DescParams &P, int f, 
 // Calls visit(j, type_j) on the lanes that own a member; every lane must call this function.
 template <class Visit>
 __device__ __forceinline__ void sphere_scan(const DescParams &P, int f, int a, Visit visit) {
-    if (P.rec_mode == 0) {  // batch with a general cell (uniform over the launch)
-        sphere_scan_general(P, f, a, visit);
-        return;
-    }
     const int lane = threadIdx.x & 31;
     const FrameGeom &G = P.geom[f];
     const size_t fbase = (size_t)f * P.N;
@@ -334,6 +334,7 @@ __device__ __forceinline__ void gather_scan(const DescParams &P, int f, int a, l
 // ---------------------------------------------------------------------------------------------
 // K5: element composition of every target's sphere; running per-element maximum
 // ---------------------------------------------------------------------------------------------
+template <bool GENERAL>
 __global__ void __launch_bounds__(256) k_composition(const __grid_constant__ DescParams P, int *__restrict__ counts,
                                                      int *__restrict__ maxcount) {
     __shared__ int s_cnt[8][MDB_MAXT];
@@ -350,13 +351,17 @@ __global__ void __launch_bounds__(256) k_composition(const __grid_constant__ Des
         if (lane == 0) s_n[w] = 0;
         __syncwarp();
         int *mo = P.members_out ? P.members_out + (size_t)t * P.memcap : nullptr;
-        sphere_scan(P, f, a, [&](int j, int tj) {
+        auto visit = [&](int j, int tj) {
             atomicAdd(&s_cnt[w][tj], 1);
             if (mo) {
                 const int k = atomicAdd(&s_n[w], 1);
                 if (k < P.memcap) mo[k] = j;
             }
-        });
+        };
+        if (GENERAL)
+            sphere_scan_general(P, f, a, visit);
+        else
+            sphere_scan(P, f, a, visit);
         __syncwarp();
         if (mo) {
             const int n = s_n[w];
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(256) k_composition(const __grid_constant__ Des
 
 // sphere membership lists (ascending atom index, includes the target): the `np.where(distances <
 // cutoff)` of the output cut, datasetbuilder.py:554-557.  One warp per target, cap <= 1024.
+template <bool GENERAL>
 __global__ void __launch_bounds__(256) k_members(const __grid_constant__ DescParams P, int cap, int *__restrict__ members,
                                                  int *__restrict__ nmem) {
     extern __shared__ int s_mem[];  // [8][cap]
@@ -387,10 +393,14 @@ __global__ void __launch_bounds__(256) k_members(const __grid_constant__ DescPar
     int *mine = s_mem + w * cap;
     if (lane == 0) s_n[w] = 0;
     __syncwarp();
-    sphere_scan(P, f, a, [&](int j, int) {
+    auto visit = [&](int j, int) {
         const int k = atomicAdd(&s_n[w], 1);
         if (k < cap) mine[k] = j;
-    });
+    };
+    if (GENERAL)
+        sphere_scan_general(P, f, a, visit);
+    else
+        sphere_scan(P, f, a, visit);
     __syncwarp();
     int n = s_n[w];
     if (lane == 0) nmem[t] = n;
@@ -1695,7 +1705,10 @@ int compositions_run(mdb_ctx *c, int F, int N, const double *d_pos, const double
     MDB_CUDA(cudaMemcpyAsync(d_max, h_maxcount, c->el.nt * sizeof(int), cudaMemcpyHostToDevice, stream));
     if (P.ntargets > 0) {
         ProfScope ps(c, "k_composition", stream);
-        k_composition<<<cdiv(P.ntargets, 8), 256, 0, stream>>>(P, d_counts, d_max);
+        if (P.rec_mode == 0)
+            k_composition<true><<<cdiv(P.ntargets, 8), 256, 0, stream>>>(P, d_counts, d_max);
+        else
+            k_composition<false><<<cdiv(P.ntargets, 8), 256, 0, stream>>>(P, d_counts, d_max);
         c->launches++;
     }
     MDB_CUDA(cudaGetLastError());
@@ -1715,7 +1728,10 @@ int members_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_c
     if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, 1024)) return -1;
     if (P.ntargets > 0) {
         ProfScope ps(c, "k_members", stream);
-        k_members<<<cdiv(P.ntargets, 8), 256, (size_t)8 * cap * sizeof(int), stream>>>(P, cap, d_members, d_nmem);
+        if (P.rec_mode == 0)
+            k_members<true><<<cdiv(P.ntargets, 8), 256, (size_t)8 * cap * sizeof(int), stream>>>(P, cap, d_members, d_nmem);
+        else
+            k_members<false><<<cdiv(P.ntargets, 8), 256, (size_t)8 * cap * sizeof(int), stream>>>(P, cap, d_members, d_nmem);
         c->launches++;
     }
     MDB_CUDA(cudaGetLastError());
@@ -1844,6 +1860,33 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     if (T >= (1LL << 31)) {
         mdb_set_error("too many targets in one call");
         return -1;
+    }
+    if (!d_members && periodic && h_cell) {
+        // general (triclinic) cells: the register kernels carry the diagonal-cell scan only; the membership comes
+        // from the composition pass (k_composition<true>) through a scratch list, then the member route runs
+        bool general = false;
+        for (int f = 0; f < F && !general; ++f)
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q)
+                    if (r != q && h_cell[(size_t)f * 9 + r * 3 + q] != 0.0) general = true;
+        if (general) {
+            int cap = 0;
+            for (int k = 0; k < nt; ++k) cap += h_maxcount[k];
+            cap = std::max(cap, 1);
+            int *tmp_members = nullptr, *tmp_counts = nullptr;
+            MDB_CUDA(cudaMalloc(&tmp_members, (size_t)T * cap * sizeof(int)));
+            MDB_CUDA(cudaMalloc(&tmp_counts, (size_t)T * nt * sizeof(int)));
+            int hmax[MDB_MAXT] = {0};
+            int rc = compositions_run(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, tmp_counts, hmax,
+                                      stream, cap, tmp_members);
+            if (!rc)
+                rc = descriptors_run(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, d_counts,
+                                     h_maxcount, d_X, d_eig, eigcap, d_n, stream, tmp_members, cap, d_eig_off);
+            cudaStreamSynchronize(stream);
+            cudaFree(tmp_members);
+            cudaFree(tmp_counts);
+            return rc;
+        }
     }
     const int chunk = 1 << 16;
     // scratch: bucket bookkeeping + lists + d/e for one chunk at the largest NMAX in use
