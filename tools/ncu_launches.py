@@ -11,7 +11,7 @@ for r in rows[rows.index(hdr) + 1:]:
     d = own if (name.startswith('k_') or ' k_' in name) else other
     e = d.setdefault(name, [0, 0.0]); e[0] += 1; e[1] += float(r[iv].replace(',', '')) / 1e3   # ns -> us
 tot = sum(v[1] for v in own.values())
-print('# r01 launch list (final code of round 1)\n')
+print('# launch list\n')
 print('`%s`' % sys.argv[2])
 print('(run after the same command exited 0 without ncu; cold-cache, serialised: compare SHARES with bench.py\'s live `kernels` shares)\n')
 print('| kernel | launches | total ms | share of own kernels | avg us |\n|---|---|---|---|---|')

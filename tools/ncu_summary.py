@@ -2,9 +2,10 @@
 usage: ncu_summary.py report.ncu-rep "<command line that was profiled>" > profiles/rNN_ncu_<kernel>.md"""
 import csv, io, subprocess, sys
 rep, cmd = sys.argv[1], sys.argv[2]
+idx = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # which captured launch
 out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-h, units, r = rows[0], rows[1], rows[2]
+h, units, r = rows[0], rows[1], rows[2 + idx]
 g = lambda k: r[h.index(k)] if k in h else None
 u = lambda k: units[h.index(k)] if k in h else ''
 print('# ncu --set full: `%s`\n' % g('Kernel Name'))
