@@ -311,6 +311,116 @@ __device__ __forceinline__ void sphere_scan(const DescParams &P, int f, int a, V
     }
 }
 
+// Flattened form of sphere_scan for the composition / member kernels (diagonal cells): ncu had the serial form at
+// 1,224 warp instructions per target -- nine (dy, dz) rows handled one after the other, each with its own bounds
+// arithmetic and a 32-lane pass over ~19 candidates.  Here lanes 0..17 work out the 18 possible segments (nine
+// x-runs + nine wrapped cells) side by side, a warp prefix sum numbers all candidates of the target, and the lanes
+// then walk ONE list of ~170 candidates, finding the segment of a candidate by a 5-step search over the prefix held
+// in the lanes.  Same candidates, same float screen, same exact re-check: the membership is unchanged.
+template <class Visit>
+__device__ __forceinline__ void sphere_scan_flat(const DescParams &P, int f, int a, Visit visit) {
+    const int lane = threadIdx.x & 31;
+    const FrameGeom &G = P.geom[f];
+    const size_t fbase = (size_t)f * P.N;
+    const int cbase = (int)G.cell_base;
+    const uint32_t v = P.cr[fbase + a];
+    const int slot = P.cell_start[cbase + (int)(v >> G.rank_bits)] + (int)(v & ((1u << G.rank_bits) - 1u));
+    const float4 me = P.rec[slot];
+    const uint32_t cc = P.ccell[slot];
+    const int c3[3] = {(int)(cc & 1023u), (int)((cc >> 10) & 1023u), (int)(cc >> 20)};
+    const int n3[3] = {G.n[0], G.n[1], G.n[2]};
+    const float per[3] = {(float)G.ortho[0], (float)G.ortho[4], (float)G.ortho[8]};
+    const float hp[3] = {0.5f * per[0], 0.5f * per[1], 0.5f * per[2]};
+    const double *pos = P.pos + fbase * 3;
+    // segment of this lane: row r = lane / 2 (dy = r % 3 - 1, dz = r / 3 - 1), part 0 = contiguous x-run, 1 = wrapped cell
+    int lo = 0, hi = 0;
+    if (lane < 18) {
+        const int r = lane >> 1, part = lane & 1;
+        const int dz = r / 3 - 1, dy = r % 3 - 1;
+        bool ok = true;
+        int z = c3[2] + dz, y = c3[1] + dy;
+        if (G.reduce[2]) {
+            ok = dz == 0;
+            z = 0;
+        } else if (z < 0 || z >= n3[2]) {
+            ok = P.periodic != 0;
+            z += z < 0 ? n3[2] : -n3[2];
+        }
+        if (G.reduce[1]) {
+            ok = ok && dy == 0;
+            y = 0;
+        } else if (y < 0 || y >= n3[1]) {
+            ok = ok && P.periodic != 0;
+            y += y < 0 ? n3[1] : -n3[1];
+        }
+        if (ok) {
+            const int rowbase = cbase + (z * n3[1] + y) * n3[0];
+            int xa, xb, xw = -1;
+            if (G.reduce[0]) {
+                xa = xb = 0;
+            } else {
+                xa = c3[0] - 1;
+                xb = c3[0] + 1;
+                if (xa < 0) {
+                    xa = 0;
+                    if (P.periodic) xw = n3[0] - 1;
+                }
+                if (xb >= n3[0]) {
+                    xb = n3[0] - 1;
+                    if (P.periodic) xw = 0;
+                }
+            }
+            if (part == 0) {
+                lo = P.cell_start[rowbase + xa];
+                hi = P.cell_start[rowbase + xb + 1];
+            } else if (xw >= 0) {
+                lo = P.cell_start[rowbase + xw];
+                hi = P.cell_start[rowbase + xw + 1];
+            }
+        }
+    }
+    // inclusive prefix of the segment lengths over the lanes
+    int end = hi - lo;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, end, o);
+        if (lane >= o) end += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, end, 31);
+    const int base = lo - (end - (hi - lo));  // candidate p of this segment sits at rec[base + p]
+    for (int p0 = 0; p0 < total; p0 += 32) {
+        const int p = p0 + lane;
+        // smallest segment s with end[s] > p (18 segments: lanes 0..17; lanes >= 18 repeat end[17] = total)
+        int sidx = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int e = __shfl_sync(0xffffffffu, end, sidx + step - 1);
+            if (e <= p) sidx += step;
+        }
+        const int sb = __shfl_sync(0xffffffffu, base, sidx);
+        if (p < total) {
+            const float4 o = P.rec[sb + p];
+            float dx = o.x - me.x, dy2 = o.y - me.y, dz2 = o.z - me.z;
+            if (P.periodic) {
+                dx += dx > hp[0] ? -per[0] : (dx < -hp[0] ? per[0] : 0.f);
+                dy2 += dy2 > hp[1] ? -per[1] : (dy2 < -hp[1] ? per[1] : 0.f);
+                dz2 += dz2 > hp[2] ? -per[2] : (dz2 < -hp[2] ? per[2] : 0.f);
+            }
+            const float d2 = fmaf(dz2, dz2, fmaf(dy2, dy2, dx * dx));
+            if (d2 <= P.cut2f + P.margin) {
+                const unsigned ow = (unsigned)__float_as_int(o.w);
+                const int j = (int)(ow & MDB_IDX_MASK);
+                bool in = true;
+                if (!(d2 < P.cut2f - P.margin)) {
+                    in = sphere_exact(P, G, pos, a, j);
+                    atomicAdd(&P.stats->exact_tests, 1ull);
+                }
+                if (in) visit(j, (int)(ow >> MDB_IDX_BITS));
+            }
+        }
+    }
+}
+
 // The same visit over a stored membership list (written by k_composition) instead of the cell scan.
 template <class Visit>
 __device__ __forceinline__ void member_scan(const DescParams &P, long long ord, Visit visit) {
@@ -361,7 +471,7 @@ __global__ void __launch_bounds__(256) k_composition(const __grid_constant__ Des
         if (GENERAL)
             sphere_scan_general(P, f, a, visit);
         else
-            sphere_scan(P, f, a, visit);
+            sphere_scan_flat(P, f, a, visit);
         __syncwarp();
         if (mo) {
             const int n = s_n[w];
@@ -400,7 +510,7 @@ __global__ void __launch_bounds__(256) k_members(const __grid_constant__ DescPar
     if (GENERAL)
         sphere_scan_general(P, f, a, visit);
     else
-        sphere_scan(P, f, a, visit);
+        sphere_scan_flat(P, f, a, visit);
     __syncwarp();
     int n = s_n[w];
     if (lane == 0) nmem[t] = n;

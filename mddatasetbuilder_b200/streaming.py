@@ -450,7 +450,7 @@ class StreamingSelector:
             for part in gathered:
                 self.fit_stats.update(part)
             self._sync()
-            self.comm["centres_broadcast"] = {"ms": (time.perf_counter() - t0) * 1e3,
+            self.comm["centres_broadcast_incl_wait_for_slowest_rank"] = {"ms": (time.perf_counter() - t0) * 1e3,
                                               "bytes": int(sum(self.K * self.D[k] * 8 for k in todo))}
         self.pool = None
         return self
