@@ -113,10 +113,12 @@ class DatasetBuilder:
         atom_pref=False,
         seed=0,
         perceive_bond_orders=True,
+        max_bonds=8,
     ):
-        """Init the builder.  ``seed`` and ``perceive_bond_orders`` are additions: the latter switches the
-        dump-only keys between perceived bond orders (the reference's behaviour, detect.py:279-280) and
-        all-single levels."""
+        """Init the builder.  ``seed``, ``perceive_bond_orders`` and ``max_bonds`` are additions: the second switches
+        the dump-only keys between perceived bond orders (the reference's behaviour, detect.py:279-280) and
+        all-single levels; ``max_bonds`` (8 or 16) is the width of a neighbour row, for bond files or crowded
+        frames with more than 8 partners per atom."""
         print(__doc__)
         print(f"Author:{__author__}  Email:{__email__}")
         atomname = np.array(atomname) if atomname is not None and len(atomname) else np.array(["C", "H", "O"])
@@ -162,6 +164,7 @@ class DatasetBuilder:
         self.atom_pref = atom_pref
         self.pbc = pbc
         self.seed = seed
+        self.max_bonds = int(max_bonds)
         self.frames_per_batch = int(os.environ.get("MDB_FRAMES_PER_BATCH", "0"))
         self._cache_bytes = int(float(os.environ.get("MDB_CACHE_GB", "8")) * (1 << 30))
         # rows of a bond type the clustering trains on at most (all of them when the type has fewer)
@@ -172,7 +175,10 @@ class DatasetBuilder:
     def engine(self):
         from .engine import get_engine
 
-        return get_engine(int(os.environ.get("LOCAL_RANK", "0")), [str(a) for a in self.atomname])
+        eng = get_engine(int(os.environ.get("LOCAL_RANK", "0")), [str(a) for a in self.atomname])
+        if eng.max_bonds != self.max_bonds:
+            eng.set_option("max_bonds", self.max_bonds)
+        return eng
 
     def _rank_world(self):
         d = _dist()
@@ -624,6 +630,8 @@ def _commandline():
         "-e", "--errorlimit",
         help="Model deviation lower threshold. Atoms whose model deviation is less than the threshold will not be collected.",
         type=float, default=0.0)
+    parser.add_argument("--max-bonds", help="Neighbour slots per atom (8 or 16); addition of the B200 build.", type=int,
+                        default=8, choices=[8, 16])
     parser.add_argument("--version", action="version", version=f"MDDatasetBuilder {__version__}")
     args = parser.parse_args()
     DatasetBuilder(
@@ -638,4 +646,5 @@ def _commandline():
         nproc=args.nproc,
         errorfilename=args.errorfile,
         errorlimit=args.errorlimit,
+        max_bonds=args.max_bonds,
     ).builddataset()

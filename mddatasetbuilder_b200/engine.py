@@ -354,8 +354,11 @@ class Engine:
                                            self.stream())
             _lib.check(rc, "mdb_sphere_members")
             n = nmem.cpu().numpy()
-            if T == 0 or n.max() <= cap or cap >= 1024:
+            if T == 0 or n.max() <= cap:
                 break
+            if cap >= 1024:
+                raise RuntimeError(f"a cutoff sphere holds {int(n.max())} atoms; the member kernel lists at most 1024 "
+                                   "(reduce the cutoff)")
             cap = min(1024, 2 * cap)
         m = members.cpu().numpy()
         return [m[k, : min(n[k], cap)] for k in range(T)]
