@@ -330,6 +330,15 @@ int mdb_kmeans_update_exact(mdb_ctx *ctx, long long nbatch, int D, const double 
                             const int32_t *d_rowidx, const double *d_weights, const int32_t *d_labels,
                             double *d_centers, double *d_weight_sums, void *stream);
 
+/* One whole mini-batch step (sklearn _mini_batch_step, cluster/_kmeans.py:1601-1697, minus the random
+ * reassignment, which stays with the caller): rows h_rowidx [nbatch] (HOST indices into d_X) are assigned to
+ * the centres, the centres and weight sums are updated like mdb_kmeans_update_exact; *h_inertia = the batch
+ * inertia before the update (summed in a fixed order), *h_nzero = centres whose weight sum is still zero after
+ * it.  nbatch <= 4096, D <= 256.  Synchronises once. */
+int mdb_kmeans_minibatch_step(mdb_ctx *ctx, long long nbatch, int D, int K, const double *d_X, long long ldx,
+                              const int32_t *h_rowidx, double *d_centers, double *d_weight_sums,
+                              double *h_inertia, int *h_nzero, void *stream);
+
 /* k-means++ seeding step (sklearn cluster/_kmeans.py:180-279, run by MiniBatchKMeans on
  * its init subset): for ncand (<= 32) candidate rows, d_dist[t][i] = min(d_closest[i],
  * ||x_i - x_cand[t]||^2) and d_pot[t] = sum_i weight_i * d_dist[t][i].  d_closest may be

@@ -73,6 +73,8 @@ SIGNATURES = {
     "mdb_kmeans_partial_sums": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp,
                                           _vp, _vp]),
     "mdb_kmeans_update_exact": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mdb_kmeans_minibatch_step": (C.c_int, [c_ctx, C.c_longlong, C.c_int, C.c_int, _vp, C.c_longlong, _vp, _vp, _vp,
+                                            C.POINTER(C.c_double), C.POINTER(C.c_int), _vp]),
     "mdb_kmeans_apply_update": (C.c_int, [c_ctx, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdb_kpp_step": (C.c_int, [c_ctx, C.c_longlong, C.c_int, _vp, C.c_longlong, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
                                _vp]),

@@ -402,6 +402,20 @@ extern "C" int mdb_kmeans_update_exact(mdb_ctx *c, long long nbatch, int D, cons
                                    (cudaStream_t)stream);
 }
 
+int kmeans_minibatch_step_run(mdb_ctx *c, long long B, int D, int K, const double *d_X, long long ldx, const int *h_idx,
+                              double *d_C, double *d_weight_sums, double *h_out, cudaStream_t stream);
+extern "C" int mdb_kmeans_minibatch_step(mdb_ctx *c, long long nbatch, int D, int K, const double *d_X, long long ldx,
+                                         const int32_t *h_rowidx, double *d_centers, double *d_weight_sums,
+                                         double *h_inertia, int *h_nzero, void *stream) {
+    if (check_ctx(c, "mdb_kmeans_minibatch_step", false)) return -1;
+    double out[2] = {0.0, 0.0};
+    int rc = kmeans_minibatch_step_run(c, nbatch, D, K, d_X, ldx, h_rowidx, d_centers, d_weight_sums, out,
+                                       (cudaStream_t)stream);
+    if (h_inertia) *h_inertia = out[0];
+    if (h_nzero) *h_nzero = (int)out[1];
+    return rc;
+}
+
 extern "C" int mdb_kmeans_apply_update(mdb_ctx *c, int K, int D, double *d_centers, double *d_weight_sums,
                                        const double *d_sums, const double *d_wsum, void *stream) {
     if (check_ctx(c, "mdb_kmeans_apply_update", false)) return -1;

@@ -61,6 +61,10 @@ struct mdb_ctx {
     int opt_max_bonds = 8;
     int opt_frames_per_launch = 0;
     int opt_perceive = 0;
+    // staging of the fused mini-batch step (page-locked indices + two result scalars; device idx | labels | mindist | out)
+    void *mb_hidx = nullptr;
+    void *mb_didx = nullptr;
+    size_t mb_cap = 0;
     const int *cur_eig_off = nullptr;  // compact-spectra offsets of the descriptor call in flight
     int opt_ql_pwk = 1;      // 1: square-root-free QL (dsterf recurrence) in k_tql, 0: the tqli form
     int opt_desc_legacy = 0;  // 1: round-1 descriptor kernels (one column per lane / warp pairs) for A/B runs  // dump-only keys carry perceived bond orders (perceive.cu)

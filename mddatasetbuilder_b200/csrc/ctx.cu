@@ -81,6 +81,8 @@ extern "C" void mdb_destroy(mdb_ctx *c) {
     }
     if (c->pipe_types) cudaFree(c->pipe_types);
     if (c->tc_mem) cudaFree(c->tc_mem);
+    if (c->mb_hidx) cudaFreeHost(c->mb_hidx);
+    if (c->mb_didx) cudaFree(c->mb_didx);
     for (int i = 0; i < mdb_ctx::kRing; ++i) {
         if (c->h_geom[i]) cudaFreeHost(c->h_geom[i]);
         if (c->h_geom_ev[i]) cudaEventDestroy(c->h_geom_ev[i]);

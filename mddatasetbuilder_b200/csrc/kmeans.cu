@@ -349,6 +349,36 @@ __global__ void __launch_bounds__(256) k_mb_update_exact(const double *__restric
     if (lane == 0) weight_sums[lab] = wn;
 }
 
+// Fixed-order sum (one block): the batch inertia feeds an early-stopping comparison, so it must not depend on
+// the order in which atomics land (k_sum's block partials do).
+__global__ void __launch_bounds__(1024) k_sum_det(const double *__restrict__ v, long long n, double *__restrict__ out) {
+    __shared__ double s[1024];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) acc += v[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+
+__global__ void __launch_bounds__(1024) k_count_zero(const double *__restrict__ w, int K, double *__restrict__ out) {
+    __shared__ int s[32];
+    int c = 0;
+    for (int i = threadIdx.x; i < K; i += 1024) c += w[i] == 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int q = 0; q < 32; ++q) t += s[q];
+        out[0] = (double)t;
+    }
+}
+
 int kmeans_update_exact_run(mdb_ctx *c, long long B, int D, const double *d_X, long long ldx, const int *d_rowidx,
                             const double *d_w, const int *d_labels, double *d_C, double *d_weight_sums, cudaStream_t stream) {
     if (B <= 0) return 0;
@@ -362,6 +392,49 @@ int kmeans_update_exact_run(mdb_ctx *c, long long B, int D, const double *d_X, l
     MDB_CUDA(cudaGetLastError());
     return 0;
 }
+
+// One whole mini-batch step of MiniBatchKMeans (sklearn _mini_batch_step without the reassignment) as ONE call:
+// indices host -> device through a page-locked staging buffer, assignment, fixed-order batch inertia, the M-step in
+// sklearn's operation order, the number of centres still without weight -- and one synchronisation for the two
+// scalars the host needs (the Python loop around it had 120 us of host time per step in separate calls).
+int kmeans_minibatch_step_run(mdb_ctx *c, long long B, int D, int K, const double *d_X, long long ldx, const int *h_idx,
+                              double *d_C, double *d_weight_sums, double *h_out, cudaStream_t stream) {
+    if (B <= 0 || B > MB_MAX || D > 32 * MBX_MAXD) {
+        mdb_set_error("mdb_kmeans_minibatch_step: 1..4096 rows per mini-batch and at most 256 features");
+        return -1;
+    }
+    if (c->mb_cap < (size_t)B) {
+        if (c->mb_hidx) cudaFreeHost(c->mb_hidx);
+        if (c->mb_didx) cudaFree(c->mb_didx);
+        c->mb_hidx = nullptr;
+        c->mb_didx = nullptr;
+        const size_t cap = MB_MAX;
+        MDB_CUDA(cudaMallocHost(&c->mb_hidx, cap * sizeof(int) + 64));
+        // device block: idx | labels | mindist | out[2]
+        MDB_CUDA(cudaMalloc(&c->mb_didx, cap * (2 * sizeof(int) + sizeof(double)) + 64));
+        c->mb_cap = cap;
+    }
+    int *hidx = (int *)c->mb_hidx;
+    double *hout = (double *)((char *)c->mb_hidx + MB_MAX * sizeof(int));
+    int *didx = (int *)c->mb_didx;
+    int *dlab = didx + MB_MAX;
+    double *dmind = (double *)(dlab + MB_MAX);
+    double *dout = (double *)((char *)c->mb_didx + MB_MAX * (2 * sizeof(int) + sizeof(double)));  // 64 spare bytes
+    memcpy(hidx, h_idx, (size_t)B * sizeof(int));
+    MDB_CUDA(cudaMemcpyAsync(didx, hidx, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (kmeans_assign_run(c, B, D, K, d_X, ldx, didx, d_C, dlab, dmind, nullptr, nullptr, stream)) return -1;
+    k_sum_det<<<1, 1024, 0, stream>>>(dmind, B, dout);
+    if (kmeans_update_exact_run(c, B, D, d_X, ldx, didx, nullptr, dlab, d_C, d_weight_sums, stream)) return -1;
+    k_count_zero<<<1, 1024, 0, stream>>>(d_weight_sums, K, dout + 1);
+    c->launches += 2;
+    MDB_CUDA(cudaMemcpyAsync(hout, dout, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    MDB_CUDA(cudaStreamSynchronize(stream));
+    h_out[0] = hout[0];
+    h_out[1] = hout[1];
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // MinMaxScaler
@@ -1044,8 +1117,12 @@ int kmeans_assign_run(mdb_ctx *c, long long rows, int D, int K, const double *d_
     }
     c->launches += 3;
     if (h_inertia) {
-        MDB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), stream));
-        k_sum<<<std::min<unsigned>(cdiv(rows, 256), 1024u), 256, 0, stream>>>(mind, d_w, rows, acc);
+        if (!d_w && rows <= (1LL << 20)) {
+            k_sum_det<<<1, 1024, 0, stream>>>(mind, rows, acc);  // fixed order: reproducible to the last bit
+        } else {
+            MDB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), stream));
+            k_sum<<<std::min<unsigned>(cdiv(rows, 256), 1024u), 256, 0, stream>>>(mind, d_w, rows, acc);
+        }
         c->launches++;
         MDB_CUDA(cudaMemcpyAsync(h_inertia, acc, sizeof(double), cudaMemcpyDeviceToHost, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));

@@ -519,6 +519,18 @@ class Engine:
                                             self.stream())
         _lib.check(rc, "mdb_kmeans_update_exact")
 
+    def kmeans_minibatch_step(self, X, idx, centers, weight_sums):
+        """One fused mini-batch step: idx = host int32 array of row indices.  Returns (batch inertia before the
+        update, number of centres whose weight is still zero after it); centers / weight_sums change in place."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        inertia = C.c_double(0.0)
+        nzero = C.c_int(0)
+        rc = self.L.mdb_kmeans_minibatch_step(self.ctx, int(idx.size), int(X.shape[1]), int(centers.shape[0]), _ptr(X),
+                                              int(X.stride(0)), _np_ptr(idx), _ptr(centers), _ptr(weight_sums),
+                                              C.byref(inertia), C.byref(nzero), self.stream())
+        _lib.check(rc, "mdb_kmeans_minibatch_step")
+        return inertia.value, nzero.value
+
     def kpp_step(self, X, cand, closest, dist_out, pot_out, rowidx=None, weights=None):
         """One k-means++ seeding step: distances of the candidate rows to every row (clipped
         against `closest`) and the weighted potential of each candidate."""

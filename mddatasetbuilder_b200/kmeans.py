@@ -88,8 +88,9 @@ class MiniBatchKMeansB200:
         return [X[rowidx[b].long()[idx[b].long()]].clone() for b in range(self.n_init)]
 
     # ------------------------------------------------------------------ one mini-batch step
-    def _mini_batch_step(self, X, batch_idx, centers, weight_sums, rs, random_reassign):
-        """sklearn _mini_batch_step; updates centers / weight_sums in place, returns inertia.
+    def _mini_batch_step(self, X, batch_idx, centers, weight_sums, rs, random_reassign, idx_host=None):
+        """sklearn _mini_batch_step; updates centers / weight_sums in place, returns (inertia, whether any centre
+        still has zero weight -- None when not known without a read-back).
 
         With ``exchange == "allreduce"`` and torch.distributed initialised, every rank holds the same rows
         X and the same batch; rank r assigns and sums only its slice of the batch, and ONE packed
@@ -99,8 +100,11 @@ class MiniBatchKMeansB200:
         eng = self.eng
         K = self.n_clusters
         d = _dist() if self.exchange == "allreduce" else None
-        B = int(batch_idx.numel())
+        B = int(idx_host.size) if batch_idx is None else int(batch_idx.numel())
+        any_zero = None
         if d is not None and d.get_world_size() > 1:
+            if batch_idx is None:
+                batch_idx = torch.as_tensor(idx_host, dtype=torch.int32, device=eng.device)
             w, r = d.get_world_size(), d.get_rank()
             lo, hi = (B * r) // w, (B * (r + 1)) // w
             part = batch_idx[lo:hi]
@@ -120,7 +124,13 @@ class MiniBatchKMeansB200:
             self._comm_events.append((t0, t1))
             inertia = float(self._packed[-1].item())
             eng.kmeans_apply_update(centers, weight_sums, sums, wsum)
+        elif B <= 4096 and int(X.shape[1]) <= 256 and idx_host is not None:
+            # the whole step as one library call (indices from the host, one synchronisation)
+            inertia, nzero = eng.kmeans_minibatch_step(X, idx_host, centers, weight_sums)
+            any_zero = nzero > 0
         else:
+            if batch_idx is None:
+                batch_idx = torch.as_tensor(idx_host, dtype=torch.int32, device=eng.device)
             labels, inertia, _ = eng.kmeans_assign(X, centers, rowidx=batch_idx, want_inertia=True)
             if B <= 4096 and int(X.shape[1]) <= 256:      # sklearn's own operation order: bit-identical centres
                 eng.kmeans_update_exact(X, labels, centers, weight_sums, rowidx=batch_idx)
@@ -136,14 +146,17 @@ class MiniBatchKMeansB200:
             n_reassigns = int(to_reassign.sum())
             if n_reassigns:
                 new_centers = rs.choice(B, replace=False, size=n_reassigns)
-                rows = batch_idx.long()[torch.as_tensor(new_centers, device=eng.device)]
+                if idx_host is not None:
+                    rows = torch.as_tensor(np.asarray(idx_host)[new_centers], dtype=torch.int64, device=eng.device)
+                else:
+                    rows = batch_idx.long()[torch.as_tensor(new_centers, device=eng.device)]
                 centers[torch.as_tensor(np.nonzero(to_reassign)[0], device=eng.device)] = X[rows]
             if (~to_reassign).any():
                 ws[to_reassign] = np.min(ws[~to_reassign])
                 weight_sums.copy_(torch.as_tensor(ws, device=eng.device))
-        return inertia
+            any_zero = bool((ws == 0).any())
+        return inertia, any_zero
 
-    # ------------------------------------------------------------------ fit
     def seed_centers(self, X):
         """First half of ``MiniBatchKMeans.fit``: the validation draw and the n_init k-means++ seedings, best one
         kept.  Returns the state ``run_loop`` continues from (the RandomState goes along, so the split changes
@@ -187,6 +200,7 @@ class MiniBatchKMeansB200:
         ewa, ewa_min, no_improvement = None, None, 0
         n_since_last_reassign = 0
         counts_zero = True
+        zero_unknown = False         # all weights are zero before the first step
         n_steps = (self.max_iter * n_samples) // batch_size
         # scikit-learn >= 1.4 draws the mini-batch with `random_state.choice(n, batch, p=sample_weight / sum, replace=True)`
         # = searchsorted(cumsum(p) / cumsum(p)[-1], random_sample(batch), side="right") (numpy RandomState.choice);
@@ -209,15 +223,21 @@ class MiniBatchKMeansB200:
         i = -1
         for i in range(n_steps):
             idx = draw()
-            batch_idx = torch.as_tensor(idx, dtype=torch.int32, device=eng.device)
             n_since_last_reassign += batch_size
-            # weights only grow, so once no centre has a zero count the test never fires again (one sync less per step)
-            if counts_zero:
+            # weights only grow, so once no centre has a zero count the test never fires again; the fused step
+            # reports the count, other paths read it back while it is still needed
+            if counts_zero and zero_unknown:
                 counts_zero = bool((weight_sums == 0).any().item())
             random_reassign = counts_zero or n_since_last_reassign >= 10 * K
             if random_reassign:
                 n_since_last_reassign = 0
-            batch_inertia = self._mini_batch_step(X, batch_idx, centers, weight_sums, rs, random_reassign)
+            batch_inertia, any_zero = self._mini_batch_step(X, None, centers, weight_sums, rs, random_reassign,
+                                                            idx_host=idx.astype(np.int32))
+            if any_zero is None:
+                zero_unknown = True
+            else:
+                zero_unknown = False
+                counts_zero = counts_zero and any_zero
             # _mini_batch_convergence (tol = 0)
             batch_inertia /= batch_size
             step = i + 1
