@@ -955,6 +955,225 @@ double dv[3];
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6a-bord, clusters of 33..40 atoms (round 2): the first n - 32 Householder steps run on the staging copy in
+// shared memory (one warp, two rows per lane), which leaves a trailing matrix of at most 32 columns -- and that
+// one goes through the one-column register loop of k_tridiag_reg<32> unchanged.  The two-columns-per-lane kernel
+// needed 32 ns per 33..36-atom matrix (a second register slot of which 4 lanes in 32 are used) against 13 ns
+// for a 32-atom matrix; a handful of shared-memory steps costs far less than doubling the register work.
+// ---------------------------------------------------------------------------------------------
+template <int NS>
+struct BordSmem {
+    double A[NS][NS + 1];
+    double vec[NS][3];
+    double xs[NS < 32 ? 32 : NS];
+    double2 vw[NS < 32 ? 32 : NS];
+    int z[NS];
+    int t[NS];
+    int idx[NS];
+    double L[3];
+    const FrameGeom *gp;
+    int n;
+    int pad;
+};
+
+template <int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_tridiag_bord(const __grid_constant__ DescParams P, const int *__restrict__ list,
+                                                                int nlist, int slot0, int nslots, double *__restrict__ dsc,
+                                                                double *__restrict__ esc, int *__restrict__ nsc) {
+    static_assert(NS > 32 && NS <= 64, "two staged rows per lane");
+    constexpr int NMAX = 32;
+    typedef BordSmem<NS> Sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Sm *S = reinterpret_cast<Sm *>(smem_raw) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, gl = lane;
+    const int s = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    const bool valid = s < nslots;
+    if (lane == 0) S->n = 0;
+    if (valid) {
+        const int ord = list[slot0 + s];
+        const int gt = P.targets ? P.targets[ord] : ord;
+        const int f = gt / P.N, at = gt - f * P.N;
+        const FrameGeom &G0 = P.geom[f];
+        const double *pos = P.pos + (size_t)f * P.N * 3;
+        __syncwarp();
+        const double pa[3] = {pos[(size_t)at * 3], pos[(size_t)at * 3 + 1], pos[(size_t)at * 3 + 2]};
+        gather_scan(P, f, at, ord, [&](int j, int tj) {
+            const int k = atomicAdd(&S->n, 1);
+            if (k < NS) {
+                double dv[3];
+                member_delta(P.periodic, G0, pos, j, pa, dv);
+                S->vec[k][0] = dv[0];
+                S->vec[k][1] = dv[1];
+                S->vec[k][2] = dv[2];
+                S->z[k] = P.Z[tj];
+                S->t[k] = tj;
+                S->idx[k] = j;
+            }
+        });
+        if (lane == 0) {
+            S->L[0] = G0.ortho[0];
+            S->L[1] = G0.ortho[4];
+            S->L[2] = G0.ortho[8];
+            S->gp = &G0;
+        }
+    }
+    __syncwarp();
+    int n = S->n;
+    if (n > NS) {
+        if (gl == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        n = NS;
+    }
+    {   // canonical member order (ascending atom index), two entries per lane
+        double v0[2], v1[2], v2[2];
+        int zz[2], tt[2], rank[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int e = c * 32 + gl;
+            rank[c] = -1;
+            if (e < n) {
+                v0[c] = S->vec[e][0];
+                v1[c] = S->vec[e][1];
+                v2[c] = S->vec[e][2];
+                zz[c] = S->z[e];
+                tt[c] = S->t[e];
+                const int ii = S->idx[e];
+                int r = 0;
+                for (int q = 0; q < n; ++q) r += S->idx[q] < ii;
+                rank[c] = r;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (rank[c] >= 0) {
+                S->vec[rank[c]][0] = v0[c];
+                S->vec[rank[c]][1] = v1[c];
+                S->vec[rank[c]][2] = v2[c];
+                S->z[rank[c]] = zz[c];
+                S->t[rank[c]] = tt[c];
+            }
+        __syncwarp();
+    }
+    for (int q = gl; q < NS * NS; q += 32) S->A[q / NS][q % NS] = 0.0;
+    __syncwarp();
+    for (int i = gl; i < n; i += 32) S->A[i][i] = P.diag[S->t[i]];
+    coulomb_pairs(P, S, n, gl, 32);
+    __syncwarp();
+    // ---- border: steps 0 .. nb-1 on the staged matrix, rows gl and gl + 32 of the trailing block per lane
+    const int nb = n > NMAX ? n - NMAX : 0;
+    for (int k = 0; k < nb; ++k) {
+        const int r0 = k + 1 + gl, r1 = r0 + 32;
+        const double x0 = r0 < n ? S->A[r0][k] : 0.0;
+        const double x1r = r1 < n ? S->A[r1][k] : 0.0;
+        if (r0 < NS) S->xs[r0] = x0;
+        if (r1 < NS) S->xs[r1] = x1r;
+        __syncwarp();
+        double p0 = 0.0, p1 = 0.0;
+        for (int j = k + 1; j < n; ++j) {
+            const double xj = S->xs[j];
+            if (r0 < n) p0 = fma(S->A[r0][j], xj, p0);
+            if (r1 < n) p1 = fma(S->A[r1][j], xj, p1);
+        }
+        double sig = x0 * x0 + x1r * x1r, tau = x0 * p0 + x1r * p1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sig += __shfl_xor_sync(0xffffffffu, sig, o);
+            tau += __shfl_xor_sync(0xffffffffu, tau, o);
+        }
+        const double xk1 = S->xs[k + 1];
+        const double pt1 = __shfl_sync(0xffffffffu, p0, 0);  // row k + 1 is lane 0's first row
+        const double t00 = S->A[k + 1][k + 1];
+        const bool doit = sig > 0.0;
+        const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
+        const double alpha = xk1 >= 0.0 ? -rs : rs;
+        const double H = sig - alpha * xk1;
+        const double iH = doit ? fast_rcp(H) : 0.0;
+        const double Kc = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
+        const double va = (gl == 0) ? x0 - alpha : x0;  // r0 == k + 1 for lane 0
+        const double vb = x1r;
+        const double wa = r0 < n ? (p0 - alpha * S->A[r0][k + 1]) * iH - Kc * va : 0.0;
+        const double wb = r1 < n ? (p1 - alpha * S->A[r1][k + 1]) * iH - Kc * vb : 0.0;
+        if (gl == 0 && valid) {
+            dsc[s + (size_t)k * nslots] = S->A[k][k];
+            esc[s + (size_t)k * nslots] = alpha;
+        }
+        __syncwarp();
+        if (r0 < NS) S->vw[r0] = make_double2(r0 < n ? va : 0.0, wa);
+        if (r1 < NS) S->vw[r1] = make_double2(r1 < n ? vb : 0.0, wb);
+        __syncwarp();
+        if (doit) {
+            for (int j = k + 1; j < n; ++j) {
+                const double2 q = S->vw[j];
+                if (r0 < n) S->A[r0][j] = fma(-q.x, wa, fma(-q.y, va, S->A[r0][j]));
+                if (r1 < n) S->A[r1][j] = fma(-q.x, wb, fma(-q.y, vb, S->A[r1][j]));
+            }
+        }
+        __syncwarp();
+    }
+    // ---- trailing matrix (at most 32 columns) into registers: lane g holds column nb + g
+    const int nt2 = n - nb;
+    double a[NMAX];
+    {
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) a[i] = (nb + i < n && nb + gl < n) ? S->A[nb + i][nb + gl] : 0.0;
+    }
+    double *dptr = dsc + s + (size_t)(nb + gl) * nslots;
+    double *eptr = esc + s + (size_t)(nb + gl) * nslots;
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < NMAX - 1; ++k) {
+        if ((k & 3) == 0) __syncthreads();
+        const double x = (gl > k && gl < nt2) ? a[k] : 0.0;
+        S->xs[gl] = x;
+        __syncwarp();
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+        for (int i = k + 1; i < NMAX; ++i) {
+            const double xi = S->xs[i];
+            if (((i - k - 1) & 3) == 0) acc0 = fma(a[i], xi, acc0);
+            if (((i - k - 1) & 3) == 1) acc1 = fma(a[i], xi, acc1);
+            if (((i - k - 1) & 3) == 2) acc2 = fma(a[i], xi, acc2);
+            if (((i - k - 1) & 3) == 3) acc3 = fma(a[i], xi, acc3);
+        }
+        const double pt = (acc0 + acc1) + (acc2 + acc3);
+        const double sg0 = x * x, ta0 = x * pt;
+        double keep = hi ? ta0 : sg0;
+        keep += __shfl_xor_sync(0xffffffffu, hi ? sg0 : ta0, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+        const double other = __shfl_xor_sync(0xffffffffu, keep, 16);
+        const double sig = hi ? other : keep, tau = hi ? keep : other;
+        const double x1 = S->xs[k + 1];
+        const double pt1 = __shfl_sync(0xffffffffu, pt, k + 1);
+        const double t00 = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
+        const bool doit = sig > 0.0;
+        const double rs = doit ? sig * fast_rsqrt(sig) : 0.0;
+        const double alpha = x1 >= 0.0 ? -rs : rs;
+        const double H = sig - alpha * x1;
+        const double iH = doit ? fast_rcp(H) : 0.0;
+        const double K = (tau - 2.0 * alpha * pt1 + alpha * alpha * t00) * (0.5 * iH * iH);
+        const double v = (gl == k + 1) ? x - alpha : x;
+        const double pg = (pt - alpha * a[k + 1]) * iH;
+        const double w = (gl > k) ? pg - K * v : 0.0;
+        if (gl == k && valid && k < nt2) {
+            *dptr = a[k];
+            if (k + 1 < nt2) *eptr = alpha;
+        }
+        S->vw[gl] = make_double2(v, w);
+        __syncwarp();
+#pragma unroll
+        for (int i = k + 1; i < NMAX; ++i) {
+            const double2 q = S->vw[i];
+            a[i] = fma(-q.x, w, fma(-q.y, v, a[i]));
+        }
+    }
+    if (valid) {
+        if (gl == NMAX - 1 && nt2 == NMAX) *dptr = a[NMAX - 1];
+        if (gl == 0) nsc[s] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6a-mc, clusters of up to 48 atoms (round 2): the register-resident Householder scheme with SEVERAL
 // columns per lane.  A group of LPM lanes owns one matrix, lane g holds columns g, g + LPM, ... (CPL
 // "slots" of NMAX doubles each), so a warp works on 32 / LPM matrices and
@@ -1959,6 +2178,33 @@ static int run_bucket_mc(mdb_ctx *c, const DescParams &P, const int *d_list, int
     return 0;
 }
 
+// bordered register kernel + QL for the 33..40-atom classes
+template <int NS, int WARPS, int QTHREADS>
+static int run_bucket_bord(mdb_ctx *c, const DescParams &P, const int *d_list, int ofs, int cnt, double *dsc, double *esc,
+                           int *nsc, int chunk, const int *d_counts, const int *d_padorder, const double *d_padval,
+                           const int *d_maxcount, int D, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream) {
+    const size_t smem_tri = sizeof(BordSmem<NS>) * WARPS;
+    const size_t smem_ql = (size_t)2 * NS * QTHREADS * sizeof(double);
+    MDB_CUDA(cudaFuncSetAttribute(k_tridiag_bord<NS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+    MDB_CUDA(cudaFuncSetAttribute(k_tql<NS, QTHREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ql));
+    for (int s0 = 0; s0 < cnt; s0 += chunk) {
+        const int ns = std::min(chunk, cnt - s0);
+        {
+            ProfScope ps(c, NS == 36 ? "k_tridiag_bord<36>" : "k_tridiag_bord<40>", stream);
+            k_tridiag_bord<NS, WARPS><<<cdiv(ns, WARPS), WARPS * 32, smem_tri, stream>>>(P, d_list, cnt, ofs + s0, ns, dsc, esc, nsc);
+        }
+        {
+            ProfScope ps(c, bucket_name(NS, true), stream);
+            k_tql<NS, QTHREADS><<<cdiv(ns, QTHREADS), QTHREADS, smem_ql, stream>>>(
+                d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder, d_padval, d_maxcount, D, d_X, d_eig, eigcap,
+                d_n, c->d_stats, c->cur_eig_off, c->opt_ql_pwk);
+        }
+        c->launches += 2;
+    }
+    MDB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double *h_cell, const uint8_t *d_types,
                     int periodic, double cutoff, const int *d_targets, long long ntargets, const int *d_counts,
                     const int *h_maxcount, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream,
@@ -2102,8 +2348,17 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
             MDB_BUCKET(5, 28, 8, 32, 128, 1)
             MDB_BUCKET(6, 32, 8, 32, 128, 1)
         }
-        MDB_BUCKET_MC(7, 36, 32, 2, 8, 1, 64)
-        MDB_BUCKET_MC(8, 40, 32, 2, 8, 1, 64)
+        if (c->opt_desc_legacy == 2) {
+            MDB_BUCKET_MC(7, 36, 32, 2, 8, 1, 64)
+            MDB_BUCKET_MC(8, 40, 32, 2, 8, 1, 64)
+        } else {
+            if (hb[7] && run_bucket_bord<36, 8, 64>(c, P, d_list, ofs[7], hb[7], dsc, esc, nsc, chunk, d_counts, d_padorder,
+                                                    d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
+                return -1;
+            if (hb[8] && run_bucket_bord<40, 6, 64>(c, P, d_list, ofs[8], hb[8], dsc, esc, nsc, chunk, d_counts, d_padorder,
+                                                    d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
+                return -1;
+        }
         MDB_BUCKET_MC(9, 44, 32, 2, 8, 1, 64)
         MDB_BUCKET_MC(10, 48, 32, 2, 8, 1, 64)
     }
