@@ -1834,7 +1834,7 @@ __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ co
     int n = 0;
     for (int k = 0; k < nt; ++k) n += counts[t * nt + k];
     nsum[t] = n;
-    atomicAdd(&bucket_n[desc_bucket(n)], 1);
+    atomicAdd(&bucket_n[n > 160 ? 161 : n], 1);  // histogram by exact size (slot 161: too large)
 }
 
 __global__ void __launch_bounds__(256) k_bucket_fill(const int *__restrict__ nsum, long long ntargets,
@@ -1842,7 +1842,9 @@ __global__ void __launch_bounds__(256) k_bucket_fill(const int *__restrict__ nsu
                                                      int *__restrict__ list) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntargets) return;
-    const int b = desc_bucket(nsum[t]);
+    // matrices of equal size sit together (ascending size, so a size class is still one contiguous range): the
+    // threads of a QL warp and the warps of a bordered block then run loops of equal length
+    const int b = min(nsum[t], 161);
     const int k = atomicAdd(&cursor[b], 1);
     list[bucket_ofs[b] + k] = (int)t;
 }
@@ -2247,7 +2249,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     const int chunk = 1 << 16;
     // scratch: bucket bookkeeping + lists + d/e for one chunk at the largest NMAX in use
     size_t extra = align256(T * sizeof(int)) * 2 + align256((size_t)chunk * 160 * sizeof(double)) * 2 +
-                   align256((size_t)chunk * sizeof(int)) + 16 * 256 + (d_eig_off ? align256(scan_scratch_bytes(T + 1)) : 0);
+                   align256((size_t)chunk * sizeof(int)) + 32 * 256 + (d_eig_off ? align256(scan_scratch_bytes(T + 1)) : 0);
     DescParams P;
     if (desc_setup(c, F, N, d_pos, h_cell, d_types, periodic, cutoff, d_targets, ntargets, stream, &P, extra, d_members == nullptr))
         return -1;
@@ -2258,7 +2260,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     double *dsc = (double *)arena_alloc(c, (size_t)chunk * 160 * sizeof(double));
     double *esc = (double *)arena_alloc(c, (size_t)chunk * 160 * sizeof(double));
     int *nsc = (int *)arena_alloc(c, (size_t)chunk * sizeof(int));
-    int *d_book = (int *)arena_alloc(c, 512);            // bucket_n[32] | cursor[32] | ofs[32]
+    int *d_book = (int *)arena_alloc(c, 3 * 192 * sizeof(int));   // per sphere size: count[192] | cursor[192] | first position[192]
     int *d_maxcount = (int *)arena_alloc(c, 256);
     int *d_padorder = (int *)arena_alloc(c, 256);
     double *d_padval = (double *)arena_alloc(c, 256);
@@ -2280,7 +2282,7 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
         }
         order[y + 1] = v;
     }
-    MDB_CUDA(cudaMemsetAsync(d_book, 0, 512, stream));
+    MDB_CUDA(cudaMemsetAsync(d_book, 0, 3 * 192 * sizeof(int), stream));
     MDB_CUDA(cudaMemcpyAsync(d_maxcount, h_maxcount, nt * sizeof(int), cudaMemcpyHostToDevice, stream));
     MDB_CUDA(cudaMemcpyAsync(d_padorder, order, nt * sizeof(int), cudaMemcpyHostToDevice, stream));
     MDB_CUDA(cudaMemcpyAsync(d_padval, c->el.diag, nt * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -2298,9 +2300,19 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
         if (device_exclusive_scan(c, d_eig_off, T + 1, tmp, stream)) return -1;
         c->cur_eig_off = d_eig_off;
     }
-    int hb[DESC_NB + 1];
-    MDB_CUDA(cudaMemcpyAsync(hb, d_book, sizeof(hb), cudaMemcpyDeviceToHost, stream));
+    int hn[192], hb[DESC_NB + 1];
+    MDB_CUDA(cudaMemcpyAsync(hn, d_book, sizeof(hn), cudaMemcpyDeviceToHost, stream));
     MDB_CUDA(cudaStreamSynchronize(stream));
+    int ofs_n[192];
+    memset(hb, 0, sizeof(hb));
+    {
+        int run = 0;
+        for (int q = 0; q < 192; ++q) {
+            ofs_n[q] = run;
+            run += hn[q];
+            if (q <= 161) hb[q == 161 ? DESC_NB : desc_bucket(q)] += hn[q];
+        }
+    }
     if (hb[DESC_NB] > 0) {
         mdb_set_error("a cutoff sphere holds more than 160 atoms; reduce the cutoff");
         return -1;
@@ -2308,8 +2320,8 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     int ofs[DESC_NB + 1];
     ofs[0] = 0;
     for (int b = 0; b < DESC_NB; ++b) ofs[b + 1] = ofs[b] + hb[b];
-    MDB_CUDA(cudaMemcpyAsync(d_book + 64, ofs, sizeof(ofs), cudaMemcpyHostToDevice, stream));
-    k_bucket_fill<<<cdiv(T, 256), 256, 0, stream>>>(d_nsum, T, d_book + 64, d_book + 32, d_list);
+    MDB_CUDA(cudaMemcpyAsync(d_book + 384, ofs_n, sizeof(ofs_n), cudaMemcpyHostToDevice, stream));
+    k_bucket_fill<<<cdiv(T, 256), 256, 0, stream>>>(d_nsum, T, d_book + 384, d_book + 192, d_list);
     c->launches++;
 #define MDB_BUCKET(B, NMAX, WARPS, LPM, QT, REG)                                                                              \
     if (hb[B] && run_bucket<NMAX, WARPS, LPM, QT, REG>(c, P, d_list, ofs[B], hb[B], dsc, esc, nsc, chunk, d_counts, d_padorder, \
