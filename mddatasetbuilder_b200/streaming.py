@@ -596,6 +596,7 @@ class StreamingSelector:
                      "memcap": self.memcap, "rings": getattr(self, "rings", 0), "comm": self.comm,
                      "spectra_cache": {"batches": getattr(self, "cached_batches", 0), "of": len(self.stores),
                                        "gb": self.cache_bytes / 1e9},
+                     "hbm_peak_allocated_gb": self.torch.cuda.max_memory_allocated(self.eng.device) / 1e9,
                      "fit_comm": getattr(self, "fit_comm", None)}
         return res
 
