@@ -746,6 +746,140 @@ double dv[3];
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6a'', clusters of 161..512 atoms (cutoffs of 7 A and more in condensed phases): one block of 512 threads
+// per matrix, the matrix in a global-memory scratch row-major with stride 512 (2 MB, L2-resident while a few
+// hundred blocks are in flight), member list and the two vectors of a step in shared memory.  Textbook
+// Householder step (EISPACK tred1): u = x - alpha e1, H = u.u / 2, p = T u / H, K = u.p / (2 H), q = p - K u,
+// T -= u q^T + q u^T, with IEEE sqrt and divide -- this class is a fallback for completeness, not a hot path.
+// One warp per row of T, the lanes along the row (coalesced).  Output as k_tridiag_blk.
+// ---------------------------------------------------------------------------------------------
+#define GLB_NMAX 512
+#define GLB_THREADS 512
+struct GlbMatrix {
+    double *p;
+    __device__ __forceinline__ double *operator[](int a) const { return p + (size_t)a * GLB_NMAX; }
+};
+struct GlbSmem {
+    GlbMatrix A;
+    double vec[GLB_NMAX][3];
+    double u[GLB_NMAX];
+    double q[GLB_NMAX];
+    double red[GLB_THREADS / 32];
+    double bc[2];
+    int z[GLB_NMAX];
+    int t[GLB_NMAX];
+    int idx[GLB_NMAX];
+    double L[3];
+    const FrameGeom *gp;
+    int n;
+};
+
+__device__ __forceinline__ double glb_block_sum(GlbSmem *S, double v, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // red[] of the previous reduction has been read by everyone
+    if ((tid & 31) == 0) S->red[tid >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < GLB_THREADS / 32; ++w) r += S->red[w];
+    return r;
+}
+
+__global__ void __launch_bounds__(GLB_THREADS) k_tridiag_glb(const __grid_constant__ DescParams P, const int *__restrict__ list,
+                                                             int slot0, int sub0, int nslots, double *__restrict__ Ascr,
+                                                             double *__restrict__ dsc, double *__restrict__ esc,
+                                                             int *__restrict__ nsc) {
+    __shared__ GlbSmem Sm;
+    GlbSmem *S = &Sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = sub0 + blockIdx.x;  // slot of this block inside the [k][slot] scratch
+    if (tid == 0) {
+        S->n = 0;
+        S->A.p = Ascr + (size_t)blockIdx.x * GLB_NMAX * GLB_NMAX;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int ord = list[slot0 + s];
+        const int gt = P.targets ? P.targets[ord] : ord;
+        const int f = gt / P.N, a = gt - f * P.N;
+        const FrameGeom &G0 = P.geom[f];
+        const double *pos = P.pos + (size_t)f * P.N * 3;
+        const double pa[3] = {pos[(size_t)a * 3], pos[(size_t)a * 3 + 1], pos[(size_t)a * 3 + 2]};
+        gather_scan(P, f, a, ord, [&](int j, int tj) {
+            const int k = atomicAdd(&S->n, 1);
+            if (k < GLB_NMAX) {
+                double dv[3];
+                member_delta(P.periodic, G0, pos, j, pa, dv);
+                S->vec[k][0] = dv[0];
+                S->vec[k][1] = dv[1];
+                S->vec[k][2] = dv[2];
+                S->z[k] = P.Z[tj];
+                S->t[k] = tj;
+                S->idx[k] = j;
+            }
+        });
+        if (lane == 0) {
+            S->L[0] = G0.ortho[0];
+            S->L[1] = G0.ortho[4];
+            S->L[2] = G0.ortho[8];
+            S->gp = &G0;
+        }
+    }
+    __syncthreads();
+    int n = S->n;
+    if (n > GLB_NMAX) {
+        if (tid == 0) atomicExch(&P.stats->err, MDB_ERR_BOND_OVERFLOW);
+        n = GLB_NMAX;
+    }
+    canonical_member_order(S, n, tid, [] { __syncthreads(); });
+    for (int i = tid; i < n; i += GLB_THREADS) S->A[i][i] = P.diag[S->t[i]];
+    coulomb_pairs(P, S, n, tid, GLB_THREADS);
+    __syncthreads();
+    const GlbMatrix A = S->A;
+    for (int k = 0; k + 1 < n; ++k) {
+        const int m = n - k - 1;  // order of the trailing block T = A[k+1.., k+1..]; x = A[k][k+1..]
+        const double x = tid < m ? A[k][k + 1 + tid] : 0.0;
+        const double sig = glb_block_sum(S, x * x, tid);
+        const double x0 = A[k][k + 1];
+        const double alpha = sig > 0.0 ? (x0 >= 0.0 ? -sqrt(sig) : sqrt(sig)) : 0.0;
+        if (tid == 0) {
+            dsc[(size_t)k * nslots + s] = A[k][k];
+            esc[(size_t)k * nslots + s] = alpha;
+        }
+        if (!(sig > 0.0)) continue;  // column already reduced (uniform over the block)
+        const double H = sig - alpha * x0;
+        const double uval = tid == 0 ? x - alpha : x;
+        if (tid < m) S->u[tid] = uval;
+        __syncthreads();
+        // p = T u / H
+        for (int i = warp; i < m; i += GLB_THREADS / 32) {
+            const double *row = A[k + 1 + i] + k + 1;
+            double acc = 0.0;
+            for (int j = lane; j < m; j += 32) acc = fma(row[j], S->u[j], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) S->q[i] = acc / H;
+        }
+        __syncthreads();
+        const double pv = tid < m ? S->q[tid] : 0.0;
+        const double K = glb_block_sum(S, uval * pv, tid) / (2.0 * H);
+        if (tid < m) S->q[tid] = pv - K * uval;
+        __syncthreads();
+        for (int i = warp; i < m; i += GLB_THREADS / 32) {
+            double *row = A[k + 1 + i] + k + 1;
+            const double ui = S->u[i], qi = S->q[i];
+            for (int j = lane; j < m; j += 32) row[j] = fma(-ui, S->q[j], fma(-qi, S->u[j], row[j]));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (n > 0) dsc[(size_t)(n - 1) * nslots + s] = A[n - 1][n - 1];
+        nsc[s] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6a', clusters of up to 32 atoms: the matrix lives in registers.  LPM lanes own one matrix, lane g
 // holds column g (= row g) as NMAX doubles, so a warp works on 32 / LPM matrices; shared memory
 // carries the member list, a staging copy of the matrix (built pair by pair, each pair once) and the
@@ -1834,7 +1968,7 @@ __global__ void __launch_bounds__(256) k_bucket_count(const int *__restrict__ co
     int n = 0;
     for (int k = 0; k < nt; ++k) n += counts[t * nt + k];
     nsum[t] = n;
-    atomicAdd(&bucket_n[n > 160 ? 161 : n], 1);  // histogram by exact size (slot 161: too large)
+    atomicAdd(&bucket_n[n > GLB_NMAX ? 162 : n > 160 ? 161 : n], 1);  // by exact size; 161: the global-memory class, 162: too large
 }
 
 __global__ void __launch_bounds__(256) k_bucket_fill(const int *__restrict__ nsum, long long ntargets,
@@ -1844,7 +1978,7 @@ __global__ void __launch_bounds__(256) k_bucket_fill(const int *__restrict__ nsu
     if (t >= ntargets) return;
     // matrices of equal size sit together (ascending size, so a size class is still one contiguous range): the
     // threads of a QL warp and the warps of a bordered block then run loops of equal length
-    const int b = min(nsum[t], 161);
+    const int b = nsum[t] > GLB_NMAX ? 162 : min(nsum[t], 161);
     const int k = atomicAdd(&cursor[b], 1);
     list[bucket_ofs[b] + k] = (int)t;
 }
@@ -2180,6 +2314,42 @@ static int run_bucket_mc(mdb_ctx *c, const DescParams &P, const int *d_list, int
     return 0;
 }
 
+// global-memory class (161..512 atoms): the matrix scratch is allocated for this call only (two blocks per SM in
+// flight); the tridiagonals of up to `chunk * 160 / 512` matrices are collected in d/e before one QL launch
+static int run_bucket_glb(mdb_ctx *c, const DescParams &P, const int *d_list, int ofs, int cnt, double *dsc, double *esc,
+                          int *nsc, int chunk, const int *d_counts, const int *d_padorder, const double *d_padval,
+                          const int *d_maxcount, int D, double *d_X, double *d_eig, int eigcap, int *d_n, cudaStream_t stream) {
+    constexpr int QT = 8;
+    const int super = (int)((size_t)chunk * 160 / GLB_NMAX);
+    const int nb = std::min(cnt, 2 * 148);
+    double *Ascr = nullptr;
+    MDB_CUDA(cudaMalloc(&Ascr, (size_t)nb * GLB_NMAX * GLB_NMAX * sizeof(double)));
+    const size_t smem_ql = (size_t)2 * GLB_NMAX * QT * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k_tql<GLB_NMAX, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ql);
+    for (int s0 = 0; s0 < cnt && e == cudaSuccess; s0 += super) {
+        const int ns = std::min(super, cnt - s0);
+        {
+            ProfScope ps(c, "k_tridiag_glb", stream);
+            for (int b0 = 0; b0 < ns; b0 += nb) {
+                k_tridiag_glb<<<std::min(nb, ns - b0), GLB_THREADS, 0, stream>>>(P, d_list, ofs + s0, b0, ns, Ascr, dsc, esc, nsc);
+                c->launches++;
+            }
+        }
+        {
+            ProfScope ps(c, "k_tql<512>", stream);
+            k_tql<GLB_NMAX, QT><<<cdiv(ns, QT), QT, smem_ql, stream>>>(d_list, ofs + s0, ns, dsc, esc, nsc, d_counts, P.nt, d_padorder,
+                                                                     d_padval, d_maxcount, D, d_X, d_eig, eigcap, d_n, c->d_stats,
+                                                                     c->cur_eig_off, c->opt_ql_pwk);
+            c->launches++;
+        }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(Ascr);
+    MDB_CUDA(e);
+    return 0;
+}
+
 // bordered register kernel + QL for the 33..40-atom classes
 template <int NS, int WARPS, int QTHREADS>
 static int run_bucket_bord(mdb_ctx *c, const DescParams &P, const int *d_list, int ofs, int cnt, double *dsc, double *esc,
@@ -2313,8 +2483,8 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
             if (q <= 161) hb[q == 161 ? DESC_NB : desc_bucket(q)] += hn[q];
         }
     }
-    if (hb[DESC_NB] > 0) {
-        mdb_set_error("a cutoff sphere holds more than 160 atoms; reduce the cutoff");
+    if (hn[162] > 0) {
+        mdb_set_error("a cutoff sphere holds more than 512 atoms; reduce the cutoff");
         return -1;
     }
     int ofs[DESC_NB + 1];
@@ -2381,5 +2551,8 @@ int descriptors_run(mdb_ctx *c, int F, int N, const double *d_pos, const double 
     MDB_BUCKET(14, 128, 1, 32, 64, 0)
     MDB_BUCKET(15, 160, 1, 32, 64, 0)
 #undef MDB_BUCKET
+    if (hb[DESC_NB] && run_bucket_glb(c, P, d_list, ofs[DESC_NB], hb[DESC_NB], dsc, esc, nsc, chunk, d_counts, d_padorder, d_padval,
+                                      d_maxcount, D, d_X, d_eig, eigcap, d_n, stream))
+        return -1;
     return 0;
 }

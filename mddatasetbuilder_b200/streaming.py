@@ -249,9 +249,9 @@ class StreamingSelector:
                 eng.check()
                 break
             except RuntimeError as e:                      # (2) = a membership list overflowed its capacity
-                if "(2)" not in str(e) or self.memcap >= 160:
+                if "(2)" not in str(e) or self.memcap >= 512:
                     raise
-                self.memcap = min(160, self.memcap * 2)
+                self.memcap = min(512, self.memcap * 2)
         keep = None
         if fill_cache and self.cache_budget > 0:
             # sphere sizes summed per type: one read-back per batch

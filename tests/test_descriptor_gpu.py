@@ -120,8 +120,8 @@ def test_large_clusters_every_size_class(engine):
     assert worst < 1.0
 
 
-def test_clusters_up_to_160_atoms_and_the_limit(engine):
-    # 5.9 A in the dense phase: the largest class (<= 160 atoms); 7.5 A goes past it and is refused
+def test_clusters_up_to_160_atoms(engine):
+    # 5.9 A in the dense phase: the largest shared-memory class (<= 160 atoms)
     s = synth.make_system(1500, 0.11, seed=synth.BASE_SEED + 47, dense=True)
     targets = np.arange(0, 1500, 5, dtype=np.int32)
     engine.set_elements(s.atomname)
@@ -130,9 +130,42 @@ def test_clusters_up_to_160_atoms_and_the_limit(engine):
     assert n.max() > 128 and n.max() <= 160, (n.min(), n.max())
     worst = _check(engine, s, s.pos0[None], targets, cutoff=5.9)
     assert worst < 1.0
-    counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, 7.5, targets=targets[:8])
-    with pytest.raises(RuntimeError, match="more than 160 atoms"):
-        engine.descriptors(s.pos0[None], s.cell(), s.types, 7.5, counts, maxc, targets=targets[:8])
+
+
+@pytest.mark.parametrize("cutoff,lo,hi", [(8.0, 161, 320), (9.7, 330, 512)])
+def test_clusters_beyond_160_atoms_global_memory_class(engine, cutoff, lo, hi):
+    # larger cutoffs in the dense phase: 161..512 atoms per sphere go through the global-memory Householder class
+    # (k_tridiag_glb + k_tql<512>), same tolerance against numpy.linalg.eigh as every other class
+    s = synth.make_system(1500, 0.11, seed=synth.BASE_SEED + 47, dense=True)
+    targets = np.arange(0, 1500, 25, dtype=np.int32)
+    engine.set_elements(s.atomname)
+    counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, cutoff, targets=targets)
+    n = counts.sum(dim=1).cpu().numpy()
+    assert n.min() >= lo and n.max() <= hi, (n.min(), n.max())
+    worst = _check(engine, s, s.pos0[None], targets, cutoff=cutoff)
+    assert worst < 1.0
+
+
+def test_mixed_small_and_large_clusters_in_one_call(engine):
+    # 7 A in the dense phase: 133..197 atoms, the shared-memory classes and the global-memory class in one call
+    s = synth.make_system(1500, 0.11, seed=synth.BASE_SEED + 47, dense=True)
+    engine.set_elements(s.atomname)
+    targets = np.arange(0, 1500, 30, dtype=np.int32)
+    counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, 7.0, targets=targets)
+    n = counts.sum(dim=1).cpu().numpy()
+    assert n.min() <= 160 < n.max(), (n.min(), n.max())
+    worst = _check(engine, s, s.pos0[None], targets, cutoff=7.0)
+    assert worst < 1.0
+
+
+def test_more_than_512_atoms_in_a_sphere_is_refused(engine):
+    s = synth.make_system(1500, 0.11, seed=synth.BASE_SEED + 47, dense=True)
+    targets = np.arange(0, 1500, 5, dtype=np.int32)
+    engine.set_elements(s.atomname)
+    counts, maxc = engine.compositions(s.pos0[None], s.cell(), s.types, 11.5, targets=targets[:8])
+    assert int(counts.sum(dim=1).max()) > 512
+    with pytest.raises(RuntimeError, match="more than 512 atoms"):
+        engine.descriptors(s.pos0[None], s.cell(), s.types, 11.5, counts, maxc, targets=targets[:8])
 
 
 def test_descriptors_are_reproducible_bit_for_bit(engine):
