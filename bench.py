@@ -314,6 +314,8 @@ def main():
     ap.add_argument("--host-slots", type=int, default=64)
     ap.add_argument("--exchange", default="replicated", choices=["replicated", "allreduce"])
     ap.add_argument("--train-threads", type=int, default=1)
+    ap.add_argument("--host-cache-gb", type=float, default=-1.0,
+                    help="host memory for pass-B spectra beyond the HBM tier (-1: what is available minus a reserve, 0: off)")
     ap.add_argument("--overlap-seeding", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -371,7 +373,8 @@ def main():
     def job(source, nfr):
         sel = StreamingSelector(eng, sysm.types, cutoff=5.0, n_clusters=args.clusters, n_each=1, seed=synth.BASE_SEED,
                                 periodic=True, pool_rows=args.pool_rows, want_molecules=True, kmeans_kwargs=kw,
-                                train_threads=args.train_threads, overlap_seeding=args.overlap_seeding)
+                                train_threads=args.train_threads, overlap_seeding=args.overlap_seeding,
+                                host_cache_gb=None if args.host_cache_gb < 0 else args.host_cache_gb)
         res = sel.run(source)
         return sel, res
 
@@ -431,7 +434,7 @@ def main():
     del cnt, nn
     sc = res.stats.get("spectra_cache") or {"batches": 0, "of": 1}
     # pass B computes every descriptor, pass C only those of the batches whose spectra were not kept
-    ntarget_passes = frames * natoms * (2.0 - sc["batches"] / max(sc["of"], 1))
+    ntarget_passes = frames * natoms * (2.0 - (sc["batches"] + sc.get("host_batches", 0)) / max(sc["of"], 1))
     useful_flops = (8.0 / 3.0) * n3_mean * ntarget_passes
     fp64_peak = eng.fp64_peak_tflops()
     Dmean = float(np.mean([st["D"] for st in res.stats["fit"].values()])) if res.stats.get("fit") else 0.0

@@ -17,6 +17,11 @@ pass C  descriptors again -> scale -> assignment (tcgen05 screening + float64 re
 select  ``default_rng(seed)`` draws one member position per cluster and draw, resolved against the stored
         labels on the device -- the same rows ``choose_per_cluster`` picks from in-memory labels.
 
+Spectra kept from pass B for pass C live in two tiers: HBM while the budget lasts, then ordinary host memory
+behind a small page-locked ring (``_HostTier``): device -> ring -> pageable copies trail pass B on a copy stream
+and a worker thread, and a prefetcher walks pass C's batch order ahead of the compute stream.  Page-locking the
+whole tier is not an option (measured on the B200 box: 2 GiB/s, and kernel launches stall meanwhile).
+
 Multi-GPU: frame batches are dealt round-robin over the ranks; the exchanges are the key vocabulary and
 per-batch counts (objects), ``max_counter`` (MAX), scaler bounds (MIN / MAX), the pool rows (SUM of
 disjoint contributions), per-batch cluster counts and the chosen rows.  Training runs replicated on the
@@ -25,6 +30,9 @@ replicated pool, so results do not depend on the number of ranks.
 
 from __future__ import annotations
 
+import os
+import queue
+import threading
 import time
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Iterable, List, Optional
@@ -74,11 +82,234 @@ class SelectionResult:
     stats: Dict[str, object] = field(default_factory=dict)
 
 
+_RING = {}   # (device index, slots, piece) -> page-locked slots, allocated once per process (0.4 s for 768 MB)
+
+
+def _host_memory_available():
+    """Bytes of host memory this process may still take: MemAvailable, capped by the cgroup limit if one is set."""
+    avail = None
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    avail = int(line.split()[1]) * 1024
+                    break
+    except OSError:
+        pass
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            with open(lim) as f:
+                v = f.read().strip()
+            if v != "max" and int(v) < (1 << 60):
+                with open(cur) as f:
+                    left = int(v) - int(f.read().strip())
+                avail = left if avail is None else min(avail, left)
+        except (OSError, ValueError):
+            pass
+    return avail or 0
+
+
+class _HostTier:
+    """Second tier of the spectra cache: pageable host memory behind a ring of page-locked slots.
+
+    put()  (pass B) hands a batch's device tensors to a worker: device -> slot copies on a copy stream, slot ->
+           pageable copies on the worker (first touch of the pages included); the device tensors are released
+           when the last piece has landed.  At most `depth` batches wait, so HBM use stays bounded.
+    start_fetch() / take()  (pass C): a prefetcher walks the given batch order, pageable -> slot -> device, and
+           hands over (tensors, ready event) `depth` batches ahead of the compute stream.
+    """
+
+    def __init__(self, torch, device, budget_bytes, piece=128 << 20, slots=6, depth=2):
+        self.torch, self.device = torch, device
+        self.budget = int(budget_bytes)
+        self.bytes = 0
+        self.piece, self.depth = int(piece), int(depth)
+        key = (torch.device(device).index, slots, self.piece)
+        if key not in _RING:
+            _RING[key] = [torch.empty(self.piece, dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
+        self.ring = _RING[key]
+        self.cs = torch.cuda.Stream(device)
+        self.store = {}                      # gidx -> {key: [(host uint8 tensor, dtype, shape)]}
+        self.index = set()                   # batches handed to put(): what pass C will find here
+        self.err = None
+        self._q = None
+        self._worker = None
+        self._out = None
+
+    def __contains__(self, gidx):
+        return gidx in self.index
+
+    def __len__(self):
+        return len(self.index)
+
+    def room(self, need):
+        return self.err is None and self.bytes + need <= self.budget
+
+    # -------------------------------------------------------------- helpers
+    def _bytes(self, t):
+        return t.reshape(-1).view(self.torch.uint8)
+
+    def _check(self):
+        if self.err is not None:
+            raise RuntimeError("host tier of the spectra cache failed") from self.err
+
+    def _pump(self, segments, to_host):
+        """Moves (device bytes, host bytes) segments through the ring, `piece` bytes at a time."""
+        torch = self.torch
+        free = list(range(len(self.ring)))
+        pending = []                         # (slot, event, host view or None)
+
+        def retire():
+            slot, ev, hv = pending.pop(0)
+            ev.synchronize()
+            if hv is not None:
+                hv.copy_(self.ring[slot][: hv.numel()])
+            free.append(slot)
+
+        with torch.cuda.stream(self.cs):
+            for dv, hv in segments:
+                n = dv.numel()
+                for o in range(0, n, self.piece):
+                    m = min(self.piece, n - o)
+                    if not free:
+                        retire()
+                    slot = free.pop()
+                    sv = self.ring[slot][:m]
+                    if to_host:
+                        sv.copy_(dv[o:o + m], non_blocking=True)
+                    else:
+                        sv.copy_(hv[o:o + m])
+                        dv[o:o + m].copy_(sv, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.cs)
+                    pending.append((slot, ev, hv[o:o + m] if to_host else None))
+            while pending:
+                retire()
+
+    # -------------------------------------------------------------- pass B
+    def _spill_loop(self):
+        torch = self.torch
+        try:
+            torch.cuda.set_device(self.device)
+            while True:
+                job = self._q.get()
+                if job is None:
+                    return
+                gidx, ev, keep = job
+                self.cs.wait_event(ev)
+                entry, segments = {}, []
+                for k, tensors in keep.items():
+                    hs = []
+                    for t in tensors:
+                        h = torch.empty(t.numel() * t.element_size(), dtype=torch.uint8)
+                        hs.append((h, t.dtype, tuple(t.shape)))
+                        if t.numel():
+                            segments.append((self._bytes(t), h))
+                    entry[k] = hs
+                self._pump(segments, True)
+                self.store[gidx] = entry
+                del keep, segments, job      # the device tensors go back to the allocator only now
+        except BaseException as e:  # noqa: BLE001 -- reported to the main thread by _check()
+            self.err = e
+
+    def put(self, gidx, keep, need):
+        """keep: {key: (eig, off, counts)} device tensors produced on the current stream."""
+        self._check()
+        if self._worker is None:
+            self._q = queue.Queue(maxsize=self.depth)
+            self._worker = threading.Thread(target=self._spill_loop, daemon=True)
+            self._worker.start()
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream(self.device))
+        self.bytes += need
+        self.index.add(gidx)
+        while True:
+            try:
+                self._q.put((gidx, ev, keep), timeout=1.0)
+                return
+            except queue.Full:
+                self._check()
+
+    def finish_spill(self):
+        if self._worker is not None:
+            self._q.put(None)
+            self._worker.join()
+            self._worker, self._q = None, None
+        self._check()
+
+    # -------------------------------------------------------------- pass C
+    def _fetch_loop(self, order, compute_stream):
+        torch = self.torch
+        try:
+            torch.cuda.set_device(self.device)
+            for gidx in order:
+                entry = self.store[gidx]
+                out, segments = {}, []
+                with torch.cuda.stream(self.cs):
+                    for k, hs in entry.items():
+                        ts = []
+                        for h, dt, shape in hs:
+                            t = torch.empty(shape, dtype=dt, device=self.device)
+                            t.record_stream(compute_stream)
+                            ts.append(t)
+                            if t.numel():
+                                segments.append((self._bytes(t), h))
+                        out[k] = tuple(ts)
+                self._pump(segments, False)
+                ev = torch.cuda.Event()
+                ev.record(self.cs)
+                while True:
+                    try:
+                        self._out.put((gidx, out, ev), timeout=1.0)
+                        break
+                    except queue.Full:
+                        if self._stop:
+                            return
+                del self.store[gidx]         # the host copy is not needed again
+        except BaseException as e:  # noqa: BLE001
+            self.err = e
+
+    def start_fetch(self, order):
+        order = [g for g in order if g in self.index]
+        self._stop = False
+        self._out = queue.Queue(maxsize=self.depth)
+        self._worker = threading.Thread(target=self._fetch_loop,
+                                        args=(order, self.torch.cuda.current_stream(self.device)), daemon=True)
+        self._worker.start()
+
+    def take(self, gidx):
+        while True:
+            self._check()
+            try:
+                g, out, ev = self._out.get(timeout=1.0)
+                break
+            except queue.Empty:
+                if self._worker is None or not self._worker.is_alive():
+                    self._check()
+                    raise RuntimeError("host tier: prefetcher ended before batch %d" % gidx)
+        if g != gidx:
+            raise RuntimeError("host tier: batch %d delivered, %d expected" % (g, gidx))
+        self.torch.cuda.current_stream(self.device).wait_event(ev)
+        return out
+
+    def close(self):
+        self._stop = True
+        if self._worker is not None:
+            if self._q is not None:
+                self._q.put(None)
+            self._worker.join(timeout=30.0)
+        self._worker, self._q, self._out = None, None, None
+        self.store, self.index = {}, set()
+        self.bytes = 0
+
+
 class StreamingSelector:
     def __init__(self, engine, types, cutoff=5.0, n_clusters=10000, n_each=1, seed=0, periodic=True,
                  perceive_bond_orders=False, pool_rows=1 << 21, table_cap=1024, want_molecules=False,
                  only_keys: Optional[Iterable[int]] = None, log: Optional[Callable[[str], None]] = None,
                  kmeans_kwargs: Optional[dict] = None, cache_gb: Optional[float] = None, cache_reserve_gb: float = 24.0,
+                 host_cache_gb: Optional[float] = None, host_reserve_gb: float = 24.0,
                  train_threads: int = 1, overlap_seeding: bool = False):
         import torch
 
@@ -102,7 +333,10 @@ class StreamingSelector:
         self.comm = {}
         self.cache_gb = cache_gb                  # HBM for spectra kept from pass B to pass C (None: what is free)
         self.cache_reserve_gb = cache_reserve_gb
-        self.cache, self.cache_bytes, self.cache_budget = {}, 0, 0
+        self.cache, self.cache_bytes, self.cache_budget, self.cache_hits = {}, 0, 0, 0
+        self.host_cache_gb = host_cache_gb        # host memory for spectra beyond the HBM tier (None: what is free, 0: off)
+        self.host_reserve_gb = host_reserve_gb
+        self.host = None
         self.capture_rows = None
         self.train_threads = int(train_threads)
         self.overlap_seeding = bool(overlap_seeding)
@@ -235,10 +469,14 @@ class StreamingSelector:
         if not ranges:
             return
         cached = self.cache.get(st.gidx)
+        if cached is None and not fill_cache and self.host is not None and st.gidx in self.host:
+            cached = self.host.take(st.gidx)
         if cached is not None and not fill_cache:
             for k, a, e in ranges:
                 eig, off, cnt = cached[k]
                 yield k, eng.feature_rows_compact(eig, off, cnt, self.maxcount[k]), a, e
+            if self.cache.pop(st.gidx, None) is not None:   # pass C visits a batch once: its HBM goes back right away
+                self.cache_hits += 1
             return
         lo, hi = min(a for _, a, _ in ranges), max(e for _, _, e in ranges)
         tg = st.order[lo:hi]
@@ -252,8 +490,8 @@ class StreamingSelector:
                 if "(2)" not in str(e) or self.memcap >= 512:
                     raise
                 self.memcap = min(512, self.memcap * 2)
-        keep = None
-        if fill_cache and self.cache_budget > 0:
+        keep, spill = None, False
+        if fill_cache and (self.cache_budget > 0 or self.host is not None):
             # sphere sizes summed per type: one read-back per batch
             csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=eng.device), counts.sum(dim=1).cumsum(0)])
             ends = csum[torch.as_tensor([x - lo for _, a, e in ranges for x in (a, e)], device=eng.device)].cpu().numpy()
@@ -263,6 +501,8 @@ class StreamingSelector:
                 self.cache_budget -= need
                 self.cache_bytes += need
                 keep = {}
+            elif self.host is not None and self.host.room(need):
+                keep, spill = {}, True
         for k, a, e in ranges:
             cn = counts[a - lo:e - lo]
             mem = members[a - lo:e - lo]
@@ -274,7 +514,9 @@ class StreamingSelector:
                 X = eng.descriptors(b.pos, b.cell, self.types, self.cutoff, cn, self.maxcount[k], targets=st.order[a:e],
                                     periodic=self.periodic, want_X=True, members=mem)["X"]
             yield k, X, a, e
-        if keep is not None:
+        if spill:
+            self.host.put(st.gidx, keep, need)
+        elif keep is not None:
             self.cache[st.gidx] = keep
 
     # ------------------------------------------------------------------ pass B
@@ -299,7 +541,7 @@ class StreamingSelector:
                                     device=eng.device) for k in self.big}
         stores = {s.gidx: s for s in self.stores}
         # spectra cache for pass C: what is free now minus the labels pass C stores and its working set
-        self.cache, self.cache_bytes = {}, 0
+        self.cache, self.cache_bytes, self.cache_hits = {}, 0, 0
         if self.cache_gb is None:
             free, _ = torch.cuda.mem_get_info(eng.device)
             free += torch.cuda.memory_reserved(eng.device) - torch.cuda.memory_allocated(eng.device)
@@ -307,6 +549,19 @@ class StreamingSelector:
             self.cache_budget = int(free - 4 * rows_local - self.cache_reserve_gb * (1 << 30))
         else:
             self.cache_budget = int(self.cache_gb * (1 << 30))
+        # second tier: host memory (this rank's share of what is available minus a reserve)
+        if self.host is not None:
+            self.host.close()
+        self.host = None
+        if self.host_cache_gb is None:
+            share = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            hb = (_host_memory_available() - int(self.host_reserve_gb * (1 << 30))) // share
+        else:
+            hb = int(self.host_cache_gb * (1 << 30))
+        if hb > ((64 << 20) if self.host_cache_gb is None else 0):
+            self.host = _HostTier(torch, eng.device, hb)
+            if self.cache_gb is None:
+                self.cache_budget -= 8 << 30      # batches queued for the spill / prefetched in pass C live in HBM too
         for b in source.batches():
             st = stores[b.gidx]
             gi = self.gpos[b.gidx]
@@ -329,6 +584,8 @@ class StreamingSelector:
                 eng.gather_rows(X, src, dst, self.pool[k])
                 del X
         eng.check()
+        if self.host is not None:
+            self.host.finish_spill()
         d = _dist()
         if d is not None:
             self._sync()
@@ -468,8 +725,11 @@ class StreamingSelector:
         rechecked = 0
         # batches whose spectra were kept need no input tensors: sources that stage data (host -> device copies,
         # text parsing) may skip them
+        host = self.host
+        if host is not None and len(host):
+            host.start_fetch([g for g in self.gbatches if g in stores])
         try:
-            it = source.batches(needed=lambda g: g not in self.cache)
+            it = source.batches(needed=lambda g: g not in self.cache and (host is None or g not in host))
         except TypeError:
             it = source.batches()
         for b in it:
@@ -486,8 +746,11 @@ class StreamingSelector:
                 self.labels[k].append((b.gidx, a, e, lab))
                 del X
         eng.check()
-        self.cached_batches = len(self.cache)
+        self.cached_batches = self.cache_hits
         self.cache = {}
+        self.host_batches, self.host_bytes = (len(host), host.bytes) if host is not None else (0, 0)
+        if host is not None:
+            host.close()
         self.rechecked = rechecked
         d = _dist()
         if d is not None:
@@ -595,7 +858,8 @@ class StreamingSelector:
         res.stats = {"fit": getattr(self, "fit_stats", {}), "rechecked_in_float64": getattr(self, "rechecked", 0),
                      "memcap": self.memcap, "rings": getattr(self, "rings", 0), "comm": self.comm,
                      "spectra_cache": {"batches": getattr(self, "cached_batches", 0), "of": len(self.stores),
-                                       "gb": self.cache_bytes / 1e9},
+                                       "gb": self.cache_bytes / 1e9, "host_batches": getattr(self, "host_batches", 0),
+                                       "host_gb": getattr(self, "host_bytes", 0) / 1e9},
                      "hbm_peak_allocated_gb": self.torch.cuda.max_memory_allocated(self.eng.device) / 1e9,
                      "fit_comm": getattr(self, "fit_comm", None)}
         return res

@@ -169,8 +169,9 @@ def _in_memory_selection(engine, s, pos, bo_frames, K, n_each, seed, pool_rows):
     return out
 
 
-@pytest.mark.parametrize("pool_rows,batch,cache_gb", [(1 << 21, 2, None), (90, 3, 0.0), (90, 2, 0.002)])
-def test_streamed_selection_equals_in_memory(engine, pool_rows, batch, cache_gb):
+@pytest.mark.parametrize("pool_rows,batch,cache_gb,host_gb", [(1 << 21, 2, None, 0.0), (90, 3, 0.0, 0.0), (90, 2, 0.002, 0.0),
+                                                             (90, 2, 0.0, 1.0), (1 << 21, 1, 0.001, 0.0008), (90, 2, 0.002, None)])
+def test_streamed_selection_equals_in_memory(engine, pool_rows, batch, cache_gb, host_gb):
     """SURVEY.md hard part 3 / VERDICT item 2: the three-pass job picks exactly the rows the in-memory
     path picks -- all rows in the pool (first case) and with a seeded sub-sample as pool (second)."""
     from mddatasetbuilder_b200.streaming import ResidentSource, StreamingSelector
@@ -180,11 +181,18 @@ def test_streamed_selection_equals_in_memory(engine, pool_rows, batch, cache_gb)
     pos = _t(engine, synth.frame_positions(s, F))
     rowptr, col, bo = synth.bond_table_device(s, F, engine.device)
     sel = StreamingSelector(engine, s.types, cutoff=5.0, n_clusters=K, n_each=n_each, seed=seed, periodic=True,
-                            pool_rows=pool_rows, want_molecules=True, cache_gb=cache_gb)
+                            pool_rows=pool_rows, want_molecules=True, cache_gb=cache_gb, host_cache_gb=host_gb)
     res = sel.run(ResidentSource(pos, s.cell(), batch, rowptr=rowptr, col=col, bo=bo))
     nb = -(-F // batch)
-    nc = res.stats["spectra_cache"]["batches"]       # pass C: kept spectra / recomputed / a mix of both
+    nc = res.stats["spectra_cache"]["batches"]       # pass C: spectra kept in HBM / in host memory / recomputed / a mix
+    nh = res.stats["spectra_cache"]["host_batches"]
     assert (nc == nb) if cache_gb is None else (nc == 0) if cache_gb == 0.0 else (0 < nc < nb)
+    if host_gb == 0.0:
+        assert nh == 0
+    elif host_gb == 0.0008:
+        assert 0 < nh and 0 < nc and nc + nh < nb, (nc, nh, nb)    # all three routes in one job
+    else:
+        assert nc + nh == nb and nh > 0, (nc, nh, nb)
     want = _in_memory_selection(engine, s, pos, bo.cpu().numpy(), K, n_each, seed, sel.pool_rows)
     assert [int(k) for k in res.keys] == list(want.keys()), "bond types / first-seen order differ"
     assert len(sel.big) >= 3
