@@ -516,7 +516,6 @@ def main():
                            "l2": f"inputs are {frames * natoms * 45 / 1e9:.1f} GB per rank (> 126 MB L2)",
                            "seed": synth.BASE_SEED + 3},
                 "phases_s": phases, "roofline": roofline, "kernels": kern, "fit": {str(k): v for k, v in res.stats["fit"].items()},
-                "seeding_s": res.stats.get("seeding_s"),
                 "stages": stages, "cpu_baseline": base, "e2e": e2e, "comm": comm,
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line))

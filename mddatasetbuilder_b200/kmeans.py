@@ -45,46 +45,6 @@ class MinMaxScalerB200:
         return X
 
 
-def seed_many(fits):
-    """Seeds several fits -- [(MiniBatchKMeansB200, X)], e.g. every bond type of a job -- with as few k-means++
-    launches as possible.  The seeding kernel is bound by its per-step handshake, not by arithmetic (10,000
-    sequential picks at ~30 us, 23 MFLOP each), and it takes up to 64 independent problems per launch: the init rows
-    of all problems of equal size are gathered into one matrix (narrower types zero-padded on the right, which adds
-    exact zeros to every sum the kernel forms), so 15 types x 3 seedings cost about one launch instead of 15.  Each
-    fit keeps its own RandomState and draws exactly what ``MiniBatchKMeans.fit`` draws; the chosen rows are the
-    ones a launch per fit chooses.  Returns the states ``run_loop`` continues from, in the order given."""
-    import torch
-
-    if not fits:
-        return []
-    eng = fits[0][0].eng
-    preps = [km._seed_prepare(X) for km, X in fits]
-    groups = {}
-    for j, ((km, X), pr) in enumerate(zip(fits, preps)):
-        for i in range(km.n_init):
-            groups.setdefault((len(pr["rows"][i]), km.n_clusters, pr["T"]), []).append((j, i))
-    cands = [[None] * km.n_init for km, _ in fits]
-    for (m, K, T), plist in groups.items():
-        for c0 in range(0, len(plist), 48):
-            chunk = plist[c0:c0 + 48]
-            B = len(chunk)
-            Dmax = max(int(fits[j][1].shape[1]) for j, _ in chunk)
-            Xc = torch.zeros((B * m, Dmax), dtype=torch.float64, device=eng.device)
-            for b, (j, i) in enumerate(chunk):
-                X = fits[j][1]
-                ridx = torch.as_tensor(preps[j]["rows"][i], dtype=torch.int64, device=eng.device)
-                Xc[b * m:(b + 1) * m, : int(X.shape[1])] = X.index_select(0, ridx)
-            rowidx = torch.arange(B * m, dtype=torch.int32, device=eng.device).view(B, m)
-            rand = np.stack([preps[j]["rands"][i] for j, i in chunk])
-            first = np.array([preps[j]["firsts"][i] for j, i in chunk], dtype=np.int32)
-            idx = eng.kmeans_plusplus(Xc, K, rand, first, rowidx=rowidx)
-            for b, (j, i) in enumerate(chunk):
-                D = int(fits[j][1].shape[1])
-                cands[j][i] = Xc[b * m:(b + 1) * m].index_select(0, idx[b].long())[:, :D].contiguous()
-            del Xc
-    return [km._seed_finish(X, pr, cands[j]) for j, ((km, X), pr) in enumerate(zip(fits, preps))]
-
-
 class MiniBatchKMeansB200:
     def __init__(self, engine, n_clusters=8, init_size=None, n_init=3, batch_size=1024, max_iter=100,
                  max_no_improvement=10, reassignment_ratio=0.01, seed=0, verbose=False, exchange="replicated"):
@@ -101,6 +61,32 @@ class MiniBatchKMeansB200:
         self.exchange = exchange    # "replicated": every rank runs the whole step; "allreduce": batch slices + one all-reduce
 
     # ------------------------------------------------------------------ seeding
+    def _init_centroids_all(self, X, rs, init_size):
+        """The n_init seedings of sklearn's MiniBatchKMeans.fit (init_indices, then _kmeans_plusplus on
+        those rows), run as ONE batched device loop.  Each seeding consumes a fixed number of variates
+        (randint for the rows, one choice, (K-1) x n_local_trials uniforms) and nothing else touches the
+        RandomState in between, so drawing them up front reproduces sklearn's stream."""
+        import torch
+
+        eng = self.eng
+        n = int(X.shape[0])
+        K = self.n_clusters
+        T = 2 + int(np.log(K))
+        rows, firsts, rands = [], [], []
+        for _ in range(self.n_init):
+            if init_size is not None and init_size < n:
+                init_indices = rs.randint(0, n, init_size)
+            else:
+                init_indices = np.arange(n)
+            m = len(init_indices)
+            rows.append(init_indices.astype(np.int32))
+            firsts.append(int(rs.choice(m, p=np.full(m, 1.0 / m))))
+            rands.append(rs.uniform(size=(max(K - 1, 0), T)) if K > 1 else np.zeros((0, T)))
+        rowidx = torch.as_tensor(np.stack(rows), dtype=torch.int32, device=eng.device)
+        rand = np.stack(rands) if K > 1 else np.zeros((self.n_init, 1, T))
+        idx = eng.kmeans_plusplus(X, K, rand, np.array(firsts, dtype=np.int32), rowidx=rowidx)
+        return [X[rowidx[b].long()[idx[b].long()]].clone() for b in range(self.n_init)]
+
     # ------------------------------------------------------------------ one mini-batch step
     def _mini_batch_step(self, X, batch_idx, centers, weight_sums, rs, random_reassign, idx_host=None):
         """sklearn _mini_batch_step; updates centers / weight_sums in place, returns (inertia, whether any centre
@@ -171,9 +157,14 @@ class MiniBatchKMeansB200:
             any_zero = bool((ws == 0).any())
         return inertia, any_zero
 
-    def _seed_prepare(self, X):
-        """Host half of the seeding: every variate the validation draw and the n_init k-means++ runs consume, in
-        scikit-learn's order (nothing else touches the RandomState in between)."""
+    def seed_centers(self, X):
+        """First half of ``MiniBatchKMeans.fit``: the validation draw and the n_init k-means++ seedings, best one
+        kept.  Returns the state ``run_loop`` continues from (the RandomState goes along, so the split changes
+        no draw).  The streaming selector runs this half for the next bond type on a second stream while the
+        mini-batch loop of the current one is running."""
+        import torch
+
+        eng = self.eng
         n_samples = int(X.shape[0])
         K = self.n_clusters
         batch_size = min(self.batch_size, n_samples)
@@ -185,37 +176,13 @@ class MiniBatchKMeansB200:
         init_size = min(init_size, n_samples)
         rs = np.random.RandomState(self.seed)
         validation_indices = rs.randint(0, n_samples, init_size)
-        T = 2 + int(np.log(K))
-        rows, firsts, rands = [], [], []
-        for _ in range(self.n_init):
-            if init_size < n_samples:
-                init_indices = rs.randint(0, n_samples, init_size)
-            else:
-                init_indices = np.arange(n_samples)
-            m = len(init_indices)
-            rows.append(init_indices.astype(np.int32))
-            firsts.append(int(rs.choice(m, p=np.full(m, 1.0 / m))))
-            rands.append(rs.uniform(size=(max(K - 1, 0), T)) if K > 1 else np.zeros((1, T)))
-        return {"rs": rs, "batch_size": batch_size, "valid": validation_indices, "rows": rows, "firsts": firsts,
-                "rands": rands, "T": T}
-
-    def _seed_finish(self, X, prep, candidates):
-        """The seeding with the lowest inertia on the validation rows wins (MiniBatchKMeans.fit)."""
-        import torch
-
-        valid_idx = torch.as_tensor(prep["valid"], dtype=torch.int32, device=self.eng.device)
+        valid_idx = torch.as_tensor(validation_indices, dtype=torch.int32, device=eng.device)
         best_inertia, centers = None, None
-        for c in candidates:
-            _, inertia, _ = self.eng.kmeans_assign(X, c, rowidx=valid_idx, want_inertia=True)
+        for c in self._init_centroids_all(X, rs, init_size):
+            _, inertia, _ = eng.kmeans_assign(X, c, rowidx=valid_idx, want_inertia=True)
             if best_inertia is None or inertia < best_inertia:
                 centers, best_inertia = c, inertia
-        return {"rs": prep["rs"], "centers": centers.contiguous(), "batch_size": prep["batch_size"]}
-
-    def seed_centers(self, X):
-        """First half of ``MiniBatchKMeans.fit``: the validation draw and the n_init k-means++ seedings, best one
-        kept.  Returns the state ``run_loop`` continues from (the RandomState goes along, so the split changes
-        no draw)."""
-        return seed_many([(self, X)])[0]
+        return {"rs": rs, "centers": centers.contiguous(), "batch_size": batch_size}
 
     def run_loop(self, X, state):
         """Second half of ``MiniBatchKMeans.fit``: the mini-batch steps until the smoothed inertia stops improving."""

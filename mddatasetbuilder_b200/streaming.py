@@ -39,7 +39,7 @@ from typing import Callable, Dict, Iterable, List, Optional
 
 import numpy as np
 
-from .kmeans import MiniBatchKMeansB200, _dist, seed_many
+from .kmeans import MiniBatchKMeansB200, _dist
 
 KEY_EMPTY = np.uint64(0xFFFFFFFFFFFFFFFF)
 
@@ -618,8 +618,7 @@ class StreamingSelector:
         handshake-bound kernel) followed by a loop of small mini-batch steps with a host decision after each;
         the seeding of the next type runs on a second context / stream while the loop of the current one runs
         (`overlap_seeding`).  With several ranks the types are dealt over the ranks and the centres broadcast by
-        their owner.  Every fit carries its own RandomState, so neither changes any result.  By default the seedings
-        of all types run first, batched into one k-means++ launch per 48 problems (`kmeans.seed_many`).  The "allreduce"
+        their owner.  Every fit carries its own RandomState, so neither changes any result.  The "allreduce"
         exchange keeps every rank in every fit instead (mini-batch slices + one packed all-reduce per step).
         Measured on B200 (15 types, K = 10,000): the overlap is a loss -- the persistent seeding kernel spins on its
         flags and the step kernels of the other stream starve each other (train 8.2 -> 17.4 s) -- so it is off by
@@ -646,24 +645,8 @@ class StreamingSelector:
         mine = [k for k in todo if owner[k] == rank]
         self._sync()
         if not self.overlap_seeding or len(mine) < 2:
-            # all seedings of this rank's types first, batched into as few k-means++ launches as possible
-            # (kmeans.seed_many: the kernel is handshake-bound, 45 problems cost about what 3 do), then the loops
-            fits = []
             for k in mine:
-                pool = self.pool[k]
-                eng.minmax_transform(pool, self.mn_h[k], self.mx_h[k])
-                n = int(pool.shape[0])
-                fits.append((MiniBatchKMeansB200(eng, n_clusters=self.K, init_size=min(3 * self.K, n), n_init=3,
-                                                 seed=self.seed, **self.kmeans_kwargs), pool))
-            t0 = time.perf_counter()
-            states = seed_many(fits)
-            self._sync()
-            self.seeding_s = time.perf_counter() - t0
-            for k, (km, pool), state in zip(mine, fits, states):
-                km.run_loop(pool, state)
-                self.centers[k] = km.cluster_centers_
-                self.fit_stats[k] = {"steps": km.n_steps_, "pool_rows": int(pool.shape[0]), "rows": self.counts[k],
-                                     "D": self.D[k]}
+                self.centers[k], self.fit_stats[k], _ = self._fit_one(eng, k)
         else:
             # seeding (scaling of the pool, validation draw, 3 x k-means++: one long co-operative kernel that is
             # bound by its own handshakes) of type t + 1 on a second context / stream while the mini-batch loop of
@@ -872,8 +855,7 @@ class StreamingSelector:
         res = self.select()
         tm["select"] = lap()
         res.timings = tm
-        res.stats = {"fit": getattr(self, "fit_stats", {}), "seeding_s": getattr(self, "seeding_s", None),
-                     "rechecked_in_float64": getattr(self, "rechecked", 0),
+        res.stats = {"fit": getattr(self, "fit_stats", {}), "rechecked_in_float64": getattr(self, "rechecked", 0),
                      "memcap": self.memcap, "rings": getattr(self, "rings", 0), "comm": self.comm,
                      "spectra_cache": {"batches": getattr(self, "cached_batches", 0), "of": len(self.stores),
                                        "gb": self.cache_bytes / 1e9, "host_batches": getattr(self, "host_batches", 0),
