@@ -116,11 +116,14 @@ class _HostTier:
     put()  (pass B) hands a batch's device tensors to a worker: device -> slot copies on a copy stream, slot ->
            pageable copies on the worker (first touch of the pages included); the device tensors are released
            when the last piece has landed.  At most `depth` batches wait, so HBM use stays bounded.
-    start_fetch() / take()  (pass C): a prefetcher walks the given batch order, pageable -> slot -> device, and
-           hands over (tensors, ready event) `depth` batches ahead of the compute stream.
+    start_fetch() / take()  (pass C): two prefetchers (alternate batches, half of the ring and a copy stream each)
+           walk the given batch order, pageable -> slot -> device, and hand over (tensors, ready event) ahead of the
+           compute stream.
+    The workers' host copies run on a few threads only (`copy_threads`): the main thread launches kernels between
+    read-backs and must not wait for a core (measured: pass B 28.7 -> 31.5 s with 16 copy threads on 16 cores).
     """
 
-    def __init__(self, torch, device, budget_bytes, piece=128 << 20, slots=6, depth=2):
+    def __init__(self, torch, device, budget_bytes, piece=128 << 20, slots=8, depth=2, copy_threads=(4, 6)):
         self.torch, self.device = torch, device
         self.budget = int(budget_bytes)
         self.bytes = 0
@@ -130,6 +133,11 @@ class _HostTier:
             _RING[key] = [torch.empty(self.piece, dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
         self.ring = _RING[key]
         self.cs = torch.cuda.Stream(device)
+        self.cs2 = torch.cuda.Stream(device)
+        self.copy_threads = copy_threads
+        self._threads0 = torch.get_num_threads()
+        self._workers, self._outs, self._pos = [], [], {}
+        self.wait_put_s, self.wait_take_s, self.spill_busy_s, self.fetch_busy_s = 0.0, 0.0, 0.0, 0.0
         self.store = {}                      # gidx -> {key: [(host uint8 tensor, dtype, shape)]}
         self.index = set()                   # batches handed to put(): what pass C will find here
         self.err = None
@@ -154,10 +162,11 @@ class _HostTier:
         if self.err is not None:
             raise RuntimeError("host tier of the spectra cache failed") from self.err
 
-    def _pump(self, segments, to_host):
-        """Moves (device bytes, host bytes) segments through the ring, `piece` bytes at a time."""
+    def _pump(self, segments, to_host, slots=None, stream=None):
+        """Moves (device bytes, host bytes) segments through (part of) the ring, `piece` bytes at a time."""
         torch = self.torch
-        free = list(range(len(self.ring)))
+        free = list(range(len(self.ring))) if slots is None else list(slots)
+        stream = self.cs if stream is None else stream
         pending = []                         # (slot, event, host view or None)
 
         def retire():
@@ -167,7 +176,7 @@ class _HostTier:
                 hv.copy_(self.ring[slot][: hv.numel()])
             free.append(slot)
 
-        with torch.cuda.stream(self.cs):
+        with torch.cuda.stream(stream):
             for dv, hv in segments:
                 n = dv.numel()
                 for o in range(0, n, self.piece):
@@ -182,7 +191,7 @@ class _HostTier:
                         sv.copy_(hv[o:o + m])
                         dv[o:o + m].copy_(sv, non_blocking=True)
                     ev = torch.cuda.Event()
-                    ev.record(self.cs)
+                    ev.record(stream)
                     pending.append((slot, ev, hv[o:o + m] if to_host else None))
             while pending:
                 retire()
@@ -192,11 +201,13 @@ class _HostTier:
         torch = self.torch
         try:
             torch.cuda.set_device(self.device)
+            torch.set_num_threads(self.copy_threads[0])
             while True:
                 job = self._q.get()
                 if job is None:
                     return
                 gidx, ev, keep = job
+                tb = time.perf_counter()
                 self.cs.wait_event(ev)
                 entry, segments = {}, []
                 for k, tensors in keep.items():
@@ -208,6 +219,7 @@ class _HostTier:
                             segments.append((self._bytes(t), h))
                     entry[k] = hs
                 self._pump(segments, True)
+                self.spill_busy_s += time.perf_counter() - tb
                 self.store[gidx] = entry
                 del keep, segments, job      # the device tensors go back to the allocator only now
         except BaseException as e:  # noqa: BLE001 -- reported to the main thread by _check()
@@ -224,9 +236,11 @@ class _HostTier:
         ev.record(self.torch.cuda.current_stream(self.device))
         self.bytes += need
         self.index.add(gidx)
+        t0 = time.perf_counter()
         while True:
             try:
                 self._q.put((gidx, ev, keep), timeout=1.0)
+                self.wait_put_s += time.perf_counter() - t0
                 return
             except queue.Full:
                 self._check()
@@ -236,17 +250,20 @@ class _HostTier:
             self._q.put(None)
             self._worker.join()
             self._worker, self._q = None, None
+        self.torch.set_num_threads(self._threads0)   # no-op where the setting is per thread
         self._check()
 
     # -------------------------------------------------------------- pass C
-    def _fetch_loop(self, order, compute_stream):
+    def _fetch_loop(self, order, compute_stream, slots, stream, outq):
         torch = self.torch
         try:
             torch.cuda.set_device(self.device)
+            torch.set_num_threads(self.copy_threads[1])
             for gidx in order:
+                tb = time.perf_counter()
                 entry = self.store[gidx]
                 out, segments = {}, []
-                with torch.cuda.stream(self.cs):
+                with torch.cuda.stream(stream):
                     for k, hs in entry.items():
                         ts = []
                         for h, dt, shape in hs:
@@ -256,12 +273,13 @@ class _HostTier:
                             if t.numel():
                                 segments.append((self._bytes(t), h))
                         out[k] = tuple(ts)
-                self._pump(segments, False)
+                self._pump(segments, False, slots, stream)
                 ev = torch.cuda.Event()
-                ev.record(self.cs)
+                ev.record(stream)
+                self.fetch_busy_s += time.perf_counter() - tb
                 while True:
                     try:
-                        self._out.put((gidx, out, ev), timeout=1.0)
+                        outq.put((gidx, out, ev), timeout=1.0)
                         break
                     except queue.Full:
                         if self._stop:
@@ -273,21 +291,30 @@ class _HostTier:
     def start_fetch(self, order):
         order = [g for g in order if g in self.index]
         self._stop = False
-        self._out = queue.Queue(maxsize=self.depth)
-        self._worker = threading.Thread(target=self._fetch_loop,
-                                        args=(order, self.torch.cuda.current_stream(self.device)), daemon=True)
-        self._worker.start()
+        self._pos = {g: i for i, g in enumerate(order)}
+        half = len(self.ring) // 2
+        cur = self.torch.cuda.current_stream(self.device)
+        self._outs, self._workers = [], []
+        for w, (slots, stream) in enumerate(((range(0, half), self.cs), (range(half, len(self.ring)), self.cs2))):
+            outq = queue.Queue(maxsize=max(1, self.depth // 2))
+            th = threading.Thread(target=self._fetch_loop, args=(order[w::2], cur, slots, stream, outq), daemon=True)
+            th.start()
+            self._outs.append(outq)
+            self._workers.append(th)
 
     def take(self, gidx):
+        t0 = time.perf_counter()
+        w = self._pos[gidx] % 2
         while True:
             self._check()
             try:
-                g, out, ev = self._out.get(timeout=1.0)
+                g, out, ev = self._outs[w].get(timeout=1.0)
                 break
             except queue.Empty:
-                if self._worker is None or not self._worker.is_alive():
+                if not self._workers[w].is_alive():
                     self._check()
                     raise RuntimeError("host tier: prefetcher ended before batch %d" % gidx)
+        self.wait_take_s += time.perf_counter() - t0
         if g != gidx:
             raise RuntimeError("host tier: batch %d delivered, %d expected" % (g, gidx))
         self.torch.cuda.current_stream(self.device).wait_event(ev)
@@ -299,7 +326,11 @@ class _HostTier:
             if self._q is not None:
                 self._q.put(None)
             self._worker.join(timeout=30.0)
+        for th in self._workers:
+            th.join(timeout=30.0)
+        self.torch.set_num_threads(self._threads0)
         self._worker, self._q, self._out = None, None, None
+        self._workers, self._outs = [], []
         self.store, self.index = {}, set()
         self.bytes = 0
 
@@ -497,11 +528,22 @@ class StreamingSelector:
             ends = csum[torch.as_tensor([x - lo for _, a, e in ranges for x in (a, e)], device=eng.device)].cpu().numpy()
             totals = {k: int(ends[2 * i + 1] - ends[2 * i]) for i, (k, _, _) in enumerate(ranges)}
             need = sum(8 * totals[k] + (e - a) * (4 + 4 * self.nt) + 1024 for k, a, e in ranges)
-            if need <= self.cache_budget:
+            to_host = self.host is not None and self.host.room(need)
+            to_hbm = need <= self.cache_budget
+            if to_hbm and to_host:
+                # both tiers have room: spread the HBM share evenly over the batches instead of filling HBM first, so
+                # that pass C meets host batches between HBM batches and the prefetchers get time to run ahead
+                if self._hbm_share is None:
+                    self._hbm_share = min(1.0, self.cache_budget / float(need * max(1, len(self.stores))))
+                self._hbm_acc += self._hbm_share
+                to_hbm = self._hbm_acc >= 1.0
+                if to_hbm:
+                    self._hbm_acc -= 1.0
+            if to_hbm:
                 self.cache_budget -= need
                 self.cache_bytes += need
                 keep = {}
-            elif self.host is not None and self.host.room(need):
+            elif to_host:
                 keep, spill = {}, True
         for k, a, e in ranges:
             cn = counts[a - lo:e - lo]
@@ -542,6 +584,7 @@ class StreamingSelector:
         stores = {s.gidx: s for s in self.stores}
         # spectra cache for pass C: what is free now minus the labels pass C stores and its working set
         self.cache, self.cache_bytes, self.cache_hits = {}, 0, 0
+        self._hbm_share, self._hbm_acc = None, 0.0
         if self.cache_gb is None:
             free, _ = torch.cuda.mem_get_info(eng.device)
             free += torch.cuda.memory_reserved(eng.device) - torch.cuda.memory_allocated(eng.device)
@@ -750,6 +793,8 @@ class StreamingSelector:
         self.cache = {}
         self.host_batches, self.host_bytes = (len(host), host.bytes) if host is not None else (0, 0)
         if host is not None:
+            self.host_waits = {"pass_b_queue_full_s": round(host.wait_put_s, 3), "pass_c_waiting_for_batch_s": round(host.wait_take_s, 3),
+                               "spill_worker_busy_s": round(host.spill_busy_s, 3), "fetch_worker_busy_s": round(host.fetch_busy_s, 3)}
             host.close()
         self.rechecked = rechecked
         d = _dist()
@@ -859,7 +904,7 @@ class StreamingSelector:
                      "memcap": self.memcap, "rings": getattr(self, "rings", 0), "comm": self.comm,
                      "spectra_cache": {"batches": getattr(self, "cached_batches", 0), "of": len(self.stores),
                                        "gb": self.cache_bytes / 1e9, "host_batches": getattr(self, "host_batches", 0),
-                                       "host_gb": getattr(self, "host_bytes", 0) / 1e9},
+                                       "host_gb": getattr(self, "host_bytes", 0) / 1e9, "host_waits": getattr(self, "host_waits", None)},
                      "hbm_peak_allocated_gb": self.torch.cuda.max_memory_allocated(self.eng.device) / 1e9,
                      "fit_comm": getattr(self, "fit_comm", None)}
         return res
