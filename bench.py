@@ -511,6 +511,7 @@ def main():
                            "bond_types": len(res.keys), "clustered_types": len(res.maxcount),
                            "selected_structures": nchosen, "spectra_cache": res.stats.get("spectra_cache"),
                            "hbm_peak_allocated_gb": res.stats.get("hbm_peak_allocated_gb"),
+                           "allocator": res.stats.get("allocator"),
                            "parallelism": f"frame batches interleaved over {world} rank(s); training {args.exchange}, "
                                           f"bond types dealt over the ranks, {args.train_threads} concurrent fits per rank",
                            "l2": f"inputs are {frames * natoms * 45 / 1e9:.1f} GB per rank (> 126 MB L2)",

@@ -2087,27 +2087,61 @@ __global__ void __launch_bounds__(128) k_feature_rows(long long T, const double 
     while (w < D) o[w++] = 0.0;
 }
 
-__global__ void __launch_bounds__(128) k_feature_rows_compact(long long T, const double *__restrict__ eig,
+// One warp per row: the row is the merge of the ascending spectrum with the ascending pad values, the spectrum first on
+// ties (the sequential loop of k_feature_rows), so eigenvalue k lands at k + (pads below it) and the pads of class q start
+// at (pads of earlier classes) + (eigenvalues <= their value).  Reads and writes are contiguous per row.
+__global__ void __launch_bounds__(256) k_feature_rows_compact(long long T, const double *__restrict__ eig,
                                                               const int *__restrict__ off, const int *__restrict__ counts, int nt,
                                                               const int *__restrict__ padorder, const double *__restrict__ padval,
                                                               const int *__restrict__ maxcount, int D, double *__restrict__ X) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const int n = off[t + 1] - off[t];
-    const double *d = eig + off[t];
-    double *o = X + (size_t)t * D;
-    int w = 0, k = 0;
-    for (int q = 0; q < nt; ++q) {
-        const int el = padorder[q];
-        const int reps = maxcount[el] - counts[(size_t)t * nt + el];
-        const double pv = padval[el];
-        for (int r = 0; r < reps; ++r) {
-            while (k < n && d[k] <= pv && w < D) o[w++] = d[k++];
-            if (w < D) o[w++] = pv;
-        }
+    __shared__ double s_pv[MDB_MAXT];
+    __shared__ int s_el[MDB_MAXT], s_mc[MDB_MAXT];
+    if (threadIdx.x < nt) {
+        const int el = padorder[threadIdx.x];
+        s_el[threadIdx.x] = el;
+        s_pv[threadIdx.x] = padval[el];
+        s_mc[threadIdx.x] = maxcount[el];
     }
-    while (k < n && w < D) o[w++] = d[k++];
-    while (w < D) o[w++] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int o0 = off[t], n = off[t + 1] - o0;
+    const double *d = eig + o0;
+    double *o = X + (size_t)t * D;
+    // pads of class q (lane q < nt): how many, and how many pads precede the class
+    int reps = lane < nt ? s_mc[lane] - counts[(size_t)t * nt + s_el[lane]] : 0;
+    int before = reps;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, before, s);
+        if (lane >= s) before += v;
+    }
+    before -= reps;
+    int le = 0;  // lane q: eigenvalues <= the pad value of class q
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        const double v = k < n ? d[k] : 0.0;
+        int pads_below = 0;
+        for (int q = 0; q < nt; ++q) {
+            const int rq = __shfl_sync(0xffffffffu, reps, q);
+            const bool lei = k < n && v <= s_pv[q];
+            if (k < n && !lei) pads_below += rq;
+            const unsigned bl = __ballot_sync(0xffffffffu, lei);
+            if (lane == q) le += __popc(bl);
+        }
+        if (k < n && k + pads_below < D) o[k + pads_below] = v;
+    }
+    for (int q = 0; q < nt; ++q) {
+        const int rq = __shfl_sync(0xffffffffu, reps, q);
+        const int start = __shfl_sync(0xffffffffu, before + le, q);
+        const double pv = s_pv[q];
+        for (int r = lane; r < rq; r += 32)
+            if (start + r < D) o[start + r] = pv;
+    }
+    // (n + pads = D by construction: D = sum(maxcount), n = sum(counts))
+    const int total = n + __shfl_sync(0xffffffffu, before + reps, 31);
+    for (int w = total + lane; w < D; w += 32) o[w] = 0.0;
 }
 
 int feature_rows_run(mdb_ctx *c, long long T, const double *d_eig, int eigcap, const int *d_n, const int *d_counts,
@@ -2140,7 +2174,7 @@ int feature_rows_run(mdb_ctx *c, long long T, const double *d_eig, int eigcap, c
     {
         ProfScope ps(c, "k_feature_rows", stream);
         if (d_eig_off)
-            k_feature_rows_compact<<<cdiv(T, 128), 128, 0, stream>>>(T, d_eig, d_eig_off, d_counts, nt, d_padorder, d_padval,
+            k_feature_rows_compact<<<cdiv(T, 8), 256, 0, stream>>>(T, d_eig, d_eig_off, d_counts, nt, d_padorder, d_padval,
                                                                     d_maxcount, D, d_X);
         else
             k_feature_rows<<<cdiv(T, 128), 128, 0, stream>>>(T, d_eig, eigcap, d_n, d_counts, nt, d_padorder, d_padval,

@@ -1199,6 +1199,7 @@ int minmax_fit_run(mdb_ctx *c, long long rows, int D, const double *d_X, long lo
     if (!omin || !omax) return -1;
     k_minmax_init<<<cdiv(D, 256), 256, 0, stream>>>(omin, omax, D);
     if (rows > 0) {
+        ProfScope ps(c, "k_colminmax", stream);
         dim3 grid((unsigned)std::min<long long>(2048, (rows + 7) / 8), cdiv(D, 32));
         k_colminmax<<<grid, 256, 0, stream>>>(d_X, ldx, rows, D, omin, omax);
     }
@@ -1227,6 +1228,7 @@ int minmax_transform_run(mdb_ctx *c, long long rows, int D, double *d_X, long lo
     MDB_CUDA(cudaMemcpyAsync(d_sc, sc.data(), 2 * (size_t)D * sizeof(double), cudaMemcpyHostToDevice, stream));
     MDB_CUDA(cudaStreamSynchronize(stream));  // sc is a stack-lifetime host buffer
     if (rows > 0) {
+        ProfScope ps(c, "k_scale", stream);
         k_scale<<<cdiv(rows * D, 256), 256, 0, stream>>>(d_X, ldx, rows, D, d_sc, d_sc + D);
         c->launches++;
     }

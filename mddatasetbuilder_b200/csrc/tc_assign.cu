@@ -716,11 +716,17 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     unsigned long long *cbest = (unsigned long long *)take((size_t)ambcap * sizeof(unsigned long long));
 
     MDB_CUDA(cudaMemsetAsync(namb, 0, 2 * sizeof(int), stream));
-    k_col_mean<<<D, 256, 0, stream>>>(d_C, K, D, mu);
-    k_split_fp16<<<cdiv(Kpad, 8), 256, 0, stream>>>(d_C, D, nullptr, K, Kpad, D, Kd, mu, 1, nullptr, B, cn);
-    k_fmax<<<1, 256, 0, stream>>>(cn, K, cmax2);
-    k_norm_block<<<cdiv(K, 8), 256, 0, stream>>>(d_C, K, D, Kd, mu, cmax2, B);
-    k_split_fp16<<<cdiv(rows, 8), 256, 0, stream>>>(d_X, ldx, d_rowidx, rows, rows, D, Kd, mu, 0, cmax2, A, xn2);
+    {
+        ProfScope ps(c, "k_tc_prep", stream);
+        k_col_mean<<<D, 256, 0, stream>>>(d_C, K, D, mu);
+        k_split_fp16<<<cdiv(Kpad, 8), 256, 0, stream>>>(d_C, D, nullptr, K, Kpad, D, Kd, mu, 1, nullptr, B, cn);
+        k_fmax<<<1, 256, 0, stream>>>(cn, K, cmax2);
+        k_norm_block<<<cdiv(K, 8), 256, 0, stream>>>(d_C, K, D, Kd, mu, cmax2, B);
+    }
+    {
+        ProfScope ps(c, "k_split_fp16", stream);
+        k_split_fp16<<<cdiv(rows, 8), 256, 0, stream>>>(d_X, ldx, d_rowidx, rows, rows, D, Kd, mu, 0, cmax2, A, xn2);
+    }
     c->launches += 5;
     CUtensorMap tmA, tmB;
     if (make_map(&tmA, A, rows, Kin) || make_map(&tmB, B, Kpad, Kin)) return -1;
@@ -822,7 +828,7 @@ int kmeans_assign_tc_run(mdb_ctx *c, long long rows, int D, int K, const double 
     }
     // self-check: a strided sample of the rows is re-decided in float64; any disagreement (a violated
     // error model) sends the whole call through the float64 kernel -- "used only if it matches"
-    const int ns = (int)std::min<long long>(rows, 4096);
+    const int ns = (int)std::min<long long>(rows, 1024);
     k_sample_rows<<<cdiv(ns, 256), 256, 0, stream>>>(rows, ns, d_rowidx, amb_pos, amb_row);
     if (kmeans_assign_run(c, ns, D, K, d_X, ldx, amb_row, d_C, amb_lab, nullptr, nullptr, nullptr, stream)) return -1;
     MDB_CUDA(cudaMemsetAsync(namb, 0, sizeof(int), stream));

@@ -92,7 +92,7 @@ class Engine:
         _lib.check(self.L.mdb_profile_read(self.ctx, buf, len(buf)), "mdb_profile_read")
         out = {}
         for line in buf.value.decode().splitlines():
-            name, cnt, ms = line.split()
+            name, cnt, ms = line.rsplit(None, 2)
             out[name] = (int(cnt), float(ms))
         return out
 

@@ -906,6 +906,9 @@ class StreamingSelector:
                                        "gb": self.cache_bytes / 1e9, "host_batches": getattr(self, "host_batches", 0),
                                        "host_gb": getattr(self, "host_bytes", 0) / 1e9, "host_waits": getattr(self, "host_waits", None)},
                      "hbm_peak_allocated_gb": self.torch.cuda.max_memory_allocated(self.eng.device) / 1e9,
+                     "allocator": {k: int(v) for k, v in self.torch.cuda.memory_stats(self.eng.device).items()
+                                   if k in ("num_alloc_retries", "num_ooms", "segment.all.allocated", "segment.all.freed",
+                                            "num_device_alloc", "num_device_free")},
                      "fit_comm": getattr(self, "fit_comm", None)}
         return res
 
