@@ -16,7 +16,7 @@ dev = eng.device
 pos = synth.frame_positions_device(s, F, dev)
 rowptr, col, bo = synth.bond_table_device(s, F, dev)
 eng.profile(True)
-sel = StreamingSelector(eng, s.types, n_clusters=64, seed=1, periodic=True, want_molecules=True, cache_gb=0.0,
+sel = StreamingSelector(eng, s.types, n_clusters=64, seed=1, periodic=True, want_molecules=True, cache_gb=0.0, host_cache_gb=0.0,
                         kmeans_kwargs={"max_no_improvement": 2})
 res = sel.run(ResidentSource(pos, s.cell(), F, rowptr=rowptr, col=col, bo=bo))
 torch.cuda.synchronize()
