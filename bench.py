@@ -314,6 +314,8 @@ def main():
     ap.add_argument("--host-slots", type=int, default=64)
     ap.add_argument("--exchange", default="replicated", choices=["replicated", "allreduce"])
     ap.add_argument("--train-threads", type=int, default=1)
+    ap.add_argument("--cache-gb", type=float, default=-1.0,
+                    help="HBM for pass-B spectra (-1: what is free minus a reserve); small values force the host tier in short test runs")
     ap.add_argument("--host-cache-gb", type=float, default=-1.0,
                     help="host memory for pass-B spectra beyond the HBM tier (-1: what is available minus a reserve, 0: off)")
     ap.add_argument("--overlap-seeding", action="store_true")
@@ -374,6 +376,7 @@ def main():
         sel = StreamingSelector(eng, sysm.types, cutoff=5.0, n_clusters=args.clusters, n_each=1, seed=synth.BASE_SEED,
                                 periodic=True, pool_rows=args.pool_rows, want_molecules=True, kmeans_kwargs=kw,
                                 train_threads=args.train_threads, overlap_seeding=args.overlap_seeding,
+                                cache_gb=None if args.cache_gb < 0 else args.cache_gb,
                                 host_cache_gb=None if args.host_cache_gb < 0 else args.host_cache_gb)
         res = sel.run(source)
         return sel, res
