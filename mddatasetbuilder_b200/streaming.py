@@ -12,14 +12,14 @@ pass B  descriptors of all types at once -> running column bounds of the scaler 
         nothing else), rows of the seeded training pool collected on the fly;
 train   ``MiniBatchKMeans`` per type on its scaled pool (all rows when the type has no more than
         ``pool_rows`` of them -- then this is exactly the in-memory fit);
-pass C  descriptors again -> scale -> assignment (tcgen05 screening + float64 re-check) -> labels and
-        per-(batch, cluster) member counts;
+pass C  rows again (from the spectra pass B kept; recomputed only when neither cache tier had room) -> scale ->
+        assignment (tcgen05 screening + float64 re-check) -> labels and per-(batch, cluster) member counts;
 select  ``default_rng(seed)`` draws one member position per cluster and draw, resolved against the stored
         labels on the device -- the same rows ``choose_per_cluster`` picks from in-memory labels.
 
 Spectra kept from pass B for pass C live in two tiers: HBM while the budget lasts, then ordinary host memory
 behind a small page-locked ring (``_HostTier``): device -> ring -> pageable copies trail pass B on a copy stream
-and a worker thread, and a prefetcher walks pass C's batch order ahead of the compute stream.  Page-locking the
+and a worker thread, and two prefetchers walk pass C's batch order ahead of the compute stream.  Page-locking the
 whole tier is not an option (measured on the B200 box: 2 GiB/s, and kernel launches stall meanwhile).
 
 Multi-GPU: frame batches are dealt round-robin over the ranks; the exchanges are the key vocabulary and
