@@ -427,3 +427,11 @@ def test_minibatch_draw_equals_numpy_choice():
                 c = c - ((c > 0) & (cdf[np.maximum(c - 1, 0)] > u))
                 c = c + ((c <= n - 1) & (cdf[np.minimum(c, n - 1)] <= u))
             assert np.array_equal(want, c)
+
+
+def test_host_memory_budget_helper():
+    """The host tier of the spectra cache sizes itself from MemAvailable capped by the cgroup limit."""
+    from mddatasetbuilder_b200.streaming import _host_memory_available
+
+    v = _host_memory_available()
+    assert isinstance(v, int) and 0 < v < (1 << 50)
