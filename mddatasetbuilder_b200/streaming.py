@@ -522,11 +522,13 @@ class StreamingSelector:
                     raise
                 self.memcap = min(512, self.memcap * 2)
         keep, spill = None, False
+        # sphere sizes summed per type: one read-back per batch
+        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=eng.device), counts.sum(dim=1).cumsum(0)])
+        ends = csum[torch.as_tensor([x - lo for _, a, e in ranges for x in (a, e)] + [hi - lo], device=eng.device)].cpu().numpy()
+        first = {k: int(ends[2 * i]) for i, (k, _, _) in enumerate(ranges)}
+        totals = {k: int(ends[2 * i + 1] - ends[2 * i]) for i, (k, _, _) in enumerate(ranges)}
+        del csum
         if fill_cache and (self.cache_budget > 0 or self.host is not None):
-            # sphere sizes summed per type: one read-back per batch
-            csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=eng.device), counts.sum(dim=1).cumsum(0)])
-            ends = csum[torch.as_tensor([x - lo for _, a, e in ranges for x in (a, e)], device=eng.device)].cpu().numpy()
-            totals = {k: int(ends[2 * i + 1] - ends[2 * i]) for i, (k, _, _) in enumerate(ranges)}
             need = sum(8 * totals[k] + (e - a) * (4 + 4 * self.nt) + 1024 for k, a, e in ranges)
             to_host = self.host is not None and self.host.room(need)
             to_hbm = need <= self.cache_budget
@@ -545,16 +547,25 @@ class StreamingSelector:
                 keep = {}
             elif to_host:
                 keep, spill = {}, True
+        # ONE eigen-solve call for every type of the batch (the spectrum of a sphere does not depend on the type it is
+        # filed under): one size histogram and one read-back instead of one per type, and launches that fill the GPU
+        # also for the rare types.  Each type's slice of the compact spectra is copied out (the long-lived tensors then
+        # have the same sizes as with one call per type, which the allocator handles without fragmenting -- views of
+        # the whole buffer did not survive the full-size job) and its rows are merged from the slice.
+        _, eig_all, off_all = eng.descriptors_compact(b.pos, b.cell, self.types, counts, self.maxcount[ranges[0][0]], tg, members,
+                                                      int(ends[-1]), periodic=self.periodic, want_X=False)
+        del members
+        parts = {}
         for k, a, e in ranges:
-            cn = counts[a - lo:e - lo]
-            mem = members[a - lo:e - lo]
+            parts[k] = (eig_all[first[k]:first[k] + totals[k]].clone(), off_all[a - lo:e - lo + 1] - off_all[a - lo],
+                        counts[a - lo:e - lo].clone())
+        del eig_all, off_all, counts
+        for k, a, e in ranges:
+            eig, off, cn = parts.pop(k)
+            X = eng.feature_rows_compact(eig, off, cn, self.maxcount[k])
             if keep is not None:
-                X, eig, off = eng.descriptors_compact(b.pos, b.cell, self.types, cn, self.maxcount[k], st.order[a:e], mem,
-                                                      totals[k], periodic=self.periodic)
-                keep[k] = (eig, off, cn.clone())
-            else:
-                X = eng.descriptors(b.pos, b.cell, self.types, self.cutoff, cn, self.maxcount[k], targets=st.order[a:e],
-                                    periodic=self.periodic, want_X=True, members=mem)["X"]
+                keep[k] = (eig, off, cn)
+            del eig, off, cn
             yield k, X, a, e
         if spill:
             self.host.put(st.gidx, keep, need)
