@@ -1,5 +1,6 @@
 """Streaming selection: bond typing, descriptors, clustering and per-cluster choice of EVERY bond type in
-three passes over the frames, with nothing descriptor-wide kept for all rows (SURVEY.md §7 hard part 3).
+three passes over the frames; no feature matrix is ever held for all rows (SURVEY.md §7 hard part 3) -- the
+compact spectra are, in HBM and host memory, as long as they fit, and are recomputed where they do not.
 
 The reference holds, per bond type, the whole feature matrix in RAM (``feedvector``, reference
 datasetbuilder.py:238,255-260) and re-reads the trajectory once per type (:243).  At 1e9 atom-frames
