@@ -248,7 +248,12 @@ class _HostTier:
 
     def finish_spill(self):
         if self._worker is not None:
-            self._q.put(None)
+            while True:                      # a worker that died with a full queue must not hang the job
+                try:
+                    self._q.put(None, timeout=1.0)
+                    break
+                except queue.Full:
+                    self._check()
             self._worker.join()
             self._worker, self._q = None, None
         self.torch.set_num_threads(self._threads0)   # no-op where the setting is per thread
@@ -325,7 +330,10 @@ class _HostTier:
         self._stop = True
         if self._worker is not None:
             if self._q is not None:
-                self._q.put(None)
+                try:
+                    self._q.put_nowait(None)
+                except queue.Full:
+                    pass                     # daemon thread: left behind after an error, never waited for
             self._worker.join(timeout=30.0)
         for th in self._workers:
             th.join(timeout=30.0)
